@@ -1,0 +1,253 @@
+"""ORACLE - test infrastructure, NOT product code.
+
+CPU fp32 restatement of the reference's autoencoder hot path
+(Encoder -> discrete bottleneck -> speaker-conditioned Decoder), written as
+plain functions over a reference-layout ``state_dict``.  It exists so the
+`-m gpu` parity tests, ``__graft_entry__.smoke()`` and ``bench.py``'s
+``cpu_baseline``/``--impl reference`` arm have something to check and time the
+CUDA path against on a box where /root/reference does not exist.  Nothing under
+``zerospeech-tts-without-t_b200/`` may import it.
+
+Parity pin: the reference has no tests or golden vectors (SURVEY.md section 4,
+8c), so this file is pinned against the *live* reference modules
+(``/root/reference/model/model.py`` imported in the build container) by
+``tests/golden/make_golden.py``, which stores reference outputs under
+``tests/golden/*.npz``; ``tests/test_oracle_golden.py`` replays them against
+this restatement (max-abs <= 1e-5, unit ids bit-exact).
+
+Every function cites the reference lines it restates.  All tensors are
+(batch, channel, time) float32 like the reference's.
+"""
+import math
+
+import torch
+import torch.nn.functional as F
+
+IN_EPS = 1e-5          # nn.InstanceNorm1d default (model/model.py:303-307, 402-407)
+GUMBEL_EPS = 1e-20     # model/model.py:95
+GUMBEL_TAU = 0.1       # model/model.py:93
+
+
+# ----------------------------------------------------------------------------
+# helpers: model/model.py:20-110
+# ----------------------------------------------------------------------------
+def _pad_mode(seg_len):
+    # model/model.py:38 - keyed on the hyper-parameter, not on the tensor length
+    return 'constant' if seg_len < 64 else 'reflect'
+
+
+def conv_same(x, w, b, seg_len, stride=1):
+    """pad_layer + nn.Conv1d: model/model.py:20-40 (even k pads (k/2, k/2-1))."""
+    k = w.shape[2]
+    pad = (k // 2, k // 2 - 1) if k % 2 == 0 else (k // 2, k // 2)
+    return F.conv1d(F.pad(x, pad, mode=_pad_mode(seg_len)), w, b, stride=stride)
+
+
+def frame_linear(x, w, b):
+    """linear(): per-frame nn.Linear on (B, C, T); model/model.py:69-78."""
+    return torch.einsum('oc,bct->bot', w, x) + b.view(1, -1, 1)
+
+
+def instance_norm(x):
+    """nn.InstanceNorm1d, no affine, no running stats, biased variance."""
+    mu = x.mean(dim=2, keepdim=True)
+    var = ((x - mu) ** 2).mean(dim=2, keepdim=True)
+    return (x - mu) / torch.sqrt(var + IN_EPS)
+
+
+def pixel_shuffle_1d(x):
+    """model/model.py:43-51: out[b, c, 2w+r] = in[b, 2c+r, w]."""
+    b, c2, w = x.shape
+    return x.view(b, c2 // 2, 2, w).permute(0, 1, 3, 2).reshape(b, c2 // 2, 2 * w)
+
+
+def nearest_up2(x):
+    """upsample(): model/model.py:54-56 (always x2)."""
+    return x.repeat_interleave(2, dim=2)
+
+
+def bi_gru(x, sd, prefix='RNN.'):
+    """RNN() with zero initial state: model/model.py:59-66, PyTorch gate order r,z,n."""
+    B, _, T = x.shape
+    outs = []
+    for sfx, order in (('', range(T)), ('_reverse', range(T - 1, -1, -1))):
+        w_ih, w_hh = sd[f'{prefix}weight_ih_l0{sfx}'], sd[f'{prefix}weight_hh_l0{sfx}']
+        b_ih, b_hh = sd[f'{prefix}bias_ih_l0{sfx}'], sd[f'{prefix}bias_hh_l0{sfx}']
+        H = w_hh.shape[1]
+        gx = torch.einsum('gc,bct->btg', w_ih, x) + b_ih
+        h = x.new_zeros(B, H)
+        out = x.new_zeros(B, H, T)
+        for t in order:
+            gh = h @ w_hh.t() + b_hh
+            r = torch.sigmoid(gx[:, t, :H] + gh[:, :H])
+            z = torch.sigmoid(gx[:, t, H:2 * H] + gh[:, H:2 * H])
+            n = torch.tanh(gx[:, t, 2 * H:] + r * gh[:, 2 * H:])
+            h = (1 - z) * n + z * h
+            out[:, :, t] = h
+        outs.append(out)
+    return torch.cat(outs, dim=1)
+
+
+def gumbel_noise(uniform):
+    """_sample_gumbel(): model/model.py:95-98, from an explicit uniform draw."""
+    return -torch.log(-torch.log(uniform + GUMBEL_EPS) + GUMBEL_EPS)
+
+
+def gumbel_hard(logits_last, uniform):
+    """gumbel_softmax(): model/model.py:93-110 forward value (exact 0/1) + indices.
+
+    Follows the reference literally: softmax((l+g)/tau) first, then max over the
+    last axis (first index wins ties, like torch.max)."""
+    y = F.softmax((logits_last + gumbel_noise(uniform)) / GUMBEL_TAU, dim=-1)
+    ind = y.max(dim=-1)[1]
+    hard = torch.zeros_like(y).scatter_(-1, ind.unsqueeze(-1), 1.0)
+    return (hard - y) + y, ind
+
+
+# ----------------------------------------------------------------------------
+# Encoder: model/model.py:416-489
+# ----------------------------------------------------------------------------
+def _enc_conv_block(x, sd, names, strides, ns, seg_len, res=True):
+    out = x
+    for n, s in zip(names, strides):                         # :418-420
+        out = F.leaky_relu(conv_same(out, sd[n + '.weight'], sd[n + '.bias'], seg_len, s), ns)
+    out = instance_norm(out)                                  # :421-422 (dropout: eval = identity)
+    if res:                                                   # :423-426
+        xp = F.pad(x, (0, x.shape[2] % 2), mode=_pad_mode(seg_len))
+        out = F.avg_pool1d(xp, 2) + out
+    return out
+
+
+def _enc_dense_block(x, sd, names, ns):
+    out = x
+    for n in names:                                           # :431-433
+        out = F.leaky_relu(frame_linear(out, sd[n + '.weight'], sd[n + '.bias']), ns)
+    return instance_norm(out) + x                             # :434-437
+
+
+def encoder_trunk(sd, x, ns=0.01, seg_len=128):
+    """Everything up to (and including) the final Linear: model/model.py:440-455 + linear."""
+    bank = [conv_same(x, sd[f'conv1s.{i}.weight'], sd[f'conv1s.{i}.bias'], seg_len) for i in range(7)]
+    out = F.leaky_relu(torch.cat(bank + [x], dim=1), ns)      # :445-446
+    out = _enc_conv_block(out, sd, ['conv2'], [1], ns, seg_len, res=False)
+    out = _enc_conv_block(out, sd, ['conv3', 'conv4'], [1, 2], ns, seg_len)
+    out = _enc_conv_block(out, sd, ['conv5', 'conv6'], [1, 2], ns, seg_len)
+    out = _enc_conv_block(out, sd, ['conv7', 'conv8'], [1, 2], ns, seg_len)
+    out = _enc_dense_block(out, sd, ['dense1', 'dense2'], ns)
+    out = _enc_dense_block(out, sd, ['dense3', 'dense4'], ns)
+    out = torch.cat([out, bi_gru(out, sd)], dim=1)            # :454-455
+    return frame_linear(out, sd['linear.weight'], sd['linear.bias'])
+
+
+def encoder_forward(sd, x, uniform=None, ns=0.01, seg_len=128, enc_mode='one_hot', enc_size=None):
+    """Encoder.forward in eval mode: returns (out_act, out, unit_ids or None).
+
+    `uniform` is the torch.rand draw of gumbel_softmax (shape (B,T8,enc) for one_hot,
+    (B,T8,enc,2) for multilabel_binary, (B,enc,T8) for gumbel_t)."""
+    logits = encoder_trunk(sd, x, ns, seg_len)
+    ids = None
+    if enc_mode == 'continues':                               # :457-459
+        act = F.leaky_relu(logits, ns)
+    elif enc_mode == 'one_hot':                               # :461-464
+        hard, ids = gumbel_hard(logits.permute(0, 2, 1), uniform)
+        act = hard.permute(0, 2, 1).contiguous()
+    elif enc_mode == 'multilabel_binary':                     # :474-480
+        B, C2, T8 = logits.shape
+        proj = logits.permute(0, 2, 1).reshape(B, T8, C2 // 2, 2)
+        hard, _ = gumbel_hard(proj, uniform)
+        act = hard[..., 0].permute(0, 2, 1).contiguous()
+    elif enc_mode == 'gumbel_t':                              # :482-484 (softmax over time)
+        act, _ = gumbel_hard(logits, uniform)
+    else:
+        raise NotImplementedError(enc_mode)
+    return act, logits, ids
+
+
+# ----------------------------------------------------------------------------
+# Decoder: model/model.py:317-365
+# ----------------------------------------------------------------------------
+def _dec_conv_block(x, sd, n1, n2, emb, ns, seg_len):
+    e = emb.unsqueeze(2)
+    out = F.leaky_relu(conv_same(x + e, sd[n1 + '.weight'], sd[n1 + '.bias'], seg_len), ns)   # :319-321
+    out = pixel_shuffle_1d(out) + e                                                           # :323-324
+    out = F.leaky_relu(conv_same(out, sd[n2 + '.weight'], sd[n2 + '.bias'], seg_len), ns)     # :325-326
+    return instance_norm(out) + nearest_up2(x)                                                # :327-330
+
+
+def _dec_dense_block(x, sd, names, emb, ns):
+    e = emb.unsqueeze(2)
+    out = x
+    for n in names:                                                                           # :335-338
+        out = F.leaky_relu(frame_linear(out + e, sd[n + '.weight'], sd[n + '.bias']), ns)
+    return instance_norm(out) + x                                                             # :339-341
+
+
+def decoder_forward(sd, enc_act, c, ns=0.01, seg_len=128, output_mask=False):
+    """Decoder.forward: model/model.py:344-365 (emb4 is used by both dense blocks)."""
+    e = [sd[f'emb{j}.weight'][c] for j in range(1, 6)]
+    out = frame_linear(enc_act, sd['input_emb.weight'], sd['input_emb.bias'])
+    out = _dec_conv_block(out, sd, 'conv1', 'conv2', e[0], ns, seg_len)
+    out = _dec_conv_block(out, sd, 'conv3', 'conv4', e[1], ns, seg_len)
+    out = _dec_conv_block(out, sd, 'conv5', 'conv6', e[2], ns, seg_len)
+    out = _dec_dense_block(out, sd, ['dense1', 'dense2'], e[3], ns)
+    out = _dec_dense_block(out, sd, ['dense3', 'dense4'], e[3], ns)
+    rnn = bi_gru(out + e[4].unsqueeze(2), sd)                                                 # :352-355
+    out = torch.cat([out, rnn, e[4].unsqueeze(2).expand(-1, -1, out.shape[2])], dim=1)        # :356-357
+    out = F.leaky_relu(frame_linear(out, sd['dense5.weight'], sd['dense5.bias']), ns)         # :358-359
+    out = frame_linear(out, sd['linear.weight'], sd['linear.bias'])                           # :360
+    return torch.tanh(out) if output_mask else torch.sigmoid(out)                             # :361-364
+
+
+def test_step(enc_sd, dec_sd, x, c, uniform, ns=0.01, seg_len=128, enc_mode='one_hot',
+              gen_sd=None, g_mode='targeted', shift=100):
+    """Trainer.test_step: trainer.py:194-221 (enc_only when gen_sd is None)."""
+    act, logits, ids = encoder_forward(enc_sd, x, uniform, ns, seg_len, enc_mode)
+    x_dec = decoder_forward(dec_sd, act, c, ns, seg_len)
+    if gen_sd is not None:
+        if g_mode == 'naive':                                 # :206-207
+            x_dec = x_dec + decoder_forward(gen_sd, act, c, ns, seg_len)
+        elif g_mode == 'targeted':                            # :208-209
+            x_dec = x_dec + decoder_forward(gen_sd, act, c - shift, ns, seg_len)
+        elif g_mode == 'targeted_residual':                   # :210-211
+            x_dec = x_dec + x_dec * decoder_forward(gen_sd, act, c - shift, ns, seg_len, output_mask=True)
+        else:
+            raise NotImplementedError(g_mode)
+    return x_dec, act, logits, ids
+
+
+# ----------------------------------------------------------------------------
+# Driver glue: convert.py:36, 120-221
+# ----------------------------------------------------------------------------
+MIN_LEN = 9  # convert.py:36
+
+
+def segment_plan(n_frames, seg_len):
+    """Chunking rule of convert()/encode(): convert.py:139-165, 189-213.
+
+    Returns (padded_len, [(start, stop), ...], keep_units) where the model is
+    called once per (start, stop) slice of the (zero-padded to MIN_LEN) utterance
+    and `keep_units` is the number of unit frames kept from a padded utterance
+    (None = all)."""
+    padded = max(n_frames, MIN_LEN)                           # :140-143
+    keep = MIN_LEN // 8 if n_frames < MIN_LEN else None       # :147-148
+    if padded <= seg_len:                                     # :145
+        return padded, [(0, padded)], keep
+    plan = []
+    for idx in range(0, padded, seg_len):                     # :153
+        if idx + 2 * seg_len > padded:                        # :154-155 tail drops the last frame
+            start, stop = idx, padded - 1
+        else:
+            start, stop = idx, idx + seg_len
+        if stop - start >= seg_len:                           # :159
+            plan.append((start, stop))
+        elif idx == 0:
+            raise RuntimeError('Please check if input is too short!')
+    return padded, plan, None
+
+
+def format_encodings(encodings):
+    """write_encodings(): convert.py:120-126 - one line per unit frame, ints, space separated."""
+    lines = []
+    for enc in encodings:
+        lines.append(' '.join(str(int(e)) for e in enc))
+    return '\n'.join(lines) + ('\n' if lines else '')
