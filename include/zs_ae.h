@@ -1,0 +1,203 @@
+/*
+ * zs_ae.h - C ABI of libzsae.so: the B200 (sm_100a) hot path of the ZeroSpeech
+ * "TTS without T" ASR-TTS autoencoder.
+ *
+ * The reference is pure Python/PyTorch and has no FFI of its own; the boundary
+ * it exposes for this path is the nn.Module API of
+ *   model/model.py:368-489  Encoder.__init__/forward
+ *   model/model.py:283-365  Decoder.__init__/forward
+ * called from trainer.py:194-228 (test_step / encoder_test_step) and
+ * trainer.py:246-254 (encode_step / decode_step).  Each entry point below names
+ * the reference lines it replaces.  INTEGRATION.md shows the ctypes stub a
+ * maintainer of the reference would add.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer owned by the caller unless it says "host";
+ *    the library never frees caller memory;
+ *  - tensors named like the reference's are fp32, (batch, channel, time)
+ *    contiguous, exactly as model/model.py passes them;
+ *  - all work is enqueued on `stream` (a cudaStream_t passed as void*), nothing
+ *    synchronises the device;
+ *  - return 0 = ok; non-zero = error, message via zs_last_error() (thread local);
+ *  - there is no CPU fallback: without a CUDA device every compute entry fails.
+ */
+#ifndef ZS_AE_H
+#define ZS_AE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ZS_OK 0
+#define ZS_ERR_ARG 1      /* bad argument / unsupported shape or mode */
+#define ZS_ERR_CUDA 2     /* CUDA runtime / driver error */
+#define ZS_ERR_WORKSPACE 3 /* workspace too small */
+
+/* Encoder.enc_mode (model/model.py:457-487); 'binary' is not supported. */
+enum { ZS_ENC_CONTINUES = 0, ZS_ENC_ONE_HOT = 1, ZS_ENC_MULTILABEL_BINARY = 2, ZS_ENC_GUMBEL_T = 3 };
+/* tensor-core operand type of activations/weights (accumulation is always fp32) */
+enum { ZS_OPERAND_FP16 = 0, ZS_OPERAND_BF16 = 1 };
+
+typedef struct zs_encoder zs_encoder;   /* packed Encoder weights (library owned) */
+typedef struct zs_decoder zs_decoder;   /* packed Decoder weights + per-speaker bias tables */
+
+/* Encoder(c_in, c_h1, c_h2, c_h3, ns, dp, enc_size, seg_len, enc_mode): model/model.py:369 */
+typedef struct {
+    int32_t c_in, c_h1, c_h2, c_h3;
+    int32_t enc_size;
+    int32_t enc_mode;     /* ZS_ENC_* */
+    int32_t seg_len;      /* hyper-parameter; reflect padding iff >= 64 (model/model.py:38). < 64 is rejected */
+    int32_t operand;      /* ZS_OPERAND_* */
+    float ns;             /* leaky-relu negative slope */
+} zs_encoder_cfg;
+
+/* fp32 parameter pointers in state_dict order (SURVEY.md Appendix B / model/model.py:373-393) */
+typedef struct {
+    const float* conv1s_w[7];   /* (c_h1, c_in, k) k = 1..7 */
+    const float* conv1s_b[7];
+    const float* conv_w[7];     /* conv2 (c_h2, 7*c_h1+c_in, 1), conv3..conv8 (c_h2, c_h2, 5) */
+    const float* conv_b[7];
+    const float* dense_w[4];    /* (c_h2, c_h2) */
+    const float* dense_b[4];
+    const float* gru_w_ih[2];   /* [0] forward, [1] reverse: (3*c_h3, c_h2) */
+    const float* gru_w_hh[2];   /* (3*c_h3, c_h3) */
+    const float* gru_b_ih[2];
+    const float* gru_b_hh[2];
+    const float* linear_w;      /* (n_out, c_h2 + 2*c_h3), n_out = enc_size or 2*enc_size */
+    const float* linear_b;
+} zs_encoder_weights;
+
+/* Decoder(c_in, c_out, c_h, c_a, ns, seg_len, output_mask): model/model.py:284 */
+typedef struct {
+    int32_t c_in;         /* enc_size */
+    int32_t c_out;        /* 513 */
+    int32_t c_h;          /* emb_size */
+    int32_t c_a;          /* number of speakers */
+    int32_t seg_len;
+    int32_t output_mask;  /* 1: tanh (g_mode targeted_residual), 0: sigmoid */
+    int32_t operand;
+    float ns;
+} zs_decoder_cfg;
+
+typedef struct {
+    const float* conv_w[6];     /* conv1..conv6: odd (2*c_h, c_h, 3), even (c_h, c_h, 3) */
+    const float* conv_b[6];
+    const float* dense_w[4];    /* (c_h, c_h) */
+    const float* dense_b[4];
+    const float* gru_w_ih[2];   /* (3*c_h/2, c_h) */
+    const float* gru_w_hh[2];   /* (3*c_h/2, c_h/2) */
+    const float* gru_b_ih[2];
+    const float* gru_b_hh[2];
+    const float* dense5_w;      /* (c_h, 3*c_h) */
+    const float* dense5_b;
+    const float* linear_w;      /* (c_out, c_h) */
+    const float* linear_b;
+    const float* input_emb_w;   /* (c_h, c_in) */
+    const float* input_emb_b;
+    const float* emb[5];        /* emb1..emb5 (c_a, c_h) */
+} zs_decoder_weights;
+
+const char* zs_last_error(void);
+/* 10000*major + 100*minor + patch of this library */
+int zs_version(void);
+/* 0 when the current CUDA device is sm_100 class and the driver entry points resolve */
+int zs_device_check(void);
+
+/* Packs fp32 parameters (device pointers) into tensor-core operand layout (fp16/bf16,
+ * K-major rows of [taps][c_in padded to 64]) and, for the decoder, folds the five speaker
+ * embeddings into per-(speaker, layer) fp32 bias tables (valid because a time-constant
+ * survives reflect padding: conv(x+e) = conv(x) + sum_k W_k e).  Replaces what
+ * Encoder.__init__/load_state_dict materialise (trainer.py:58-59, 135-140). */
+int zs_encoder_pack(const zs_encoder_cfg* cfg, const zs_encoder_weights* w, void* stream, zs_encoder** out);
+int zs_decoder_pack(const zs_decoder_cfg* cfg, const zs_decoder_weights* w, void* stream, zs_decoder** out);
+void zs_encoder_free(zs_encoder* h);
+void zs_decoder_free(zs_decoder* h);
+
+/* bytes of scratch the forward needs for B segments of T frames (T <= 256) */
+size_t zs_encoder_workspace_bytes(const zs_encoder* h, int B, int T);
+size_t zs_decoder_workspace_bytes(const zs_decoder* h, int B, int T8);
+
+/* Encoder.forward in eval mode (model/model.py:440-489; trainer.py:197, 227).
+ *   x            (B, c_in, T) fp32
+ *   gumbel_noise one_hot: (B, T8, enc_size); multilabel_binary: (B, T8, enc_size, 2);
+ *                gumbel_t: (B, enc_size, T8) - the value of _sample_gumbel() (model/model.py:95-98);
+ *                NULL for `continues`
+ *   logits       (B, n_out, T8) fp32  - the reference's second return value `out`
+ *   act          (B, enc_size, T8) fp32 - the reference's first return value `out_act`
+ *   unit_ids     (B, T8) int32, one_hot only (argmax over units, first index wins ties); may be NULL
+ * T8 = ceil(ceil(ceil(T/2)/2)/2). */
+int zs_encoder_forward(zs_encoder* h, const float* x, int B, int T, const float* gumbel_noise,
+                       float* logits, float* act, int32_t* unit_ids,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
+/* Decoder.forward (model/model.py:344-365; trainer.py:199, 253).
+ *   enc_act  (B, c_in, T8) fp32 dense activations, or NULL when unit_ids is given
+ *   unit_ids (B, T8) int32 one-hot fast path (input_emb becomes a column gather), or NULL
+ *   spk      (B,) int64 speaker ids in [0, c_a)
+ *   spec     (B, c_out, 8*T8) fp32
+ *   accumulate 0: spec = y; 1: spec += y (trainer.py:207-209 'naive'/'targeted');
+ *              2: spec += spec * y (trainer.py:211 'targeted_residual') */
+int zs_decoder_forward(zs_decoder* h, const float* enc_act, const int32_t* unit_ids, const int64_t* spk,
+                       int B, int T8, float* spec, int accumulate,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- building blocks, exported for the unit tests -------------------------------- */
+
+/* gumbel_softmax forward value (model/model.py:93-110) on logits laid out (B, C, T8):
+ * ids[b,t] = argmax_c(logits[b,c,t] + noise[b,t,c]); act[b,c,t] = (c == ids[b,t]). */
+int zs_bottleneck_one_hot(const float* logits, const float* noise, int B, int C, int T8,
+                          float* act, int32_t* unit_ids, void* stream);
+
+/* One fused conv1d / per-frame-linear layer on channels-last operand buffers:
+ * implicit GEMM on tcgen05 tensor cores, TMA-fed, fp32 accumulate in TMEM, epilogue =
+ * bias (+ per-speaker table) -> leaky-relu -> InstanceNorm -> residual -> activation -> store. */
+typedef struct {
+    /* A operand: packed weights [m_rows (multiple of 128)][k_total] operand-type, K-major */
+    const void* w;
+    int32_t m_rows, m_valid;
+    int32_t taps;            /* taps per output frame (kernel size) */
+    int32_t c_in_pad;        /* channels per tap, multiple of 64; k_total = w_taps * c_in_pad */
+    int32_t w_taps;          /* taps stored per weight row (>= taps; 7 for the merged conv bank) */
+    int32_t bank;            /* 1: m-tile i uses kernel size i+1 placed at tap 3-(i+1)/2 (conv bank) */
+    /* B operand: activations [B][in_rows][in_pitch] operand-type, channels-last, halo rows included */
+    const void* in;
+    int32_t in_rows, in_pitch, in_row0;  /* in_row0: buffer row read by tap 0 of output frame 0 */
+    int32_t c_in_valid;      /* channels that exist in `in` (<= in_pitch); TMA zero-fills up to c_in_pad */
+    int32_t stride;          /* 1 or 2 */
+    int32_t B, T_out;        /* segments, valid output frames per segment */
+    /* epilogue */
+    const float* bias;       /* [m_rows] or per-speaker table [n_spk][m_rows] */
+    const int64_t* spk;      /* NULL = shared bias */
+    int32_t lrelu; float ns;
+    int32_t inorm;           /* InstanceNorm over the T_out frames of each (segment, channel) */
+    int32_t res_mode;        /* 0 none, 1 same frame, 2 avg of frames 2t,2t+1, 3 frame t/2 */
+    const void* res; int32_t res_rows, res_pitch, res_halo;
+    int32_t act;             /* 0 none, 1 sigmoid, 2 tanh */
+    int32_t out_mode;        /* 0 channels-last operand-type, 1 pixel-shuffle channels-last, 2 fp32 (B, m_valid, T_out),
+                                3 channels-last fp32 */
+    void* out; int32_t out_rows, out_pitch, out_halo, out_choff;
+    int32_t accumulate;      /* out_mode 2 only: 0 store, 1 out += y, 2 out += out*y */
+    int32_t operand;         /* ZS_OPERAND_* */
+    int32_t nb_hint;         /* segments per N tile, 0 = auto */
+} zs_conv_desc;
+int zs_conv1d_cl(const zs_conv_desc* d, void* stream);
+
+/* (B, C, T) fp32 -> channels-last operand buffer [B][rows][pitch] with `halo` reflected rows each side;
+ * optional leaky-relu; channels C..pitch-1 are zero-filled. */
+int zs_pack_nct(const float* x, int B, int C, int T, void* out, int rows, int pitch, int halo, int choff,
+                int lrelu, float ns, int operand, int zero_pad_channels, void* stream);
+
+/* bidirectional GRU recurrence with zero initial state (model/model.py:59-66) on precomputed
+ * input projections gx [B][T][2][3H] fp32 (b_ih folded in), w_hh [2][3H][H] fp32, b_hh [2][3H];
+ * writes h_t (operand type) to out[b][out_halo+t][out_choff + dir*H + j]. */
+int zs_gru_recurrence(const float* gx, const float* w_hh, const float* b_hh, int B, int T, int H,
+                      void* out, int out_rows, int out_pitch, int out_halo, int out_choff,
+                      int operand, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ZS_AE_H */

@@ -1,0 +1,128 @@
+"""ctypes binding of libzsae.so (include/zs_ae.h) and its in-tree build recipe.
+
+The library is built IN-TREE (next to this file) with nvcc for sm_100a so that it
+travels with the repository snapshot; there is no JIT cache and no CPU fallback -
+`lib()` raises if the shared object is missing.
+"""
+import ctypes as C
+import os
+import shutil
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_CSRC = os.path.join(_HERE, 'csrc')
+SO_PATH = os.path.join(_HERE, 'libzsae.so')
+HEADER = os.path.join(os.path.dirname(_HERE), 'include', 'zs_ae.h')
+_SOURCES = ['zs_ae.cu', 'conv_gemm.cuh', 'kernels.cuh', 'gru_cluster.cuh', 'ptx.cuh']
+
+NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
+              '-Xcompiler', '-fPIC', '-shared']
+
+ENC_MODES = {'continues': 0, 'one_hot': 1, 'multilabel_binary': 2, 'gumbel_t': 3}
+OPERANDS = {'fp16': 0, 'bf16': 1}
+
+
+def _stale():
+    if not os.path.exists(SO_PATH):
+        return True
+    t = os.path.getmtime(SO_PATH)
+    deps = [os.path.join(_CSRC, s) for s in _SOURCES] + [HEADER]
+    return any(os.path.exists(d) and os.path.getmtime(d) > t for d in deps)
+
+
+def build(force=False, verbose=False):
+    """Compile csrc/zs_ae.cu -> libzsae.so for sm_100a (cross-compiles without a GPU)."""
+    if not force and not _stale():
+        return SO_PATH
+    nvcc = shutil.which('nvcc') or '/usr/local/cuda/bin/nvcc'
+    if not os.path.exists(nvcc):
+        raise RuntimeError('nvcc not found: libzsae.so cannot be built')
+    cmd = [nvcc] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-o', SO_PATH, os.path.join(_CSRC, 'zs_ae.cu')]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError('nvcc failed:\n' + res.stdout + res.stderr)
+    if verbose:
+        print(res.stderr)
+    return SO_PATH
+
+
+class EncoderCfg(C.Structure):
+    _fields_ = [('c_in', C.c_int32), ('c_h1', C.c_int32), ('c_h2', C.c_int32), ('c_h3', C.c_int32),
+                ('enc_size', C.c_int32), ('enc_mode', C.c_int32), ('seg_len', C.c_int32), ('operand', C.c_int32),
+                ('ns', C.c_float)]
+
+
+class EncoderWeights(C.Structure):
+    _fields_ = [('conv1s_w', C.c_void_p * 7), ('conv1s_b', C.c_void_p * 7), ('conv_w', C.c_void_p * 7),
+                ('conv_b', C.c_void_p * 7), ('dense_w', C.c_void_p * 4), ('dense_b', C.c_void_p * 4),
+                ('gru_w_ih', C.c_void_p * 2), ('gru_w_hh', C.c_void_p * 2), ('gru_b_ih', C.c_void_p * 2),
+                ('gru_b_hh', C.c_void_p * 2), ('linear_w', C.c_void_p), ('linear_b', C.c_void_p)]
+
+
+class DecoderCfg(C.Structure):
+    _fields_ = [('c_in', C.c_int32), ('c_out', C.c_int32), ('c_h', C.c_int32), ('c_a', C.c_int32),
+                ('seg_len', C.c_int32), ('output_mask', C.c_int32), ('operand', C.c_int32), ('ns', C.c_float)]
+
+
+class DecoderWeights(C.Structure):
+    _fields_ = [('conv_w', C.c_void_p * 6), ('conv_b', C.c_void_p * 6), ('dense_w', C.c_void_p * 4),
+                ('dense_b', C.c_void_p * 4), ('gru_w_ih', C.c_void_p * 2), ('gru_w_hh', C.c_void_p * 2),
+                ('gru_b_ih', C.c_void_p * 2), ('gru_b_hh', C.c_void_p * 2), ('dense5_w', C.c_void_p),
+                ('dense5_b', C.c_void_p), ('linear_w', C.c_void_p), ('linear_b', C.c_void_p),
+                ('input_emb_w', C.c_void_p), ('input_emb_b', C.c_void_p), ('emb', C.c_void_p * 5)]
+
+
+class ConvDesc(C.Structure):
+    _fields_ = [('w', C.c_void_p), ('m_rows', C.c_int32), ('m_valid', C.c_int32), ('taps', C.c_int32),
+                ('c_in_pad', C.c_int32), ('w_taps', C.c_int32), ('bank', C.c_int32),
+                ('in_', C.c_void_p), ('in_rows', C.c_int32), ('in_pitch', C.c_int32), ('in_row0', C.c_int32),
+                ('c_in_valid', C.c_int32), ('stride', C.c_int32), ('B', C.c_int32), ('T_out', C.c_int32),
+                ('bias', C.c_void_p), ('spk', C.c_void_p), ('lrelu', C.c_int32), ('ns', C.c_float),
+                ('inorm', C.c_int32), ('res_mode', C.c_int32), ('res', C.c_void_p), ('res_rows', C.c_int32),
+                ('res_pitch', C.c_int32), ('res_halo', C.c_int32), ('act', C.c_int32), ('out_mode', C.c_int32),
+                ('out', C.c_void_p), ('out_rows', C.c_int32), ('out_pitch', C.c_int32), ('out_halo', C.c_int32),
+                ('out_choff', C.c_int32), ('accumulate', C.c_int32), ('operand', C.c_int32), ('nb_hint', C.c_int32)]
+
+
+# every symbol include/zs_ae.h declares: name -> (restype, argtypes)
+_vp, _i, _sz = C.c_void_p, C.c_int, C.c_size_t
+SYMBOLS = {
+    'zs_last_error': (C.c_char_p, []),
+    'zs_version': (_i, []),
+    'zs_device_check': (_i, []),
+    'zs_encoder_pack': (_i, [C.POINTER(EncoderCfg), C.POINTER(EncoderWeights), _vp, C.POINTER(_vp)]),
+    'zs_decoder_pack': (_i, [C.POINTER(DecoderCfg), C.POINTER(DecoderWeights), _vp, C.POINTER(_vp)]),
+    'zs_encoder_free': (None, [_vp]),
+    'zs_decoder_free': (None, [_vp]),
+    'zs_encoder_workspace_bytes': (_sz, [_vp, _i, _i]),
+    'zs_decoder_workspace_bytes': (_sz, [_vp, _i, _i]),
+    'zs_encoder_forward': (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    'zs_decoder_forward': (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _i, _vp, _sz, _vp]),
+    'zs_bottleneck_one_hot': (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
+    'zs_conv1d_cl': (_i, [C.POINTER(ConvDesc), _vp]),
+    'zs_pack_nct': (_i, [_vp, _i, _i, _i, _vp, _i, _i, _i, _i, _i, C.c_float, _i, _i, _vp]),
+    'zs_gru_recurrence': (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _i, _i, _i, _i, _i, _vp]),
+}
+
+_LIB = None
+
+
+def lib():
+    """The loaded library; raises (never falls back) when it has not been built."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(SO_PATH):
+            raise RuntimeError(f'{SO_PATH} is missing: run `python -c "import __graft_entry__ as g; g.build()"` '
+                               '(the autoencoder path has no CPU fallback)')
+        handle = C.CDLL(SO_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(handle, name)
+            fn.restype = res
+            fn.argtypes = args
+        _LIB = handle
+    return _LIB
+
+
+def check(rc):
+    if rc != 0:
+        raise RuntimeError('libzsae: ' + lib().zs_last_error().decode())

@@ -1,0 +1,262 @@
+// HBM-bound companion kernels of the autoencoder path: layout packing, the discrete bottleneck,
+// the GRU recurrence, weight packing and speaker-embedding bias folding.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+
+#include "conv_gemm.cuh"
+
+namespace zs {
+
+// ---------------------------------------------------------------------------------------------
+// (B, C, T) fp32  ->  channels-last operand buffer [B][rows][pitch] with reflected halo rows.
+// 32x32 tile transpose through shared memory: reads coalesced along T, writes coalesced along C.
+// ---------------------------------------------------------------------------------------------
+template <typename OT>
+__global__ void pack_nct_kernel(const float* __restrict__ x, OT* __restrict__ out, int C, int T, int rows, int pitch,
+                                int halo, int choff, int c_fill, int lrelu, float ns) {
+    __shared__ float tile[32][33];
+    const int t0 = blockIdx.x * 32, c0 = blockIdx.y * 32, b = blockIdx.z;
+    const int tx = threadIdx.x, ty = threadIdx.y;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int c = c0 + ty + 8 * i, t = t0 + tx;
+        float v = 0.f;
+        if (c < C && t < T) v = x[(static_cast<size_t>(b) * C + c) * T + t];
+        tile[ty + 8 * i][tx] = v;
+    }
+    __syncthreads();
+    OT* ob = out + static_cast<size_t>(b) * rows * pitch + choff;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int t = t0 + ty + 8 * i, c = c0 + tx;
+        if (t >= T || c >= c_fill) continue;
+        float v = tile[tx][ty + 8 * i];
+        if (lrelu) v = fmaxf(v, v * ns);
+        const OT y = float_to_ot<OT>(v);
+        ob[static_cast<size_t>(halo + t) * pitch + c] = y;
+        if (halo > 0) {
+            if (t >= 1 && t <= halo) ob[static_cast<size_t>(halo - t) * pitch + c] = y;
+            if (t >= T - 1 - halo && t <= T - 2) ob[static_cast<size_t>(halo + 2 * (T - 1) - t) * pitch + c] = y;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Discrete bottleneck, one_hot mode: ids[b,t] = argmax_c(logits[b,c,t] + noise[b,t,c]) with first-index
+// tie-break (torch.max), act = one-hot.  One CTA per segment; the (C x T8) logits tile is staged in shared
+// memory so both the logits (time-fastest) and the noise (unit-fastest) are read coalesced.
+// ---------------------------------------------------------------------------------------------
+__global__ void bottleneck_onehot_kernel(const float* __restrict__ logits, const float* __restrict__ noise, int C,
+                                         int T8, float* __restrict__ act, int* __restrict__ ids) {
+    extern __shared__ float s_log[];  // [C][T8 + 1]
+    int* s_id = reinterpret_cast<int*>(s_log + static_cast<size_t>(C) * (T8 + 1));
+    const int b = blockIdx.x;
+    const int n = C * T8;
+    const float* lb = logits + static_cast<size_t>(b) * n;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) s_log[(i / T8) * (T8 + 1) + (i % T8)] = lb[i];
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    for (int t = warp; t < T8; t += nwarps) {
+        const float* nz = noise + (static_cast<size_t>(b) * T8 + t) * C;
+        float best = -INFINITY;
+        int bi = 0x7fffffff;
+        for (int c = lane; c < C; c += 32) {
+            const float v = s_log[c * (T8 + 1) + t] + nz[c];
+            if (v > best || bi == 0x7fffffff) {
+                best = v;
+                bi = c;
+            }
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, best, off);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+            if (ov > best || (ov == best && oi < bi)) {
+                best = ov;
+                bi = oi;
+            }
+        }
+        if (lane == 0) {
+            s_id[t] = bi;
+            if (ids) ids[b * T8 + t] = bi;
+        }
+    }
+    __syncthreads();
+    if (act) {
+        float* ab = act + static_cast<size_t>(b) * n;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) ab[i] = (i / T8 == s_id[i % T8]) ? 1.f : 0.f;
+    }
+}
+
+// continues / multilabel_binary / gumbel_t epilogues of Encoder.forward (model/model.py:457-484)
+__global__ void bottleneck_misc_kernel(const float* __restrict__ logits, const float* __restrict__ noise, int mode,
+                                       int B, int E, int T8, float ns, float* __restrict__ act) {
+    const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (mode == 0) {  // continues: leaky-relu of the logits
+        if (i < static_cast<size_t>(B) * E * T8) {
+            const float v = logits[i];
+            act[i] = fmaxf(v, v * ns);
+        }
+    } else if (mode == 2) {  // multilabel_binary: bit = (argmax over the pair == 0); ties -> index 0
+        if (i < static_cast<size_t>(B) * E * T8) {
+            const int t = i % T8, e = (i / T8) % E, b = i / (static_cast<size_t>(T8) * E);
+            const float* lb = logits + static_cast<size_t>(b) * 2 * E * T8;
+            const float* nz = noise + ((static_cast<size_t>(b) * T8 + t) * E + e) * 2;
+            const float v0 = lb[(2 * e) * T8 + t] + nz[0], v1 = lb[(2 * e + 1) * T8 + t] + nz[1];
+            act[i] = (v0 >= v1) ? 1.f : 0.f;
+        }
+    } else {  // gumbel_t: one-hot over the TIME axis of each (segment, unit) row
+        if (i < static_cast<size_t>(B) * E) {
+            const float* lb = logits + i * T8;
+            const float* nz = noise + i * T8;
+            float best = lb[0] + nz[0];
+            int bi = 0;
+            for (int t = 1; t < T8; ++t) {
+                const float v = lb[t] + nz[t];
+                if (v > best) {
+                    best = v;
+                    bi = t;
+                }
+            }
+            for (int t = 0; t < T8; ++t) act[i * T8 + t] = (t == bi) ? 1.f : 0.f;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Bidirectional GRU recurrence, zero initial state (model/model.py:59-66).  Straightforward CUDA-core
+// version: one CTA per (direction, group of NBG segments), one thread per hidden unit, W_hh^T streamed
+// from L2 each step.  gx = W_ih x + b_ih (+ folded speaker term) comes from the tensor-core GEMM.
+// ---------------------------------------------------------------------------------------------
+template <typename OT, int NBG>
+__global__ void gru_simple_kernel(const float* __restrict__ gx, const float* __restrict__ whhT,
+                                  const float* __restrict__ bhh, int B, int T, int H, OT* __restrict__ out,
+                                  int rows, int pitch, int halo, int choff) {
+    extern __shared__ float s_h[];  // [NBG][H]
+    const int dir = blockIdx.y, b0 = blockIdx.x * NBG, j = threadIdx.x;
+    const float* W = whhT + static_cast<size_t>(dir) * H * 3 * H;
+    const float br = bhh[dir * 3 * H + j], bz = bhh[dir * 3 * H + H + j], bn = bhh[dir * 3 * H + 2 * H + j];
+    float h[NBG];
+#pragma unroll
+    for (int s = 0; s < NBG; ++s) {
+        h[s] = 0.f;
+        s_h[s * H + j] = 0.f;
+    }
+    __syncthreads();
+    for (int step = 0; step < T; ++step) {
+        const int t = dir ? T - 1 - step : step;
+        float ar[NBG], az[NBG], an[NBG];
+#pragma unroll
+        for (int s = 0; s < NBG; ++s) ar[s] = az[s] = an[s] = 0.f;
+        for (int k = 0; k < H; ++k) {
+            const float wr = W[static_cast<size_t>(k) * 3 * H + j], wz = W[static_cast<size_t>(k) * 3 * H + H + j],
+                        wn = W[static_cast<size_t>(k) * 3 * H + 2 * H + j];
+#pragma unroll
+            for (int s = 0; s < NBG; ++s) {
+                const float hk = s_h[s * H + k];
+                ar[s] = fmaf(wr, hk, ar[s]);
+                az[s] = fmaf(wz, hk, az[s]);
+                an[s] = fmaf(wn, hk, an[s]);
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int s = 0; s < NBG; ++s) {
+            const int b = b0 + s;
+            if (b < B) {
+                const float* g = gx + ((static_cast<size_t>(b) * T + t) * 2 + dir) * 3 * H;
+                const float r = 1.f / (1.f + expf(-(g[j] + ar[s] + br)));
+                const float z = 1.f / (1.f + expf(-(g[H + j] + az[s] + bz)));
+                const float n = tanhf(g[2 * H + j] + r * (an[s] + bn));
+                h[s] = (1.f - z) * n + z * h[s];
+                s_h[s * H + j] = h[s];
+                out[(static_cast<size_t>(b) * rows + halo + t) * pitch + choff + dir * H + j] = float_to_ot<OT>(h[s]);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Weight packing (runs once per load_state_dict)
+// ---------------------------------------------------------------------------------------------
+// pixel-shuffle row permutation: conv output channel co = 2c + r  ->  row tile(c/64)*128 + r*64 + c%64
+__host__ __device__ inline int ps_row(int co) {
+    const int c = co >> 1, r = co & 1;
+    return (c >> 6) * 128 + r * 64 + (c & 63);
+}
+
+// W (C_out, C_in, k) fp32 -> dst[row_off + row(co)][(tap_off + j) * c_in_pad + ci] operand type,
+// for input channels ci_lo <= ci_lo + ci < ci_lo + ci_n.  dst is pre-zeroed.
+template <typename OT>
+__global__ void pack_weight_kernel(const float* __restrict__ W, OT* __restrict__ dst, int C_out, int C_in, int k,
+                                   int ci_lo, int ci_n, long long k_total, int c_in_pad, int tap_off, int row_off,
+                                   int ps) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const long long total = static_cast<long long>(C_out) * ci_n * k;
+    if (i >= total) return;
+    const int j = i % k;
+    const int ci = (i / k) % ci_n;
+    const int co = i / (static_cast<long long>(k) * ci_n);
+    const float v = W[(static_cast<long long>(co) * C_in + ci_lo + ci) * k + j];
+    const int row = row_off + (ps ? ps_row(co) : co);
+    dst[row * k_total + static_cast<long long>(tap_off + j) * c_in_pad + ci] = float_to_ot<OT>(v);
+}
+
+// tab[s][row_off + row(co)] = (b ? b[co] : 0) + sum_{ci < C_e, j < k} W[co][ci_lo + ci][j] * emb[s][ci]
+// one warp per (speaker, out channel).  C_e = 0 gives the plain (padded, permuted) bias vector.
+__global__ void fold_bias_kernel(const float* __restrict__ W, const float* __restrict__ b,
+                                 const float* __restrict__ emb, float* __restrict__ tab, int C_out, int C_in, int k,
+                                 int ci_lo, int C_e, int n_spk, int m_rows, int row_off, int ps) {
+    const long long w = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (w >= static_cast<long long>(n_spk) * C_out) return;
+    const int co = w % C_out, s = w / C_out;
+    float acc = 0.f;
+    const float* wr = W + (static_cast<long long>(co) * C_in + ci_lo) * k;
+    const float* e = emb + static_cast<long long>(s) * C_e;
+    for (int i = lane; i < C_e * k; i += 32) acc = fmaf(wr[i], e[i / k], acc);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    if (lane == 0) tab[static_cast<long long>(s) * m_rows + row_off + (ps ? ps_row(co) : co)] = acc + (b ? b[co] : 0.f);
+}
+
+// W_hh (3H, H) fp32 -> W^T [H][3H] fp32 for the CUDA-core recurrence
+__global__ void transpose_whh_kernel(const float* __restrict__ W, float* __restrict__ WT, int H) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 3 * H * H) return;
+    const int k = i % H, g = i / H;
+    WT[static_cast<size_t>(k) * 3 * H + g] = W[i];
+}
+
+// input_emb (c_h, c_in) -> table [c_in][c_h] operand type (rounded like the GEMM operand would be)
+template <typename OT>
+__global__ void transpose_emb_kernel(const float* __restrict__ W, OT* __restrict__ WT, int c_h, int c_in) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= static_cast<long long>(c_h) * c_in) return;
+    const int u = i % c_in, c = i / c_in;
+    WT[static_cast<long long>(u) * c_h + c] = float_to_ot<OT>(W[i]);
+}
+
+// Decoder input from unit ids: x0[b][halo + t][c] = input_emb.weight[c][id] + bias[c], reflected halo rows.
+template <typename OT>
+__global__ void unit_gather_kernel(const int* __restrict__ ids, const OT* __restrict__ WT,
+                                   const float* __restrict__ bias, OT* __restrict__ out, int T8, int c_h, int rows,
+                                   int pitch, int halo, int n_units) {
+    const int t = blockIdx.x, b = blockIdx.y;
+    int id = ids[b * T8 + t];
+    id = min(max(id, 0), n_units - 1);
+    OT* ob = out + static_cast<size_t>(b) * rows * pitch;
+    for (int c = threadIdx.x; c < c_h; c += blockDim.x) {
+        const OT y = float_to_ot<OT>(ot_to_float<OT>(WT[static_cast<size_t>(id) * c_h + c]) + bias[c]);
+        ob[static_cast<size_t>(halo + t) * pitch + c] = y;
+        if (halo > 0) {
+            if (t >= 1 && t <= halo) ob[static_cast<size_t>(halo - t) * pitch + c] = y;
+            if (t >= T8 - 1 - halo && t <= T8 - 2) ob[static_cast<size_t>(halo + 2 * (T8 - 1) - t) * pitch + c] = y;
+        }
+    }
+}
+
+}  // namespace zs

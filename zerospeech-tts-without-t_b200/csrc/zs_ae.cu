@@ -1,0 +1,683 @@
+// libzsae.so - C ABI (include/zs_ae.h) over the sm_100a kernels of the autoencoder hot path.
+// Host side: weight packing, workspace carving, TMA descriptors, layer sequencing.
+#include "../../include/zs_ae.h"
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "conv_gemm.cuh"
+#include "kernels.cuh"
+
+using namespace zs;
+
+// -------------------------------------------------------------------------------------------------
+// errors
+// -------------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+static int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+#define CUDA_TRY(expr)                                                                                    \
+    do {                                                                                                  \
+        cudaError_t e_ = (expr);                                                                          \
+        if (e_ != cudaSuccess) return fail(ZS_ERR_CUDA, "%s: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+#define ZS_TRY(expr)              \
+    do {                          \
+        int r_ = (expr);          \
+        if (r_ != ZS_OK) return r_; \
+    } while (0)
+
+extern "C" const char* zs_last_error(void) { return g_err; }
+extern "C" int zs_version(void) { return 100; }
+
+// -------------------------------------------------------------------------------------------------
+// driver entry point for TMA descriptors (no -lcuda link dependency)
+// -------------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_encodeTiled g_encode = nullptr;
+static int g_num_sms = 0;
+static bool g_attr_set[2] = {false, false};
+
+static int ensure_device() {
+    if (g_encode && g_num_sms) return ZS_OK;
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
+    if (prop.major != 10)
+        return fail(ZS_ERR_CUDA, "libzsae needs an sm_100-class GPU (tcgen05/TMEM); found sm_%d%d", prop.major,
+                    prop.minor);
+    g_num_sms = prop.multiProcessorCount;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (!fn || qres != cudaDriverEntryPointSuccess) return fail(ZS_ERR_CUDA, "cuTensorMapEncodeTiled not available");
+    g_encode = reinterpret_cast<PFN_encodeTiled>(fn);
+    return ZS_OK;
+}
+extern "C" int zs_device_check(void) { return ensure_device(); }
+
+static inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+static inline size_t align256(size_t v) { return (v + 255) & ~static_cast<size_t>(255); }
+static inline int buf_rows(int T, int halo) { return round_up(T + 2 * halo, 2); }
+
+// -------------------------------------------------------------------------------------------------
+// one conv / linear layer
+// -------------------------------------------------------------------------------------------------
+static int make_map(CUtensorMap* m, int operand, void* base, int rank, const cuuint64_t* dims,
+                    const cuuint64_t* strides, const cuuint32_t* box) {
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = g_encode(m, operand == ZS_OPERAND_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16,
+                          rank, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(ZS_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d), rank %d", (int)r, rank);
+    return ZS_OK;
+}
+
+static int launch_conv(const zs_conv_desc* d, cudaStream_t stream) {
+    ZS_TRY(ensure_device());
+    if (!d->w || !d->in || !d->out) return fail(ZS_ERR_ARG, "conv: null operand pointer");
+    if (d->m_rows % BM || d->m_rows <= 0 || d->m_valid > d->m_rows) return fail(ZS_ERR_ARG, "conv: m_rows %d must be a multiple of 128 >= m_valid %d", d->m_rows, d->m_valid);
+    if (d->c_in_pad % BK || d->c_in_pad <= 0) return fail(ZS_ERR_ARG, "conv: c_in_pad %d must be a multiple of 64", d->c_in_pad);
+    if (d->in_pitch % 8 || d->c_in_valid > d->in_pitch) return fail(ZS_ERR_ARG, "conv: in_pitch %d must be a multiple of 8 and >= c_in_valid %d", d->in_pitch, d->c_in_valid);
+    if (d->stride != 1 && d->stride != 2) return fail(ZS_ERR_ARG, "conv: stride %d", d->stride);
+    if (d->stride == 2 && (d->in_rows & 1)) return fail(ZS_ERR_ARG, "conv: stride 2 needs an even in_rows");
+    if (d->T_out < 1 || d->T_out > MAX_BN) return fail(ZS_ERR_ARG, "conv: T_out %d outside [1, 256] (segments are at most 2*seg_len-1 frames)", d->T_out);
+    if (d->B < 1) return fail(ZS_ERR_ARG, "conv: B %d", d->B);
+    if (d->bank && (d->w_taps != 7 || d->m_rows != 7 * BM)) return fail(ZS_ERR_ARG, "conv: bank mode needs 7 x 128 rows of 7 taps");
+    if (d->out_mode == OUT_PS && (d->m_rows != d->m_valid)) return fail(ZS_ERR_ARG, "conv: pixel-shuffle needs m_valid == m_rows");
+    if (reinterpret_cast<uintptr_t>(d->w) % 16 || reinterpret_cast<uintptr_t>(d->in) % 16) return fail(ZS_ERR_ARG, "conv: operand pointers must be 16-byte aligned");
+
+    GemmParams p;
+    memset(&p, 0, sizeof(p));
+    const int Tt = round_up(d->T_out, 16);
+    const int m_tiles = d->m_rows / BM;
+    int nb = d->nb_hint;
+    if (nb <= 0) {
+        // minimise waves x tile cost: a tile costs ~ (columns + fixed overhead) per k-step
+        const int max_nb = std::max(1, std::min(MAX_BN / Tt, d->B));
+        long best_cost = -1;
+        for (int cand = 1; cand <= max_nb; ++cand) {
+            const long tiles = static_cast<long>(m_tiles) * ((d->B + cand - 1) / cand);
+            const long waves = (tiles + g_num_sms - 1) / g_num_sms;
+            const long cost = waves * (cand * Tt + 48);
+            if (best_cost < 0 || cost <= best_cost) {
+                best_cost = cost;
+                nb = cand;
+            }
+        }
+    }
+    if (nb * Tt > MAX_BN) return fail(ZS_ERR_ARG, "conv: nb %d x Tt %d exceeds 256 columns", nb, Tt);
+    const int n_tiles = (d->B + nb - 1) / nb;
+    const long long k_total = static_cast<long long>(d->w_taps) * d->c_in_pad;
+
+    {   // A: weights [m_rows][k_total]
+        cuuint64_t dims[2] = {static_cast<cuuint64_t>(k_total), static_cast<cuuint64_t>(d->m_rows)};
+        cuuint64_t strides[1] = {static_cast<cuuint64_t>(k_total) * 2};
+        cuuint32_t box[2] = {BK, BM};
+        ZS_TRY(make_map(&p.tmA, d->operand, const_cast<void*>(d->w), 2, dims, strides, box));
+    }
+    if (d->stride == 1) {   // B: (channel, row, segment)
+        cuuint64_t dims[3] = {static_cast<cuuint64_t>(d->c_in_valid), static_cast<cuuint64_t>(d->in_rows), static_cast<cuuint64_t>(d->B)};
+        cuuint64_t strides[2] = {static_cast<cuuint64_t>(d->in_pitch) * 2, static_cast<cuuint64_t>(d->in_rows) * d->in_pitch * 2};
+        cuuint32_t box[3] = {BK, static_cast<cuuint32_t>(Tt), static_cast<cuuint32_t>(nb)};
+        ZS_TRY(make_map(&p.tmB, d->operand, const_cast<void*>(d->in), 3, dims, strides, box));
+    } else {                // B: (channel, row parity, row pair, segment)
+        cuuint64_t dims[4] = {static_cast<cuuint64_t>(d->c_in_valid), 2, static_cast<cuuint64_t>(d->in_rows / 2), static_cast<cuuint64_t>(d->B)};
+        cuuint64_t strides[3] = {static_cast<cuuint64_t>(d->in_pitch) * 2, static_cast<cuuint64_t>(d->in_pitch) * 4,
+                                 static_cast<cuuint64_t>(d->in_rows) * d->in_pitch * 2};
+        cuuint32_t box[4] = {BK, 1, static_cast<cuuint32_t>(Tt), static_cast<cuuint32_t>(nb)};
+        ZS_TRY(make_map(&p.tmB, d->operand, const_cast<void*>(d->in), 4, dims, strides, box));
+    }
+    p.m_tiles = m_tiles; p.n_tiles = n_tiles; p.nb = nb; p.Tt = Tt; p.T = d->T_out; p.B = d->B; p.N = nb * Tt;
+    p.kc = d->c_in_pad / BK; p.taps = d->taps; p.bank = d->bank; p.stride = d->stride; p.in_row0 = d->in_row0;
+    p.c_in_pad = d->c_in_pad; p.m_valid = d->m_valid;
+    p.bias = d->bias; p.spk = reinterpret_cast<const long long*>(d->spk); p.bias_stride = d->m_rows;
+    p.lrelu = d->lrelu; p.ns = d->ns; p.inorm = d->inorm;
+    p.res_mode = d->res_mode; p.res = d->res; p.res_rows = d->res_rows; p.res_pitch = d->res_pitch; p.res_halo = d->res_halo;
+    p.act = d->act; p.out_mode = d->out_mode; p.out = d->out; p.out_rows = d->out_rows; p.out_pitch = d->out_pitch;
+    p.out_halo = d->out_halo; p.out_choff = d->out_choff; p.accumulate = d->accumulate;
+    p.idesc = umma_idesc_f16(d->operand == ZS_OPERAND_BF16 ? 1 : 0, p.N);
+
+    const int grid = std::min(m_tiles * n_tiles, g_num_sms);
+    const int which = d->operand == ZS_OPERAND_BF16 ? 1 : 0;
+    if (!g_attr_set[which]) {
+        if (which) CUDA_TRY(cudaFuncSetAttribute(conv_gemm_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+        else CUDA_TRY(cudaFuncSetAttribute(conv_gemm_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+        g_attr_set[which] = true;
+    }
+    if (which) conv_gemm_kernel<__nv_bfloat16><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, stream>>>(p);
+    else conv_gemm_kernel<__half><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, stream>>>(p);
+    CUDA_TRY(cudaGetLastError());
+    return ZS_OK;
+}
+extern "C" int zs_conv1d_cl(const zs_conv_desc* d, void* stream) { return launch_conv(d, static_cast<cudaStream_t>(stream)); }
+
+// -------------------------------------------------------------------------------------------------
+// small launchers
+// -------------------------------------------------------------------------------------------------
+static int launch_pack_nct(const float* x, int B, int C, int T, void* out, int rows, int pitch, int halo, int choff,
+                           int lrelu, float ns, int operand, int zero_pad, cudaStream_t st) {
+    if (halo >= T && halo > 0) return fail(ZS_ERR_ARG, "pack: reflect halo %d needs more than %d frames", halo, T);
+    const int c_fill = zero_pad ? pitch - choff : C;
+    dim3 grid((T + 31) / 32, (c_fill + 31) / 32, B), block(32, 8);
+    if (operand == ZS_OPERAND_BF16)
+        pack_nct_kernel<__nv_bfloat16><<<grid, block, 0, st>>>(x, static_cast<__nv_bfloat16*>(out), C, T, rows, pitch, halo, choff, c_fill, lrelu, ns);
+    else
+        pack_nct_kernel<__half><<<grid, block, 0, st>>>(x, static_cast<__half*>(out), C, T, rows, pitch, halo, choff, c_fill, lrelu, ns);
+    CUDA_TRY(cudaGetLastError());
+    return ZS_OK;
+}
+extern "C" int zs_pack_nct(const float* x, int B, int C, int T, void* out, int rows, int pitch, int halo, int choff,
+                           int lrelu, float ns, int operand, int zero_pad_channels, void* stream) {
+    return launch_pack_nct(x, B, C, T, out, rows, pitch, halo, choff, lrelu, ns, operand, zero_pad_channels, static_cast<cudaStream_t>(stream));
+}
+
+static int launch_onehot(const float* logits, const float* noise, int B, int C, int T8, float* act, int32_t* ids, cudaStream_t st) {
+    const size_t smem = static_cast<size_t>(C) * (T8 + 1) * 4 + static_cast<size_t>(T8) * 4;
+    if (smem > 200 * 1024) return fail(ZS_ERR_ARG, "bottleneck: C %d x T8 %d does not fit shared memory", C, T8);
+    static size_t attr = 0;
+    if (smem > 48 * 1024 && smem > attr) {
+        CUDA_TRY(cudaFuncSetAttribute(bottleneck_onehot_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr = 200 * 1024;
+    }
+    bottleneck_onehot_kernel<<<B, 512, smem, st>>>(logits, noise, C, T8, act, ids);
+    CUDA_TRY(cudaGetLastError());
+    return ZS_OK;
+}
+extern "C" int zs_bottleneck_one_hot(const float* logits, const float* noise, int B, int C, int T8, float* act,
+                                     int32_t* unit_ids, void* stream) {
+    if (!logits || !noise) return fail(ZS_ERR_ARG, "bottleneck: null logits/noise");
+    return launch_onehot(logits, noise, B, C, T8, act, unit_ids, static_cast<cudaStream_t>(stream));
+}
+
+static int launch_gru(const float* gx, const float* whhT, const float* bhh, int B, int T, int H, void* out, int rows,
+                      int pitch, int halo, int choff, int operand, cudaStream_t st) {
+    if (H < 1 || H > 1024) return fail(ZS_ERR_ARG, "gru: hidden size %d outside [1, 1024]", H);
+    constexpr int NBG = 4;
+    dim3 grid((B + NBG - 1) / NBG, 2);
+    const size_t smem = static_cast<size_t>(NBG) * H * 4;
+    if (operand == ZS_OPERAND_BF16)
+        gru_simple_kernel<__nv_bfloat16, NBG><<<grid, H, smem, st>>>(gx, whhT, bhh, B, T, H, static_cast<__nv_bfloat16*>(out), rows, pitch, halo, choff);
+    else
+        gru_simple_kernel<__half, NBG><<<grid, H, smem, st>>>(gx, whhT, bhh, B, T, H, static_cast<__half*>(out), rows, pitch, halo, choff);
+    CUDA_TRY(cudaGetLastError());
+    return ZS_OK;
+}
+
+extern "C" int zs_gru_recurrence(const float* gx, const float* w_hh, const float* b_hh, int B, int T, int H, void* out,
+                                 int out_rows, int out_pitch, int out_halo, int out_choff, int operand, void* stream) {
+    // test entry: transposes w_hh into a temporary (stream-ordered) buffer, then runs the recurrence
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    float* wt = nullptr;
+    CUDA_TRY(cudaMallocAsync(&wt, static_cast<size_t>(2) * 3 * H * H * 4, st));
+    for (int dir = 0; dir < 2; ++dir)
+        transpose_whh_kernel<<<(3 * H * H + 255) / 256, 256, 0, st>>>(w_hh + static_cast<size_t>(dir) * 3 * H * H, wt + static_cast<size_t>(dir) * 3 * H * H, H);
+    int r = launch_gru(gx, wt, b_hh, B, T, H, out, out_rows, out_pitch, out_halo, out_choff, operand, st);
+    cudaFreeAsync(wt, st);
+    return r;
+}
+
+// -------------------------------------------------------------------------------------------------
+// packed weights
+// -------------------------------------------------------------------------------------------------
+struct Layer {          // one GEMM's worth of packed weights
+    void* w = nullptr;      // operand type [m_rows][w_taps * c_in_pad]
+    float* bias = nullptr;  // [n_tab][m_rows]
+    int m_rows = 0, m_valid = 0, taps = 1, w_taps = 1, c_in_pad = 0, c_in_valid = 0, per_spk = 0, ps = 0;
+};
+
+struct DevPool {        // owns every device allocation of a handle
+    std::vector<void*> ptrs;
+    int alloc(void** p, size_t bytes, cudaStream_t st) {
+        CUDA_TRY(cudaMalloc(p, bytes));
+        CUDA_TRY(cudaMemsetAsync(*p, 0, bytes, st));
+        ptrs.push_back(*p);
+        return ZS_OK;
+    }
+    void release() {
+        for (void* p : ptrs) cudaFree(p);
+        ptrs.clear();
+    }
+};
+
+// conv / linear weight W (C_out, C_in, k) -> Layer; only input channels [ci_lo, ci_lo + ci_n) enter the GEMM.
+// emb != null folds  sum_{j, ci} W[co][ci_emb_lo + ci][j] * emb[s][ci]  into a per-speaker bias table.
+static int pack_layer(DevPool& pool, Layer& L, int operand, const float* W, const float* b, int C_out, int C_in, int k,
+                      int ci_lo, int ci_n, int ps, const float* emb, int emb_ci_lo, int C_e, int n_spk,
+                      cudaStream_t st) {
+    L.m_rows = round_up(C_out, BM); L.m_valid = C_out; L.taps = k; L.w_taps = k;
+    L.c_in_pad = round_up(ci_n, BK); L.c_in_valid = ci_n; L.ps = ps; L.per_spk = emb ? 1 : 0;
+    const long long k_total = static_cast<long long>(k) * L.c_in_pad;
+    ZS_TRY(pool.alloc(&L.w, static_cast<size_t>(L.m_rows) * k_total * 2, st));
+    const long long total = static_cast<long long>(C_out) * ci_n * k;
+    const int blocks = static_cast<int>((total + 255) / 256);
+    if (operand == ZS_OPERAND_BF16)
+        pack_weight_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(W, static_cast<__nv_bfloat16*>(L.w), C_out, C_in, k, ci_lo, ci_n, k_total, L.c_in_pad, 0, 0, ps);
+    else
+        pack_weight_kernel<__half><<<blocks, 256, 0, st>>>(W, static_cast<__half*>(L.w), C_out, C_in, k, ci_lo, ci_n, k_total, L.c_in_pad, 0, 0, ps);
+    CUDA_TRY(cudaGetLastError());
+    const int n_tab = emb ? n_spk : 1;
+    ZS_TRY(pool.alloc(reinterpret_cast<void**>(&L.bias), static_cast<size_t>(n_tab) * L.m_rows * 4, st));
+    const long long warps = static_cast<long long>(n_tab) * C_out;
+    fold_bias_kernel<<<static_cast<int>((warps * 32 + 255) / 256), 256, 0, st>>>(W, b, emb, L.bias, C_out, C_in, k, emb_ci_lo, emb ? C_e : 0, n_tab, L.m_rows, 0, ps);
+    CUDA_TRY(cudaGetLastError());
+    return ZS_OK;
+}
+
+struct zs_encoder {
+    zs_encoder_cfg cfg;
+    DevPool pool;
+    int n_out = 0;          // linear rows: enc_size or 2 * enc_size
+    bool bank_merged = false;
+    Layer bank[7];          // merged: bank[0] holds all 7 kernels
+    Layer conv[7];          // conv2..conv8
+    Layer dense[4];
+    Layer gru_ih;           // both directions stacked: rows [0, 3H) forward, [3H, 6H) reverse
+    float* whhT = nullptr;  // [2][H][3H] fp32
+    float* bhh = nullptr;   // [2][3H]
+    Layer linear;
+};
+
+struct zs_decoder {
+    zs_decoder_cfg cfg;
+    DevPool pool;
+    Layer input_emb;
+    void* emb_table = nullptr;   // [c_in][c_h] operand type, for the unit-id gather
+    Layer conv[6];
+    Layer dense[4];
+    Layer gru_ih;
+    float* whhT = nullptr;
+    float* bhh = nullptr;
+    Layer dense5;
+    Layer linear;
+};
+
+static int pack_gru(DevPool& pool, Layer& ih, float** whhT, float** bhh, int operand, const float* const* w_ih,
+                    const float* const* w_hh, const float* const* b_ih, const float* const* b_hh, int C, int H,
+                    const float* emb, int n_spk, cudaStream_t st) {
+    ih.m_rows = round_up(6 * H, BM); ih.m_valid = 6 * H; ih.taps = ih.w_taps = 1;
+    ih.c_in_pad = round_up(C, BK); ih.c_in_valid = C; ih.per_spk = emb ? 1 : 0;
+    ZS_TRY(pool.alloc(&ih.w, static_cast<size_t>(ih.m_rows) * ih.c_in_pad * 2, st));
+    const int n_tab = emb ? n_spk : 1;
+    ZS_TRY(pool.alloc(reinterpret_cast<void**>(&ih.bias), static_cast<size_t>(n_tab) * ih.m_rows * 4, st));
+    ZS_TRY(pool.alloc(reinterpret_cast<void**>(whhT), static_cast<size_t>(2) * 3 * H * H * 4, st));
+    ZS_TRY(pool.alloc(reinterpret_cast<void**>(bhh), static_cast<size_t>(2) * 3 * H * 4, st));
+    for (int dir = 0; dir < 2; ++dir) {
+        const long long total = static_cast<long long>(3) * H * C;
+        const int blocks = static_cast<int>((total + 255) / 256);
+        if (operand == ZS_OPERAND_BF16)
+            pack_weight_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(w_ih[dir], static_cast<__nv_bfloat16*>(ih.w), 3 * H, C, 1, 0, C, ih.c_in_pad, ih.c_in_pad, 0, dir * 3 * H, 0);
+        else
+            pack_weight_kernel<__half><<<blocks, 256, 0, st>>>(w_ih[dir], static_cast<__half*>(ih.w), 3 * H, C, 1, 0, C, ih.c_in_pad, ih.c_in_pad, 0, dir * 3 * H, 0);
+        const long long warps = static_cast<long long>(n_tab) * 3 * H;
+        fold_bias_kernel<<<static_cast<int>((warps * 32 + 255) / 256), 256, 0, st>>>(w_ih[dir], b_ih[dir], emb, ih.bias, 3 * H, C, 1, 0, emb ? C : 0, n_tab, ih.m_rows, dir * 3 * H, 0);
+        transpose_whh_kernel<<<(3 * H * H + 255) / 256, 256, 0, st>>>(w_hh[dir], *whhT + static_cast<size_t>(dir) * 3 * H * H, H);
+        CUDA_TRY(cudaMemcpyAsync(*bhh + static_cast<size_t>(dir) * 3 * H, b_hh[dir], static_cast<size_t>(3) * H * 4, cudaMemcpyDeviceToDevice, st));
+    }
+    CUDA_TRY(cudaGetLastError());
+    return ZS_OK;
+}
+
+extern "C" int zs_encoder_pack(const zs_encoder_cfg* cfg, const zs_encoder_weights* w, void* stream, zs_encoder** out) {
+    if (!cfg || !w || !out) return fail(ZS_ERR_ARG, "encoder_pack: null argument");
+    ZS_TRY(ensure_device());
+    if (cfg->seg_len < 64) return fail(ZS_ERR_ARG, "encoder: seg_len %d < 64 selects zero padding (model/model.py:38); only the reflect mode is implemented", cfg->seg_len);
+    if (cfg->enc_mode < 0 || cfg->enc_mode > 3) return fail(ZS_ERR_ARG, "encoder: enc_mode %d not supported ('binary' needs an enc_size^2 projection)", cfg->enc_mode);
+    if (cfg->c_h2 % 8 || cfg->c_h1 % 8 || cfg->c_h3 < 1) return fail(ZS_ERR_ARG, "encoder: c_h1/c_h2 must be multiples of 8");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    zs_encoder* h = new zs_encoder();
+    h->cfg = *cfg;
+    h->n_out = cfg->enc_mode == ZS_ENC_MULTILABEL_BINARY ? 2 * cfg->enc_size : cfg->enc_size;
+    const int op = cfg->operand, c_in = cfg->c_in, h1 = cfg->c_h1, h2 = cfg->c_h2, h3 = cfg->c_h3;
+    int rc = ZS_OK;
+    auto run = [&]() -> int {
+        h->bank_merged = (h1 == BM);
+        if (h->bank_merged) {   // 7 kernels in one [896][7 taps][c_in_pad] matrix, kernel k at tap 3 - k/2
+            Layer& L = h->bank[0];
+            L.m_rows = 7 * BM; L.m_valid = 7 * BM; L.taps = 7; L.w_taps = 7; L.c_in_pad = round_up(c_in, BK); L.c_in_valid = c_in;
+            const long long k_total = 7LL * L.c_in_pad;
+            ZS_TRY(h->pool.alloc(&L.w, static_cast<size_t>(L.m_rows) * k_total * 2, st));
+            ZS_TRY(h->pool.alloc(reinterpret_cast<void**>(&L.bias), static_cast<size_t>(L.m_rows) * 4, st));
+            for (int i = 0; i < 7; ++i) {
+                const int k = i + 1;
+                const long long total = static_cast<long long>(h1) * c_in * k;
+                const int blocks = static_cast<int>((total + 255) / 256);
+                if (op == ZS_OPERAND_BF16)
+                    pack_weight_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(w->conv1s_w[i], static_cast<__nv_bfloat16*>(L.w), h1, c_in, k, 0, c_in, k_total, L.c_in_pad, 3 - k / 2, i * BM, 0);
+                else
+                    pack_weight_kernel<__half><<<blocks, 256, 0, st>>>(w->conv1s_w[i], static_cast<__half*>(L.w), h1, c_in, k, 0, c_in, k_total, L.c_in_pad, 3 - k / 2, i * BM, 0);
+                fold_bias_kernel<<<(h1 * 32 + 255) / 256, 256, 0, st>>>(w->conv1s_w[i], w->conv1s_b[i], nullptr, L.bias, h1, c_in, k, 0, 0, 1, L.m_rows, i * BM, 0);
+            }
+            CUDA_TRY(cudaGetLastError());
+        } else {
+            for (int i = 0; i < 7; ++i)
+                ZS_TRY(pack_layer(h->pool, h->bank[i], op, w->conv1s_w[i], w->conv1s_b[i], h1, c_in, i + 1, 0, c_in, 0, nullptr, 0, 0, 1, st));
+        }
+        ZS_TRY(pack_layer(h->pool, h->conv[0], op, w->conv_w[0], w->conv_b[0], h2, 7 * h1 + c_in, 1, 0, 7 * h1 + c_in, 0, nullptr, 0, 0, 1, st));
+        for (int i = 1; i < 7; ++i)
+            ZS_TRY(pack_layer(h->pool, h->conv[i], op, w->conv_w[i], w->conv_b[i], h2, h2, 5, 0, h2, 0, nullptr, 0, 0, 1, st));
+        for (int i = 0; i < 4; ++i)
+            ZS_TRY(pack_layer(h->pool, h->dense[i], op, w->dense_w[i], w->dense_b[i], h2, h2, 1, 0, h2, 0, nullptr, 0, 0, 1, st));
+        ZS_TRY(pack_gru(h->pool, h->gru_ih, &h->whhT, &h->bhh, op, w->gru_w_ih, w->gru_w_hh, w->gru_b_ih, w->gru_b_hh, h2, h3, nullptr, 1, st));
+        ZS_TRY(pack_layer(h->pool, h->linear, op, w->linear_w, w->linear_b, h->n_out, h2 + 2 * h3, 1, 0, h2 + 2 * h3, 0, nullptr, 0, 0, 1, st));
+        return ZS_OK;
+    };
+    rc = run();
+    if (rc != ZS_OK) {
+        h->pool.release();
+        delete h;
+        return rc;
+    }
+    *out = h;
+    return ZS_OK;
+}
+
+extern "C" void zs_encoder_free(zs_encoder* h) {
+    if (!h) return;
+    h->pool.release();
+    delete h;
+}
+
+extern "C" int zs_decoder_pack(const zs_decoder_cfg* cfg, const zs_decoder_weights* w, void* stream, zs_decoder** out) {
+    if (!cfg || !w || !out) return fail(ZS_ERR_ARG, "decoder_pack: null argument");
+    ZS_TRY(ensure_device());
+    if (cfg->seg_len < 64) return fail(ZS_ERR_ARG, "decoder: seg_len %d < 64 selects zero padding (model/model.py:38); the speaker-embedding bias fold needs the reflect mode", cfg->seg_len);
+    if (cfg->c_h % 64) return fail(ZS_ERR_ARG, "decoder: c_h %d must be a multiple of 64 (pixel-shuffle tile permutation)", cfg->c_h);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    zs_decoder* h = new zs_decoder();
+    h->cfg = *cfg;
+    const int op = cfg->operand, ch = cfg->c_h, ca = cfg->c_a;
+    auto run = [&]() -> int {
+        ZS_TRY(pack_layer(h->pool, h->input_emb, op, w->input_emb_w, w->input_emb_b, ch, cfg->c_in, 1, 0, cfg->c_in, 0, nullptr, 0, 0, 1, st));
+        ZS_TRY(h->pool.alloc(&h->emb_table, static_cast<size_t>(cfg->c_in) * ch * 2, st));
+        {
+            const long long total = static_cast<long long>(ch) * cfg->c_in;
+            const int blocks = static_cast<int>((total + 255) / 256);
+            if (op == ZS_OPERAND_BF16) transpose_emb_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(w->input_emb_w, static_cast<__nv_bfloat16*>(h->emb_table), ch, cfg->c_in);
+            else transpose_emb_kernel<__half><<<blocks, 256, 0, st>>>(w->input_emb_w, static_cast<__half*>(h->emb_table), ch, cfg->c_in);
+            CUDA_TRY(cudaGetLastError());
+        }
+        for (int i = 0; i < 6; ++i) {   // conv1,3,5: 2*c_h rows pixel-shuffle-permuted; block b uses emb[b] for both convs
+            const bool up = (i % 2 == 0);
+            ZS_TRY(pack_layer(h->pool, h->conv[i], op, w->conv_w[i], w->conv_b[i], up ? 2 * ch : ch, ch, 3, 0, ch, up ? 1 : 0, w->emb[i / 2], 0, ch, ca, st));
+        }
+        for (int i = 0; i < 4; ++i)     // emb4 conditions all four dense layers (model/model.py:350-351)
+            ZS_TRY(pack_layer(h->pool, h->dense[i], op, w->dense_w[i], w->dense_b[i], ch, ch, 1, 0, ch, 0, w->emb[3], 0, ch, ca, st));
+        ZS_TRY(pack_gru(h->pool, h->gru_ih, &h->whhT, &h->bhh, op, w->gru_w_ih, w->gru_w_hh, w->gru_b_ih, w->gru_b_hh, ch, ch / 2, w->emb[4], ca, st));
+        // dense5 sees cat([out, rnn, emb5]): the first 2*c_h inputs go through the GEMM, the last c_h fold into the bias
+        ZS_TRY(pack_layer(h->pool, h->dense5, op, w->dense5_w, w->dense5_b, ch, 3 * ch, 1, 0, 2 * ch, 0, w->emb[4], 2 * ch, ch, ca, st));
+        ZS_TRY(pack_layer(h->pool, h->linear, op, w->linear_w, w->linear_b, cfg->c_out, ch, 1, 0, ch, 0, nullptr, 0, 0, 1, st));
+        return ZS_OK;
+    };
+    int rc = run();
+    if (rc != ZS_OK) {
+        h->pool.release();
+        delete h;
+        return rc;
+    }
+    *out = h;
+    return ZS_OK;
+}
+
+extern "C" void zs_decoder_free(zs_decoder* h) {
+    if (!h) return;
+    h->pool.release();
+    delete h;
+}
+
+// -------------------------------------------------------------------------------------------------
+// workspace carving
+// -------------------------------------------------------------------------------------------------
+struct Buf {            // channels-last activation buffer [B][rows][pitch]
+    void* p = nullptr;
+    int rows = 0, pitch = 0, halo = 0, T = 0;
+};
+struct Carver {
+    uint8_t* base;
+    size_t off = 0;
+    explicit Carver(void* b) : base(static_cast<uint8_t*>(b)) {}
+    void* take(size_t bytes) {
+        void* p = base ? base + off : nullptr;
+        off += align256(bytes);
+        return p;
+    }
+    Buf act(int B, int T, int halo, int channels) {
+        Buf b;
+        b.rows = buf_rows(T, halo); b.pitch = round_up(channels, 8); b.halo = halo; b.T = T;
+        b.p = take(static_cast<size_t>(B) * b.rows * b.pitch * 2);
+        return b;
+    }
+};
+
+struct EncWs {
+    Buf xp, cat, a[7], d[3], catr;
+    float* gx;
+    int T[4];
+    size_t bytes;
+};
+static EncWs carve_encoder(const zs_encoder* h, void* ws, int B, int T) {
+    EncWs w;
+    Carver c(ws);
+    const zs_encoder_cfg& g = h->cfg;
+    w.T[0] = T; w.T[1] = (T + 1) / 2; w.T[2] = (w.T[1] + 1) / 2; w.T[3] = (w.T[2] + 1) / 2;
+    w.xp = c.act(B, T, 3, g.c_in);
+    w.cat = c.act(B, T, 0, 7 * g.c_h1 + g.c_in);
+    w.a[0] = c.act(B, w.T[0], 2, g.c_h2);   // conv2 out
+    w.a[1] = c.act(B, w.T[0], 2, g.c_h2);   // conv3 out
+    w.a[2] = c.act(B, w.T[1], 2, g.c_h2);   // conv4 out
+    w.a[3] = c.act(B, w.T[1], 2, g.c_h2);   // conv5 out
+    w.a[4] = c.act(B, w.T[2], 2, g.c_h2);   // conv6 out
+    w.a[5] = c.act(B, w.T[2], 2, g.c_h2);   // conv7 out
+    w.a[6] = c.act(B, w.T[3], 0, g.c_h2);   // conv8 out
+    for (int i = 0; i < 3; ++i) w.d[i] = c.act(B, w.T[3], 0, g.c_h2);
+    w.catr = c.act(B, w.T[3], 0, g.c_h2 + 2 * g.c_h3);
+    w.gx = static_cast<float*>(c.take(static_cast<size_t>(B) * w.T[3] * 6 * g.c_h3 * 4));
+    w.bytes = c.off;
+    return w;
+}
+extern "C" size_t zs_encoder_workspace_bytes(const zs_encoder* h, int B, int T) {
+    if (!h || B < 1 || T < 1) return 0;
+    return carve_encoder(h, nullptr, B, T).bytes;
+}
+
+struct DecWs {
+    Buf actp, x0, p[3], y[3], d[3], catr, d5;
+    float* gx;
+    size_t bytes;
+};
+static DecWs carve_decoder(const zs_decoder* h, void* ws, int B, int T8) {
+    DecWs w;
+    Carver c(ws);
+    const int ch = h->cfg.c_h;
+    w.actp = c.act(B, T8, 0, h->cfg.c_in);
+    w.x0 = c.act(B, T8, 1, ch);
+    for (int i = 0; i < 3; ++i) {
+        const int To = T8 << (i + 1);
+        w.p[i] = c.act(B, To, 1, ch);
+        w.y[i] = c.act(B, To, i == 2 ? 0 : 1, ch);
+    }
+    const int Tf = 8 * T8;
+    for (int i = 0; i < 3; ++i) w.d[i] = c.act(B, Tf, 0, ch);
+    w.catr = c.act(B, Tf, 0, 2 * ch);
+    w.d5 = c.act(B, Tf, 0, ch);
+    w.gx = static_cast<float*>(c.take(static_cast<size_t>(B) * Tf * 3 * ch * 4));
+    w.bytes = c.off;
+    return w;
+}
+extern "C" size_t zs_decoder_workspace_bytes(const zs_decoder* h, int B, int T8) {
+    if (!h || B < 1 || T8 < 1) return 0;
+    return carve_decoder(h, nullptr, B, T8).bytes;
+}
+
+// -------------------------------------------------------------------------------------------------
+// layer sequencing
+// -------------------------------------------------------------------------------------------------
+struct ConvOpts {
+    int stride = 1, lrelu = 1, inorm = 0, res_mode = RES_NONE, act = ACT_NONE, out_mode = OUT_CL, out_choff = 0,
+        accumulate = 0, bank = 0, c_in_valid = -1;
+    const Buf* res = nullptr;
+    const int64_t* spk = nullptr;
+};
+// runs layer L on `in`, writing T_out frames per segment into `out` (a Buf, or raw fp32 for NCT32/CL32)
+static int run_layer(const Layer& L, int operand, float ns, const Buf& in, int B, int T_out, const Buf* out, void* out_raw,
+                     int out_raw_rows, int out_raw_pitch, const ConvOpts& o, cudaStream_t st) {
+    zs_conv_desc d;
+    memset(&d, 0, sizeof(d));
+    d.w = L.w; d.m_rows = L.m_rows; d.m_valid = L.m_valid; d.taps = L.taps; d.c_in_pad = L.c_in_pad; d.w_taps = L.w_taps;
+    d.bank = o.bank;
+    d.in = in.p; d.in_rows = in.rows; d.in_pitch = in.pitch;
+    const int pad_left = o.bank ? 3 : L.taps / 2;
+    d.in_row0 = in.halo - pad_left;
+    if (d.in_row0 < 0) return fail(ZS_ERR_ARG, "layer: input halo %d < pad %d", in.halo, pad_left);
+    d.c_in_valid = o.c_in_valid >= 0 ? o.c_in_valid : L.c_in_valid;
+    d.stride = o.stride; d.B = B; d.T_out = T_out;
+    d.bias = L.bias; d.spk = L.per_spk ? o.spk : nullptr;
+    if (L.per_spk && !o.spk) return fail(ZS_ERR_ARG, "layer: speaker ids required");
+    d.lrelu = o.lrelu; d.ns = ns; d.inorm = o.inorm;
+    d.res_mode = o.res_mode;
+    if (o.res) { d.res = o.res->p; d.res_rows = o.res->rows; d.res_pitch = o.res->pitch; d.res_halo = o.res->halo; }
+    d.act = o.act; d.out_mode = o.out_mode;
+    if (out) { d.out = out->p; d.out_rows = out->rows; d.out_pitch = out->pitch; d.out_halo = out->halo; }
+    else { d.out = out_raw; d.out_rows = out_raw_rows; d.out_pitch = out_raw_pitch; d.out_halo = 0; }
+    d.out_choff = o.out_choff; d.accumulate = o.accumulate; d.operand = operand; d.nb_hint = 0;
+    return launch_conv(&d, st);
+}
+
+extern "C" int zs_encoder_forward(zs_encoder* h, const float* x, int B, int T, const float* gumbel_noise, float* logits,
+                                  float* act, int32_t* unit_ids, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!h || !x || !logits) return fail(ZS_ERR_ARG, "encoder_forward: null argument");
+    if (B < 1) return fail(ZS_ERR_ARG, "encoder_forward: B %d", B);
+    if (T < 9 || T > 256) return fail(ZS_ERR_ARG, "encoder_forward: T %d outside [9, 256] (convert.py MIN_LEN=9; segments are < 2*seg_len frames)", T);
+    const zs_encoder_cfg& g = h->cfg;
+    if (g.enc_mode != ZS_ENC_CONTINUES && !gumbel_noise) return fail(ZS_ERR_ARG, "encoder_forward: enc_mode %d needs the Gumbel noise tensor", g.enc_mode);
+    EncWs w = carve_encoder(h, workspace, B, T);
+    if (!workspace || workspace_bytes < w.bytes) return fail(ZS_ERR_WORKSPACE, "encoder_forward: workspace %zu < %zu bytes", workspace_bytes, w.bytes);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int op = g.operand;
+    const float ns = g.ns;
+
+    // model/model.py:441-446: conv bank on x, concatenated with x, leaky-relu
+    ZS_TRY(launch_pack_nct(x, B, g.c_in, T, w.xp.p, w.xp.rows, w.xp.pitch, 3, 0, 0, ns, op, 0, st));
+    ZS_TRY(launch_pack_nct(x, B, g.c_in, T, w.cat.p, w.cat.rows, w.cat.pitch, 0, 7 * g.c_h1, 1, ns, op, 0, st));
+    if (h->bank_merged) {
+        ConvOpts o; o.bank = 1;
+        ZS_TRY(run_layer(h->bank[0], op, ns, w.xp, B, T, &w.cat, nullptr, 0, 0, o, st));
+    } else {
+        for (int i = 0; i < 7; ++i) {
+            ConvOpts o; o.out_choff = i * g.c_h1;
+            // every kernel reads the halo-3 buffer; its own left pad is (i+1)/2
+            ZS_TRY(run_layer(h->bank[i], op, ns, w.xp, B, T, &w.cat, nullptr, 0, 0, o, st));
+        }
+    }
+    {   // :447 conv2 -> lrelu -> IN (dropout is identity in eval)
+        ConvOpts o; o.inorm = 1;
+        ZS_TRY(run_layer(h->conv[0], op, ns, w.cat, B, T, &w.a[0], nullptr, 0, 0, o, st));
+    }
+    for (int blk = 0; blk < 3; ++blk) {   // :448-450 three (conv k5, conv k5 stride 2) blocks with avg-pool residual
+        const Buf& xin = w.a[2 * blk];
+        ConvOpts o1;
+        ZS_TRY(run_layer(h->conv[1 + 2 * blk], op, ns, xin, B, w.T[blk], &w.a[2 * blk + 1], nullptr, 0, 0, o1, st));
+        ConvOpts o2; o2.stride = 2; o2.inorm = 1; o2.res_mode = RES_AVG2; o2.res = &xin;
+        ZS_TRY(run_layer(h->conv[2 + 2 * blk], op, ns, w.a[2 * blk + 1], B, w.T[blk + 1], &w.a[2 * blk + 2], nullptr, 0, 0, o2, st));
+    }
+    const int T8 = w.T[3];
+    {   // :452-453 two dense blocks
+        ConvOpts o;
+        ZS_TRY(run_layer(h->dense[0], op, ns, w.a[6], B, T8, &w.d[0], nullptr, 0, 0, o, st));
+        ConvOpts r; r.inorm = 1; r.res_mode = RES_SAME; r.res = &w.a[6];
+        ZS_TRY(run_layer(h->dense[1], op, ns, w.d[0], B, T8, &w.d[1], nullptr, 0, 0, r, st));
+        ZS_TRY(run_layer(h->dense[2], op, ns, w.d[1], B, T8, &w.d[2], nullptr, 0, 0, o, st));
+        ConvOpts r2; r2.inorm = 1; r2.res_mode = RES_SAME; r2.res = &w.d[1];
+        ZS_TRY(run_layer(h->dense[3], op, ns, w.d[2], B, T8, &w.catr, nullptr, 0, 0, r2, st));
+    }
+    {   // :454-455 bi-GRU: input projection on tensor cores, then the recurrence
+        ConvOpts o; o.lrelu = 0; o.out_mode = OUT_CL32; o.c_in_valid = g.c_h2;
+        ZS_TRY(run_layer(h->gru_ih, op, ns, w.catr, B, T8, nullptr, w.gx, T8, 6 * g.c_h3, o, st));
+        ZS_TRY(launch_gru(w.gx, h->whhT, h->bhh, B, T8, g.c_h3, w.catr.p, w.catr.rows, w.catr.pitch, 0, g.c_h2, op, st));
+    }
+    {   // linear -> logits in the reference's (B, n_out, T8) fp32 layout
+        ConvOpts o; o.lrelu = 0; o.out_mode = OUT_NCT32;
+        ZS_TRY(run_layer(h->linear, op, ns, w.catr, B, T8, nullptr, logits, 0, 0, o, st));
+    }
+    if (g.enc_mode == ZS_ENC_ONE_HOT) {
+        ZS_TRY(launch_onehot(logits, gumbel_noise, B, g.enc_size, T8, act, unit_ids, st));
+    } else if (act) {
+        const size_t n = g.enc_mode == ZS_ENC_GUMBEL_T ? static_cast<size_t>(B) * g.enc_size : static_cast<size_t>(B) * g.enc_size * T8;
+        bottleneck_misc_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(logits, gumbel_noise, g.enc_mode, B, g.enc_size, T8, ns, act);
+        CUDA_TRY(cudaGetLastError());
+    }
+    return ZS_OK;
+}
+
+extern "C" int zs_decoder_forward(zs_decoder* h, const float* enc_act, const int32_t* unit_ids, const int64_t* spk, int B,
+                                  int T8, float* spec, int accumulate, void* workspace, size_t workspace_bytes,
+                                  void* stream) {
+    if (!h || !spk || !spec || (!enc_act && !unit_ids)) return fail(ZS_ERR_ARG, "decoder_forward: null argument");
+    if (B < 1 || T8 < 2 || T8 > 32) return fail(ZS_ERR_ARG, "decoder_forward: B %d, T8 %d (T8 must be in [2, 32])", B, T8);
+    if (accumulate < 0 || accumulate > 2) return fail(ZS_ERR_ARG, "decoder_forward: accumulate %d", accumulate);
+    const zs_decoder_cfg& g = h->cfg;
+    DecWs w = carve_decoder(h, workspace, B, T8);
+    if (!workspace || workspace_bytes < w.bytes) return fail(ZS_ERR_WORKSPACE, "decoder_forward: workspace %zu < %zu bytes", workspace_bytes, w.bytes);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int op = g.operand, ch = g.c_h;
+    const float ns = g.ns;
+
+    if (unit_ids) {   // one-hot input: input_emb is a column gather (model/model.py:346)
+        dim3 grid(T8, B);
+        if (op == ZS_OPERAND_BF16)
+            unit_gather_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(unit_ids, static_cast<const __nv_bfloat16*>(h->emb_table), h->input_emb.bias, static_cast<__nv_bfloat16*>(w.x0.p), T8, ch, w.x0.rows, w.x0.pitch, 1, g.c_in);
+        else
+            unit_gather_kernel<__half><<<grid, 256, 0, st>>>(unit_ids, static_cast<const __half*>(h->emb_table), h->input_emb.bias, static_cast<__half*>(w.x0.p), T8, ch, w.x0.rows, w.x0.pitch, 1, g.c_in);
+        CUDA_TRY(cudaGetLastError());
+    } else {
+        ZS_TRY(launch_pack_nct(enc_act, B, g.c_in, T8, w.actp.p, w.actp.rows, w.actp.pitch, 0, 0, 0, ns, op, 0, st));
+        ConvOpts o; o.lrelu = 0;
+        ZS_TRY(run_layer(h->input_emb, op, ns, w.actp, B, T8, &w.x0, nullptr, 0, 0, o, st));
+    }
+    const Buf* xin = &w.x0;
+    for (int blk = 0; blk < 3; ++blk) {   // model/model.py:317-331, speaker embedding folded into the bias tables
+        const int Ti = T8 << blk;
+        ConvOpts o1; o1.out_mode = OUT_PS; o1.spk = spk;
+        ZS_TRY(run_layer(h->conv[2 * blk], op, ns, *xin, B, Ti, &w.p[blk], nullptr, 0, 0, o1, st));
+        ConvOpts o2; o2.inorm = 1; o2.res_mode = RES_UP2; o2.res = xin; o2.spk = spk;
+        ZS_TRY(run_layer(h->conv[2 * blk + 1], op, ns, w.p[blk], B, 2 * Ti, &w.y[blk], nullptr, 0, 0, o2, st));
+        xin = &w.y[blk];
+    }
+    const int Tf = 8 * T8;
+    {   // :350-351 two dense blocks, both conditioned on emb4
+        ConvOpts o; o.spk = spk;
+        ZS_TRY(run_layer(h->dense[0], op, ns, w.y[2], B, Tf, &w.d[0], nullptr, 0, 0, o, st));
+        ConvOpts r; r.inorm = 1; r.res_mode = RES_SAME; r.res = &w.y[2]; r.spk = spk;
+        ZS_TRY(run_layer(h->dense[1], op, ns, w.d[0], B, Tf, &w.d[1], nullptr, 0, 0, r, st));
+        ZS_TRY(run_layer(h->dense[2], op, ns, w.d[1], B, Tf, &w.d[2], nullptr, 0, 0, o, st));
+        ConvOpts r2; r2.inorm = 1; r2.res_mode = RES_SAME; r2.res = &w.d[1]; r2.spk = spk;
+        ZS_TRY(run_layer(h->dense[3], op, ns, w.d[2], B, Tf, &w.catr, nullptr, 0, 0, r2, st));
+    }
+    {   // :352-355 bi-GRU on out + emb5
+        ConvOpts o; o.lrelu = 0; o.out_mode = OUT_CL32; o.c_in_valid = ch; o.spk = spk;
+        ZS_TRY(run_layer(h->gru_ih, op, ns, w.catr, B, Tf, nullptr, w.gx, Tf, 3 * ch, o, st));
+        ZS_TRY(launch_gru(w.gx, h->whhT, h->bhh, B, Tf, ch / 2, w.catr.p, w.catr.rows, w.catr.pitch, 0, ch, op, st));
+    }
+    {   // :356-364 dense5 on cat([out, rnn, emb5]) -> lrelu -> linear -> sigmoid | tanh
+        ConvOpts o; o.spk = spk;
+        ZS_TRY(run_layer(h->dense5, op, ns, w.catr, B, Tf, &w.d5, nullptr, 0, 0, o, st));
+        ConvOpts f; f.lrelu = 0; f.act = g.output_mask ? ACT_TANH : ACT_SIGMOID; f.out_mode = OUT_NCT32; f.accumulate = accumulate;
+        ZS_TRY(run_layer(h->linear, op, ns, w.d5, B, Tf, nullptr, spec, 0, 0, f, st));
+    }
+    return ZS_OK;
+}
