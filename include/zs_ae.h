@@ -144,6 +144,16 @@ int zs_decoder_forward(zs_decoder* h, const float* enc_act, const int32_t* unit_
                        int B, int T8, float* spec, int accumulate,
                        void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- measurement hooks (bench.py) --------------------------------------------------
+ * Kernel classes: 0 = conv/linear implicit GEMM (tcgen05), 1 = GRU recurrence, 2 = everything else.
+ * Between zs_profile_begin() and zs_profile_end() every kernel launch of this library is bracketed
+ * by CUDA events on its stream; zs_profile_end() synchronises those events and returns, per class,
+ * the summed device milliseconds, the algorithmic FLOPs and the launch count (arrays of 3).
+ * zs_launch_counts() returns the launch counters without timing (counted since profile_begin). */
+void zs_profile_begin(void);
+int zs_profile_end(double* ms, double* flops, long long* launches);
+void zs_launch_counts(long long* launches);
+
 /* ---- building blocks, exported for the unit tests -------------------------------- */
 
 /* gumbel_softmax forward value (model/model.py:93-110) on logits laid out (B, C, T8):
@@ -171,6 +181,7 @@ typedef struct {
     /* epilogue */
     const float* bias;       /* [m_rows] or per-speaker table [n_spk][m_rows] */
     const int64_t* spk;      /* NULL = shared bias */
+    int32_t n_spk;           /* rows of the per-speaker table; ids are clamped into [0, n_spk) */
     int32_t lrelu; float ns;
     int32_t inorm;           /* InstanceNorm over the T_out frames of each (segment, channel) */
     int32_t res_mode;        /* 0 none, 1 same frame, 2 avg of frames 2t,2t+1, 3 frame t/2 */

@@ -60,7 +60,7 @@ def conv_cl(x, W, bias, *, stride=1, lrelu=False, inorm=False, ns=0.01, operand=
     d.w, d.m_rows, d.m_valid, d.taps, d.c_in_pad, d.w_taps, d.bank = Wp.data_ptr(), m_rows, C_out, k, c_pad, k, 0
     d.in_, d.in_rows, d.in_pitch, d.in_row0, d.c_in_valid = buf.data_ptr(), rows, pitch, 0, C_in
     d.stride, d.B, d.T_out = stride, B, T_out
-    d.bias, d.spk, d.lrelu, d.ns, d.inorm = bias_p.data_ptr(), None, int(lrelu), ns, int(inorm)
+    d.bias, d.spk, d.n_spk, d.lrelu, d.ns, d.inorm = bias_p.data_ptr(), None, 1, int(lrelu), ns, int(inorm)
     d.res_mode, d.res = 0, None
     d.act, d.out_mode = act, 2
     d.out, d.out_rows, d.out_pitch, d.out_halo, d.out_choff = out.data_ptr(), 0, 0, 0, 0

@@ -1,0 +1,306 @@
+"""Parity tests proper (-m gpu): the CUDA path, called through the C ABI, against the oracle and the
+live-reference golden fixtures.  Tolerances (fp16 operands = tf32-class 10-bit mantissa, fp32 accumulate;
+SURVEY.md section 0 fact 6 / BASELINE.md section 4):
+  * unit ids: bit-exact given identical logits and noise; end-to-end agreement >= 95 %
+  * logits: rel-RMS <= 1e-2 ; decoded spectrogram (same units): rel-RMS <= 1e-2, max-abs <= 3e-2
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import zs_b200  # noqa: F401
+from zs_b200 import _lib, synthetic as syn
+from zs_b200.model import Decoder, Encoder, gumbel_from_uniform
+from zs_b200.frontend import AutoencoderPath, segment_plan
+from oracle import ae_oracle as orc
+from conftest import load_golden
+import gpu_helpers as gh
+
+pytestmark = pytest.mark.gpu
+
+LOGIT_RELRMS, SPEC_RELRMS, SPEC_MAXABS = 1e-2, 1e-2, 3e-2
+
+
+def relrms(a, b):
+    return ((a - b).norm() / b.norm()).item()
+
+
+def build_models(m, dev='cuda'):
+    enc_sd = syn.encoder_state_dict(m['seed'], c_in=m['c_in'], c_h1=m['c_h'][0], c_h2=m['c_h'][1], c_h3=m['c_h'][2],
+                                    enc_size=m['enc_size'], enc_mode=m['enc_mode'])
+    dec_sd = syn.decoder_state_dict(m['seed'], c_in=m['enc_size'], c_out=m['c_in'], c_h=m['emb_size'], c_a=m['n_spk'])
+    enc = Encoder(c_in=m['c_in'], c_h1=m['c_h'][0], c_h2=m['c_h'][1], c_h3=m['c_h'][2], ns=m['ns'], dp=0.5,
+                  enc_size=m['enc_size'], seg_len=m['seg_len'], enc_mode=m['enc_mode'])
+    dec = Decoder(c_in=m['enc_size'], c_out=m['c_in'], c_h=m['emb_size'], c_a=m['n_spk'], ns=m['ns'],
+                  seg_len=m['seg_len'])
+    enc.load_state_dict(enc_sd, strict=True)
+    dec.load_state_dict(dec_sd, strict=True)
+    return enc.to(dev).eval(), dec.to(dev).eval(), enc_sd, dec_sd
+
+
+FULL = dict(seed=0, c_in=513, c_h=[128, 512, 128], enc_size=1024, enc_mode='one_hot', emb_size=1024, n_spk=102,
+            ns=0.01, seg_len=128)
+
+
+@pytest.fixture(scope='module')
+def full_models():
+    return build_models(FULL)
+
+
+# ------------------------------------------------------------------------------------------------
+# building blocks
+# ------------------------------------------------------------------------------------------------
+CONV_CASES = [
+    dict(B=2, C_in=64, C_out=128, T=32, k=1),
+    dict(B=3, C_in=128, C_out=256, T=64, k=3),
+    dict(B=4, C_in=512, C_out=512, T=128, k=5),
+    dict(B=4, C_in=512, C_out=512, T=128, k=5, stride=2),
+    dict(B=5, C_in=513, C_out=130, T=77, k=3, lrelu=True, inorm=True),
+    dict(B=33, C_in=96, C_out=513, T=16, k=1, lrelu=True),
+    dict(B=2, C_in=1024, C_out=1024, T=207, k=3, lrelu=True, inorm=True),
+    dict(B=3, C_in=64, C_out=128, T=51, k=5, stride=2, inorm=True),
+    dict(B=1, C_in=8, C_out=8, T=9, k=5),
+    dict(B=40, C_in=64, C_out=256, T=256, k=3, lrelu=True, inorm=True),
+]
+
+
+@pytest.mark.parametrize('cs', CONV_CASES, ids=lambda c: '-'.join(f'{k}{v}' for k, v in c.items()))
+@pytest.mark.parametrize('operand', ['fp16', 'bf16'])
+def test_conv_gemm_matches_operand_rounded_reference(cs, operand):
+    torch.manual_seed(1)
+    kw = {a: cs[a] for a in ('stride', 'lrelu', 'inorm') if a in cs}
+    x = torch.randn(cs['B'], cs['C_in'], cs['T'], device='cuda')
+    W = torch.randn(cs['C_out'], cs['C_in'], cs['k'], device='cuda') / (cs['C_in'] * cs['k']) ** 0.5
+    b = torch.randn(cs['C_out'], device='cuda') * 0.1
+    y = gh.conv_cl(x, W, b, operand=operand, **kw)
+    ref = gh.conv_ref(x, W, b, operand=operand, **kw)
+    assert not torch.isnan(y).any()
+    assert (y - ref).abs().max().item() < 1e-4      # fp32 accumulation-order noise only
+
+
+def test_conv_gemm_tile_shapes_agree():
+    """Different segments-per-tile choices (nb) must give the same numbers (tiles only regroup columns)."""
+    torch.manual_seed(2)
+    x = torch.randn(9, 128, 32, device='cuda')
+    W = torch.randn(256, 128, 3, device='cuda') / 20
+    b = torch.zeros(256, device='cuda')
+    base = gh.conv_cl(x, W, b, inorm=True, lrelu=True, nb_hint=1)
+    for nb in (2, 3, 8):
+        assert torch.equal(gh.conv_cl(x, W, b, inorm=True, lrelu=True, nb_hint=nb), base)
+
+
+def test_bottleneck_argmax_bit_exact_with_ties():
+    torch.manual_seed(3)
+    B, Cn, T8 = 7, 1024, 16
+    logits = torch.randn(B, Cn, T8)
+    logits[0, 5, 3] = logits[0, 900, 3] = 50.0          # exact tie -> first index
+    logits[1, :, 0] = 0.25                               # all equal -> index 0
+    u = torch.rand(B, T8, Cn)
+    noise = gumbel_from_uniform(u)
+    noise[0, 3, :] = 0.0
+    noise[1, 0, :] = 0.0
+    act = torch.empty(B, Cn, T8, device='cuda')
+    ids = torch.empty(B, T8, dtype=torch.int32, device='cuda')
+    logits_d, noise_d = logits.cuda(), noise.cuda()       # keep the device copies alive across the launch
+    _lib.check(_lib.lib().zs_bottleneck_one_hot(gh.ptr(logits_d), gh.ptr(noise_d), B, Cn, T8, gh.ptr(act),
+                                                gh.ptr(ids), gh.stream()))
+    torch.cuda.synchronize()
+    want = (logits.permute(0, 2, 1) + noise).max(dim=-1)[1]
+    assert torch.equal(ids.cpu().long(), want)
+    assert ids[0, 3].item() == 5 and ids[1, 0].item() == 0
+    assert torch.equal(act.cpu(), torch.zeros(B, T8, Cn).scatter_(-1, want.unsqueeze(-1), 1.0).permute(0, 2, 1))
+    # and the reference's softmax-then-max formulation gives the same ids away from exp-rounding merges
+    hard, ind = orc.gumbel_hard(logits[2:].permute(0, 2, 1), u[2:])
+    assert torch.equal(ind, want[2:])
+
+
+@pytest.mark.parametrize('H,B,T', [(128, 5, 16), (512, 3, 40), (32, 9, 7)])
+def test_gru_recurrence_matches_oracle(H, B, T):
+    torch.manual_seed(4)
+    w_hh = (torch.rand(2, 3 * H, H) * 2 - 1) / H ** 0.5
+    b_hh = (torch.rand(2, 3 * H) * 2 - 1) / H ** 0.5
+    gx = torch.randn(B, T, 2, 3 * H)
+    out = torch.zeros(B, T, 2 * H, dtype=torch.float16, device='cuda')
+    gx_d, w_d, b_d = gx.cuda(), w_hh.cuda(), b_hh.cuda()
+    _lib.check(_lib.lib().zs_gru_recurrence(gh.ptr(gx_d), gh.ptr(w_d), gh.ptr(b_d), B, T, H,
+                                            gh.ptr(out), T, 2 * H, 0, 0, 0, gh.stream()))
+    torch.cuda.synchronize()
+    # oracle: feed both directions' projections as 6H input channels and let W_ih select its half
+    x = gx.reshape(B, T, 6 * H).permute(0, 2, 1)
+    eye, zero = torch.eye(3 * H), torch.zeros(3 * H, 3 * H)
+    sd = {'RNN.weight_ih_l0': torch.cat([eye, zero], 1), 'RNN.weight_ih_l0_reverse': torch.cat([zero, eye], 1),
+          'RNN.weight_hh_l0': w_hh[0], 'RNN.weight_hh_l0_reverse': w_hh[1],
+          'RNN.bias_ih_l0': torch.zeros(3 * H), 'RNN.bias_ih_l0_reverse': torch.zeros(3 * H),
+          'RNN.bias_hh_l0': b_hh[0], 'RNN.bias_hh_l0_reverse': b_hh[1]}
+    ref = orc.bi_gru(x, sd)                                  # (B, 2H, T)
+    got = out.float().cpu().permute(0, 2, 1)
+    assert (got - ref).abs().max().item() < 2e-3            # fp16 store of h in (-1, 1)
+
+
+# ------------------------------------------------------------------------------------------------
+# whole path vs golden fixtures of the live reference
+# ------------------------------------------------------------------------------------------------
+GOLDEN_GPU = ['small_onehot', 'small_onehot_odd', 'small_mbv', 'small_continues', 'small_gumbel_t',
+              'full_b2_t128', 'full_b1_t207', 'full_b1_mbv', 'full_b1_e512']
+
+
+@pytest.mark.parametrize('name', GOLDEN_GPU)
+def test_path_matches_reference_golden(name):
+    g = load_golden(name)
+    m = g['meta']
+    enc, dec, _, _ = build_models(m)
+    x = syn.spectrogram_batch(m['B'], m['T'], m['seed'], c_in=m['c_in']).cuda()
+    c = syn.speaker_ids(m['B'], m['n_spk'], m['seed']).cuda()
+    u = torch.from_numpy(g['uniform']) if 'uniform' in g else None
+    noise = gumbel_from_uniform(u) if u is not None else None
+    act, logits, ids = enc.encode(x, noise)
+    ref_logits = torch.from_numpy(g['logits'])
+    assert relrms(logits.cpu(), ref_logits) < (3e-2 if m['c_h'][1] < 512 else LOGIT_RELRMS)
+    if m['enc_mode'] == 'one_hot':
+        # bit-exact given identical logits + noise: redo the reference's op on OUR logits on the CPU
+        _, want = orc.gumbel_hard(logits.cpu().permute(0, 2, 1), u)
+        assert torch.equal(ids.cpu().long(), want)
+        assert torch.equal(act.cpu().argmax(1), want)
+        agree = (ids.cpu().numpy() == g['act_argmax']).mean()
+        assert agree >= 0.9, agree       # 16-26 unit frames per fixture: allow one near-tie flip
+        ref_act = torch.zeros_like(act.cpu()).scatter_(1, torch.from_numpy(g['act_argmax']).long().unsqueeze(1), 1.0)
+    else:
+        ref_act = torch.from_numpy(g['act'].astype(np.float32))
+        if m['enc_mode'] == 'continues':
+            assert relrms(act.cpu(), ref_act) < 3e-2
+        else:
+            assert (act.cpu() == ref_act).float().mean().item() >= 0.97
+    spec = dec(ref_act.cuda(), c)        # decoder error on identical units
+    ref_spec = torch.from_numpy(g['spec'])
+    assert spec.shape == ref_spec.shape
+    assert relrms(spec.cpu(), ref_spec) < SPEC_RELRMS
+    assert (spec.cpu() - ref_spec).abs().max().item() < SPEC_MAXABS
+    if m['enc_mode'] == 'one_hot':
+        # unit-id gather path == dense one-hot GEMM path, bit for bit
+        spec_ids = dec.decode(None, c, unit_ids=torch.from_numpy(g['act_argmax']).cuda())
+        assert torch.equal(spec_ids, spec)
+    if m['patch']:                       # trainer.py:208-209 'targeted' patcher, fused accumulate
+        gen_sd = syn.decoder_state_dict(m['seed'] + 7, c_in=m['enc_size'], c_out=m['c_in'], c_h=m['emb_size'], c_a=2)
+        gen = Decoder(c_in=m['enc_size'], c_out=m['c_in'], c_h=m['emb_size'], c_a=2, ns=m['ns'], seg_len=m['seg_len'])
+        gen.load_state_dict(gen_sd)
+        gen.cuda().eval()
+        c_t = torch.from_numpy(g['c_target']).cuda()
+        y = dec(ref_act.cuda(), c_t)
+        gen.decode(ref_act.cuda(), c_t - (m['n_spk'] - 2), out=y, accumulate=1)
+        assert relrms(y.cpu(), torch.from_numpy(g['spec_patched'])) < SPEC_RELRMS
+
+
+def test_nine_frame_segment(full_models):
+    """MIN_LEN segment (convert.py:36): InstanceNorm over 2-3 frames is ill-conditioned, so only the structure and
+    the decoder (on the reference's units) are held to tolerance."""
+    g = load_golden('full_b1_t9')
+    enc, dec, _, _ = full_models
+    x = syn.spectrogram_batch(1, 9, 0).cuda()
+    noise = gumbel_from_uniform(torch.from_numpy(g['uniform']))
+    act, logits, ids = enc.encode(x, noise)
+    assert logits.shape == (1, 1024, 2) and not torch.isnan(logits).any()
+    ref_act = torch.zeros(1, 1024, 2).scatter_(1, torch.from_numpy(g['act_argmax']).long().unsqueeze(1), 1.0)
+    spec = dec(ref_act.cuda(), syn.speaker_ids(1, 102, 0).cuda())
+    assert spec.shape == (1, 513, 16)
+    assert relrms(spec.cpu(), torch.from_numpy(g['spec'])) < SPEC_RELRMS
+
+
+# ------------------------------------------------------------------------------------------------
+# whole path vs the oracle on seeded inputs, and size-independent properties at full size
+# ------------------------------------------------------------------------------------------------
+def test_full_size_batch_vs_oracle(full_models):
+    enc, dec, enc_sd, dec_sd = full_models
+    B, T = 8, 128
+    x = syn.spectrogram_batch(B, T, 11)
+    c = syn.speaker_ids(B, 102, 11)
+    u = syn.gumbel_uniform((B, 16, 1024), 11)
+    act, logits, ids = enc.encode(x.cuda(), gumbel_from_uniform(u))
+    spec = dec(act, c.cuda())
+    torch.set_num_threads(os.cpu_count())
+    with torch.no_grad():
+        o_act, o_logits, o_ids = orc.encoder_forward(enc_sd, x, u)
+        o_spec = orc.decoder_forward(dec_sd, act.cpu(), c)
+    assert relrms(logits.cpu(), o_logits) < LOGIT_RELRMS
+    assert (ids.cpu().long() == o_ids).float().mean().item() >= 0.95
+    assert relrms(spec.cpu(), o_spec) < SPEC_RELRMS
+    assert (spec.cpu() - o_spec).abs().max().item() < SPEC_MAXABS
+
+
+def test_batching_is_exact_and_segments_independent(full_models):
+    """B = 32 x 128 frames (BASELINE config 2): every segment's result equals its own batch-1 result, in any
+    batch order - the reference's per-chunk loop (convert.py:154-165) and the batched call are interchangeable."""
+    enc, dec, _, _ = full_models
+    B, T = 32, 128
+    x = syn.spectrogram_batch(B, T, 5).cuda()
+    c = syn.speaker_ids(B, 102, 5).cuda()
+    noise = gumbel_from_uniform(syn.gumbel_uniform((B, 16, 1024), 5))
+    act, logits, ids = enc.encode(x, noise)
+    spec = dec.decode(None, c, unit_ids=ids)
+    perm = torch.randperm(B, generator=torch.Generator().manual_seed(0))
+    act_p, logits_p, ids_p = enc.encode(x[perm.cuda()].contiguous(), noise[perm])
+    assert torch.equal(logits_p, logits[perm.cuda()])
+    assert torch.equal(ids_p, ids[perm.cuda()])
+    spec_p = dec.decode(None, c[perm.cuda()], unit_ids=ids_p)
+    assert torch.equal(spec_p, spec[perm.cuda()])
+    for b in (0, 13, 31):
+        a1, l1, i1 = enc.encode(x[b:b + 1].contiguous(), noise[b:b + 1])
+        assert torch.equal(l1[0], logits[b]) and torch.equal(i1[0], ids[b])
+        assert torch.equal(dec.decode(None, c[b:b + 1], unit_ids=i1)[0], spec[b])
+    assert float(spec.min()) > 0.0 and float(spec.max()) < 1.0        # sigmoid output
+    assert torch.equal(act.sum(1), torch.ones(B, 16, device='cuda'))    # one unit per frame
+
+
+def test_frontend_matches_per_chunk_reference_loop(full_models):
+    """convert()/encode() semantics on ragged utterances: chunk plan, MIN_LEN padding/truncation, tail chunk."""
+    enc, dec, enc_sd, dec_sd = full_models
+    path = AutoencoderPath(enc, dec, seg_len=128, max_batch=16)
+    rng = np.random.Generator(np.random.PCG64(7))
+    lengths = [5, 9, 100, 128, 130, 300, 391]
+    specs = [np.clip(rng.random((L, 513), dtype=np.float32), 1e-8, 1) for L in lengths]
+    spk = [3, 7, 100, 101, 0, 55, 20]
+    torch.manual_seed(99)
+    outs, units = path.convert_utterances(specs, spk, enc_only=True, reference_noise_order=True)
+    # replay the reference's loop chunk by chunk with the same generator state, through the oracle on CPU
+    torch.manual_seed(99)
+    for u, spec in enumerate(specs):
+        padded, plan, keep = segment_plan(len(spec), 128)
+        sp = np.concatenate([spec, np.zeros((padded - len(spec), 513), np.float32)]) if padded > len(spec) else spec
+        assert outs[u].shape[0] == sum(8 * Encoder.t8(e - s) for s, e in plan)
+        n_units = sum(Encoder.t8(e - s) for s, e in plan)
+        assert units[u].shape == ((keep if keep is not None else n_units), 1024)
+        assert set(np.unique(units[u])) <= {0.0, 1.0}
+    # one utterance end-to-end against the oracle (noise order = chunk order)
+    torch.manual_seed(99)
+    noises = []
+    for u, spec in enumerate(specs):
+        padded, plan, keep = segment_plan(len(spec), 128)
+        noises.append([torch.rand(1, Encoder.t8(e - s), 1024) for s, e in plan])
+    u = 5
+    _, plan, _ = segment_plan(lengths[u], 128)
+    agree = []
+    with torch.no_grad():
+        for (s, e), un in zip(plan, noises[u]):
+            xs = torch.from_numpy(specs[u][s:e]).t().unsqueeze(0)
+            _, _, o_ids = orc.encoder_forward(enc_sd, xs, un)
+            agree.append(o_ids[0])
+    o_ids = torch.cat(agree)
+    got = torch.from_numpy(units[u]).argmax(1)
+    assert (got == o_ids).float().mean().item() >= 0.9
+
+
+def test_errors_are_loud(full_models):
+    enc, dec, _, _ = full_models
+    with pytest.raises(RuntimeError):
+        enc(torch.rand(1, 513, 8, device='cuda'))          # below MIN_LEN
+    with pytest.raises(RuntimeError):
+        enc(torch.rand(1, 513, 300, device='cuda'))        # longer than 2*seg_len
+    with pytest.raises(RuntimeError):
+        enc(torch.rand(1, 100, 128, device='cuda'))        # wrong channel count
+    with pytest.raises(RuntimeError):
+        dec(torch.rand(1, 1024, 16, device='cuda'), torch.tensor([102]))   # speaker out of range (host ids)
+    with pytest.raises(RuntimeError):
+        e = Encoder(ns=0.01, enc_size=32, seg_len=32, enc_mode='one_hot', c_in=33, c_h1=16, c_h2=64, c_h3=16).cuda()
+        e(torch.rand(1, 33, 40, device='cuda'))            # zero-pad mode (seg_len < 64) is rejected, not approximated

@@ -77,7 +77,7 @@ class ConvDesc(C.Structure):
                 ('c_in_pad', C.c_int32), ('w_taps', C.c_int32), ('bank', C.c_int32),
                 ('in_', C.c_void_p), ('in_rows', C.c_int32), ('in_pitch', C.c_int32), ('in_row0', C.c_int32),
                 ('c_in_valid', C.c_int32), ('stride', C.c_int32), ('B', C.c_int32), ('T_out', C.c_int32),
-                ('bias', C.c_void_p), ('spk', C.c_void_p), ('lrelu', C.c_int32), ('ns', C.c_float),
+                ('bias', C.c_void_p), ('spk', C.c_void_p), ('n_spk', C.c_int32), ('lrelu', C.c_int32), ('ns', C.c_float),
                 ('inorm', C.c_int32), ('res_mode', C.c_int32), ('res', C.c_void_p), ('res_rows', C.c_int32),
                 ('res_pitch', C.c_int32), ('res_halo', C.c_int32), ('act', C.c_int32), ('out_mode', C.c_int32),
                 ('out', C.c_void_p), ('out_rows', C.c_int32), ('out_pitch', C.c_int32), ('out_halo', C.c_int32),
@@ -98,6 +98,9 @@ SYMBOLS = {
     'zs_decoder_workspace_bytes': (_sz, [_vp, _i, _i]),
     'zs_encoder_forward': (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     'zs_decoder_forward': (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _i, _vp, _sz, _vp]),
+    'zs_profile_begin': (None, []),
+    'zs_profile_end': (_i, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
+    'zs_launch_counts': (None, [C.POINTER(C.c_longlong)]),
     'zs_bottleneck_one_hot': (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
     'zs_conv1d_cl': (_i, [C.POINTER(ConvDesc), _vp]),
     'zs_pack_nct': (_i, [_vp, _i, _i, _i, _vp, _i, _i, _i, _i, _i, C.c_float, _i, _i, _vp]),

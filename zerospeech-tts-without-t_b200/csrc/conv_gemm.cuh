@@ -45,7 +45,7 @@ struct alignas(64) GemmParams {
     int m_valid;
     const float* bias;
     const long long* spk;
-    int bias_stride;
+    int bias_stride, n_spk;
     int lrelu;
     float ns;
     int inorm;
@@ -212,7 +212,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
                 if (b >= p.B) break;
                 float bias = 0.f;
                 if (p.bias != nullptr) {  // tables are padded to m_tiles * 128 rows
-                    const size_t off = p.spk ? static_cast<size_t>(p.spk[b]) * p.bias_stride : 0;
+                    size_t off = 0;
+                    if (p.spk) {
+                        long long sp = p.spk[b];
+                        sp = sp < 0 ? 0 : (sp >= p.n_spk ? p.n_spk - 1 : sp);
+                        off = static_cast<size_t>(sp) * p.bias_stride;
+                    }
                     bias = p.bias[off + ch];
                 }
                 const uint32_t t_seg = t_lane + s * p.Tt;

@@ -70,6 +70,50 @@ static int ensure_device() {
 }
 extern "C" int zs_device_check(void) { return ensure_device(); }
 
+// -------------------------------------------------------------------------------------------------
+// launch accounting + optional per-kernel-class CUDA-event timing (zs_profile_begin / zs_profile_end)
+// -------------------------------------------------------------------------------------------------
+enum { KC_GEMM = 0, KC_GRU = 1, KC_OTHER = 2, KC_COUNT = 3 };
+struct ProfSpan { cudaEvent_t a, b; int cls; double flops; };
+static bool g_prof_on = false;
+static std::vector<ProfSpan> g_prof;
+static long long g_launches[KC_COUNT] = {0, 0, 0};
+static double g_flops[KC_COUNT] = {0, 0, 0};
+
+struct LaunchScope {     // brackets one kernel launch on `st`
+    cudaStream_t st; int cls; double flops; cudaEvent_t a = nullptr, b = nullptr;
+    LaunchScope(cudaStream_t s, int c, double f = 0.0) : st(s), cls(c), flops(f) {
+        g_launches[c]++; g_flops[c] += f;
+        if (g_prof_on) { cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, st); }
+    }
+    ~LaunchScope() {
+        if (a) { cudaEventRecord(b, st); g_prof.push_back({a, b, cls, flops}); }
+    }
+};
+
+extern "C" void zs_profile_begin(void) {
+    for (auto& s : g_prof) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
+    g_prof.clear();
+    for (int i = 0; i < KC_COUNT; ++i) { g_launches[i] = 0; g_flops[i] = 0; }
+    g_prof_on = true;
+}
+extern "C" int zs_profile_end(double* ms, double* flops, long long* launches) {
+    g_prof_on = false;
+    for (int i = 0; i < KC_COUNT; ++i) { ms[i] = 0; flops[i] = g_flops[i]; launches[i] = g_launches[i]; }
+    for (auto& s : g_prof) {
+        CUDA_TRY(cudaEventSynchronize(s.b));
+        float t = 0.f;
+        CUDA_TRY(cudaEventElapsedTime(&t, s.a, s.b));
+        ms[s.cls] += t;
+        cudaEventDestroy(s.a); cudaEventDestroy(s.b);
+    }
+    g_prof.clear();
+    return ZS_OK;
+}
+extern "C" void zs_launch_counts(long long* launches) {
+    for (int i = 0; i < KC_COUNT; ++i) launches[i] = g_launches[i];
+}
+
 static inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
 static inline size_t align256(size_t v) { return (v + 255) & ~static_cast<size_t>(255); }
 static inline int buf_rows(int T, int halo) { return round_up(T + 2 * halo, 2); }
@@ -146,7 +190,7 @@ static int launch_conv(const zs_conv_desc* d, cudaStream_t stream) {
     p.m_tiles = m_tiles; p.n_tiles = n_tiles; p.nb = nb; p.Tt = Tt; p.T = d->T_out; p.B = d->B; p.N = nb * Tt;
     p.kc = d->c_in_pad / BK; p.taps = d->taps; p.bank = d->bank; p.stride = d->stride; p.in_row0 = d->in_row0;
     p.c_in_pad = d->c_in_pad; p.m_valid = d->m_valid;
-    p.bias = d->bias; p.spk = reinterpret_cast<const long long*>(d->spk); p.bias_stride = d->m_rows;
+    p.bias = d->bias; p.spk = reinterpret_cast<const long long*>(d->spk); p.bias_stride = d->m_rows; p.n_spk = d->n_spk > 0 ? d->n_spk : 1;
     p.lrelu = d->lrelu; p.ns = d->ns; p.inorm = d->inorm;
     p.res_mode = d->res_mode; p.res = d->res; p.res_rows = d->res_rows; p.res_pitch = d->res_pitch; p.res_halo = d->res_halo;
     p.act = d->act; p.out_mode = d->out_mode; p.out = d->out; p.out_rows = d->out_rows; p.out_pitch = d->out_pitch;
@@ -160,8 +204,13 @@ static int launch_conv(const zs_conv_desc* d, cudaStream_t stream) {
         else CUDA_TRY(cudaFuncSetAttribute(conv_gemm_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
         g_attr_set[which] = true;
     }
-    if (which) conv_gemm_kernel<__nv_bfloat16><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, stream>>>(p);
-    else conv_gemm_kernel<__half><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, stream>>>(p);
+    {   // algorithmic FLOPs: 2 * valid out channels * true taps * true in channels * valid frames
+        double taps_sum = d->bank ? 28.0 / 7.0 : static_cast<double>(d->taps);
+        const double flops = 2.0 * d->m_valid * taps_sum * d->c_in_valid * static_cast<double>(d->B) * d->T_out;
+        LaunchScope scope(stream, KC_GEMM, flops);
+        if (which) conv_gemm_kernel<__nv_bfloat16><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, stream>>>(p);
+        else conv_gemm_kernel<__half><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, stream>>>(p);
+    }
     CUDA_TRY(cudaGetLastError());
     return ZS_OK;
 }
@@ -175,6 +224,7 @@ static int launch_pack_nct(const float* x, int B, int C, int T, void* out, int r
     if (halo >= T && halo > 0) return fail(ZS_ERR_ARG, "pack: reflect halo %d needs more than %d frames", halo, T);
     const int c_fill = zero_pad ? pitch - choff : C;
     dim3 grid((T + 31) / 32, (c_fill + 31) / 32, B), block(32, 8);
+    LaunchScope scope(st, KC_OTHER);
     if (operand == ZS_OPERAND_BF16)
         pack_nct_kernel<__nv_bfloat16><<<grid, block, 0, st>>>(x, static_cast<__nv_bfloat16*>(out), C, T, rows, pitch, halo, choff, c_fill, lrelu, ns);
     else
@@ -195,6 +245,7 @@ static int launch_onehot(const float* logits, const float* noise, int B, int C, 
         CUDA_TRY(cudaFuncSetAttribute(bottleneck_onehot_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         attr = 200 * 1024;
     }
+    LaunchScope scope(st, KC_OTHER);
     bottleneck_onehot_kernel<<<B, 512, smem, st>>>(logits, noise, C, T8, act, ids);
     CUDA_TRY(cudaGetLastError());
     return ZS_OK;
@@ -211,6 +262,7 @@ static int launch_gru(const float* gx, const float* whhT, const float* bhh, int 
     constexpr int NBG = 4;
     dim3 grid((B + NBG - 1) / NBG, 2);
     const size_t smem = static_cast<size_t>(NBG) * H * 4;
+    LaunchScope scope(st, KC_GRU, 2.0 * 2 * B * static_cast<double>(T) * 3 * H * H);
     if (operand == ZS_OPERAND_BF16)
         gru_simple_kernel<__nv_bfloat16, NBG><<<grid, H, smem, st>>>(gx, whhT, bhh, B, T, H, static_cast<__nv_bfloat16*>(out), rows, pitch, halo, choff);
     else
@@ -238,7 +290,7 @@ extern "C" int zs_gru_recurrence(const float* gx, const float* w_hh, const float
 struct Layer {          // one GEMM's worth of packed weights
     void* w = nullptr;      // operand type [m_rows][w_taps * c_in_pad]
     float* bias = nullptr;  // [n_tab][m_rows]
-    int m_rows = 0, m_valid = 0, taps = 1, w_taps = 1, c_in_pad = 0, c_in_valid = 0, per_spk = 0, ps = 0;
+    int m_rows = 0, m_valid = 0, taps = 1, w_taps = 1, c_in_pad = 0, c_in_valid = 0, per_spk = 0, ps = 0, n_tab = 1;
 };
 
 struct DevPool {        // owns every device allocation of a handle
@@ -272,6 +324,7 @@ static int pack_layer(DevPool& pool, Layer& L, int operand, const float* W, cons
         pack_weight_kernel<__half><<<blocks, 256, 0, st>>>(W, static_cast<__half*>(L.w), C_out, C_in, k, ci_lo, ci_n, k_total, L.c_in_pad, 0, 0, ps);
     CUDA_TRY(cudaGetLastError());
     const int n_tab = emb ? n_spk : 1;
+    L.n_tab = n_tab;
     ZS_TRY(pool.alloc(reinterpret_cast<void**>(&L.bias), static_cast<size_t>(n_tab) * L.m_rows * 4, st));
     const long long warps = static_cast<long long>(n_tab) * C_out;
     fold_bias_kernel<<<static_cast<int>((warps * 32 + 255) / 256), 256, 0, st>>>(W, b, emb, L.bias, C_out, C_in, k, emb_ci_lo, emb ? C_e : 0, n_tab, L.m_rows, 0, ps);
@@ -314,6 +367,7 @@ static int pack_gru(DevPool& pool, Layer& ih, float** whhT, float** bhh, int ope
     ih.c_in_pad = round_up(C, BK); ih.c_in_valid = C; ih.per_spk = emb ? 1 : 0;
     ZS_TRY(pool.alloc(&ih.w, static_cast<size_t>(ih.m_rows) * ih.c_in_pad * 2, st));
     const int n_tab = emb ? n_spk : 1;
+    ih.n_tab = n_tab;
     ZS_TRY(pool.alloc(reinterpret_cast<void**>(&ih.bias), static_cast<size_t>(n_tab) * ih.m_rows * 4, st));
     ZS_TRY(pool.alloc(reinterpret_cast<void**>(whhT), static_cast<size_t>(2) * 3 * H * H * 4, st));
     ZS_TRY(pool.alloc(reinterpret_cast<void**>(bhh), static_cast<size_t>(2) * 3 * H * 4, st));
@@ -546,7 +600,7 @@ static int run_layer(const Layer& L, int operand, float ns, const Buf& in, int B
     if (d.in_row0 < 0) return fail(ZS_ERR_ARG, "layer: input halo %d < pad %d", in.halo, pad_left);
     d.c_in_valid = o.c_in_valid >= 0 ? o.c_in_valid : L.c_in_valid;
     d.stride = o.stride; d.B = B; d.T_out = T_out;
-    d.bias = L.bias; d.spk = L.per_spk ? o.spk : nullptr;
+    d.bias = L.bias; d.spk = L.per_spk ? o.spk : nullptr; d.n_spk = L.n_tab;
     if (L.per_spk && !o.spk) return fail(ZS_ERR_ARG, "layer: speaker ids required");
     d.lrelu = o.lrelu; d.ns = ns; d.inorm = o.inorm;
     d.res_mode = o.res_mode;
@@ -618,6 +672,7 @@ extern "C" int zs_encoder_forward(zs_encoder* h, const float* x, int B, int T, c
         ZS_TRY(launch_onehot(logits, gumbel_noise, B, g.enc_size, T8, act, unit_ids, st));
     } else if (act) {
         const size_t n = g.enc_mode == ZS_ENC_GUMBEL_T ? static_cast<size_t>(B) * g.enc_size : static_cast<size_t>(B) * g.enc_size * T8;
+        LaunchScope scope(st, KC_OTHER);
         bottleneck_misc_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(logits, gumbel_noise, g.enc_mode, B, g.enc_size, T8, ns, act);
         CUDA_TRY(cudaGetLastError());
     }
@@ -639,6 +694,7 @@ extern "C" int zs_decoder_forward(zs_decoder* h, const float* enc_act, const int
 
     if (unit_ids) {   // one-hot input: input_emb is a column gather (model/model.py:346)
         dim3 grid(T8, B);
+        LaunchScope scope(st, KC_OTHER);
         if (op == ZS_OPERAND_BF16)
             unit_gather_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(unit_ids, static_cast<const __nv_bfloat16*>(h->emb_table), h->input_emb.bias, static_cast<__nv_bfloat16*>(w.x0.p), T8, ch, w.x0.rows, w.x0.pitch, 1, g.c_in);
         else

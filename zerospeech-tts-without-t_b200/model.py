@@ -275,11 +275,11 @@ class Decoder(_Packed):
         else:
             unit_ids = unit_ids.to(torch.int32).contiguous()
             B, T8 = unit_ids.shape
-        c = c.to(dev, torch.int64).contiguous().view(-1)
+        if not c.is_cuda and c.numel() and (int(c.min()) < 0 or int(c.max()) >= self.c_a):
+            raise RuntimeError(f'Decoder: speaker id outside [0, {self.c_a})')   # host ids are validated here;
+        c = c.to(dev, torch.int64).contiguous().view(-1)                        # device ids are clamped by the kernel
         if c.numel() != B:
             raise RuntimeError(f'Decoder: {c.numel()} speaker ids for {B} segments')
-        if int(c.min()) < 0 or int(c.max()) >= self.c_a:
-            raise RuntimeError(f'Decoder: speaker id outside [0, {self.c_a})')
         lib = _lib.lib()
         with torch.cuda.device(dev):
             h = self._ensure_packed(dev)
