@@ -203,10 +203,12 @@ int zs_pack_nct(const float* x, int B, int C, int T, void* out, int rows, int pi
 
 /* bidirectional GRU recurrence with zero initial state (model/model.py:59-66) on precomputed
  * input projections gx [B][T][2][3H] fp32 (b_ih folded in), w_hh [2][3H][H] fp32, b_hh [2][3H];
- * writes h_t (operand type) to out[b][out_halo+t][out_choff + dir*H + j]. */
+ * writes h_t (operand type) to out[b][out_halo+t][out_choff + dir*H + j].
+ * impl: 0 = what the forward passes use (tensor-core cluster kernel when H % 64 == 0 and H <= 512, else the
+ * CUDA-core kernel), 1 = CUDA-core kernel, 2 = cluster kernel. */
 int zs_gru_recurrence(const float* gx, const float* w_hh, const float* b_hh, int B, int T, int H,
                       void* out, int out_rows, int out_pitch, int out_halo, int out_choff,
-                      int operand, void* stream);
+                      int operand, int impl, void* stream);
 
 #ifdef __cplusplus
 }

@@ -117,8 +117,9 @@ def test_bottleneck_argmax_bit_exact_with_ties():
     assert torch.equal(ind, want[2:])
 
 
-@pytest.mark.parametrize('H,B,T', [(128, 5, 16), (512, 3, 40), (32, 9, 7)])
-def test_gru_recurrence_matches_oracle(H, B, T):
+@pytest.mark.parametrize('H,B,T,impl', [(128, 5, 16, 1), (128, 5, 16, 2), (512, 3, 40, 1), (512, 3, 40, 2),
+                                        (512, 37, 128, 2), (64, 20, 9, 2), (32, 9, 7, 0), (256, 16, 33, 2)])
+def test_gru_recurrence_matches_oracle(H, B, T, impl):
     torch.manual_seed(4)
     w_hh = (torch.rand(2, 3 * H, H) * 2 - 1) / H ** 0.5
     b_hh = (torch.rand(2, 3 * H) * 2 - 1) / H ** 0.5
@@ -126,7 +127,7 @@ def test_gru_recurrence_matches_oracle(H, B, T):
     out = torch.zeros(B, T, 2 * H, dtype=torch.float16, device='cuda')
     gx_d, w_d, b_d = gx.cuda(), w_hh.cuda(), b_hh.cuda()
     _lib.check(_lib.lib().zs_gru_recurrence(gh.ptr(gx_d), gh.ptr(w_d), gh.ptr(b_d), B, T, H,
-                                            gh.ptr(out), T, 2 * H, 0, 0, 0, gh.stream()))
+                                            gh.ptr(out), T, 2 * H, 0, 0, 0, impl, gh.stream()))
     torch.cuda.synchronize()
     # oracle: feed both directions' projections as 6H input channels and let W_ih select its half
     x = gx.reshape(B, T, 6 * H).permute(0, 2, 1)

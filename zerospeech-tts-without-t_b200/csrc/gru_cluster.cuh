@@ -1,0 +1,273 @@
+// Bidirectional GRU recurrence (model/model.py:59-66, zero initial state) on tcgen05 tensor cores.
+//
+// One thread-block CLUSTER of NC = H/64 CTAs runs the T sequential steps of one (direction, group of 16
+// sequences).  CTA r owns hidden units [64r, 64r+64): its 192 rows of W_hh (r|z|n gates of those units, all
+// K = H columns, fp16/bf16) stay resident in shared memory for the whole kernel as the A operand; the hidden
+// state of the 16 sequences is the B operand ([16 rows][H], K-major, 128-byte swizzled), double-buffered.
+// Per step:  D_rz[128 x 16] = W_rz h^T (M = 128),  D_n[64 x 16] = W_n h^T (M = 64)  -> TMEM;
+// the 4 epilogue warps read D, add the precomputed input projections gx (from the GEMM kernel) and b_hh,
+// apply the gates, keep h in fp32 registers, write h_t to the output buffer and publish their 64-unit slice of
+// the new state to every CTA of the cluster with one bulk shared->shared::cluster copy per peer that
+// completes on the peer's mbarrier (no cluster-wide barrier inside the time loop).
+//
+// Row order of the A tiles is chosen so a unit's three gate pre-activations land in the same warp:
+//   tile RZ (M = 128): TMEM lane 32q + l  = r-gate of unit 16q + l (l < 16), z-gate of unit 16q + l - 16 (l >= 16)
+//   tile N  (M = 64):  TMEM lane 32q + l  = n-gate of unit 16q + l (l < 16)      [M = 64 uses 16 lanes per quadrant]
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+#include "conv_gemm.cuh"
+#include "ptx.cuh"
+
+namespace zs {
+
+constexpr int GRU_NSEQ = 16;        // sequences per cluster (UMMA N)
+constexpr int GRU_UNITS = 64;       // hidden units per CTA
+constexpr int GRU_THREADS = 160;    // warps 0-3: gate math (one TMEM quadrant each), warp 4: MMA issue / control
+constexpr int GRU_TMEM_COLS = 64;
+
+__host__ __device__ inline int gru_w_image_bytes(int H) { return 192 * H * 2; }
+__host__ __device__ inline int gru_smem_bytes(int H) {
+    return gru_w_image_bytes(H) + 2 * GRU_NSEQ * H * 2 + 1024 /*align*/ + 128 /*barriers*/;
+}
+
+// byte offset of element (row, k) inside a K-major tile of `rows` rows stored as K/64 consecutive chunks of
+// [rows][64] elements, each row 128 bytes with the 128-byte swizzle (16-byte unit index XOR (row % 8))
+__host__ __device__ inline int sw128_offset(int rows, int row, int k) {
+    const int chunk = k >> 6, kk = k & 63;
+    return chunk * rows * 128 + row * 128 + ((((kk >> 3) ^ (row & 7)) << 4) | ((kk & 7) << 1));
+}
+
+// W_hh (3H, H) fp32 of one direction -> per-CTA shared-memory images [NC][192 * H] operand type:
+// tile RZ (128 rows) followed by tile N (64 rows), rows ordered as described above.
+template <typename OT>
+__global__ void gru_pack_whh_kernel(const float* __restrict__ W, OT* __restrict__ img, int H) {
+    const int NC = H / GRU_UNITS;
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= static_cast<long long>(3) * H * H) return;
+    const int k = i % H, grow = i / H;          // grow: row of W_hh = gate * H + unit
+    const int gate = grow / H, unit = grow % H;
+    const int cta = unit / GRU_UNITS, u = unit % GRU_UNITS;
+    const int q = u >> 4, l = u & 15;
+    int off;
+    if (gate < 2) off = sw128_offset(128, 32 * q + 16 * gate + l, k);
+    else off = 128 * H * 2 + sw128_offset(64, u, k);
+    (void)NC;
+    OT* dst = reinterpret_cast<OT*>(reinterpret_cast<char*>(img) + static_cast<long long>(cta) * gru_w_image_bytes(H) + off);
+    *dst = float_to_ot<OT>(W[i]);
+}
+
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t cta) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(cta));
+    return r;
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t cluster_id_x() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// local shared -> peer CTA shared, completion (bytes) signalled on the PEER's mbarrier
+__device__ __forceinline__ void dsmem_bulk_copy(uint32_t dst_cluster_addr, uint32_t src_cta_addr, uint32_t bytes,
+                                                uint32_t mbar_cluster_addr) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            dst_cluster_addr),
+        "r"(src_cta_addr), "r"(bytes), "r"(mbar_cluster_addr)
+        : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__host__ __device__ inline uint32_t umma_idesc_f16_m(int fmt, int m, int n) {
+    uint32_t d = 0;
+    d |= 1u << 4;
+    d |= static_cast<uint32_t>(fmt) << 7;
+    d |= static_cast<uint32_t>(fmt) << 10;
+    d |= static_cast<uint32_t>(n >> 3) << 17;
+    d |= static_cast<uint32_t>(m >> 4) << 24;
+    return d;
+}
+
+struct GruParams {
+    const void* w_img;      // [2 dirs][NC][192 * H] operand type (gru_pack_whh_kernel)
+    const float* bhh;       // [2][3H]
+    const float* gx;        // [B][T][2][3H] fp32, b_ih (+ speaker term) folded in
+    void* out;              // operand type [B][out_rows][out_pitch]
+    int B, T, H, out_rows, out_pitch, out_halo, out_choff, fmt;
+};
+
+template <typename OT>
+__global__ void __launch_bounds__(GRU_THREADS, 1) gru_cluster_kernel(const GruParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw_addr = smem_u32(smem_raw);
+    uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+    const int H = p.H, KCH = H >> 6, NC = KCH;
+    uint8_t* sW = smem;                                   // [192 * H * 2]
+    uint8_t* sH = smem + gru_w_image_bytes(H);            // 2 x [KCH chunks][16 rows][128 B]
+    const int hbuf_bytes = GRU_NSEQ * H * 2;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sH + 2 * hbuf_bytes);
+    uint64_t* h_full = bars;          // [2]
+    uint64_t* mma_done = bars + 2;    // [1]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int cl = cluster_id_x();
+    const int n_groups = (p.B + GRU_NSEQ - 1) / GRU_NSEQ;
+    const int dir = cl / n_groups, b0 = (cl % n_groups) * GRU_NSEQ;
+
+    // ---- one-time setup: W_hh slice -> smem, zero h buffers, barriers, TMEM ----
+    {
+        const uint4* src = reinterpret_cast<const uint4*>(static_cast<const uint8_t*>(p.w_img) +
+                                                          (static_cast<size_t>(dir) * NC + rank) * gru_w_image_bytes(H));
+        uint4* dst = reinterpret_cast<uint4*>(sW);
+        const int n16 = gru_w_image_bytes(H) / 16;
+        for (int i = threadIdx.x; i < n16; i += GRU_THREADS) dst[i] = src[i];
+        uint4* hz = reinterpret_cast<uint4*>(sH);
+        for (int i = threadIdx.x; i < 2 * hbuf_bytes / 16; i += GRU_THREADS) hz[i] = make_uint4(0, 0, 0, 0);
+    }
+    if (threadIdx.x == 0) {
+        mbar_init(&h_full[0], 2);
+        mbar_init(&h_full[1], 2);
+        mbar_init(mma_done, 1);
+        fence_barrier_init();
+    }
+    if (warp == 4) tmem_alloc<GRU_TMEM_COLS>(tmem_slot);
+    fence_proxy_async_smem();          // generic-proxy smem writes -> visible to the tensor-core (async) proxy
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    cluster_sync_all();                // every CTA's barriers are initialised before any peer signals them
+
+    const uint32_t slice_bytes = GRU_NSEQ * 128;          // one 64-unit chunk of the state: [16 rows][128 B]
+    const uint32_t peer_tx = (NC - 1) * slice_bytes;
+
+    if (warp == 4) {
+        // ------------------------------ control / MMA issue ------------------------------
+        if (lane == 0) {
+            const uint32_t idesc_rz = umma_idesc_f16_m(p.fmt, 128, GRU_NSEQ);
+            const uint32_t idesc_n = umma_idesc_f16_m(p.fmt, 64, GRU_NSEQ);
+            const uint32_t w_rz = smem_u32(sW), w_n = smem_u32(sW) + 128 * H * 2, hb = smem_u32(sH);
+            if (NC > 1) {              // arm the first use of each state buffer (steps 1 and 2)
+                if (p.T > 1) mbar_expect_tx(&h_full[1], peer_tx);
+                if (p.T > 2) mbar_expect_tx(&h_full[0], peer_tx);
+            } else {
+                if (p.T > 1) mbar_arrive(&h_full[1]);
+                if (p.T > 2) mbar_arrive(&h_full[0]);
+            }
+            for (int t = 0; t < p.T; ++t) {
+                const int pb = t & 1;
+                if (t > 0) {
+                    mbar_wait(&h_full[pb], ((t - 1) >> 1) & 1);
+                    if (t + 2 < p.T) {   // re-arm this buffer for step t + 2
+                        if (NC > 1) mbar_expect_tx(&h_full[pb], peer_tx);
+                        else mbar_arrive(&h_full[pb]);
+                    }
+                }
+                tc_fence_after();
+                const uint32_t hcur = hb + pb * hbuf_bytes;
+                for (int c = 0; c < KCH; ++c) {
+                    const uint64_t da = umma_desc_sw128(w_rz + c * (128 * 128));
+                    const uint64_t dn = umma_desc_sw128(w_n + c * (64 * 128));
+                    const uint64_t db = umma_desc_sw128(hcur + c * slice_bytes);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        umma_f16(tmem_base, da + 2 * k, db + 2 * k, idesc_rz, (c | k) != 0);
+                        umma_f16(tmem_base + 32, dn + 2 * k, db + 2 * k, idesc_n, (c | k) != 0);
+                    }
+                }
+                umma_commit(mma_done);
+            }
+        }
+    } else {
+        // ------------------------------ gate math (warps 0..3) ------------------------------
+        const int q = warp, l = lane & 15, hi = lane >> 4;     // hi = 0: sequences 0..7, hi = 1: sequences 8..15
+        const int u_loc = 16 * q + l;                          // unit within this CTA's 64
+        const int unit = rank * GRU_UNITS + u_loc;
+        const float* bh = p.bhh + static_cast<size_t>(dir) * 3 * H;
+        const float b_r = bh[unit], b_z = bh[H + unit], b_n = bh[2 * H + unit];
+        float h[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) h[i] = 0.f;
+        OT* out = reinterpret_cast<OT*>(p.out);
+        const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(32 * q) << 16);
+        const int seq0 = b0 + 8 * hi;
+        for (int t = 0; t < p.T; ++t) {
+            const int tt = dir ? p.T - 1 - t : t;
+            const int pb = t & 1;
+            // input projections of this step: issued before the MMA wait so their latency overlaps it
+            float gr[8], gz[8], gn[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int b = seq0 + i;
+                if (b < p.B) {
+                    const float* g = p.gx + ((static_cast<size_t>(b) * p.T + tt) * 2 + dir) * 3 * H + unit;
+                    gr[i] = g[0]; gz[i] = g[H]; gn[i] = g[2 * H];
+                } else {
+                    gr[i] = gz[i] = gn[i] = 0.f;
+                }
+            }
+            mbar_wait(mma_done, t & 1);
+            tc_fence_after();
+            uint32_t a[16], nn[16];
+            tmem_ld16(t_addr, a);            // lanes 0-15: W_hr h, lanes 16-31: W_hz h   (16 sequences)
+            tmem_ld16(t_addr + 32, nn);      // lanes 0-15: W_hn h
+            tmem_ld_wait();
+            tc_fence_before();
+            float hr[8], hzv[8], hn[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const uint32_t send = hi ? a[i] : a[8 + i];
+                const uint32_t got = __shfl_xor_sync(0xffffffffu, send, 16);
+                const uint32_t gotn = __shfl_xor_sync(0xffffffffu, nn[8 + i], 16);
+                hr[i] = __uint_as_float(hi ? got : a[i]);
+                hzv[i] = __uint_as_float(hi ? a[8 + i] : got);
+                hn[i] = __uint_as_float(hi ? gotn : nn[i]);
+            }
+            uint8_t* hnext = sH + (pb ^ 1) * hbuf_bytes + rank * slice_bytes;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float r = 1.f / (1.f + __expf(-(gr[i] + hr[i] + b_r)));
+                const float z = 1.f / (1.f + __expf(-(gz[i] + hzv[i] + b_z)));
+                const float n = tanh_f(gn[i] + r * (hn[i] + b_n));
+                h[i] = (1.f - z) * n + z * h[i];
+                const OT y = float_to_ot<OT>(h[i]);
+                const int s = 8 * hi + i;      // row of the state tile
+                *reinterpret_cast<OT*>(hnext + s * 128 + ((((u_loc >> 3) ^ (s & 7)) << 4) | ((u_loc & 7) << 1))) = y;
+                const int b = seq0 + i;
+                if (b < p.B)
+                    out[(static_cast<size_t>(b) * p.out_rows + p.out_halo + tt) * p.out_pitch + p.out_choff + dir * H + unit] = y;
+            }
+            if (t + 1 < p.T) {
+                fence_proxy_async_smem();                       // my slice -> visible to the bulk-copy engine / MMA
+                asm volatile("bar.sync 1, 128;" ::: "memory");   // the 4 gate warps only
+                if (threadIdx.x == 0) {
+                    const uint32_t src = smem_u32(hnext);
+                    const uint32_t bar_local = smem_u32(&h_full[pb ^ 1]);
+                    for (uint32_t d = 1; d < static_cast<uint32_t>(NC); ++d) {
+                        const uint32_t peer = (rank + d) % NC;
+                        dsmem_bulk_copy(mapa_shared(src, peer), src, slice_bytes, mapa_shared(bar_local, peer));
+                    }
+                    mbar_arrive(&h_full[pb ^ 1]);                // my own slice is in place
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                // nobody leaves while a peer may still be reading its slices
+    if (warp == 4) tmem_dealloc<GRU_TMEM_COLS>(tmem_base);
+}
+
+}  // namespace zs

@@ -13,6 +13,7 @@
 
 #include "conv_gemm.cuh"
 #include "kernels.cuh"
+#include "gru_cluster.cuh"
 
 using namespace zs;
 
@@ -271,10 +272,67 @@ static int launch_gru(const float* gx, const float* whhT, const float* bhh, int 
     return ZS_OK;
 }
 
+static bool gru_cluster_ok(int H) { return H % GRU_UNITS == 0 && H / GRU_UNITS >= 1 && H / GRU_UNITS <= 8; }
+
+static int launch_gru_cluster(const void* w_img, const float* bhh, const float* gx, int B, int T, int H, void* out, int rows,
+                              int pitch, int halo, int choff, int operand, cudaStream_t st) {
+    ZS_TRY(ensure_device());
+    GruParams p;
+    p.w_img = w_img; p.bhh = bhh; p.gx = gx; p.out = out; p.B = B; p.T = T; p.H = H;
+    p.out_rows = rows; p.out_pitch = pitch; p.out_halo = halo; p.out_choff = choff;
+    p.fmt = operand == ZS_OPERAND_BF16 ? 1 : 0;
+    const int NC = H / GRU_UNITS, n_groups = (B + GRU_NSEQ - 1) / GRU_NSEQ;
+    const int smem = gru_smem_bytes(H);
+    static int attr_set[2] = {0, 0};
+    const int which = p.fmt;
+    if (attr_set[which] < smem) {
+        if (which) CUDA_TRY(cudaFuncSetAttribute(gru_cluster_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        else CUDA_TRY(cudaFuncSetAttribute(gru_cluster_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_set[which] = smem;
+    }
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(2 * n_groups * NC);
+    cfg.blockDim = dim3(GRU_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = NC; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    LaunchScope scope(st, KC_GRU, 2.0 * 2 * B * static_cast<double>(T) * 3 * H * H);
+    if (which) CUDA_TRY(cudaLaunchKernelEx(&cfg, gru_cluster_kernel<__nv_bfloat16>, p));
+    else CUDA_TRY(cudaLaunchKernelEx(&cfg, gru_cluster_kernel<__half>, p));
+    return ZS_OK;
+}
+
+static int pack_gru_image(void* img, const float* const* w_hh_dirs, const float* w_hh_packed, int H, int operand, cudaStream_t st) {
+    const int NC = H / GRU_UNITS;
+    for (int dir = 0; dir < 2; ++dir) {
+        const float* W = w_hh_dirs ? w_hh_dirs[dir] : w_hh_packed + static_cast<size_t>(dir) * 3 * H * H;
+        void* dst = static_cast<uint8_t*>(img) + static_cast<size_t>(dir) * NC * gru_w_image_bytes(H);
+        const int blocks = (3 * H * H + 255) / 256;
+        if (operand == ZS_OPERAND_BF16) gru_pack_whh_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(W, static_cast<__nv_bfloat16*>(dst), H);
+        else gru_pack_whh_kernel<__half><<<blocks, 256, 0, st>>>(W, static_cast<__half*>(dst), H);
+    }
+    CUDA_TRY(cudaGetLastError());
+    return ZS_OK;
+}
+
 extern "C" int zs_gru_recurrence(const float* gx, const float* w_hh, const float* b_hh, int B, int T, int H, void* out,
-                                 int out_rows, int out_pitch, int out_halo, int out_choff, int operand, void* stream) {
-    // test entry: transposes w_hh into a temporary (stream-ordered) buffer, then runs the recurrence
+                                 int out_rows, int out_pitch, int out_halo, int out_choff, int operand, int impl, void* stream) {
+    // test entry: packs w_hh into a temporary (stream-ordered) buffer, then runs the recurrence
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (impl == 2 && !gru_cluster_ok(H)) return fail(ZS_ERR_ARG, "gru: the cluster kernel needs H %% 64 == 0 and H <= 512 (H = %d)", H);
+    if (impl == 2 || (impl == 0 && gru_cluster_ok(H))) {
+        void* img = nullptr;
+        const size_t bytes = static_cast<size_t>(2) * (H / GRU_UNITS) * gru_w_image_bytes(H);
+        CUDA_TRY(cudaMallocAsync(&img, bytes, st));
+        int r = pack_gru_image(img, nullptr, w_hh, H, operand, st);
+        if (r == ZS_OK) r = launch_gru_cluster(img, b_hh, gx, B, T, H, out, out_rows, out_pitch, out_halo, out_choff, operand, st);
+        cudaFreeAsync(img, st);
+        return r;
+    }
     float* wt = nullptr;
     CUDA_TRY(cudaMallocAsync(&wt, static_cast<size_t>(2) * 3 * H * H * 4, st));
     for (int dir = 0; dir < 2; ++dir)
@@ -343,6 +401,7 @@ struct zs_encoder {
     Layer gru_ih;           // both directions stacked: rows [0, 3H) forward, [3H, 6H) reverse
     float* whhT = nullptr;  // [2][H][3H] fp32
     float* bhh = nullptr;   // [2][3H]
+    void* whh_img = nullptr;  // cluster-kernel shared-memory images (H % 64 == 0)
     Layer linear;
 };
 
@@ -356,11 +415,12 @@ struct zs_decoder {
     Layer gru_ih;
     float* whhT = nullptr;
     float* bhh = nullptr;
+    void* whh_img = nullptr;
     Layer dense5;
     Layer linear;
 };
 
-static int pack_gru(DevPool& pool, Layer& ih, float** whhT, float** bhh, int operand, const float* const* w_ih,
+static int pack_gru(DevPool& pool, Layer& ih, float** whhT, float** bhh, void** whh_img, int operand, const float* const* w_ih,
                     const float* const* w_hh, const float* const* b_ih, const float* const* b_hh, int C, int H,
                     const float* emb, int n_spk, cudaStream_t st) {
     ih.m_rows = round_up(6 * H, BM); ih.m_valid = 6 * H; ih.taps = ih.w_taps = 1;
@@ -384,6 +444,10 @@ static int pack_gru(DevPool& pool, Layer& ih, float** whhT, float** bhh, int ope
         CUDA_TRY(cudaMemcpyAsync(*bhh + static_cast<size_t>(dir) * 3 * H, b_hh[dir], static_cast<size_t>(3) * H * 4, cudaMemcpyDeviceToDevice, st));
     }
     CUDA_TRY(cudaGetLastError());
+    if (gru_cluster_ok(H)) {
+        ZS_TRY(pool.alloc(whh_img, static_cast<size_t>(2) * (H / GRU_UNITS) * gru_w_image_bytes(H), st));
+        ZS_TRY(pack_gru_image(*whh_img, w_hh, nullptr, H, operand, st));
+    }
     return ZS_OK;
 }
 
@@ -427,7 +491,7 @@ extern "C" int zs_encoder_pack(const zs_encoder_cfg* cfg, const zs_encoder_weigh
             ZS_TRY(pack_layer(h->pool, h->conv[i], op, w->conv_w[i], w->conv_b[i], h2, h2, 5, 0, h2, 0, nullptr, 0, 0, 1, st));
         for (int i = 0; i < 4; ++i)
             ZS_TRY(pack_layer(h->pool, h->dense[i], op, w->dense_w[i], w->dense_b[i], h2, h2, 1, 0, h2, 0, nullptr, 0, 0, 1, st));
-        ZS_TRY(pack_gru(h->pool, h->gru_ih, &h->whhT, &h->bhh, op, w->gru_w_ih, w->gru_w_hh, w->gru_b_ih, w->gru_b_hh, h2, h3, nullptr, 1, st));
+        ZS_TRY(pack_gru(h->pool, h->gru_ih, &h->whhT, &h->bhh, &h->whh_img, op, w->gru_w_ih, w->gru_w_hh, w->gru_b_ih, w->gru_b_hh, h2, h3, nullptr, 1, st));
         ZS_TRY(pack_layer(h->pool, h->linear, op, w->linear_w, w->linear_b, h->n_out, h2 + 2 * h3, 1, 0, h2 + 2 * h3, 0, nullptr, 0, 0, 1, st));
         return ZS_OK;
     };
@@ -472,7 +536,7 @@ extern "C" int zs_decoder_pack(const zs_decoder_cfg* cfg, const zs_decoder_weigh
         }
         for (int i = 0; i < 4; ++i)     // emb4 conditions all four dense layers (model/model.py:350-351)
             ZS_TRY(pack_layer(h->pool, h->dense[i], op, w->dense_w[i], w->dense_b[i], ch, ch, 1, 0, ch, 0, w->emb[3], 0, ch, ca, st));
-        ZS_TRY(pack_gru(h->pool, h->gru_ih, &h->whhT, &h->bhh, op, w->gru_w_ih, w->gru_w_hh, w->gru_b_ih, w->gru_b_hh, ch, ch / 2, w->emb[4], ca, st));
+        ZS_TRY(pack_gru(h->pool, h->gru_ih, &h->whhT, &h->bhh, &h->whh_img, op, w->gru_w_ih, w->gru_w_hh, w->gru_b_ih, w->gru_b_hh, ch, ch / 2, w->emb[4], ca, st));
         // dense5 sees cat([out, rnn, emb5]): the first 2*c_h inputs go through the GEMM, the last c_h fold into the bias
         ZS_TRY(pack_layer(h->pool, h->dense5, op, w->dense5_w, w->dense5_b, ch, 3 * ch, 1, 0, 2 * ch, 0, w->emb[4], 2 * ch, ch, ca, st));
         ZS_TRY(pack_layer(h->pool, h->linear, op, w->linear_w, w->linear_b, cfg->c_out, ch, 1, 0, ch, 0, nullptr, 0, 0, 1, st));
@@ -662,7 +726,8 @@ extern "C" int zs_encoder_forward(zs_encoder* h, const float* x, int B, int T, c
     {   // :454-455 bi-GRU: input projection on tensor cores, then the recurrence
         ConvOpts o; o.lrelu = 0; o.out_mode = OUT_CL32; o.c_in_valid = g.c_h2;
         ZS_TRY(run_layer(h->gru_ih, op, ns, w.catr, B, T8, nullptr, w.gx, T8, 6 * g.c_h3, o, st));
-        ZS_TRY(launch_gru(w.gx, h->whhT, h->bhh, B, T8, g.c_h3, w.catr.p, w.catr.rows, w.catr.pitch, 0, g.c_h2, op, st));
+        if (h->whh_img) ZS_TRY(launch_gru_cluster(h->whh_img, h->bhh, w.gx, B, T8, g.c_h3, w.catr.p, w.catr.rows, w.catr.pitch, 0, g.c_h2, op, st));
+        else ZS_TRY(launch_gru(w.gx, h->whhT, h->bhh, B, T8, g.c_h3, w.catr.p, w.catr.rows, w.catr.pitch, 0, g.c_h2, op, st));
     }
     {   // linear -> logits in the reference's (B, n_out, T8) fp32 layout
         ConvOpts o; o.lrelu = 0; o.out_mode = OUT_NCT32;
@@ -727,7 +792,8 @@ extern "C" int zs_decoder_forward(zs_decoder* h, const float* enc_act, const int
     {   // :352-355 bi-GRU on out + emb5
         ConvOpts o; o.lrelu = 0; o.out_mode = OUT_CL32; o.c_in_valid = ch; o.spk = spk;
         ZS_TRY(run_layer(h->gru_ih, op, ns, w.catr, B, Tf, nullptr, w.gx, Tf, 3 * ch, o, st));
-        ZS_TRY(launch_gru(w.gx, h->whhT, h->bhh, B, Tf, ch / 2, w.catr.p, w.catr.rows, w.catr.pitch, 0, ch, op, st));
+        if (h->whh_img) ZS_TRY(launch_gru_cluster(h->whh_img, h->bhh, w.gx, B, Tf, ch / 2, w.catr.p, w.catr.rows, w.catr.pitch, 0, ch, op, st));
+        else ZS_TRY(launch_gru(w.gx, h->whhT, h->bhh, B, Tf, ch / 2, w.catr.p, w.catr.rows, w.catr.pitch, 0, ch, op, st));
     }
     {   // :356-364 dense5 on cat([out, rnn, emb5]) -> lrelu -> linear -> sigmoid | tanh
         ConvOpts o; o.spk = spk;
