@@ -74,11 +74,147 @@ __device__ __forceinline__ __half float_to_ot<__half>(float v) {
 template <>
 __device__ __forceinline__ __nv_bfloat16 float_to_ot<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
 
-__device__ __forceinline__ float sigmoid_f(float v) { return 1.f / (1.f + __expf(-v)); }
+// MUFU.RCP (1 ulp): the IEEE-rounded reciprocal compiles to a branchy slow-path call that serialises the gates
+__device__ __forceinline__ float rcp_approx(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float sigmoid_f(float v) { return rcp_approx(1.f + __expf(-v)); }
 __device__ __forceinline__ float tanh_f(float v) {
     float e = __expf(-2.f * fabsf(v));
-    float r = (1.f - e) / (1.f + e);
+    float r = (1.f - e) * rcp_approx(1.f + e);
     return copysignf(r, v);
+}
+
+// Epilogue of one (segment, channel): all T frames of the segment are columns [t_seg, t_seg + T) of this
+// thread's TMEM lane.  RES / OUT are compile-time so the per-element code has no mode branches and the
+// residual loads of a 16-frame chunk are issued together, ahead of the TMEM load they overlap with.
+template <typename OT, int RES, int OUT>
+__device__ __forceinline__ void epilogue_segment(const GemmParams& p, uint32_t t_seg, int b, int ch, bool ch_ok,
+                                                 int out_ch, int ps_r, float bias) {
+    const OT* __restrict__ res = reinterpret_cast<const OT*>(p.res);
+    OT* __restrict__ out_cl = reinterpret_cast<OT*>(p.out);
+    float* __restrict__ out_f = reinterpret_cast<float*>(p.out);
+    const int T = p.T;
+    const float inv_T = 1.f / static_cast<float>(T);
+    const bool lrelu = p.lrelu != 0;
+    const float ns = p.ns;
+    float mean = 0.f, rstd = 1.f;
+    if (p.inorm) {
+        float sum = 0.f;
+        for (int c0 = 0; c0 < T; c0 += 16) {
+            uint32_t v[16];
+            tmem_ld16(t_seg + c0, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                float x = __uint_as_float(v[i]) + bias;
+                if (lrelu) x = fmaxf(x, x * ns);
+                if (c0 + i < T) sum += x;
+            }
+        }
+        mean = sum * inv_T;
+        float sq = 0.f;
+        for (int c0 = 0; c0 < T; c0 += 16) {
+            uint32_t v[16];
+            tmem_ld16(t_seg + c0, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                float x = __uint_as_float(v[i]) + bias;
+                if (lrelu) x = fmaxf(x, x * ns);
+                const float d = x - mean;
+                if (c0 + i < T) sq += d * d;
+            }
+        }
+        rstd = rsqrtf(sq * inv_T + IN_EPS);
+    }
+    const OT* res_ch = res + static_cast<size_t>(b) * p.res_rows * p.res_pitch +
+                       static_cast<size_t>(p.res_halo) * p.res_pitch + ch;
+    const int T_out = (OUT == OUT_PS) ? 2 * T : T;
+    const size_t out_base = static_cast<size_t>(b) * p.out_rows * p.out_pitch + p.out_choff + out_ch;
+    float* nct = out_f + (static_cast<size_t>(b) * p.m_valid + ch) * T;
+    const bool vec4 = (T & 3) == 0 && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0;
+    for (int c0 = 0; c0 < T; c0 += 16) {
+        __syncwarp();  // stores below are predicated per lane; re-converge for the aligned TMEM load
+        uint32_t v[16];
+        tmem_ld16(t_seg + c0, v);
+        float r[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) r[i] = 0.f;
+        if (ch_ok) {
+            if (RES == RES_SAME) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i)
+                    if (c0 + i < T) r[i] = ot_to_float<OT>(res_ch[static_cast<size_t>(c0 + i) * p.res_pitch]);
+            } else if (RES == RES_UP2) {
+#pragma unroll
+                for (int i = 0; i < 16; i += 2)
+                    if (c0 + i < T) r[i] = r[i + 1] = ot_to_float<OT>(res_ch[static_cast<size_t>((c0 + i) >> 1) * p.res_pitch]);
+            } else if (RES == RES_AVG2) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i)
+                    if (c0 + i < T) {
+                        const OT* q = res_ch + static_cast<size_t>(2 * (c0 + i)) * p.res_pitch;
+                        r[i] = 0.5f * (ot_to_float<OT>(q[0]) + ot_to_float<OT>(q[p.res_pitch]));
+                    }
+            }
+            if (OUT == OUT_NCT32 && p.accumulate) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i)
+                    if (c0 + i < T) r[i] = nct[c0 + i];
+            }
+        }
+        tmem_ld_wait();
+        float x[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            float y = __uint_as_float(v[i]) + bias;
+            if (lrelu) y = fmaxf(y, y * ns);
+            y = (y - mean) * rstd;
+            if (RES != RES_NONE) y += r[i];
+            if (p.act == ACT_SIGMOID) y = sigmoid_f(y);
+            else if (p.act == ACT_TANH) y = tanh_f(y);
+            if (OUT == OUT_NCT32) {
+                if (p.accumulate == 1) y = r[i] + y;
+                else if (p.accumulate == 2) y = r[i] + r[i] * y;
+            }
+            x[i] = y;
+        }
+        if (!ch_ok) continue;
+        if (OUT == OUT_NCT32) {
+            if (vec4 && c0 + 16 <= T) {
+#pragma unroll
+                for (int i = 0; i < 16; i += 4)
+                    *reinterpret_cast<float4*>(nct + c0 + i) = make_float4(x[i], x[i + 1], x[i + 2], x[i + 3]);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i)
+                    if (c0 + i < T) nct[c0 + i] = x[i];
+            }
+        } else if (OUT == OUT_CL32) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+                if (c0 + i < T) out_f[out_base + static_cast<size_t>(p.out_halo + c0 + i) * p.out_pitch] = x[i];
+        } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const int t = c0 + i;
+                if (t < T) {
+                    const int f = (OUT == OUT_PS) ? 2 * t + ps_r : t;
+                    const OT y = float_to_ot<OT>(x[i]);
+                    out_cl[out_base + static_cast<size_t>(p.out_halo + f) * p.out_pitch] = y;
+                    if (p.out_halo > 0) {  // reflected halo rows for the next conv's taps
+                        if (f >= 1 && f <= p.out_halo)
+                            out_cl[out_base + static_cast<size_t>(p.out_halo - f) * p.out_pitch] = y;
+                        if (f >= T_out - 1 - p.out_halo && f <= T_out - 2)
+                            out_cl[out_base + static_cast<size_t>(p.out_halo + 2 * (T_out - 1) - f) * p.out_pitch] = y;
+                    }
+                }
+            }
+        }
+    }
 }
 
 template <typename OT>
@@ -120,8 +256,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
     const uint32_t stage_tx = A_STAGE_BYTES + static_cast<uint32_t>(p.N) * (BK * 2);
 
     if (warp == 0) {
-        // ------------------------------ TMA producer ------------------------------
-        if (lane == 0) {
+        // ------------------------------ TMA producer (whole warp, one elected lane issues) ------
+        {
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -136,15 +272,18 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
                     const int row_b = p.in_row0 + tap;
                     for (int c = 0; c < p.kc; ++c) {
                         mbar_wait(&empty[stage], phase ^ 1);
-                        mbar_expect_tx(&full[stage], stage_tx);
-                        tma_load_2d(&p.tmA, sA + stage * A_STAGE_BYTES, &full[stage], tap * p.c_in_pad + c * BK,
-                                    mt * BM);
-                        if (p.stride == 2)  // buffer viewed as (channel, row parity, row pair, segment)
-                            tma_load_4d(&p.tmB, sB + stage * B_STAGE_BYTES, &full[stage], c * BK, row_b & 1,
-                                        row_b >> 1, nt * p.nb);
-                        else
-                            tma_load_3d(&p.tmB, sB + stage * B_STAGE_BYTES, &full[stage], c * BK, row_b,
-                                        nt * p.nb);
+                        if (elect_one()) {
+                            mbar_expect_tx(&full[stage], stage_tx);
+                            tma_load_2d(&p.tmA, sA + stage * A_STAGE_BYTES, &full[stage], tap * p.c_in_pad + c * BK,
+                                        mt * BM);
+                            if (p.stride == 2)  // buffer viewed as (channel, row parity, row pair, segment)
+                                tma_load_4d(&p.tmB, sB + stage * B_STAGE_BYTES, &full[stage], c * BK, row_b & 1,
+                                            row_b >> 1, nt * p.nb);
+                            else
+                                tma_load_3d(&p.tmB, sB + stage * B_STAGE_BYTES, &full[stage], c * BK, row_b,
+                                            nt * p.nb);
+                        }
+                        __syncwarp();
                         if (++stage == STAGES) {
                             stage = 0;
                             phase ^= 1;
@@ -154,8 +293,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
             }
         }
     } else if (warp == 1) {
-        // ------------------------------ MMA issuer --------------------------------
-        if (lane == 0) {
+        // ------------------------------ MMA issuer (whole warp, one elected lane issues) --------
+        {
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
@@ -172,28 +311,28 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
                     tc_fence_after();
                     const uint64_t da = umma_desc_sw128(a0 + stage * A_STAGE_BYTES);
                     const uint64_t db = umma_desc_sw128(b0 + stage * B_STAGE_BYTES);
+                    if (elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < BK / 16; ++k) {
-                        // advance 16 elements (32 B) along K inside the swizzle row: +2 in the >>4 address field
-                        umma_f16(d_tmem, da + 2 * k, db + 2 * k, p.idesc, (ks | k) != 0);
+                        for (int k = 0; k < BK / 16; ++k) {
+                            // advance 16 elements (32 B) along K inside the swizzle row: +2 in the >>4 address field
+                            umma_f16(d_tmem, da + 2 * k, db + 2 * k, p.idesc, (ks | k) != 0);
+                        }
+                        umma_commit(&empty[stage]);
                     }
-                    umma_commit(&empty[stage]);
+                    __syncwarp();
                     if (++stage == STAGES) {
                         stage = 0;
                         phase ^= 1;
                     }
                 }
-                umma_commit(&tfull[as]);
+                if (elect_one()) umma_commit(&tfull[as]);
+                __syncwarp();
             }
         }
     } else {
         // ------------------------------ epilogue ----------------------------------
         const int quad = warp & 3;  // TMEM lane quadrant this warp may access
         const int row = quad * 32 + lane;
-        OT* out_cl = reinterpret_cast<OT*>(p.out);
-        float* out_f = reinterpret_cast<float*>(p.out);
-        const OT* res = reinterpret_cast<const OT*>(p.res);
-        const float inv_T = 1.f / static_cast<float>(p.T);
         int it = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
             const int mt = tile % p.m_tiles, nt = tile / p.m_tiles;
@@ -205,7 +344,6 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
             // pixel shuffle: weight rows are packed so rows [0,64) of a tile hold r = 0, [64,128) r = 1
             const int ps_r = row >> 6;
             const int out_ch = (p.out_mode == OUT_PS) ? (mt * 64 + (row & 63)) : ch;
-            const int T_out = (p.out_mode == OUT_PS) ? 2 * p.T : p.T;
             const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * MAX_BN;
             for (int s = 0; s < p.nb; ++s) {
                 const int b = nt * p.nb + s;
@@ -221,86 +359,17 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
                     bias = p.bias[off + ch];
                 }
                 const uint32_t t_seg = t_lane + s * p.Tt;
-                float mean = 0.f, rstd = 1.f;
-                if (p.inorm) {
-                    float sum = 0.f;
-                    for (int c0 = 0; c0 < p.T; c0 += 16) {
-                        uint32_t v[16];
-                        tmem_ld16(t_seg + c0, v);
-                        tmem_ld_wait();
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) {
-                            float x = __uint_as_float(v[i]) + bias;
-                            if (p.lrelu) x = fmaxf(x, x * p.ns);
-                            if (c0 + i < p.T) sum += x;
-                        }
-                    }
-                    mean = sum * inv_T;
-                    float sq = 0.f;
-                    for (int c0 = 0; c0 < p.T; c0 += 16) {
-                        uint32_t v[16];
-                        tmem_ld16(t_seg + c0, v);
-                        tmem_ld_wait();
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) {
-                            float x = __uint_as_float(v[i]) + bias;
-                            if (p.lrelu) x = fmaxf(x, x * p.ns);
-                            const float d = x - mean;
-                            if (c0 + i < p.T) sq += d * d;
-                        }
-                    }
-                    rstd = rsqrtf(sq * inv_T + IN_EPS);
-                }
-                const size_t res_base = static_cast<size_t>(b) * p.res_rows * p.res_pitch;
-                const size_t out_base = static_cast<size_t>(b) * p.out_rows * p.out_pitch;
-                for (int c0 = 0; c0 < p.T; c0 += 16) {
-                    uint32_t v[16];
-                    __syncwarp();  // the stores below are predicated per lane; re-converge for the aligned load
-                    tmem_ld16(t_seg + c0, v);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const int t = c0 + i;
-                        if (t >= p.T || !ch_ok) continue;
-                        float x = __uint_as_float(v[i]) + bias;
-                        if (p.lrelu) x = fmaxf(x, x * p.ns);
-                        x = (x - mean) * rstd;
-                        if (p.res_mode == RES_SAME) {
-                            x += ot_to_float<OT>(res[res_base + static_cast<size_t>(p.res_halo + t) * p.res_pitch + ch]);
-                        } else if (p.res_mode == RES_AVG2) {
-                            const size_t r0 = res_base + static_cast<size_t>(p.res_halo + 2 * t) * p.res_pitch + ch;
-                            x += 0.5f * (ot_to_float<OT>(res[r0]) + ot_to_float<OT>(res[r0 + p.res_pitch]));
-                        } else if (p.res_mode == RES_UP2) {
-                            x += ot_to_float<OT>(
-                                res[res_base + static_cast<size_t>(p.res_halo + (t >> 1)) * p.res_pitch + ch]);
-                        }
-                        if (p.act == ACT_SIGMOID) x = sigmoid_f(x);
-                        else if (p.act == ACT_TANH) x = tanh_f(x);
-                        if (p.out_mode == OUT_NCT32) {
-                            float* dst = out_f + (static_cast<size_t>(b) * p.m_valid + ch) * p.T + t;
-                            if (p.accumulate == 1) x = *dst + x;
-                            else if (p.accumulate == 2) x = *dst + *dst * x;
-                            *dst = x;
-                        } else {
-                            const int f = (p.out_mode == OUT_PS) ? 2 * t + ps_r : t;
-                            const size_t col = static_cast<size_t>(p.out_choff + out_ch);
-                            const size_t o = out_base + static_cast<size_t>(p.out_halo + f) * p.out_pitch + col;
-                            if (p.out_mode == OUT_CL32) {
-                                out_f[o] = x;
-                            } else {
-                                const OT y = float_to_ot<OT>(x);
-                                out_cl[o] = y;
-                                if (p.out_halo > 0) {  // reflected halo rows for the next conv's taps
-                                    if (f >= 1 && f <= p.out_halo)
-                                        out_cl[out_base + static_cast<size_t>(p.out_halo - f) * p.out_pitch + col] = y;
-                                    if (f >= T_out - 1 - p.out_halo && f <= T_out - 2)
-                                        out_cl[out_base +
-                                               static_cast<size_t>(p.out_halo + 2 * (T_out - 1) - f) * p.out_pitch +
-                                               col] = y;
-                                }
-                            }
-                        }
-                    }
+                if (p.out_mode == OUT_CL) {
+                    if (p.res_mode == RES_NONE) epilogue_segment<OT, RES_NONE, OUT_CL>(p, t_seg, b, ch, ch_ok, out_ch, ps_r, bias);
+                    else if (p.res_mode == RES_SAME) epilogue_segment<OT, RES_SAME, OUT_CL>(p, t_seg, b, ch, ch_ok, out_ch, ps_r, bias);
+                    else if (p.res_mode == RES_AVG2) epilogue_segment<OT, RES_AVG2, OUT_CL>(p, t_seg, b, ch, ch_ok, out_ch, ps_r, bias);
+                    else epilogue_segment<OT, RES_UP2, OUT_CL>(p, t_seg, b, ch, ch_ok, out_ch, ps_r, bias);
+                } else if (p.out_mode == OUT_PS) {
+                    epilogue_segment<OT, RES_NONE, OUT_PS>(p, t_seg, b, ch, ch_ok, out_ch, ps_r, bias);
+                } else if (p.out_mode == OUT_NCT32) {
+                    epilogue_segment<OT, RES_NONE, OUT_NCT32>(p, t_seg, b, ch, ch_ok, out_ch, ps_r, bias);
+                } else {
+                    epilogue_segment<OT, RES_NONE, OUT_CL32>(p, t_seg, b, ch, ch_ok, out_ch, ps_r, bias);
                 }
             }
             tc_fence_before();

@@ -102,7 +102,8 @@ struct GruParams {
     const float* bhh;       // [2][3H]
     const float* gx;        // [B][T][2][3H] fp32, b_ih (+ speaker term) folded in
     void* out;              // operand type [B][out_rows][out_pitch]
-    int B, T, H, out_rows, out_pitch, out_halo, out_choff, fmt;
+    int B, T, H, out_rows, out_pitch, out_halo, out_choff, fmt, debug;
+    long long* dbg;        // debug bit 3: per-step clock64 stamps of cluster 0 / CTA 0 ([T][8])
 };
 
 template <typename OT>
@@ -110,7 +111,8 @@ __global__ void __launch_bounds__(GRU_THREADS, 1) gru_cluster_kernel(const GruPa
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_addr = smem_u32(smem_raw);
     uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
-    const int H = p.H, KCH = H >> 6, NC = KCH;
+    const int H = p.H, KCH = H >> 6;
+    const int NC = (p.debug & 1) ? 1 : KCH;      // debug bit 0: pretend to be alone (no exchange, no peer waits)
     uint8_t* sW = smem;                                   // [192 * H * 2]
     uint8_t* sH = smem + gru_w_image_bytes(H);            // 2 x [KCH chunks][16 rows][128 B]
     const int hbuf_bytes = GRU_NSEQ * H * 2;
@@ -128,7 +130,7 @@ __global__ void __launch_bounds__(GRU_THREADS, 1) gru_cluster_kernel(const GruPa
     // ---- one-time setup: W_hh slice -> smem, zero h buffers, barriers, TMEM ----
     {
         const uint4* src = reinterpret_cast<const uint4*>(static_cast<const uint8_t*>(p.w_img) +
-                                                          (static_cast<size_t>(dir) * NC + rank) * gru_w_image_bytes(H));
+                                                          (static_cast<size_t>(dir) * KCH + rank) * gru_w_image_bytes(H));
         uint4* dst = reinterpret_cast<uint4*>(sW);
         const int n16 = gru_w_image_bytes(H) / 16;
         for (int i = threadIdx.x; i < n16; i += GRU_THREADS) dst[i] = src[i];
@@ -153,40 +155,51 @@ __global__ void __launch_bounds__(GRU_THREADS, 1) gru_cluster_kernel(const GruPa
     const uint32_t peer_tx = (NC - 1) * slice_bytes;
 
     if (warp == 4) {
-        // ------------------------------ control / MMA issue ------------------------------
-        if (lane == 0) {
+        // ------------------------------ control / MMA issue (whole warp, elected lane issues) ----
+        {
             const uint32_t idesc_rz = umma_idesc_f16_m(p.fmt, 128, GRU_NSEQ);
             const uint32_t idesc_n = umma_idesc_f16_m(p.fmt, 64, GRU_NSEQ);
             const uint32_t w_rz = smem_u32(sW), w_n = smem_u32(sW) + 128 * H * 2, hb = smem_u32(sH);
-            if (NC > 1) {              // arm the first use of each state buffer (steps 1 and 2)
-                if (p.T > 1) mbar_expect_tx(&h_full[1], peer_tx);
-                if (p.T > 2) mbar_expect_tx(&h_full[0], peer_tx);
-            } else {
-                if (p.T > 1) mbar_arrive(&h_full[1]);
-                if (p.T > 2) mbar_arrive(&h_full[0]);
+            if (elect_one()) {
+                if (NC > 1) {              // arm the first use of each state buffer (steps 1 and 2)
+                    if (p.T > 1) mbar_expect_tx(&h_full[1], peer_tx);
+                    if (p.T > 2) mbar_expect_tx(&h_full[0], peer_tx);
+                } else {
+                    if (p.T > 1) mbar_arrive(&h_full[1]);
+                    if (p.T > 2) mbar_arrive(&h_full[0]);
+                }
             }
+            __syncwarp();
             for (int t = 0; t < p.T; ++t) {
                 const int pb = t & 1;
                 if (t > 0) {
                     mbar_wait(&h_full[pb], ((t - 1) >> 1) & 1);
-                    if (t + 2 < p.T) {   // re-arm this buffer for step t + 2
+                    if (t + 2 < p.T && elect_one()) {   // re-arm this buffer for step t + 2
                         if (NC > 1) mbar_expect_tx(&h_full[pb], peer_tx);
                         else mbar_arrive(&h_full[pb]);
                     }
+                    __syncwarp();
                 }
                 tc_fence_after();
+                const bool rec = (p.debug & 8) && p.dbg && blockIdx.x == 0 && lane == 0;
+                if (rec) p.dbg[t * 8 + 0] = clock64();
                 const uint32_t hcur = hb + pb * hbuf_bytes;
-                for (int c = 0; c < KCH; ++c) {
-                    const uint64_t da = umma_desc_sw128(w_rz + c * (128 * 128));
-                    const uint64_t dn = umma_desc_sw128(w_n + c * (64 * 128));
-                    const uint64_t db = umma_desc_sw128(hcur + c * slice_bytes);
+                if (elect_one()) {
+                    uint64_t da = umma_desc_sw128(w_rz), dn = umma_desc_sw128(w_n), db = umma_desc_sw128(hcur);
+                    for (int c = 0; c < KCH; ++c) {
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        umma_f16(tmem_base, da + 2 * k, db + 2 * k, idesc_rz, (c | k) != 0);
-                        umma_f16(tmem_base + 32, dn + 2 * k, db + 2 * k, idesc_n, (c | k) != 0);
+                        for (int k = 0; k < 4; ++k) {
+                            umma_f16(tmem_base, da + 2 * k, db + 2 * k, idesc_rz, (c | k) != 0);
+                            umma_f16(tmem_base + 32, dn + 2 * k, db + 2 * k, idesc_n, (c | k) != 0);
+                        }
+                        da += (128 * 128) >> 4;      // next 64-wide K chunk of each operand (address field is >> 4)
+                        dn += (64 * 128) >> 4;
+                        db += slice_bytes >> 4;
                     }
+                    umma_commit(mma_done);
                 }
-                umma_commit(mma_done);
+                __syncwarp();
+                if (rec) p.dbg[t * 8 + 1] = clock64();
             }
         }
     } else {
@@ -202,28 +215,40 @@ __global__ void __launch_bounds__(GRU_THREADS, 1) gru_cluster_kernel(const GruPa
         OT* out = reinterpret_cast<OT*>(p.out);
         const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(32 * q) << 16);
         const int seq0 = b0 + 8 * hi;
-        for (int t = 0; t < p.T; ++t) {
-            const int tt = dir ? p.T - 1 - t : t;
-            const int pb = t & 1;
-            // input projections of this step: issued before the MMA wait so their latency overlaps it
-            float gr[8], gz[8], gn[8];
+        // input projections are prefetched one full step ahead (their HBM latency would otherwise sit on the
+        // critical path of every step)
+        float gr[8], gz[8], gn[8], pr[8], pz[8], pn[8];
+        auto load_gx = [&](int step, float (&xr)[8], float (&xz)[8], float (&xn)[8]) {
+            const int ts = dir ? p.T - 1 - step : step;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const int b = seq0 + i;
-                if (b < p.B) {
-                    const float* g = p.gx + ((static_cast<size_t>(b) * p.T + tt) * 2 + dir) * 3 * H + unit;
-                    gr[i] = g[0]; gz[i] = g[H]; gn[i] = g[2 * H];
+                if (b < p.B && step < p.T && !(p.debug & 2)) {
+                    const float* g = p.gx + ((static_cast<size_t>(b) * p.T + ts) * 2 + dir) * 3 * H + unit;
+                    xr[i] = __ldg(g); xz[i] = __ldg(g + H); xn[i] = __ldg(g + 2 * H);
                 } else {
-                    gr[i] = gz[i] = gn[i] = 0.f;
+                    xr[i] = xz[i] = xn[i] = 0.f;
                 }
             }
+        };
+        load_gx(0, pr, pz, pn);
+        for (int t = 0; t < p.T; ++t) {
+            const int tt = dir ? p.T - 1 - t : t;
+            const int pb = t & 1;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { gr[i] = pr[i]; gz[i] = pz[i]; gn[i] = pn[i]; }
+            load_gx(t + 1, pr, pz, pn);
+            const bool rec = (p.debug & 8) && p.dbg && blockIdx.x == 0 && threadIdx.x == 0;
+            if (rec) p.dbg[t * 8 + 2] = clock64();
             mbar_wait(mma_done, t & 1);
             tc_fence_after();
+            if (rec) p.dbg[t * 8 + 3] = clock64();
             uint32_t a[16], nn[16];
             tmem_ld16(t_addr, a);            // lanes 0-15: W_hr h, lanes 16-31: W_hz h   (16 sequences)
             tmem_ld16(t_addr + 32, nn);      // lanes 0-15: W_hn h
             tmem_ld_wait();
             tc_fence_before();
+            if (rec) p.dbg[t * 8 + 4] = clock64();
             float hr[8], hzv[8], hn[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
@@ -237,29 +262,33 @@ __global__ void __launch_bounds__(GRU_THREADS, 1) gru_cluster_kernel(const GruPa
             uint8_t* hnext = sH + (pb ^ 1) * hbuf_bytes + rank * slice_bytes;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                const float r = 1.f / (1.f + __expf(-(gr[i] + hr[i] + b_r)));
-                const float z = 1.f / (1.f + __expf(-(gz[i] + hzv[i] + b_z)));
+                const float r = sigmoid_f(gr[i] + hr[i] + b_r);
+                const float z = sigmoid_f(gz[i] + hzv[i] + b_z);
                 const float n = tanh_f(gn[i] + r * (hn[i] + b_n));
                 h[i] = (1.f - z) * n + z * h[i];
                 const OT y = float_to_ot<OT>(h[i]);
                 const int s = 8 * hi + i;      // row of the state tile
                 *reinterpret_cast<OT*>(hnext + s * 128 + ((((u_loc >> 3) ^ (s & 7)) << 4) | ((u_loc & 7) << 1))) = y;
                 const int b = seq0 + i;
-                if (b < p.B)
+                if (b < p.B && !(p.debug & 4))
                     out[(static_cast<size_t>(b) * p.out_rows + p.out_halo + tt) * p.out_pitch + p.out_choff + dir * H + unit] = y;
             }
+            if (rec) p.dbg[t * 8 + 5] = clock64();
             if (t + 1 < p.T) {
                 fence_proxy_async_smem();                       // my slice -> visible to the bulk-copy engine / MMA
                 asm volatile("bar.sync 1, 128;" ::: "memory");   // the 4 gate warps only
-                if (threadIdx.x == 0) {
+                if (rec) p.dbg[t * 8 + 6] = clock64();
+                if (elect_one()) {      // each gate warp publishes the slice to its share of the peers
                     const uint32_t src = smem_u32(hnext);
                     const uint32_t bar_local = smem_u32(&h_full[pb ^ 1]);
-                    for (uint32_t d = 1; d < static_cast<uint32_t>(NC); ++d) {
+                    for (uint32_t d = 1 + warp; d < static_cast<uint32_t>(NC); d += 4) {
                         const uint32_t peer = (rank + d) % NC;
                         dsmem_bulk_copy(mapa_shared(src, peer), src, slice_bytes, mapa_shared(bar_local, peer));
                     }
-                    mbar_arrive(&h_full[pb ^ 1]);                // my own slice is in place
+                    if (warp == 0) mbar_arrive(&h_full[pb ^ 1]);   // my own slice is in place
                 }
+                __syncwarp();
+                if (rec) p.dbg[t * 8 + 7] = clock64();
             }
         }
     }

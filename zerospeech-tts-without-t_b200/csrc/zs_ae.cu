@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -145,6 +146,8 @@ static int launch_conv(const zs_conv_desc* d, cudaStream_t stream) {
     if (d->B < 1) return fail(ZS_ERR_ARG, "conv: B %d", d->B);
     if (d->bank && (d->w_taps != 7 || d->m_rows != 7 * BM)) return fail(ZS_ERR_ARG, "conv: bank mode needs 7 x 128 rows of 7 taps");
     if (d->out_mode == OUT_PS && (d->m_rows != d->m_valid)) return fail(ZS_ERR_ARG, "conv: pixel-shuffle needs m_valid == m_rows");
+    if (d->res_mode != RES_NONE && d->out_mode != OUT_CL) return fail(ZS_ERR_ARG, "conv: a residual needs the channels-last operand output mode");
+    if (d->res_mode != RES_NONE && !d->res) return fail(ZS_ERR_ARG, "conv: null residual buffer");
     if (reinterpret_cast<uintptr_t>(d->w) % 16 || reinterpret_cast<uintptr_t>(d->in) % 16) return fail(ZS_ERR_ARG, "conv: operand pointers must be 16-byte aligned");
 
     GemmParams p;
@@ -281,6 +284,29 @@ static int launch_gru_cluster(const void* w_img, const float* bhh, const float* 
     p.w_img = w_img; p.bhh = bhh; p.gx = gx; p.out = out; p.B = B; p.T = T; p.H = H;
     p.out_rows = rows; p.out_pitch = pitch; p.out_halo = halo; p.out_choff = choff;
     p.fmt = operand == ZS_OPERAND_BF16 ? 1 : 0;
+    {   // timing experiments only (results are wrong with any bit set): 1 = no state exchange, 2 = no gx loads, 4 = no stores
+        const char* dbg = getenv("ZS_GRU_DEBUG");
+        p.debug = dbg ? atoi(dbg) : 0;
+        p.dbg = nullptr;
+        if (p.debug & 8) {
+            static long long* dbuf = nullptr;
+            if (!dbuf) cudaMalloc(&dbuf, 8 * 512 * sizeof(long long));
+            p.dbg = dbuf;
+            if (T <= 512) {   // dump the previous call's stamps (host-synchronous; experiments only)
+                static bool first = true;
+                if (!first) {
+                    std::vector<long long> hbuf(8 * T);
+                    cudaMemcpy(hbuf.data(), dbuf, hbuf.size() * 8, cudaMemcpyDeviceToHost);
+                    const int t = T / 2;
+                    const long long* r = &hbuf[t * 8];
+                    const long long* rn = &hbuf[(t + 1) * 8];
+                    fprintf(stderr, "gru step %d: mma_issue %lld | gate: wait_mma %lld ld %lld math %lld fence+bar %lld copy_issue %lld | ctrl next-step start +%lld (step period %lld)\n",
+                            t, r[1] - r[0], r[3] - r[2], r[4] - r[3], r[5] - r[4], r[6] - r[5], r[7] - r[6], rn[0] - r[7], rn[0] - r[0]);
+                }
+                first = false;
+            }
+        }
+    }
     const int NC = H / GRU_UNITS, n_groups = (B + GRU_NSEQ - 1) / GRU_NSEQ;
     const int smem = gru_smem_bytes(H);
     static int attr_set[2] = {0, 0};
