@@ -187,8 +187,7 @@ typedef struct {
     int32_t res_mode;        /* 0 none, 1 same frame, 2 avg of frames 2t,2t+1, 3 frame t/2 */
     const void* res; int32_t res_rows, res_pitch, res_halo;
     int32_t act;             /* 0 none, 1 sigmoid, 2 tanh */
-    int32_t out_mode;        /* 0 channels-last operand-type, 1 pixel-shuffle channels-last, 2 fp32 (B, m_valid, T_out),
-                                3 channels-last fp32 */
+    int32_t out_mode;        /* 0 channels-last operand-type, 1 pixel-shuffle channels-last, 2 fp32 (B, m_valid, T_out) */
     void* out; int32_t out_rows, out_pitch, out_halo, out_choff;
     int32_t accumulate;      /* out_mode 2 only: 0 store, 1 out += y, 2 out += out*y */
     int32_t operand;         /* ZS_OPERAND_* */
@@ -202,7 +201,8 @@ int zs_pack_nct(const float* x, int B, int C, int T, void* out, int rows, int pi
                 int lrelu, float ns, int operand, int zero_pad_channels, void* stream);
 
 /* bidirectional GRU recurrence with zero initial state (model/model.py:59-66) on precomputed
- * input projections gx [B][T][2][3H] fp32 (b_ih folded in), w_hh [2][3H][H] fp32, b_hh [2][3H];
+ * input projections gx [B][T][2][3H] fp32 (b_ih folded in; rounded to the operand type like the GEMM's output),
+ * w_hh [2][3H][H] fp32, b_hh [2][3H];
  * writes h_t (operand type) to out[b][out_halo+t][out_choff + dir*H + j].
  * impl: 0 = what the forward passes use (tensor-core cluster kernel when H % 64 == 0 and H <= 512, else the
  * CUDA-core kernel), 1 = CUDA-core kernel, 2 = cluster kernel. */

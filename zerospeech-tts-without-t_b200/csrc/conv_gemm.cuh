@@ -30,16 +30,19 @@ constexpr int A_STAGE_BYTES = BM * BK * 2;
 constexpr int B_STAGE_BYTES = MAX_BN * BK * 2;
 constexpr int GEMM_THREADS = 192;
 constexpr int TMEM_COLS = 512;
-constexpr int GEMM_SMEM_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int STAGING_BYTES = 32768;   // epilogue staging tile: 128 columns x 128 channels (or 256 x 64) x 2 B
+constexpr int GEMM_SMEM_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + STAGING_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 constexpr float IN_EPS = 1e-5f;
 
 enum { RES_NONE = 0, RES_SAME = 1, RES_AVG2 = 2, RES_UP2 = 3 };
 enum { ACT_NONE = 0, ACT_SIGMOID = 1, ACT_TANH = 2 };
-enum { OUT_CL = 0, OUT_PS = 1, OUT_NCT32 = 2, OUT_CL32 = 3 };
+enum { OUT_CL = 0, OUT_PS = 1, OUT_NCT32 = 2 };
 
 struct alignas(64) GemmParams {
     CUtensorMap tmA;
     CUtensorMap tmB;
+    CUtensorMap tmOut;   // channels-last output (OUT_CL / OUT_PS): box {128|64 channels, rows, segments}
+    int rnd_ns, rnd_rows, rnd_sub;   // epilogue rounds: segments per round, box rows per segment, halves per segment
     int m_tiles, n_tiles, nb, Tt, T, B, N;
     int kc, taps, bank, stride, in_row0, c_in_pad;
     int m_valid;
@@ -56,6 +59,7 @@ struct alignas(64) GemmParams {
     void* out;
     int out_rows, out_pitch, out_halo, out_choff, accumulate;
     uint32_t idesc;
+    int debug;   // timing experiments (results wrong): 1 = no TMA loads, 2 = no MMA issue, 4 = no epilogue stores/loads
 };
 
 template <typename OT>
@@ -87,132 +91,161 @@ __device__ __forceinline__ float tanh_f(float v) {
     return copysignf(r, v);
 }
 
-// Epilogue of one (segment, channel): all T frames of the segment are columns [t_seg, t_seg + T) of this
-// thread's TMEM lane.  RES / OUT are compile-time so the per-element code has no mode branches and the
-// residual loads of a 16-frame chunk are issued together, ahead of the TMEM load they overlap with.
-template <typename OT, int RES, int OUT>
-__device__ __forceinline__ void epilogue_segment(const GemmParams& p, uint32_t t_seg, int b, int ch, bool ch_ok,
-                                                 int out_ch, int ps_r, float bias) {
-    const OT* __restrict__ res = reinterpret_cast<const OT*>(p.res);
-    OT* __restrict__ out_cl = reinterpret_cast<OT*>(p.out);
-    float* __restrict__ out_f = reinterpret_cast<float*>(p.out);
-    const int T = p.T;
-    const float inv_T = 1.f / static_cast<float>(T);
-    const bool lrelu = p.lrelu != 0;
-    const float ns = p.ns;
-    float mean = 0.f, rstd = 1.f;
-    if (p.inorm) {
-        float sum = 0.f;
-        for (int c0 = 0; c0 < T; c0 += 16) {
-            uint32_t v[16];
-            tmem_ld16(t_seg + c0, v);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                float x = __uint_as_float(v[i]) + bias;
-                if (lrelu) x = fmaxf(x, x * ns);
-                if (c0 + i < T) sum += x;
-            }
-        }
-        mean = sum * inv_T;
-        float sq = 0.f;
-        for (int c0 = 0; c0 < T; c0 += 16) {
-            uint32_t v[16];
-            tmem_ld16(t_seg + c0, v);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                float x = __uint_as_float(v[i]) + bias;
-                if (lrelu) x = fmaxf(x, x * ns);
-                const float d = x - mean;
-                if (c0 + i < T) sq += d * d;
-            }
-        }
-        rstd = rsqrtf(sq * inv_T + IN_EPS);
-    }
-    const OT* res_ch = res + static_cast<size_t>(b) * p.res_rows * p.res_pitch +
-                       static_cast<size_t>(p.res_halo) * p.res_pitch + ch;
-    const int T_out = (OUT == OUT_PS) ? 2 * T : T;
-    const size_t out_base = static_cast<size_t>(b) * p.out_rows * p.out_pitch + p.out_choff + out_ch;
-    float* nct = out_f + (static_cast<size_t>(b) * p.m_valid + ch) * T;
-    const bool vec4 = (T & 3) == 0 && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0;
+// ---- epilogue building blocks ---------------------------------------------------------------------
+// One thread = one output channel = one TMEM lane; the frames of a segment are that lane's columns.
+
+struct ChanNorm {      // y = act(lrelu(acc + bias)) * scale + shift   (InstanceNorm folded into scale/shift)
+    float bias, scale, shift;
+};
+
+// InstanceNorm statistics of one (segment, channel) in ONE pass over TMEM: sums are taken relative to the
+// first frame's value so the variance does not cancel catastrophically.
+__device__ __forceinline__ void chan_stats(uint32_t t_seg, int T, float bias, bool lrelu, float ns, float& mean,
+                                           float& rstd) {
+    float s1 = 0.f, s2 = 0.f, x0 = 0.f;
     for (int c0 = 0; c0 < T; c0 += 16) {
-        __syncwarp();  // stores below are predicated per lane; re-converge for the aligned TMEM load
+        uint32_t v[16];
+        tmem_ld16(t_seg + c0, v);
+        tmem_ld_wait();
+        if (c0 == 0) {
+            x0 = __uint_as_float(v[0]) + bias;
+            if (lrelu) x0 = fmaxf(x0, x0 * ns);
+        }
+        if (c0 + 16 <= T) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                float x = __uint_as_float(v[i]) + bias;
+                if (lrelu) x = fmaxf(x, x * ns);
+                const float d = x - x0;
+                s1 += d;
+                s2 = fmaf(d, d, s2);
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                float x = __uint_as_float(v[i]) + bias;
+                if (lrelu) x = fmaxf(x, x * ns);
+                const float d = (c0 + i < T) ? x - x0 : 0.f;
+                s1 += d;
+                s2 = fmaf(d, d, s2);
+            }
+        }
+    }
+    const float inv_T = 1.f / static_cast<float>(T);
+    const float m1 = s1 * inv_T;
+    mean = x0 + m1;
+    rstd = rsqrtf(fmaxf(s2 * inv_T - m1 * m1, 0.f) + IN_EPS);
+}
+
+// Frames [f_lo, f_hi) of one (segment, channel) -> shared-memory staging tile (channels-last rows that a TMA
+// store then writes out), plus the reflected halo rows written directly.  RES / PS are compile time.
+//   stg      : staging slot of (frame f_lo, this thread's channel); frame stride = STG_PITCH elements
+//   res_s    : residual buffer at (this segment, frame 0 incl. halo offset, this channel)
+//   out_s    : output buffer at (this segment, row 0, this thread's output channel) - for the halo rows only
+template <typename OT, int RES, bool PS>
+__device__ __forceinline__ void frames_to_staging(const GemmParams& p, uint32_t t_seg, int f_lo, int f_hi, int T,
+                                                  const ChanNorm& cn, bool lrelu, float ns, OT* __restrict__ stg,
+                                                  const OT* __restrict__ res_s, OT* __restrict__ out_s, int ps_r,
+                                                  bool ch_ok) {
+    constexpr int STG_PITCH = PS ? 64 : 128;          // channels per staging row
+    constexpr int FSTEP = PS ? 2 : 1;                 // staging rows per input frame
+    const int T_out = PS ? 2 * T : T;
+    const int halo = p.out_halo;
+    for (int c0 = f_lo; c0 < f_hi; c0 += 16) {
+        __syncwarp();
         uint32_t v[16];
         tmem_ld16(t_seg + c0, v);
         float r[16];
+        if (RES != RES_NONE) {
+            if (ch_ok) {
+                if (RES == RES_SAME) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) r[i] = 0.f;
-        if (ch_ok) {
-            if (RES == RES_SAME) {
+                    for (int i = 0; i < 16; ++i)
+                        r[i] = (c0 + i < T) ? ot_to_float<OT>(res_s[(c0 + i) * p.res_pitch]) : 0.f;
+                } else if (RES == RES_UP2) {
 #pragma unroll
-                for (int i = 0; i < 16; ++i)
-                    if (c0 + i < T) r[i] = ot_to_float<OT>(res_ch[static_cast<size_t>(c0 + i) * p.res_pitch]);
-            } else if (RES == RES_UP2) {
+                    for (int i = 0; i < 16; i += 2)
+                        r[i] = r[i + 1] = (c0 + i < T) ? ot_to_float<OT>(res_s[((c0 + i) >> 1) * p.res_pitch]) : 0.f;
+                } else {
 #pragma unroll
-                for (int i = 0; i < 16; i += 2)
-                    if (c0 + i < T) r[i] = r[i + 1] = ot_to_float<OT>(res_ch[static_cast<size_t>((c0 + i) >> 1) * p.res_pitch]);
-            } else if (RES == RES_AVG2) {
-#pragma unroll
-                for (int i = 0; i < 16; ++i)
-                    if (c0 + i < T) {
-                        const OT* q = res_ch + static_cast<size_t>(2 * (c0 + i)) * p.res_pitch;
-                        r[i] = 0.5f * (ot_to_float<OT>(q[0]) + ot_to_float<OT>(q[p.res_pitch]));
+                    for (int i = 0; i < 16; ++i) {
+                        if (c0 + i < T) {
+                            const OT* q = res_s + 2 * (c0 + i) * p.res_pitch;
+                            r[i] = 0.5f * (ot_to_float<OT>(q[0]) + ot_to_float<OT>(q[p.res_pitch]));
+                        } else {
+                            r[i] = 0.f;
+                        }
                     }
-            }
-            if (OUT == OUT_NCT32 && p.accumulate) {
+                }
+            } else {
 #pragma unroll
-                for (int i = 0; i < 16; ++i)
-                    if (c0 + i < T) r[i] = nct[c0 + i];
+                for (int i = 0; i < 16; ++i) r[i] = 0.f;
             }
+        }
+        tmem_ld_wait();
+        OT y[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            float x = __uint_as_float(v[i]) + cn.bias;
+            if (lrelu) x = fmaxf(x, x * ns);
+            x = fmaf(x, cn.scale, cn.shift);
+            if (RES != RES_NONE) x += r[i];
+            y[i] = float_to_ot<OT>(x);
+        }
+        OT* sp = stg + (c0 - f_lo) * (FSTEP * STG_PITCH);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) sp[i * (FSTEP * STG_PITCH)] = y[i];   // columns >= T are clipped by the TMA store
+        // reflected halo rows of the output buffer (read by the next conv's outer taps)
+        if (halo > 0 && ch_ok && (c0 == 0 || c0 + 16 + 3 >= T)) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const int t = c0 + i;
+                if (t < T) {
+                    const int f = PS ? 2 * t + ps_r : t;
+                    if (f >= 1 && f <= halo) out_s[(halo - f) * p.out_pitch] = y[i];
+                    if (f >= T_out - 1 - halo && f <= T_out - 2) out_s[(halo + 2 * (T_out - 1) - f) * p.out_pitch] = y[i];
+                }
+            }
+        }
+    }
+}
+
+// Frames of one (segment, channel) -> the reference's (B, C, T) fp32 layout, 16 contiguous floats per chunk.
+template <typename OT>
+__device__ __forceinline__ void frames_to_nct(const GemmParams& p, uint32_t t_seg, int T, const ChanNorm& cn,
+                                              bool lrelu, float ns, float* __restrict__ nct, bool ch_ok) {
+    const bool vec4 = (T & 3) == 0 && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0;
+    for (int c0 = 0; c0 < T; c0 += 16) {
+        __syncwarp();
+        uint32_t v[16];
+        tmem_ld16(t_seg + c0, v);
+        float r[16];
+        if (p.accumulate) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) r[i] = (ch_ok && c0 + i < T) ? nct[c0 + i] : 0.f;
         }
         tmem_ld_wait();
         float x[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-            float y = __uint_as_float(v[i]) + bias;
+            float y = __uint_as_float(v[i]) + cn.bias;
             if (lrelu) y = fmaxf(y, y * ns);
-            y = (y - mean) * rstd;
-            if (RES != RES_NONE) y += r[i];
+            y = fmaf(y, cn.scale, cn.shift);
             if (p.act == ACT_SIGMOID) y = sigmoid_f(y);
             else if (p.act == ACT_TANH) y = tanh_f(y);
-            if (OUT == OUT_NCT32) {
-                if (p.accumulate == 1) y = r[i] + y;
-                else if (p.accumulate == 2) y = r[i] + r[i] * y;
-            }
+            if (p.accumulate == 1) y = r[i] + y;
+            else if (p.accumulate == 2) y = fmaf(r[i], y, r[i]);
             x[i] = y;
         }
         if (!ch_ok) continue;
-        if (OUT == OUT_NCT32) {
-            if (vec4 && c0 + 16 <= T) {
+        if (vec4 && c0 + 16 <= T) {
 #pragma unroll
-                for (int i = 0; i < 16; i += 4)
-                    *reinterpret_cast<float4*>(nct + c0 + i) = make_float4(x[i], x[i + 1], x[i + 2], x[i + 3]);
-            } else {
-#pragma unroll
-                for (int i = 0; i < 16; ++i)
-                    if (c0 + i < T) nct[c0 + i] = x[i];
-            }
-        } else if (OUT == OUT_CL32) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i)
-                if (c0 + i < T) out_f[out_base + static_cast<size_t>(p.out_halo + c0 + i) * p.out_pitch] = x[i];
+            for (int i = 0; i < 16; i += 4)
+                *reinterpret_cast<float4*>(nct + c0 + i) = make_float4(x[i], x[i + 1], x[i + 2], x[i + 3]);
         } else {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                const int t = c0 + i;
-                if (t < T) {
-                    const int f = (OUT == OUT_PS) ? 2 * t + ps_r : t;
-                    const OT y = float_to_ot<OT>(x[i]);
-                    out_cl[out_base + static_cast<size_t>(p.out_halo + f) * p.out_pitch] = y;
-                    if (p.out_halo > 0) {  // reflected halo rows for the next conv's taps
-                        if (f >= 1 && f <= p.out_halo)
-                            out_cl[out_base + static_cast<size_t>(p.out_halo - f) * p.out_pitch] = y;
-                        if (f >= T_out - 1 - p.out_halo && f <= T_out - 2)
-                            out_cl[out_base + static_cast<size_t>(p.out_halo + 2 * (T_out - 1) - f) * p.out_pitch] = y;
-                    }
-                }
-            }
+            for (int i = 0; i < 16; ++i)
+                if (c0 + i < T) nct[c0 + i] = x[i];
         }
     }
 }
@@ -224,7 +257,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
     uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
     uint8_t* sA = smem;
     uint8_t* sB = smem + STAGES * A_STAGE_BYTES;
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES));
+    uint8_t* sStage = smem + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES);
+    uint64_t* full = reinterpret_cast<uint64_t*>(sStage + STAGING_BYTES);
     uint64_t* empty = full + STAGES;
     uint64_t* tfull = empty + STAGES;
     uint64_t* tempty = tfull + 2;
@@ -245,6 +279,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
         fence_barrier_init();
         tma_prefetch_desc(&p.tmA);
         tma_prefetch_desc(&p.tmB);
+        if (p.out_mode != OUT_NCT32) tma_prefetch_desc(&p.tmOut);
     }
     if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_slot);
     tc_fence_before();
@@ -272,7 +307,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
                     const int row_b = p.in_row0 + tap;
                     for (int c = 0; c < p.kc; ++c) {
                         mbar_wait(&empty[stage], phase ^ 1);
-                        if (elect_one()) {
+                        if (p.debug & 1) {
+                            if (elect_one()) mbar_arrive(&full[stage]);
+                        } else if (elect_one()) {
                             mbar_expect_tx(&full[stage], stage_tx);
                             tma_load_2d(&p.tmA, sA + stage * A_STAGE_BYTES, &full[stage], tap * p.c_in_pad + c * BK,
                                         mt * BM);
@@ -312,10 +349,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
                     const uint64_t da = umma_desc_sw128(a0 + stage * A_STAGE_BYTES);
                     const uint64_t db = umma_desc_sw128(b0 + stage * B_STAGE_BYTES);
                     if (elect_one()) {
+                        if (!(p.debug & 2)) {
 #pragma unroll
-                        for (int k = 0; k < BK / 16; ++k) {
-                            // advance 16 elements (32 B) along K inside the swizzle row: +2 in the >>4 address field
-                            umma_f16(d_tmem, da + 2 * k, db + 2 * k, p.idesc, (ks | k) != 0);
+                            for (int k = 0; k < BK / 16; ++k) {
+                                // advance 16 elements (32 B) along K inside the swizzle row: +2 in the >>4 address field
+                                umma_f16(d_tmem, da + 2 * k, db + 2 * k, p.idesc, (ks | k) != 0);
+                            }
                         }
                         umma_commit(&empty[stage]);
                     }
@@ -333,6 +372,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
         // ------------------------------ epilogue ----------------------------------
         const int quad = warp & 3;  // TMEM lane quadrant this warp may access
         const int row = quad * 32 + lane;
+        const bool lrelu = p.lrelu != 0;
+        const float ns = p.ns;
+        const int T = p.T;
+        OT* stage = reinterpret_cast<OT*>(sStage);
         int it = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
             const int mt = tile % p.m_tiles, nt = tile / p.m_tiles;
@@ -341,14 +384,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
             tc_fence_after();
             const int ch = mt * BM + row;  // weight row == bias index
             const bool ch_ok = ch < p.m_valid;
-            // pixel shuffle: weight rows are packed so rows [0,64) of a tile hold r = 0, [64,128) r = 1
-            const int ps_r = row >> 6;
-            const int out_ch = (p.out_mode == OUT_PS) ? (mt * 64 + (row & 63)) : ch;
             const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * MAX_BN;
-            for (int s = 0; s < p.nb; ++s) {
-                const int b = nt * p.nb + s;
-                if (b >= p.B) break;
-                float bias = 0.f;
+            auto chan_norm = [&](int b, uint32_t t_seg) {
+                ChanNorm cn;
+                cn.bias = 0.f;
                 if (p.bias != nullptr) {  // tables are padded to m_tiles * 128 rows
                     size_t off = 0;
                     if (p.spk) {
@@ -356,25 +395,75 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
                         sp = sp < 0 ? 0 : (sp >= p.n_spk ? p.n_spk - 1 : sp);
                         off = static_cast<size_t>(sp) * p.bias_stride;
                     }
-                    bias = p.bias[off + ch];
+                    cn.bias = p.bias[off + ch];
                 }
-                const uint32_t t_seg = t_lane + s * p.Tt;
-                if (p.out_mode == OUT_CL) {
-                    if (p.res_mode == RES_NONE) epilogue_segment<OT, RES_NONE, OUT_CL>(p, t_seg, b, ch, ch_ok, out_ch, ps_r, bias);
-                    else if (p.res_mode == RES_SAME) epilogue_segment<OT, RES_SAME, OUT_CL>(p, t_seg, b, ch, ch_ok, out_ch, ps_r, bias);
-                    else if (p.res_mode == RES_AVG2) epilogue_segment<OT, RES_AVG2, OUT_CL>(p, t_seg, b, ch, ch_ok, out_ch, ps_r, bias);
-                    else epilogue_segment<OT, RES_UP2, OUT_CL>(p, t_seg, b, ch, ch_ok, out_ch, ps_r, bias);
-                } else if (p.out_mode == OUT_PS) {
-                    epilogue_segment<OT, RES_NONE, OUT_PS>(p, t_seg, b, ch, ch_ok, out_ch, ps_r, bias);
-                } else if (p.out_mode == OUT_NCT32) {
-                    epilogue_segment<OT, RES_NONE, OUT_NCT32>(p, t_seg, b, ch, ch_ok, out_ch, ps_r, bias);
-                } else {
-                    epilogue_segment<OT, RES_NONE, OUT_CL32>(p, t_seg, b, ch, ch_ok, out_ch, ps_r, bias);
+                cn.scale = 1.f;
+                cn.shift = 0.f;
+                if (p.inorm) {
+                    float mean, rstd;
+                    chan_stats(t_seg, T, cn.bias, lrelu, ns, mean, rstd);
+                    cn.scale = rstd;
+                    cn.shift = -mean * rstd;
+                }
+                return cn;
+            };
+            if (p.out_mode == OUT_NCT32) {
+                for (int s = 0; s < p.nb; ++s) {
+                    const int b = nt * p.nb + s;
+                    if (b >= p.B) break;
+                    const uint32_t t_seg = t_lane + s * p.Tt;
+                    const ChanNorm cn = chan_norm(b, t_seg);
+                    frames_to_nct<OT>(p, t_seg, T, cn, lrelu, ns,
+                                      reinterpret_cast<float*>(p.out) + (static_cast<size_t>(b) * p.m_valid + ch) * T, ch_ok);
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty[as]);
+            } else {
+                // pixel shuffle: weight rows are packed so rows [0,64) of a tile hold r = 0, [64,128) r = 1
+                const bool ps = p.out_mode == OUT_PS;
+                const int ps_r = row >> 6;
+                const int out_ch = ps ? (mt * 64 + (row & 63)) : ch;
+                const int fstep = ps ? 2 : 1;
+                OT* stg_ch = stage + (ps ? (ps_r * 64 + (row & 63)) : row);
+                const int stg_row = ps ? 64 : 128;                    // elements per staging row
+                ChanNorm cn_keep;
+                for (int s0 = 0; s0 < p.nb; s0 += p.rnd_ns) {
+                    for (int h = 0; h < p.rnd_sub; ++h) {
+                        const int f_lo = h * 128, f_hi = min(T, f_lo + 128);
+                        for (int s = s0; s < min(s0 + p.rnd_ns, p.nb); ++s) {
+                            const int b = nt * p.nb + s;
+                            if (b >= p.B) break;
+                            const uint32_t t_seg = t_lane + s * p.Tt;
+                            if (h == 0) cn_keep = chan_norm(b, t_seg);
+                            OT* stg = stg_ch + static_cast<size_t>(s - s0) * p.rnd_rows * fstep * stg_row;
+                            const OT* res_s = reinterpret_cast<const OT*>(p.res) +
+                                              (static_cast<size_t>(b) * p.res_rows + p.res_halo) * p.res_pitch + ch;
+                            OT* out_s = reinterpret_cast<OT*>(p.out) + static_cast<size_t>(b) * p.out_rows * p.out_pitch +
+                                        p.out_choff + out_ch;
+                            if (ps) frames_to_staging<OT, RES_NONE, true>(p, t_seg, f_lo, f_hi, T, cn_keep, lrelu, ns, stg, res_s, out_s, ps_r, ch_ok);
+                            else if (p.res_mode == RES_NONE) frames_to_staging<OT, RES_NONE, false>(p, t_seg, f_lo, f_hi, T, cn_keep, lrelu, ns, stg, res_s, out_s, 0, ch_ok);
+                            else if (p.res_mode == RES_SAME) frames_to_staging<OT, RES_SAME, false>(p, t_seg, f_lo, f_hi, T, cn_keep, lrelu, ns, stg, res_s, out_s, 0, ch_ok);
+                            else if (p.res_mode == RES_UP2) frames_to_staging<OT, RES_UP2, false>(p, t_seg, f_lo, f_hi, T, cn_keep, lrelu, ns, stg, res_s, out_s, 0, ch_ok);
+                            else frames_to_staging<OT, RES_AVG2, false>(p, t_seg, f_lo, f_hi, T, cn_keep, lrelu, ns, stg, res_s, out_s, 0, ch_ok);
+                        }
+                        const bool last = (s0 + p.rnd_ns >= p.nb) && (h + 1 == p.rnd_sub);
+                        if (last) {   // every TMEM read of this tile is done: hand the accumulator back
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(&tempty[as]);
+                        }
+                        fence_proxy_async();                              // staging writes -> visible to the TMA engine
+                        asm volatile("bar.sync 1, 128;" ::: "memory");
+                        if (warp == 2 && nt * p.nb + s0 < p.B && elect_one()) {
+                            tma_store_3d(&p.tmOut, sStage, ps ? mt * 64 : mt * BM, p.out_halo + fstep * f_lo, nt * p.nb + s0);
+                            tma_store_commit();
+                            tma_store_wait_read();                        // staging may be overwritten after this
+                        }
+                        asm volatile("bar.sync 1, 128;" ::: "memory");
+                    }
                 }
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty[as]);
         }
     }
 

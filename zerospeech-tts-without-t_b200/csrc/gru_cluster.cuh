@@ -100,7 +100,7 @@ __host__ __device__ inline uint32_t umma_idesc_f16_m(int fmt, int m, int n) {
 struct GruParams {
     const void* w_img;      // [2 dirs][NC][192 * H] operand type (gru_pack_whh_kernel)
     const float* bhh;       // [2][3H]
-    const float* gx;        // [B][T][2][3H] fp32, b_ih (+ speaker term) folded in
+    const void* gx;         // [B][T][2][3H] operand type, b_ih (+ speaker term) folded in
     void* out;              // operand type [B][out_rows][out_pitch]
     int B, T, H, out_rows, out_pitch, out_halo, out_choff, fmt, debug;
     long long* dbg;        // debug bit 3: per-step clock64 stamps of cluster 0 / CTA 0 ([T][8])
@@ -224,8 +224,8 @@ __global__ void __launch_bounds__(GRU_THREADS, 1) gru_cluster_kernel(const GruPa
             for (int i = 0; i < 8; ++i) {
                 const int b = seq0 + i;
                 if (b < p.B && step < p.T && !(p.debug & 2)) {
-                    const float* g = p.gx + ((static_cast<size_t>(b) * p.T + ts) * 2 + dir) * 3 * H + unit;
-                    xr[i] = __ldg(g); xz[i] = __ldg(g + H); xn[i] = __ldg(g + 2 * H);
+                    const OT* g = reinterpret_cast<const OT*>(p.gx) + ((static_cast<size_t>(b) * p.T + ts) * 2 + dir) * 3 * H + unit;
+                    xr[i] = ot_to_float<OT>(g[0]); xz[i] = ot_to_float<OT>(g[H]); xn[i] = ot_to_float<OT>(g[2 * H]);
                 } else {
                     xr[i] = xz[i] = xn[i] = 0.f;
                 }

@@ -131,7 +131,7 @@ __global__ void bottleneck_misc_kernel(const float* __restrict__ logits, const f
 // from L2 each step.  gx = W_ih x + b_ih (+ folded speaker term) comes from the tensor-core GEMM.
 // ---------------------------------------------------------------------------------------------
 template <typename OT, int NBG>
-__global__ void gru_simple_kernel(const float* __restrict__ gx, const float* __restrict__ whhT,
+__global__ void gru_simple_kernel(const OT* __restrict__ gx, const float* __restrict__ whhT,
                                   const float* __restrict__ bhh, int B, int T, int H, OT* __restrict__ out,
                                   int rows, int pitch, int halo, int choff) {
     extern __shared__ float s_h[];  // [NBG][H]
@@ -166,10 +166,10 @@ __global__ void gru_simple_kernel(const float* __restrict__ gx, const float* __r
         for (int s = 0; s < NBG; ++s) {
             const int b = b0 + s;
             if (b < B) {
-                const float* g = gx + ((static_cast<size_t>(b) * T + t) * 2 + dir) * 3 * H;
-                const float r = 1.f / (1.f + expf(-(g[j] + ar[s] + br)));
-                const float z = 1.f / (1.f + expf(-(g[H + j] + az[s] + bz)));
-                const float n = tanhf(g[2 * H + j] + r * (an[s] + bn));
+                const OT* g = gx + ((static_cast<size_t>(b) * T + t) * 2 + dir) * 3 * H;
+                const float r = 1.f / (1.f + expf(-(ot_to_float<OT>(g[j]) + ar[s] + br)));
+                const float z = 1.f / (1.f + expf(-(ot_to_float<OT>(g[H + j]) + az[s] + bz)));
+                const float n = tanhf(ot_to_float<OT>(g[2 * H + j]) + r * (an[s] + bn));
                 h[s] = (1.f - z) * n + z * h[s];
                 s_h[s * H + j] = h[s];
                 out[(static_cast<size_t>(b) * rows + halo + t) * pitch + choff + dir * H + j] = float_to_ot<OT>(h[s]);
@@ -221,6 +221,12 @@ __global__ void fold_bias_kernel(const float* __restrict__ W, const float* __res
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
     if (lane == 0) tab[static_cast<long long>(s) * m_rows + row_off + (ps ? ps_row(co) : co)] = acc + (b ? b[co] : 0.f);
+}
+
+template <typename OT>
+__global__ void cast_to_ot_kernel(const float* __restrict__ x, OT* __restrict__ y, size_t n) {
+    const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n) y[i] = float_to_ot<OT>(x[i]);
 }
 
 // W_hh (3H, H) fp32 -> W^T [H][3H] fp32 for the CUDA-core recurrence

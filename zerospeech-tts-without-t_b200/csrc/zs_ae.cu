@@ -124,11 +124,11 @@ static inline int buf_rows(int T, int halo) { return round_up(T + 2 * halo, 2); 
 // one conv / linear layer
 // -------------------------------------------------------------------------------------------------
 static int make_map(CUtensorMap* m, int operand, void* base, int rank, const cuuint64_t* dims,
-                    const cuuint64_t* strides, const cuuint32_t* box) {
+                    const cuuint64_t* strides, const cuuint32_t* box, bool swizzle = true) {
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
     CUresult r = g_encode(m, operand == ZS_OPERAND_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16,
                           rank, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          swizzle ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(ZS_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d), rank %d", (int)r, rank);
     return ZS_OK;
@@ -191,6 +191,21 @@ static int launch_conv(const zs_conv_desc* d, cudaStream_t stream) {
         cuuint32_t box[4] = {BK, 1, static_cast<cuuint32_t>(Tt), static_cast<cuuint32_t>(nb)};
         ZS_TRY(make_map(&p.tmB, d->operand, const_cast<void*>(d->in), 4, dims, strides, box));
     }
+    if (d->out_mode != OUT_NCT32) {   // epilogue rounds + the TMA store map of the channels-last output
+        const bool ps = d->out_mode == OUT_PS;
+        p.rnd_rows = std::min(Tt, 128);
+        p.rnd_sub = Tt > 128 ? 2 : 1;
+        p.rnd_ns = Tt > 128 ? 1 : std::max(1, std::min(128 / Tt, nb));
+        if (d->out_choff % 8 || d->out_pitch % 8) return fail(ZS_ERR_ARG, "conv: out_choff %d / out_pitch %d must be multiples of 8", d->out_choff, d->out_pitch);
+        if (reinterpret_cast<uintptr_t>(d->out) % 16) return fail(ZS_ERR_ARG, "conv: output pointer must be 16-byte aligned");
+        const int T_rows = d->out_halo + (ps ? 2 * d->T_out : d->T_out);
+        if (T_rows > d->out_rows) return fail(ZS_ERR_ARG, "conv: output buffer has %d rows, needs %d", d->out_rows, T_rows);
+        cuuint64_t dims[3] = {static_cast<cuuint64_t>(ps ? d->m_valid / 2 : d->m_valid), static_cast<cuuint64_t>(T_rows), static_cast<cuuint64_t>(d->B)};
+        cuuint64_t strides[2] = {static_cast<cuuint64_t>(d->out_pitch) * 2, static_cast<cuuint64_t>(d->out_rows) * d->out_pitch * 2};
+        cuuint32_t box[3] = {static_cast<cuuint32_t>(ps ? 64 : 128), static_cast<cuuint32_t>(ps ? 2 * p.rnd_rows : p.rnd_rows), static_cast<cuuint32_t>(p.rnd_ns)};
+        void* base = static_cast<uint8_t*>(d->out) + static_cast<size_t>(d->out_choff) * 2;
+        ZS_TRY(make_map(&p.tmOut, d->operand, base, 3, dims, strides, box, false));
+    }
     p.m_tiles = m_tiles; p.n_tiles = n_tiles; p.nb = nb; p.Tt = Tt; p.T = d->T_out; p.B = d->B; p.N = nb * Tt;
     p.kc = d->c_in_pad / BK; p.taps = d->taps; p.bank = d->bank; p.stride = d->stride; p.in_row0 = d->in_row0;
     p.c_in_pad = d->c_in_pad; p.m_valid = d->m_valid;
@@ -200,6 +215,7 @@ static int launch_conv(const zs_conv_desc* d, cudaStream_t stream) {
     p.act = d->act; p.out_mode = d->out_mode; p.out = d->out; p.out_rows = d->out_rows; p.out_pitch = d->out_pitch;
     p.out_halo = d->out_halo; p.out_choff = d->out_choff; p.accumulate = d->accumulate;
     p.idesc = umma_idesc_f16(d->operand == ZS_OPERAND_BF16 ? 1 : 0, p.N);
+    { const char* dbg = getenv("ZS_GEMM_DEBUG"); p.debug = dbg ? atoi(dbg) : 0; }
 
     const int grid = std::min(m_tiles * n_tiles, g_num_sms);
     const int which = d->operand == ZS_OPERAND_BF16 ? 1 : 0;
@@ -260,7 +276,7 @@ extern "C" int zs_bottleneck_one_hot(const float* logits, const float* noise, in
     return launch_onehot(logits, noise, B, C, T8, act, unit_ids, static_cast<cudaStream_t>(stream));
 }
 
-static int launch_gru(const float* gx, const float* whhT, const float* bhh, int B, int T, int H, void* out, int rows,
+static int launch_gru(const void* gx, const float* whhT, const float* bhh, int B, int T, int H, void* out, int rows,
                       int pitch, int halo, int choff, int operand, cudaStream_t st) {
     if (H < 1 || H > 1024) return fail(ZS_ERR_ARG, "gru: hidden size %d outside [1, 1024]", H);
     constexpr int NBG = 4;
@@ -268,16 +284,16 @@ static int launch_gru(const float* gx, const float* whhT, const float* bhh, int 
     const size_t smem = static_cast<size_t>(NBG) * H * 4;
     LaunchScope scope(st, KC_GRU, 2.0 * 2 * B * static_cast<double>(T) * 3 * H * H);
     if (operand == ZS_OPERAND_BF16)
-        gru_simple_kernel<__nv_bfloat16, NBG><<<grid, H, smem, st>>>(gx, whhT, bhh, B, T, H, static_cast<__nv_bfloat16*>(out), rows, pitch, halo, choff);
+        gru_simple_kernel<__nv_bfloat16, NBG><<<grid, H, smem, st>>>(static_cast<const __nv_bfloat16*>(gx), whhT, bhh, B, T, H, static_cast<__nv_bfloat16*>(out), rows, pitch, halo, choff);
     else
-        gru_simple_kernel<__half, NBG><<<grid, H, smem, st>>>(gx, whhT, bhh, B, T, H, static_cast<__half*>(out), rows, pitch, halo, choff);
+        gru_simple_kernel<__half, NBG><<<grid, H, smem, st>>>(static_cast<const __half*>(gx), whhT, bhh, B, T, H, static_cast<__half*>(out), rows, pitch, halo, choff);
     CUDA_TRY(cudaGetLastError());
     return ZS_OK;
 }
 
 static bool gru_cluster_ok(int H) { return H % GRU_UNITS == 0 && H / GRU_UNITS >= 1 && H / GRU_UNITS <= 8; }
 
-static int launch_gru_cluster(const void* w_img, const float* bhh, const float* gx, int B, int T, int H, void* out, int rows,
+static int launch_gru_cluster(const void* w_img, const float* bhh, const void* gx, int B, int T, int H, void* out, int rows,
                               int pitch, int halo, int choff, int operand, cudaStream_t st) {
     ZS_TRY(ensure_device());
     GruParams p;
@@ -326,6 +342,11 @@ static int launch_gru_cluster(const void* w_img, const float* bhh, const float* 
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = NC; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
+    if (p.debug & 16) {
+        int ncl = 0;
+        cudaError_t e = cudaOccupancyMaxActiveClusters(&ncl, gru_cluster_kernel<__half>, &cfg);
+        fprintf(stderr, "gru: max active clusters of %d CTAs with %d B smem: %d (%s); launching %d clusters\n", NC, smem, ncl, cudaGetErrorString(e), 2 * n_groups);
+    }
     LaunchScope scope(st, KC_GRU, 2.0 * 2 * B * static_cast<double>(T) * 3 * H * H);
     if (which) CUDA_TRY(cudaLaunchKernelEx(&cfg, gru_cluster_kernel<__nv_bfloat16>, p));
     else CUDA_TRY(cudaLaunchKernelEx(&cfg, gru_cluster_kernel<__half>, p));
@@ -347,15 +368,21 @@ static int pack_gru_image(void* img, const float* const* w_hh_dirs, const float*
 
 extern "C" int zs_gru_recurrence(const float* gx, const float* w_hh, const float* b_hh, int B, int T, int H, void* out,
                                  int out_rows, int out_pitch, int out_halo, int out_choff, int operand, int impl, void* stream) {
-    // test entry: packs w_hh into a temporary (stream-ordered) buffer, then runs the recurrence
+    // test entry: packs w_hh and the fp32 projections into temporary (stream-ordered) buffers, then runs the recurrence
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    void* gx_ot = nullptr;
+    const size_t n_gx = static_cast<size_t>(B) * T * 6 * H;
+    CUDA_TRY(cudaMallocAsync(&gx_ot, n_gx * 2, st));
+    if (operand == ZS_OPERAND_BF16) cast_to_ot_kernel<__nv_bfloat16><<<static_cast<unsigned>((n_gx + 255) / 256), 256, 0, st>>>(gx, static_cast<__nv_bfloat16*>(gx_ot), n_gx);
+    else cast_to_ot_kernel<__half><<<static_cast<unsigned>((n_gx + 255) / 256), 256, 0, st>>>(gx, static_cast<__half*>(gx_ot), n_gx);
+    struct FreeLater { void* p; cudaStream_t s; ~FreeLater() { cudaFreeAsync(p, s); } } free_gx{gx_ot, st};
     if (impl == 2 && !gru_cluster_ok(H)) return fail(ZS_ERR_ARG, "gru: the cluster kernel needs H %% 64 == 0 and H <= 512 (H = %d)", H);
     if (impl == 2 || (impl == 0 && gru_cluster_ok(H))) {
         void* img = nullptr;
         const size_t bytes = static_cast<size_t>(2) * (H / GRU_UNITS) * gru_w_image_bytes(H);
         CUDA_TRY(cudaMallocAsync(&img, bytes, st));
         int r = pack_gru_image(img, nullptr, w_hh, H, operand, st);
-        if (r == ZS_OK) r = launch_gru_cluster(img, b_hh, gx, B, T, H, out, out_rows, out_pitch, out_halo, out_choff, operand, st);
+        if (r == ZS_OK) r = launch_gru_cluster(img, b_hh, gx_ot, B, T, H, out, out_rows, out_pitch, out_halo, out_choff, operand, st);
         cudaFreeAsync(img, st);
         return r;
     }
@@ -363,7 +390,7 @@ extern "C" int zs_gru_recurrence(const float* gx, const float* w_hh, const float
     CUDA_TRY(cudaMallocAsync(&wt, static_cast<size_t>(2) * 3 * H * H * 4, st));
     for (int dir = 0; dir < 2; ++dir)
         transpose_whh_kernel<<<(3 * H * H + 255) / 256, 256, 0, st>>>(w_hh + static_cast<size_t>(dir) * 3 * H * H, wt + static_cast<size_t>(dir) * 3 * H * H, H);
-    int r = launch_gru(gx, wt, b_hh, B, T, H, out, out_rows, out_pitch, out_halo, out_choff, operand, st);
+    int r = launch_gru(gx_ot, wt, b_hh, B, T, H, out, out_rows, out_pitch, out_halo, out_choff, operand, st);
     cudaFreeAsync(wt, st);
     return r;
 }
@@ -600,17 +627,16 @@ struct Carver {
         off += align256(bytes);
         return p;
     }
-    Buf act(int B, int T, int halo, int channels) {
+    Buf act(int B, int T, int halo, int channels, bool exact_rows = false) {
         Buf b;
-        b.rows = buf_rows(T, halo); b.pitch = round_up(channels, 8); b.halo = halo; b.T = T;
+        b.rows = exact_rows ? T + 2 * halo : buf_rows(T, halo); b.pitch = round_up(channels, 8); b.halo = halo; b.T = T;
         b.p = take(static_cast<size_t>(B) * b.rows * b.pitch * 2);
         return b;
     }
 };
 
 struct EncWs {
-    Buf xp, cat, a[7], d[3], catr;
-    float* gx;
+    Buf xp, cat, a[7], d[3], catr, gx;
     int T[4];
     size_t bytes;
 };
@@ -630,7 +656,7 @@ static EncWs carve_encoder(const zs_encoder* h, void* ws, int B, int T) {
     w.a[6] = c.act(B, w.T[3], 0, g.c_h2);   // conv8 out
     for (int i = 0; i < 3; ++i) w.d[i] = c.act(B, w.T[3], 0, g.c_h2);
     w.catr = c.act(B, w.T[3], 0, g.c_h2 + 2 * g.c_h3);
-    w.gx = static_cast<float*>(c.take(static_cast<size_t>(B) * w.T[3] * 6 * g.c_h3 * 4));
+    w.gx = c.act(B, w.T[3], 0, 6 * g.c_h3, true);   // the recurrence indexes it as a dense [B][T][2][3H] array
     w.bytes = c.off;
     return w;
 }
@@ -640,8 +666,7 @@ extern "C" size_t zs_encoder_workspace_bytes(const zs_encoder* h, int B, int T) 
 }
 
 struct DecWs {
-    Buf actp, x0, p[3], y[3], d[3], catr, d5;
-    float* gx;
+    Buf actp, x0, p[3], y[3], d[3], catr, d5, gx;
     size_t bytes;
 };
 static DecWs carve_decoder(const zs_decoder* h, void* ws, int B, int T8) {
@@ -659,7 +684,7 @@ static DecWs carve_decoder(const zs_decoder* h, void* ws, int B, int T8) {
     for (int i = 0; i < 3; ++i) w.d[i] = c.act(B, Tf, 0, ch);
     w.catr = c.act(B, Tf, 0, 2 * ch);
     w.d5 = c.act(B, Tf, 0, ch);
-    w.gx = static_cast<float*>(c.take(static_cast<size_t>(B) * Tf * 3 * ch * 4));
+    w.gx = c.act(B, Tf, 0, 3 * ch, true);
     w.bytes = c.off;
     return w;
 }
@@ -677,7 +702,7 @@ struct ConvOpts {
     const Buf* res = nullptr;
     const int64_t* spk = nullptr;
 };
-// runs layer L on `in`, writing T_out frames per segment into `out` (a Buf, or raw fp32 for NCT32/CL32)
+// runs layer L on `in`, writing T_out frames per segment into `out` (a Buf, or raw fp32 (B, C, T) for NCT32)
 static int run_layer(const Layer& L, int operand, float ns, const Buf& in, int B, int T_out, const Buf* out, void* out_raw,
                      int out_raw_rows, int out_raw_pitch, const ConvOpts& o, cudaStream_t st) {
     zs_conv_desc d;
@@ -750,10 +775,10 @@ extern "C" int zs_encoder_forward(zs_encoder* h, const float* x, int B, int T, c
         ZS_TRY(run_layer(h->dense[3], op, ns, w.d[2], B, T8, &w.catr, nullptr, 0, 0, r2, st));
     }
     {   // :454-455 bi-GRU: input projection on tensor cores, then the recurrence
-        ConvOpts o; o.lrelu = 0; o.out_mode = OUT_CL32; o.c_in_valid = g.c_h2;
-        ZS_TRY(run_layer(h->gru_ih, op, ns, w.catr, B, T8, nullptr, w.gx, T8, 6 * g.c_h3, o, st));
-        if (h->whh_img) ZS_TRY(launch_gru_cluster(h->whh_img, h->bhh, w.gx, B, T8, g.c_h3, w.catr.p, w.catr.rows, w.catr.pitch, 0, g.c_h2, op, st));
-        else ZS_TRY(launch_gru(w.gx, h->whhT, h->bhh, B, T8, g.c_h3, w.catr.p, w.catr.rows, w.catr.pitch, 0, g.c_h2, op, st));
+        ConvOpts o; o.lrelu = 0; o.c_in_valid = g.c_h2;
+        ZS_TRY(run_layer(h->gru_ih, op, ns, w.catr, B, T8, &w.gx, nullptr, 0, 0, o, st));
+        if (h->whh_img) ZS_TRY(launch_gru_cluster(h->whh_img, h->bhh, w.gx.p, B, T8, g.c_h3, w.catr.p, w.catr.rows, w.catr.pitch, 0, g.c_h2, op, st));
+        else ZS_TRY(launch_gru(w.gx.p, h->whhT, h->bhh, B, T8, g.c_h3, w.catr.p, w.catr.rows, w.catr.pitch, 0, g.c_h2, op, st));
     }
     {   // linear -> logits in the reference's (B, n_out, T8) fp32 layout
         ConvOpts o; o.lrelu = 0; o.out_mode = OUT_NCT32;
@@ -816,10 +841,10 @@ extern "C" int zs_decoder_forward(zs_decoder* h, const float* enc_act, const int
         ZS_TRY(run_layer(h->dense[3], op, ns, w.d[2], B, Tf, &w.catr, nullptr, 0, 0, r2, st));
     }
     {   // :352-355 bi-GRU on out + emb5
-        ConvOpts o; o.lrelu = 0; o.out_mode = OUT_CL32; o.c_in_valid = ch; o.spk = spk;
-        ZS_TRY(run_layer(h->gru_ih, op, ns, w.catr, B, Tf, nullptr, w.gx, Tf, 3 * ch, o, st));
-        if (h->whh_img) ZS_TRY(launch_gru_cluster(h->whh_img, h->bhh, w.gx, B, Tf, ch / 2, w.catr.p, w.catr.rows, w.catr.pitch, 0, ch, op, st));
-        else ZS_TRY(launch_gru(w.gx, h->whhT, h->bhh, B, Tf, ch / 2, w.catr.p, w.catr.rows, w.catr.pitch, 0, ch, op, st));
+        ConvOpts o; o.lrelu = 0; o.c_in_valid = ch; o.spk = spk;
+        ZS_TRY(run_layer(h->gru_ih, op, ns, w.catr, B, Tf, &w.gx, nullptr, 0, 0, o, st));
+        if (h->whh_img) ZS_TRY(launch_gru_cluster(h->whh_img, h->bhh, w.gx.p, B, Tf, ch / 2, w.catr.p, w.catr.rows, w.catr.pitch, 0, ch, op, st));
+        else ZS_TRY(launch_gru(w.gx.p, h->whhT, h->bhh, B, Tf, ch / 2, w.catr.p, w.catr.rows, w.catr.pitch, 0, ch, op, st));
     }
     {   // :356-364 dense5 on cat([out, rnn, emb5]) -> lrelu -> linear -> sigmoid | tanh
         ConvOpts o; o.spk = spk;
