@@ -216,18 +216,18 @@ __global__ void __launch_bounds__(GRU_THREADS, 1) gru_cluster_kernel(const GruPa
         const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(32 * q) << 16);
         const int seq0 = b0 + 8 * hi;
         // input projections are prefetched one full step ahead (their HBM latency would otherwise sit on the
-        // critical path of every step)
-        float gr[8], gz[8], gn[8], pr[8], pz[8], pn[8];
-        auto load_gx = [&](int step, float (&xr)[8], float (&xz)[8], float (&xn)[8]) {
+        // critical path of every step); they stay RAW in registers - converting them here would wait for the load
+        OT gr[8], gz[8], gn[8], pr[8], pz[8], pn[8];
+        auto load_gx = [&](int step, OT (&xr)[8], OT (&xz)[8], OT (&xn)[8]) {
             const int ts = dir ? p.T - 1 - step : step;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const int b = seq0 + i;
                 if (b < p.B && step < p.T && !(p.debug & 2)) {
                     const OT* g = reinterpret_cast<const OT*>(p.gx) + ((static_cast<size_t>(b) * p.T + ts) * 2 + dir) * 3 * H + unit;
-                    xr[i] = ot_to_float<OT>(g[0]); xz[i] = ot_to_float<OT>(g[H]); xn[i] = ot_to_float<OT>(g[2 * H]);
+                    xr[i] = g[0]; xz[i] = g[H]; xn[i] = g[2 * H];
                 } else {
-                    xr[i] = xz[i] = xn[i] = 0.f;
+                    xr[i] = xz[i] = xn[i] = float_to_ot<OT>(0.f);
                 }
             }
         };
@@ -262,9 +262,9 @@ __global__ void __launch_bounds__(GRU_THREADS, 1) gru_cluster_kernel(const GruPa
             uint8_t* hnext = sH + (pb ^ 1) * hbuf_bytes + rank * slice_bytes;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                const float r = sigmoid_f(gr[i] + hr[i] + b_r);
-                const float z = sigmoid_f(gz[i] + hzv[i] + b_z);
-                const float n = tanh_f(gn[i] + r * (hn[i] + b_n));
+                const float r = sigmoid_f(ot_to_float<OT>(gr[i]) + hr[i] + b_r);
+                const float z = sigmoid_f(ot_to_float<OT>(gz[i]) + hzv[i] + b_z);
+                const float n = tanh_f(ot_to_float<OT>(gn[i]) + r * (hn[i] + b_n));
                 h[i] = (1.f - z) * n + z * h[i];
                 const OT y = float_to_ot<OT>(h[i]);
                 const int s = 8 * hi + i;      // row of the state tile
