@@ -25,12 +25,13 @@ namespace zs {
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 x 2 B = one 128-byte swizzle row
 constexpr int MAX_BN = 256;
-constexpr int STAGES = 4;
+constexpr int STAGES = 3;
 constexpr int A_STAGE_BYTES = BM * BK * 2;
 constexpr int B_STAGE_BYTES = MAX_BN * BK * 2;
 constexpr int GEMM_THREADS = 192;
 constexpr int TMEM_COLS = 512;
-constexpr int STAGING_BYTES = 32768;   // epilogue staging tile: 128 columns x 128 channels (or 256 x 64) x 2 B
+constexpr int STAGING_BYTES = 65536;   // 2 epilogue staging tiles of 128 columns x 128 channels (or 256 x 64) x 2 B:
+                                       // output double buffer, or output + residual tile
 constexpr int GEMM_SMEM_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + STAGING_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 constexpr float IN_EPS = 1e-5f;
 
@@ -42,7 +43,9 @@ struct alignas(64) GemmParams {
     CUtensorMap tmA;
     CUtensorMap tmB;
     CUtensorMap tmOut;   // channels-last output (OUT_CL / OUT_PS): box {128|64 channels, rows, segments}
-    int rnd_ns, rnd_rows, rnd_sub;   // epilogue rounds: segments per round, box rows per segment, halves per segment
+    CUtensorMap tmRes;   // residual tile (RES_SAME: same box; RES_UP2: half the rows; RES_AVG2: twice the rows)
+    // epilogue rounds: segments per round, box rows (frames) per segment, sub-rounds per segment, frames per sub-round
+    int rnd_ns, rnd_rows, rnd_sub, rnd_frames;
     int m_tiles, n_tiles, nb, Tt, T, B, N;
     int kc, taps, bank, stride, in_row0, c_in_pad;
     int m_valid;
@@ -140,49 +143,37 @@ __device__ __forceinline__ void chan_stats(uint32_t t_seg, int T, float bias, bo
 // Frames [f_lo, f_hi) of one (segment, channel) -> shared-memory staging tile (channels-last rows that a TMA
 // store then writes out), plus the reflected halo rows written directly.  RES / PS are compile time.
 //   stg      : staging slot of (frame f_lo, this thread's channel); frame stride = STG_PITCH elements
-//   res_s    : residual buffer at (this segment, frame 0 incl. halo offset, this channel)
+//   res_stg  : residual tile in shared memory (TMA-loaded), slot of (first residual row of this sub-round, channel)
 //   out_s    : output buffer at (this segment, row 0, this thread's output channel) - for the halo rows only
 template <typename OT, int RES, bool PS>
 __device__ __forceinline__ void frames_to_staging(const GemmParams& p, uint32_t t_seg, int f_lo, int f_hi, int T,
                                                   const ChanNorm& cn, bool lrelu, float ns, OT* __restrict__ stg,
-                                                  const OT* __restrict__ res_s, OT* __restrict__ out_s, int ps_r,
+                                                  const OT* __restrict__ res_stg, OT* __restrict__ out_s, int ps_r,
                                                   bool ch_ok) {
     constexpr int STG_PITCH = PS ? 64 : 128;          // channels per staging row
     constexpr int FSTEP = PS ? 2 : 1;                 // staging rows per input frame
     const int T_out = PS ? 2 * T : T;
     const int halo = p.out_halo;
+    uint32_t v[16], vn[16];
+    tmem_ld16(t_seg + f_lo, v);
     for (int c0 = f_lo; c0 < f_hi; c0 += 16) {
-        __syncwarp();
-        uint32_t v[16];
-        tmem_ld16(t_seg + c0, v);
+        tmem_ld_wait();
+        const bool more = c0 + 16 < f_hi;
+        if (more) tmem_ld16(t_seg + c0 + 16, vn);       // next chunk's accumulators while this one is processed
         float r[16];
-        if (RES != RES_NONE) {
-            if (ch_ok) {
-                if (RES == RES_SAME) {
+        if (RES == RES_SAME) {
 #pragma unroll
-                    for (int i = 0; i < 16; ++i)
-                        r[i] = (c0 + i < T) ? ot_to_float<OT>(res_s[(c0 + i) * p.res_pitch]) : 0.f;
-                } else if (RES == RES_UP2) {
+            for (int i = 0; i < 16; ++i) r[i] = ot_to_float<OT>(res_stg[(c0 - f_lo + i) * 128]);
+        } else if (RES == RES_UP2) {
 #pragma unroll
-                    for (int i = 0; i < 16; i += 2)
-                        r[i] = r[i + 1] = (c0 + i < T) ? ot_to_float<OT>(res_s[((c0 + i) >> 1) * p.res_pitch]) : 0.f;
-                } else {
+            for (int i = 0; i < 16; i += 2) r[i] = r[i + 1] = ot_to_float<OT>(res_stg[((c0 - f_lo + i) >> 1) * 128]);
+        } else if (RES == RES_AVG2) {
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        if (c0 + i < T) {
-                            const OT* q = res_s + 2 * (c0 + i) * p.res_pitch;
-                            r[i] = 0.5f * (ot_to_float<OT>(q[0]) + ot_to_float<OT>(q[p.res_pitch]));
-                        } else {
-                            r[i] = 0.f;
-                        }
-                    }
-                }
-            } else {
-#pragma unroll
-                for (int i = 0; i < 16; ++i) r[i] = 0.f;
+            for (int i = 0; i < 16; ++i) {
+                const OT* q = res_stg + 2 * (c0 - f_lo + i) * 128;
+                r[i] = 0.5f * (ot_to_float<OT>(q[0]) + ot_to_float<OT>(q[128]));
             }
         }
-        tmem_ld_wait();
         OT y[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
@@ -206,6 +197,11 @@ __device__ __forceinline__ void frames_to_staging(const GemmParams& p, uint32_t 
                     if (f >= T_out - 1 - halo && f <= T_out - 2) out_s[(halo + 2 * (T_out - 1) - f) * p.out_pitch] = y[i];
                 }
             }
+            __syncwarp();
+        }
+        if (more) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = vn[i];
         }
     }
 }
@@ -262,7 +258,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
     uint64_t* empty = full + STAGES;
     uint64_t* tfull = empty + STAGES;
     uint64_t* tempty = tfull + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+    uint64_t* rbar = tempty + 2;   // residual tile landed in the staging buffer
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rbar + 1);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -276,10 +273,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
             mbar_init(&tfull[i], 1);
             mbar_init(&tempty[i], 4);
         }
+        mbar_init(rbar, 1);
         fence_barrier_init();
         tma_prefetch_desc(&p.tmA);
         tma_prefetch_desc(&p.tmB);
         if (p.out_mode != OUT_NCT32) tma_prefetch_desc(&p.tmOut);
+        if (p.res_mode != RES_NONE) tma_prefetch_desc(&p.tmRes);
     }
     if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_slot);
     tc_fence_before();
@@ -376,7 +375,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
         const float ns = p.ns;
         const int T = p.T;
         OT* stage = reinterpret_cast<OT*>(sStage);
-        int it = 0;
+        int it = 0, rnd = 0;
+        uint32_t res_phase = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
             const int mt = tile % p.m_tiles, nt = tile / p.m_tiles;
             const int as = it & 1;
@@ -407,7 +407,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
                 }
                 return cn;
             };
-            if (p.out_mode == OUT_NCT32) {
+            if (p.debug & 4) {            // timing experiment: main loop only
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty[as]);
+            } else if (p.out_mode == OUT_NCT32) {
                 for (int s = 0; s < p.nb; ++s) {
                     const int b = nt * p.nb + s;
                     if (b >= p.B) break;
@@ -422,31 +426,52 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
             } else {
                 // pixel shuffle: weight rows are packed so rows [0,64) of a tile hold r = 0, [64,128) r = 1
                 const bool ps = p.out_mode == OUT_PS;
+                const bool has_res = p.res_mode != RES_NONE;
                 const int ps_r = row >> 6;
                 const int out_ch = ps ? (mt * 64 + (row & 63)) : ch;
                 const int fstep = ps ? 2 : 1;
-                OT* stg_ch = stage + (ps ? (ps_r * 64 + (row & 63)) : row);
                 const int stg_row = ps ? 64 : 128;                    // elements per staging row
+                const int stg_ch = ps ? (ps_r * 64 + (row & 63)) : row;
+                // residual rows per output frame: SAME 1, UP2 1/2, AVG2 2
+                const int res_rows_per_seg = p.res_mode == RES_UP2 ? p.rnd_rows / 2 : (p.res_mode == RES_AVG2 ? 2 * p.rnd_rows : p.rnd_rows);
                 ChanNorm cn_keep;
                 for (int s0 = 0; s0 < p.nb; s0 += p.rnd_ns) {
-                    for (int h = 0; h < p.rnd_sub; ++h) {
-                        const int f_lo = h * 128, f_hi = min(T, f_lo + 128);
+                    for (int h = 0; h < p.rnd_sub; ++h, ++rnd) {
+                        const int f_lo = h * p.rnd_frames, f_hi = min(T, f_lo + p.rnd_frames);
+                        // staging: with a residual, tile 0 = output and tile 1 = residual; otherwise the two tiles
+                        // alternate as output buffers so a store's shared-memory read overlaps the next round
+                        OT* stage_out = stage + (has_res ? 0 : (rnd & 1) * (STAGING_BYTES / 4));
+                        const OT* stage_res = stage + STAGING_BYTES / 4;
+                        if (has_res) {
+                            if (warp == 2 && nt * p.nb + s0 < p.B && elect_one()) {
+                                // the previous round's readers passed the end-of-round barrier: tile 1 is free
+                                mbar_expect_tx(rbar, static_cast<uint32_t>(p.rnd_ns) * res_rows_per_seg * 256);
+                                const int r_row = p.res_halo + (p.res_mode == RES_UP2 ? f_lo / 2 : (p.res_mode == RES_AVG2 ? 2 * f_lo : f_lo));
+                                tma_load_3d(&p.tmRes, sStage + STAGING_BYTES / 2, rbar, mt * BM, r_row, nt * p.nb + s0);
+                            }
+                            __syncwarp();
+                        }
+                        bool waited = false;
                         for (int s = s0; s < min(s0 + p.rnd_ns, p.nb); ++s) {
                             const int b = nt * p.nb + s;
                             if (b >= p.B) break;
                             const uint32_t t_seg = t_lane + s * p.Tt;
                             if (h == 0) cn_keep = chan_norm(b, t_seg);
-                            OT* stg = stg_ch + static_cast<size_t>(s - s0) * p.rnd_rows * fstep * stg_row;
-                            const OT* res_s = reinterpret_cast<const OT*>(p.res) +
-                                              (static_cast<size_t>(b) * p.res_rows + p.res_halo) * p.res_pitch + ch;
+                            if (has_res && !waited) {
+                                mbar_wait(rbar, res_phase);
+                                waited = true;
+                            }
+                            OT* stg = stage_out + static_cast<size_t>(s - s0) * p.rnd_rows * fstep * stg_row + stg_ch;
+                            const OT* res_stg = stage_res + static_cast<size_t>(s - s0) * res_rows_per_seg * 128 + row;
                             OT* out_s = reinterpret_cast<OT*>(p.out) + static_cast<size_t>(b) * p.out_rows * p.out_pitch +
                                         p.out_choff + out_ch;
-                            if (ps) frames_to_staging<OT, RES_NONE, true>(p, t_seg, f_lo, f_hi, T, cn_keep, lrelu, ns, stg, res_s, out_s, ps_r, ch_ok);
-                            else if (p.res_mode == RES_NONE) frames_to_staging<OT, RES_NONE, false>(p, t_seg, f_lo, f_hi, T, cn_keep, lrelu, ns, stg, res_s, out_s, 0, ch_ok);
-                            else if (p.res_mode == RES_SAME) frames_to_staging<OT, RES_SAME, false>(p, t_seg, f_lo, f_hi, T, cn_keep, lrelu, ns, stg, res_s, out_s, 0, ch_ok);
-                            else if (p.res_mode == RES_UP2) frames_to_staging<OT, RES_UP2, false>(p, t_seg, f_lo, f_hi, T, cn_keep, lrelu, ns, stg, res_s, out_s, 0, ch_ok);
-                            else frames_to_staging<OT, RES_AVG2, false>(p, t_seg, f_lo, f_hi, T, cn_keep, lrelu, ns, stg, res_s, out_s, 0, ch_ok);
+                            if (ps) frames_to_staging<OT, RES_NONE, true>(p, t_seg, f_lo, f_hi, T, cn_keep, lrelu, ns, stg, res_stg, out_s, ps_r, ch_ok);
+                            else if (p.res_mode == RES_NONE) frames_to_staging<OT, RES_NONE, false>(p, t_seg, f_lo, f_hi, T, cn_keep, lrelu, ns, stg, res_stg, out_s, 0, ch_ok);
+                            else if (p.res_mode == RES_SAME) frames_to_staging<OT, RES_SAME, false>(p, t_seg, f_lo, f_hi, T, cn_keep, lrelu, ns, stg, res_stg, out_s, 0, ch_ok);
+                            else if (p.res_mode == RES_UP2) frames_to_staging<OT, RES_UP2, false>(p, t_seg, f_lo, f_hi, T, cn_keep, lrelu, ns, stg, res_stg, out_s, 0, ch_ok);
+                            else frames_to_staging<OT, RES_AVG2, false>(p, t_seg, f_lo, f_hi, T, cn_keep, lrelu, ns, stg, res_stg, out_s, 0, ch_ok);
                         }
+                        if (has_res && nt * p.nb + s0 < p.B) res_phase ^= 1;
                         const bool last = (s0 + p.rnd_ns >= p.nb) && (h + 1 == p.rnd_sub);
                         if (last) {   // every TMEM read of this tile is done: hand the accumulator back
                             tc_fence_before();
@@ -456,9 +481,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
                         fence_proxy_async();                              // staging writes -> visible to the TMA engine
                         asm volatile("bar.sync 1, 128;" ::: "memory");
                         if (warp == 2 && nt * p.nb + s0 < p.B && elect_one()) {
-                            tma_store_3d(&p.tmOut, sStage, ps ? mt * 64 : mt * BM, p.out_halo + fstep * f_lo, nt * p.nb + s0);
+                            tma_store_3d(&p.tmOut, stage_out, ps ? mt * 64 : mt * BM, p.out_halo + fstep * f_lo, nt * p.nb + s0);
                             tma_store_commit();
-                            tma_store_wait_read();                        // staging may be overwritten after this
+                            if (has_res) tma_store_wait_read();            // single output tile: it must be free next round
+                            else tma_store_wait_read1();                   // the other tile's store (2 rounds ago) is done
                         }
                         asm volatile("bar.sync 1, 128;" ::: "memory");
                     }

@@ -193,9 +193,13 @@ static int launch_conv(const zs_conv_desc* d, cudaStream_t stream) {
     }
     if (d->out_mode != OUT_NCT32) {   // epilogue rounds + the TMA store map of the channels-last output
         const bool ps = d->out_mode == OUT_PS;
-        p.rnd_rows = std::min(Tt, 128);
-        p.rnd_sub = Tt > 128 ? 2 : 1;
-        p.rnd_ns = Tt > 128 ? 1 : std::max(1, std::min(128 / Tt, nb));
+        // a round fills one 32 KB staging tile: 128 frames x 128 channels; avg-pool residual tiles have twice the
+        // rows of their output, so those layers run 64-frame rounds
+        const int rf = d->res_mode == RES_AVG2 ? 64 : 128;
+        p.rnd_frames = rf;
+        p.rnd_rows = std::min(Tt, rf);
+        p.rnd_sub = (Tt + rf - 1) / rf;
+        p.rnd_ns = Tt > rf ? 1 : std::max(1, std::min(rf / Tt, nb));
         if (d->out_choff % 8 || d->out_pitch % 8) return fail(ZS_ERR_ARG, "conv: out_choff %d / out_pitch %d must be multiples of 8", d->out_choff, d->out_pitch);
         if (reinterpret_cast<uintptr_t>(d->out) % 16) return fail(ZS_ERR_ARG, "conv: output pointer must be 16-byte aligned");
         const int T_rows = d->out_halo + (ps ? 2 * d->T_out : d->T_out);
@@ -205,6 +209,15 @@ static int launch_conv(const zs_conv_desc* d, cudaStream_t stream) {
         cuuint32_t box[3] = {static_cast<cuuint32_t>(ps ? 64 : 128), static_cast<cuuint32_t>(ps ? 2 * p.rnd_rows : p.rnd_rows), static_cast<cuuint32_t>(p.rnd_ns)};
         void* base = static_cast<uint8_t*>(d->out) + static_cast<size_t>(d->out_choff) * 2;
         ZS_TRY(make_map(&p.tmOut, d->operand, base, 3, dims, strides, box, false));
+        if (d->res_mode != RES_NONE) {   // residual tile: same channels, rows scaled by the mode
+            if (d->res_pitch % 8 || reinterpret_cast<uintptr_t>(d->res) % 16) return fail(ZS_ERR_ARG, "conv: residual buffer must be 16-byte aligned with a pitch multiple of 8");
+            const int rr = d->res_mode == RES_UP2 ? p.rnd_rows / 2 : (d->res_mode == RES_AVG2 ? 2 * p.rnd_rows : p.rnd_rows);
+            if (rr < 1 || rr > 256) return fail(ZS_ERR_ARG, "conv: residual box rows %d", rr);
+            cuuint64_t rdims[3] = {static_cast<cuuint64_t>(std::min(d->m_valid, d->res_pitch)), static_cast<cuuint64_t>(d->res_rows), static_cast<cuuint64_t>(d->B)};
+            cuuint64_t rstrides[2] = {static_cast<cuuint64_t>(d->res_pitch) * 2, static_cast<cuuint64_t>(d->res_rows) * d->res_pitch * 2};
+            cuuint32_t rbox[3] = {128, static_cast<cuuint32_t>(rr), static_cast<cuuint32_t>(p.rnd_ns)};
+            ZS_TRY(make_map(&p.tmRes, d->operand, const_cast<void*>(d->res), 3, rdims, rstrides, rbox, false));
+        }
     }
     p.m_tiles = m_tiles; p.n_tiles = n_tiles; p.nb = nb; p.Tt = Tt; p.T = d->T_out; p.B = d->B; p.N = nb * Tt;
     p.kc = d->c_in_pad / BK; p.taps = d->taps; p.bank = d->bank; p.stride = d->stride; p.in_row0 = d->in_row0;
