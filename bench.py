@@ -43,7 +43,8 @@ def parse():
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--segments', type=int, default=256, help='128-frame segments per GPU per step')
-    ap.add_argument('--micro-batch', type=int, default=64, help='segments per library call')
+    ap.add_argument('--micro-batch', type=int, default=256, help='segments per library call (device-resident value)')
+    ap.add_argument('--e2e-micro-batch', type=int, default=128, help='segments per pipelined copy/compute stage (e2e)')
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--operand', default='fp16', choices=['fp16', 'bf16'])
     ap.add_argument('--cpu-sample', type=int, default=32, help='segments in the CPU baseline sample')
@@ -155,6 +156,7 @@ def run_ours(args):
     import zs_b200  # noqa: F401
     from zs_b200 import _lib, synthetic as syn
     from zs_b200.model import Decoder, Encoder
+    from zs_b200.frontend import StreamingResynthesizer
 
     world = int(os.environ.get('WORLD_SIZE', 1))
     rank = int(os.environ.get('RANK', 0))
@@ -198,17 +200,11 @@ def run_ours(args):
             dec.decode(None, cs[k][s0:s1], unit_ids=ids, out=spec_out[s0:s1])
             ids_out[s0:s1] = ids
 
-    def step_e2e(i):
+    streamer = StreamingResynthesizer(enc, dec, micro_batch=min(args.e2e_micro_batch, S), device=dev)
+
+    def step_e2e(i):     # public API: pinned host spectrograms/speakers/noise in, pinned host spectrograms/units out
         k = i % n_sets
-        for s0 in range(0, S, MB):
-            s1 = min(S, s0 + MB)
-            x = xs_host[k][s0:s1].to(dev, non_blocking=True)
-            c = cs_host[k][s0:s1].to(dev, non_blocking=True)
-            n = nz_host[k][s0:s1].to(dev, non_blocking=True)
-            act, _, ids = enc.encode(x, n)
-            dec.decode(None, c, unit_ids=ids, out=spec_out[s0:s1])
-            spec_host[s0:s1].copy_(spec_out[s0:s1], non_blocking=True)
-            ids_host[s0:s1].copy_(ids, non_blocking=True)
+        streamer.run(xs_host[k], cs_host[k], spec_host, ids_host, nz_host[k])
 
     def barrier():
         if world > 1:

@@ -84,3 +84,33 @@ def conv_ref(x, W, bias, *, stride=1, lrelu=False, inorm=False, ns=0.01, operand
         var = ((y - mu) ** 2).mean(2, keepdim=True)
         y = (y - mu) / torch.sqrt(var + 1e-5)
     return y.float()
+
+
+def conv_cl_to_cl(x, W, bias, *, lrelu=False, inorm=False, ns=0.01, operand='fp16', nb_hint=0, halo_out=1):
+    """zs_conv1d_cl with the channels-last operand output (the staged / TMA-store epilogue); returns fp32 (B, C_out, T)."""
+    B, C_in, T = x.shape
+    C_out, _, k = W.shape
+    dt = torch.float16 if operand == 'fp16' else torch.bfloat16
+    buf, rows, pitch = pack_act(x, k // 2, operand)
+    Wp, m_rows, c_pad = pack_weight(W, dt)
+    bias_p = torch.zeros(m_rows, dtype=torch.float32, device=x.device)
+    bias_p[:C_out] = bias
+    out_rows, out_pitch = round_up(T + 2 * halo_out, 2), round_up(C_out, 8)
+    out = torch.full((B, out_rows, out_pitch), float('nan'), dtype=dt, device=x.device)
+    d = _lib.ConvDesc()
+    d.w, d.m_rows, d.m_valid, d.taps, d.c_in_pad, d.w_taps, d.bank = Wp.data_ptr(), m_rows, C_out, k, c_pad, k, 0
+    d.in_, d.in_rows, d.in_pitch, d.in_row0, d.c_in_valid = buf.data_ptr(), rows, pitch, 0, C_in
+    d.stride, d.B, d.T_out = 1, B, T
+    d.bias, d.spk, d.n_spk, d.lrelu, d.ns, d.inorm = bias_p.data_ptr(), None, 1, int(lrelu), ns, int(inorm)
+    d.res_mode, d.res = 0, None
+    d.act, d.out_mode = 0, 0
+    d.out, d.out_rows, d.out_pitch, d.out_halo, d.out_choff = out.data_ptr(), out_rows, out_pitch, halo_out, 0
+    d.accumulate, d.operand, d.nb_hint = 0, _lib.OPERANDS[operand], nb_hint
+    _lib.check(_lib.lib().zs_conv1d_cl(C.byref(d), stream()))
+    torch.cuda.synchronize()
+    body = out[:, halo_out:halo_out + T, :C_out].float().permute(0, 2, 1)
+    # reflected halo rows
+    for h in range(1, halo_out + 1):
+        assert torch.equal(out[:, halo_out - h, :C_out], out[:, halo_out + h, :C_out])
+        assert torch.equal(out[:, halo_out + T - 1 + h, :C_out], out[:, halo_out + T - 1 - h, :C_out])
+    return body

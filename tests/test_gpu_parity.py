@@ -93,6 +93,20 @@ def test_conv_gemm_tile_shapes_agree():
         assert torch.equal(gh.conv_cl(x, W, b, inorm=True, lrelu=True, nb_hint=nb), base)
 
 
+@pytest.mark.parametrize('B,T,nb', [(7, 64, 3), (50, 16, 12), (9, 48, 5), (300, 32, 0)])
+def test_conv_gemm_rounds_do_not_spill_across_tiles(B, T, nb):
+    """Segments-per-tile that the epilogue's 128-frame store rounds do not divide (regression: a partial round's
+    TMA store box used to overwrite the next tile's segments)."""
+    torch.manual_seed(5)
+    x = torch.randn(B, 64, T, device='cuda')
+    W = torch.randn(128, 64, 3, device='cuda') / 14
+    b = torch.randn(128, device='cuda') * 0.1
+    ref = gh.conv_ref(x, W, b, lrelu=True, inorm=True)
+    for _ in range(3):
+        y = gh.conv_cl_to_cl(x, W, b, lrelu=True, inorm=True, nb_hint=nb)
+        assert (y - ref).abs().max().item() < 2e-3       # fp16 output rounding
+
+
 def test_bottleneck_argmax_bit_exact_with_ties():
     torch.manual_seed(3)
     B, Cn, T8 = 7, 1024, 16
@@ -253,6 +267,24 @@ def test_batching_is_exact_and_segments_independent(full_models):
         assert torch.equal(dec.decode(None, c[b:b + 1], unit_ids=i1)[0], spec[b])
     assert float(spec.min()) > 0.0 and float(spec.max()) < 1.0        # sigmoid output
     assert torch.equal(act.sum(1), torch.ones(B, 16, device='cuda'))    # one unit per frame
+
+
+def test_large_batches_match_small_batches(full_models):
+    """Saturating batches (what bench.py runs) give bit-identical results to 32-segment batches, run after run."""
+    enc, dec, _, _ = full_models
+    B, T = 200, 128
+    x = syn.spectrogram_batch(B, T, 21).cuda()
+    c = syn.speaker_ids(B, 102, 21).cuda()
+    noise = gumbel_from_uniform(syn.gumbel_uniform((B, 16, 1024), 21)).cuda()
+    act, logits, ids = enc.encode(x, noise)
+    spec = dec.decode(None, c, unit_ids=ids)
+    for s0 in range(0, B, 32):
+        a1, l1, i1 = enc.encode(x[s0:s0 + 32].contiguous(), noise[s0:s0 + 32])
+        assert torch.equal(l1, logits[s0:s0 + 32]) and torch.equal(i1, ids[s0:s0 + 32])
+        assert torch.equal(dec.decode(None, c[s0:s0 + 32], unit_ids=i1), spec[s0:s0 + 32])
+    act2, logits2, ids2 = enc.encode(x, noise)
+    assert torch.equal(logits2, logits)
+    assert torch.equal(dec.decode(None, c, unit_ids=ids2), spec)
 
 
 def test_frontend_matches_per_chunk_reference_loop(full_models):

@@ -199,7 +199,12 @@ static int launch_conv(const zs_conv_desc* d, cudaStream_t stream) {
         p.rnd_frames = rf;
         p.rnd_rows = std::min(Tt, rf);
         p.rnd_sub = (Tt + rf - 1) / rf;
-        p.rnd_ns = Tt > rf ? 1 : std::max(1, std::min(rf / Tt, nb));
+        // segments per round must DIVIDE the segments per tile: a round's TMA store box always covers rnd_ns
+        // segments, so a partial last round would spill stale staging rows into the next tile's segments
+        p.rnd_ns = 1;
+        if (Tt <= rf)
+            for (int c = std::min(rf / Tt, nb); c >= 1; --c)
+                if (nb % c == 0) { p.rnd_ns = c; break; }
         if (d->out_choff % 8 || d->out_pitch % 8) return fail(ZS_ERR_ARG, "conv: out_choff %d / out_pitch %d must be multiples of 8", d->out_choff, d->out_pitch);
         if (reinterpret_cast<uintptr_t>(d->out) % 16) return fail(ZS_ERR_ARG, "conv: output pointer must be 16-byte aligned");
         const int T_rows = d->out_halo + (ps ? 2 * d->T_out : d->T_out);

@@ -45,6 +45,79 @@ def write_encodings(path, encodings):
             f.write(' '.join(str(int(e)) for e in row) + '\n')
 
 
+class StreamingResynthesizer:
+    """Host-to-host encode -> decode over many 128-frame segments with copies overlapped with compute.
+
+    The per-chunk reference loop pays one H2D, one launch train and one D2H *sync* per segment
+    (convert.py:70-76, trainer.py:221).  Here segments go through in micro-batches on three CUDA streams:
+    H2D of micro-batch i+1 and D2H of micro-batch i-1 run on the two copy engines while micro-batch i computes.
+    Host tensors must be pinned for the copies to be asynchronous."""
+
+    def __init__(self, encoder: Encoder, decoder: Decoder, micro_batch=128, n_buffers=3, device='cuda'):
+        self.enc, self.dec = encoder, decoder
+        self.mb, self.nbuf = micro_batch, n_buffers
+        self.device = torch.device(device)
+        self.s_in, self.s_cmp, self.s_out = (torch.cuda.Stream(self.device) for _ in range(3))
+        self._bufs = None
+
+    def _buffers(self, T, with_noise):
+        key = (T, with_noise)
+        if self._bufs is None or self._bufs[0] != key:
+            mb, dev, enc = self.mb, self.device, self.enc
+            T8 = Encoder.t8(T)
+            sets = []
+            for _ in range(self.nbuf):
+                sets.append(dict(
+                    x=torch.empty(mb, enc.c_in, T, device=dev), c=torch.empty(mb, dtype=torch.int64, device=dev),
+                    noise=torch.empty(enc.noise_shape(mb, T), device=dev) if with_noise else None,
+                    spec=torch.empty(mb, self.dec.c_out, 8 * T8, device=dev),
+                    ids=torch.empty(mb, T8, dtype=torch.int32, device=dev),
+                    loaded=torch.cuda.Event(), computed=torch.cuda.Event(), drained=torch.cuda.Event()))
+            self._bufs = (key, sets)
+        return self._bufs[1]
+
+    @torch.no_grad()
+    def run(self, x_host, c_host, spec_host, ids_host=None, noise_host=None):
+        """x_host (S, c_in, T) fp32, c_host (S,) int64, optional noise_host (S, T8, enc_size) -> spec_host (S, c_out, T'),
+        ids_host (S, T8) int32.  Returns after everything has landed in the host tensors."""
+        S, _, T = x_host.shape
+        sets = self._buffers(T, noise_host is not None)
+        cur = torch.cuda.current_stream(self.device)
+        for st in (self.s_in, self.s_cmp, self.s_out):
+            st.wait_stream(cur)
+        n_mb = (S + self.mb - 1) // self.mb
+        for i in range(n_mb):
+            s0, s1 = i * self.mb, min(S, (i + 1) * self.mb)
+            n = s1 - s0
+            b = sets[i % self.nbuf]
+            with torch.cuda.stream(self.s_in):
+                if i >= self.nbuf:
+                    self.s_in.wait_event(b['computed'])       # the compute that last read this input set is done
+                b['x'][:n].copy_(x_host[s0:s1], non_blocking=True)
+                b['c'][:n].copy_(c_host[s0:s1], non_blocking=True)
+                if noise_host is not None:
+                    b['noise'][:n].copy_(noise_host[s0:s1], non_blocking=True)
+                b['loaded'].record(self.s_in)
+            with torch.cuda.stream(self.s_cmp):
+                self.s_cmp.wait_event(b['loaded'])
+                if i >= self.nbuf:
+                    self.s_cmp.wait_event(b['drained'])       # its previous outputs have left the device
+                noise = b['noise'][:n] if noise_host is not None else None
+                _, _, ids = self.enc.encode(b['x'][:n], noise)
+                self.dec.decode(None, b['c'][:n], unit_ids=ids, out=b['spec'][:n])
+                b['ids'][:n].copy_(ids)
+                b['computed'].record(self.s_cmp)
+            with torch.cuda.stream(self.s_out):
+                self.s_out.wait_event(b['computed'])
+                spec_host[s0:s1].copy_(b['spec'][:n], non_blocking=True)
+                if ids_host is not None:
+                    ids_host[s0:s1].copy_(b['ids'][:n], non_blocking=True)
+                b['drained'].record(self.s_out)
+        cur.wait_stream(self.s_out)
+        cur.wait_stream(self.s_cmp)
+        cur.wait_stream(self.s_in)
+
+
 class AutoencoderPath:
     """The Trainer's inference surface for this path, backed by the B200 modules.
 
