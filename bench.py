@@ -65,7 +65,8 @@ def config(args, n):
 # ------------------------------------------------------------------------------------------------
 # reference arm / CPU baseline: the oracle on host cores
 # ------------------------------------------------------------------------------------------------
-def cpu_run(n_seg, steps, warmup):
+def cpu_run(n_seg, steps, warmup, check=None):
+    """Times the oracle; with `check=(x, c, uniform, ids, spec)` from the CUDA path also returns parity numbers."""
     from zs_b200 import synthetic as syn
     from oracle import ae_oracle as orc
     cores = os.cpu_count()
@@ -83,8 +84,18 @@ def cpu_run(n_seg, steps, warmup):
             orc.decoder_forward(dec_sd, act, c)
             if i >= warmup:
                 times.append(time.perf_counter() - t0)
+        parity = None
+        if check is not None:
+            cx, cc, cu, ids, spec = check
+            o_act, o_logits, o_ids = orc.encoder_forward(enc_sd, cx, cu)
+            ours_act = torch.zeros_like(o_act).scatter_(1, ids.long().unsqueeze(1), 1.0)
+            o_spec = orc.decoder_forward(dec_sd, ours_act, cc)     # same units -> decoder error only
+            parity = {'unit_id_agreement_pct': 100.0 * (ids.long() == o_ids).float().mean().item(),
+                      'spectrogram_rel_rms': ((spec - o_spec).norm() / o_spec.norm()).item(),
+                      'spectrogram_max_abs': (spec - o_spec).abs().max().item(), 'segments_checked': int(cx.shape[0]),
+                      'against': 'oracle/ae_oracle.py (CPU fp32), same weights, same Gumbel noise'}
     t = sum(times) / len(times)
-    return n_seg * FRAMES / t, t, cores
+    return n_seg * FRAMES / t, t, cores, parity
 
 
 def run_reference(args):
@@ -95,7 +106,7 @@ def run_reference(args):
     n_seg = min(args.segments, args.cpu_sample)
     steps = max(1, min(args.steps, 3))
     warm = 1
-    fps, t, cores = cpu_run(n_seg, steps, warm)
+    fps, t, cores, _ = cpu_run(n_seg, steps, warm)
     line = {'impl': 'reference', 'metric': METRIC, 'value': fps, 'unit': 'frames/s', 'n_gpus': args.gpus,
             'steps': steps, 'warmup': warm, 'ms_per_step': t * 1e3, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': config(args, args.gpus),
@@ -281,8 +292,17 @@ def run_ours(args):
                          'gru_ms_per_step': gru_ms, 'other_ms_per_step': other_ms},
             'whole_path_tflops': value / world * MFLOP_PER_FRAME * 1e6 / 1e12,
         }
+        # large-batch result must equal the 32-segment-batch result bit for bit (segments are independent)
+        step_device(0)
+        a32, _, i32 = enc.encode(xs[0][:32], nz[0][:32])
+        s32 = dec.decode(None, cs[0][:32], unit_ids=i32)
+        line['self_check'] = {'batch_invariant': bool(torch.equal(s32, spec_out[:32]) and torch.equal(i32, ids_out[:32]))}
         if not args.no_cpu_baseline and world == 1:
-            fps, t, cores = cpu_run(min(S, args.cpu_sample), 2, 1)
+            n_chk = min(S, 8)
+            u_chk = syn.gumbel_uniform((S, 16, ENC_SIZE), 100 * rank)[:n_chk]
+            check = (xs_host[0][:n_chk].clone(), cs_host[0][:n_chk].clone(), u_chk, ids_out[:n_chk].cpu(), spec_out[:n_chk].cpu())
+            fps, t, cores, parity = cpu_run(min(S, args.cpu_sample), 2, 1, check)
+            line['parity'] = parity
             line['cpu_baseline'] = {'value': fps, 'unit': 'frames/s', 'cores': cores, 'kind': 'port',
                                     'sample': f'{min(S, args.cpu_sample)} segments x {FRAMES} frames, 2 timed passes of '
                                               'oracle/ae_oracle.py (torch fp32, all host cores)'}
