@@ -101,50 +101,60 @@ def gumbel_hard(logits_last, uniform):
     y = F.softmax((logits_last + gumbel_noise(uniform)) / GUMBEL_TAU, dim=-1)
     ind = y.max(dim=-1)[1]
     hard = torch.zeros_like(y).scatter_(-1, ind.unsqueeze(-1), 1.0)
-    return (hard - y) + y, ind
+    return (hard - y).detach() + y, ind        # :110 straight-through: value = hard, gradient = d softmax
 
 
 # ----------------------------------------------------------------------------
 # Encoder: model/model.py:416-489
 # ----------------------------------------------------------------------------
-def _enc_conv_block(x, sd, names, strides, ns, seg_len, res=True):
+def _drop(out, keep, dp):
+    """nn.Dropout in train mode with an explicit keep-mask (None = eval / p = 0)."""
+    return out if keep is None else out * keep / (1.0 - dp)
+
+
+def _enc_conv_block(x, sd, names, strides, ns, seg_len, res=True, keep=None, dp=0.5):
     out = x
     for n, s in zip(names, strides):                         # :418-420
         out = F.leaky_relu(conv_same(out, sd[n + '.weight'], sd[n + '.bias'], seg_len, s), ns)
-    out = instance_norm(out)                                  # :421-422 (dropout: eval = identity)
+    out = _drop(instance_norm(out), keep, dp)                 # :421-422 norm_layers = [InstanceNorm, Dropout]
     if res:                                                   # :423-426
         xp = F.pad(x, (0, x.shape[2] % 2), mode=_pad_mode(seg_len))
         out = F.avg_pool1d(xp, 2) + out
     return out
 
 
-def _enc_dense_block(x, sd, names, ns):
+def _enc_dense_block(x, sd, names, ns, keep=None, dp=0.5):
     out = x
     for n in names:                                           # :431-433
         out = F.leaky_relu(frame_linear(out, sd[n + '.weight'], sd[n + '.bias']), ns)
-    return instance_norm(out) + x                             # :434-437
+    return _drop(instance_norm(out), keep, dp) + x            # :434-437
 
 
-def encoder_trunk(sd, x, ns=0.01, seg_len=128):
-    """Everything up to (and including) the final Linear: model/model.py:440-455 + linear."""
+def encoder_trunk(sd, x, ns=0.01, seg_len=128, keep_masks=None, dp=0.5):
+    """Everything up to (and including) the final Linear: model/model.py:440-455 + linear.
+
+    `keep_masks`: the six Dropout keep-masks (drop1..drop6, 0/1 tensors shaped like the block outputs) of a
+    train-mode call; None = eval mode."""
+    km = keep_masks if keep_masks is not None else [None] * 6
     bank = [conv_same(x, sd[f'conv1s.{i}.weight'], sd[f'conv1s.{i}.bias'], seg_len) for i in range(7)]
     out = F.leaky_relu(torch.cat(bank + [x], dim=1), ns)      # :445-446
-    out = _enc_conv_block(out, sd, ['conv2'], [1], ns, seg_len, res=False)
-    out = _enc_conv_block(out, sd, ['conv3', 'conv4'], [1, 2], ns, seg_len)
-    out = _enc_conv_block(out, sd, ['conv5', 'conv6'], [1, 2], ns, seg_len)
-    out = _enc_conv_block(out, sd, ['conv7', 'conv8'], [1, 2], ns, seg_len)
-    out = _enc_dense_block(out, sd, ['dense1', 'dense2'], ns)
-    out = _enc_dense_block(out, sd, ['dense3', 'dense4'], ns)
+    out = _enc_conv_block(out, sd, ['conv2'], [1], ns, seg_len, res=False, keep=km[0], dp=dp)
+    out = _enc_conv_block(out, sd, ['conv3', 'conv4'], [1, 2], ns, seg_len, keep=km[1], dp=dp)
+    out = _enc_conv_block(out, sd, ['conv5', 'conv6'], [1, 2], ns, seg_len, keep=km[2], dp=dp)
+    out = _enc_conv_block(out, sd, ['conv7', 'conv8'], [1, 2], ns, seg_len, keep=km[3], dp=dp)
+    out = _enc_dense_block(out, sd, ['dense1', 'dense2'], ns, keep=km[4], dp=dp)
+    out = _enc_dense_block(out, sd, ['dense3', 'dense4'], ns, keep=km[5], dp=dp)
     out = torch.cat([out, bi_gru(out, sd)], dim=1)            # :454-455
     return frame_linear(out, sd['linear.weight'], sd['linear.bias'])
 
 
-def encoder_forward(sd, x, uniform=None, ns=0.01, seg_len=128, enc_mode='one_hot', enc_size=None):
+def encoder_forward(sd, x, uniform=None, ns=0.01, seg_len=128, enc_mode='one_hot', enc_size=None, keep_masks=None,
+                    dp=0.5):
     """Encoder.forward in eval mode: returns (out_act, out, unit_ids or None).
 
     `uniform` is the torch.rand draw of gumbel_softmax (shape (B,T8,enc) for one_hot,
     (B,T8,enc,2) for multilabel_binary, (B,enc,T8) for gumbel_t)."""
-    logits = encoder_trunk(sd, x, ns, seg_len)
+    logits = encoder_trunk(sd, x, ns, seg_len, keep_masks, dp)
     ids = None
     if enc_mode == 'continues':                               # :457-459
         act = F.leaky_relu(logits, ns)
@@ -213,6 +223,69 @@ def test_step(enc_sd, dec_sd, x, c, uniform, ns=0.01, seg_len=128, enc_mode='one
         else:
             raise NotImplementedError(g_mode)
     return x_dec, act, logits, ids
+
+
+# ----------------------------------------------------------------------------
+# pretrain_AE step: trainer.py:321-332, utils.py:50-55
+# ----------------------------------------------------------------------------
+def dropout_mask_shapes(B, T, c_h2=512):
+    """Shapes of the six Dropout inputs of Encoder.forward (drop1..drop6), model/model.py:447-453."""
+    t = [T, (T + 1) // 2, ((T + 1) // 2 + 1) // 2, (((T + 1) // 2 + 1) // 2 + 1) // 2]
+    return [(B, c_h2, t[0]), (B, c_h2, t[1]), (B, c_h2, t[2]), (B, c_h2, t[3]), (B, c_h2, t[3]), (B, c_h2, t[3])]
+
+
+def ae_loss_and_grads(enc_sd, dec_sd, x, c, uniform, keep_masks=None, dp=0.5, ns=0.01, seg_len=128,
+                      enc_mode='one_hot'):
+    """encode_step -> decode_step -> L1 loss -> backward (trainer.py:325-329) by autograd over this
+    restatement.  Returns (loss, enc_grads, dec_grads, x_dec, unit_ids); grads are dicts keyed like the
+    state_dicts (every parameter of both networks receives a gradient)."""
+    enc_p = {k: v.detach().clone().requires_grad_(True) for k, v in enc_sd.items()}
+    dec_p = {k: v.detach().clone().requires_grad_(True) for k, v in dec_sd.items()}
+    act, _, ids = encoder_forward(enc_p, x, uniform, ns, seg_len, enc_mode, keep_masks=keep_masks, dp=dp)
+    x_dec = decoder_forward(dec_p, act, c, ns, seg_len)
+    loss = torch.mean(torch.abs(x_dec - x))                   # trainer.py:327
+    loss.backward()                                           # :329
+    g_enc = {k: v.grad if v.grad is not None else torch.zeros_like(v) for k, v in enc_p.items()}
+    g_dec = {k: v.grad if v.grad is not None else torch.zeros_like(v) for k, v in dec_p.items()}
+    return loss.detach(), g_enc, g_dec, x_dec.detach(), ids
+
+
+def clip_grad_norm(grads, max_norm):
+    """nn.utils.clip_grad_norm_ over ONE network (utils.py:53-55): returns (total_norm, scaled grads)."""
+    total = torch.sqrt(sum((g.double() ** 2).sum() for g in grads.values())).float()
+    coef = torch.clamp(max_norm / (total + 1e-6), max=1.0)
+    return total, {k: g * coef for k, g in grads.items()}
+
+
+def adam_step(params, grads, state, lr=1e-4, betas=(0.5, 0.9), eps=1e-8):
+    """torch.optim.Adam (trainer.py:64-66: lr, betas=(0.5, 0.9), no weight decay, no amsgrad), one step in place
+    on `params` / `state` ({'step': int, 'm': {...}, 'v': {...}})."""
+    state['step'] = state.get('step', 0) + 1
+    t = state['step']
+    m, v = state.setdefault('m', {}), state.setdefault('v', {})
+    b1, b2 = betas
+    for k, p in params.items():
+        g = grads[k]
+        m[k] = b1 * m.get(k, torch.zeros_like(p)) + (1 - b1) * g
+        v[k] = b2 * v.get(k, torch.zeros_like(p)) + (1 - b2) * g * g
+        denom = (v[k].sqrt() / math.sqrt(1 - b2 ** t)) + eps
+        p.sub_((lr / (1 - b1 ** t)) * m[k] / denom)
+    return params
+
+
+def pretrain_ae_step(enc_sd, dec_sd, opt_state, x, c, uniform, keep_masks=None, dp=0.5, ns=0.01, seg_len=128,
+                     enc_mode='one_hot', lr=1e-4, max_grad_norm=5.0):
+    """One iteration of Trainer.train(mode='pretrain_AE'): trainer.py:321-332.  Updates enc_sd / dec_sd in place
+    (one Adam over both networks' parameters, per-network clipping) and returns (loss, norm_enc, norm_dec)."""
+    loss, g_enc, g_dec, _, _ = ae_loss_and_grads(enc_sd, dec_sd, x, c, uniform, keep_masks, dp, ns, seg_len, enc_mode)
+    n_enc, g_enc = clip_grad_norm(g_enc, max_grad_norm)       # utils.py:53-55, one norm per network
+    n_dec, g_dec = clip_grad_norm(g_dec, max_grad_norm)
+    params = {('e', k): v for k, v in enc_sd.items()}
+    params.update({('d', k): v for k, v in dec_sd.items()})
+    grads = {('e', k): v for k, v in g_enc.items()}
+    grads.update({('d', k): v for k, v in g_dec.items()})
+    adam_step(params, grads, opt_state, lr=lr)
+    return loss, n_enc, n_dec
 
 
 # ----------------------------------------------------------------------------

@@ -79,3 +79,66 @@ def test_segment_plan_matches_reference_encode():
 def test_format_encodings():
     enc = np.array([[0.0, 1.0, 0.0], [1.0, 0.0, 0.0]], dtype=np.float32)
     assert orc.format_encodings(enc) == '0 1 0\n1 0 0\n'
+
+
+# ---- pretrain_AE step (trainer.py:321-332): oracle autograd / clip / Adam vs the live reference ----------------
+TRAIN_CASES = sorted(f[:-4] for f in os.listdir(GOLDEN) if f.startswith('train_') and f.endswith('.npz'))
+
+
+def load_train_golden(name):
+    g = dict(np.load(os.path.join(GOLDEN, name + '.npz')))
+    g['meta'] = json.loads(bytes(g['meta']).decode())
+    return g
+
+
+def train_inputs(g):
+    """(enc_sd, dec_sd, x, c, uniform, keep_masks) of a training fixture, re-derived from its seeds + stored draws."""
+    m = g['meta']
+    enc_sd, dec_sd = _weights(m)
+    x = syn.spectrogram_batch(m['B'], m['T'], m['seed'], c_in=m['c_in'])
+    c = syn.speaker_ids(m['B'], m['n_spk'], m['seed'])
+    keep = None
+    if m['dp'] > 0:
+        keep = []
+        for i, shp in enumerate(orc.dropout_mask_shapes(m['B'], m['T'], m['c_h'][1])):
+            n = int(np.prod(shp))
+            keep.append(torch.from_numpy(np.unpackbits(g[f'keep{i}'])[:n].astype(np.float32)).view(shp))
+    return enc_sd, dec_sd, x, c, torch.from_numpy(g['uniform']), keep
+
+
+def sample_idx(numel, n=512):
+    step = max(1, numel // n)
+    return np.arange(0, numel, step)[:n]
+
+
+@pytest.mark.parametrize('name', TRAIN_CASES)
+def test_oracle_train_step_matches_reference(name):
+    g = load_train_golden(name)
+    m = g['meta']
+    torch.set_num_threads(os.cpu_count())
+    enc_sd, dec_sd, x, c, u, keep = train_inputs(g)
+    loss, ge, gd, _, ids = orc.ae_loss_and_grads(enc_sd, dec_sd, x, c, u, keep, m['dp'], m['ns'], m['seg_len'])
+    assert abs(loss.item() - float(g['loss'])) < 1e-6
+    assert np.array_equal(ids.numpy().astype(np.int32), g['ids'])
+    for net, grads in (('enc', ge), ('dec', gd)):
+        for k, gr in grads.items():
+            ref_n = float(g[f'gn:{net}:{k}'])
+            assert abs(gr.norm().item() - ref_n) <= 2e-3 * ref_n + 1e-9, (net, k)
+            ref_s = g[f'g:{net}:{k}']
+            got = gr.reshape(-1)[sample_idx(gr.numel())].numpy()
+            assert np.abs(got - ref_s).max() <= 2e-3 * np.abs(ref_s).max() + 1e-10, (net, k)
+    # per-network clipping + one Adam step over both networks
+    n_enc, _ = orc.clip_grad_norm(ge, m['max_grad_norm'])
+    n_dec, _ = orc.clip_grad_norm(gd, m['max_grad_norm'])
+    assert abs(n_enc.item() - float(g['norm_enc'])) < 1e-3 * float(g['norm_enc'])
+    assert abs(n_dec.item() - float(g['norm_dec'])) < 1e-3 * float(g['norm_dec'])
+    state = {}
+    orc.pretrain_ae_step(enc_sd, dec_sd, state, x, c, u, keep, m['dp'], m['ns'], m['seg_len'], lr=m['lr'],
+                         max_grad_norm=m['max_grad_norm'])
+    for net, sd in (('enc', enc_sd), ('dec', dec_sd)):
+        for k, p in sd.items():
+            got = p.reshape(-1)[sample_idx(p.numel())].numpy()
+            # the first Adam step moves a weight by lr * g / (|g| + eps): where |g| is within ~100 eps of zero the
+            # update direction is summation-order noise, so those elements only have to stay within one lr
+            tol = np.where(np.abs(g[f'g:{net}:{k}']) > 1e-6, 2e-5, 1.1 * m['lr'])
+            assert (np.abs(got - g[f'p:{net}:{k}']) <= tol).all(), f'{net}:{k}'
