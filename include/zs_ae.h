@@ -52,6 +52,7 @@ typedef struct {
     int32_t seg_len;      /* hyper-parameter; reflect padding iff >= 64 (model/model.py:38). < 64 is rejected */
     int32_t operand;      /* ZS_OPERAND_* */
     float ns;             /* leaky-relu negative slope */
+    int32_t train;        /* 1: also pack the data-gradient operands (zs_encoder_forward_train / _backward); fp16, one_hot only */
 } zs_encoder_cfg;
 
 /* fp32 parameter pointers in state_dict order (SURVEY.md Appendix B / model/model.py:373-393) */
@@ -80,6 +81,8 @@ typedef struct {
     int32_t output_mask;  /* 1: tanh (g_mode targeted_residual), 0: sigmoid */
     int32_t operand;
     float ns;
+    int32_t train;        /* 1: training handle - speaker embeddings are added to the activations instead of being folded
+                           * into bias tables (their gradients need them), data-gradient operands are packed too */
 } zs_decoder_cfg;
 
 typedef struct {
@@ -143,6 +146,59 @@ int zs_encoder_forward(zs_encoder* h, const float* x, int B, int T, const float*
 int zs_decoder_forward(zs_decoder* h, const float* enc_act, const int32_t* unit_ids, const int64_t* spk,
                        int B, int T8, float* spec, int accumulate,
                        void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- pretrain_AE step (trainer.py:321-332: encode_step, decode_step, L1 loss, backward, clip, Adam) -------------
+ *
+ * Training handles are packed with cfg.train = 1 and re-packed from the updated fp32 parameters after every
+ * optimiser step (zs_*_repack: same allocations, no cudaMalloc).  Activation gradients travel as fp16 buffers
+ * multiplied by `loss_scale` (a power of two; 2^15 * B is a good start); weight gradients are written UNSCALED in fp32
+ * into caller-owned buffers shaped like the parameters (`zs_*_weights` used as a table of gradient pointers) and are
+ * ACCUMULATED (+=, like autograd) - zero them before a step.  An fp16 overflow surfaces as a non-finite gradient
+ * norm: zs_adam_step then skips the update and raises *skipped so the caller can halve the scale.
+ * T must be 64 or 128 (seg_len; the weight-gradient GEMM reduces over 64-row boxes). */
+int zs_encoder_repack(zs_encoder* h, const zs_encoder_weights* w, void* stream);
+int zs_decoder_repack(zs_decoder* h, const zs_decoder_weights* w, void* stream);
+size_t zs_encoder_train_workspace_bytes(const zs_encoder* h, int B, int T);
+size_t zs_decoder_train_workspace_bytes(const zs_decoder* h, int B, int T8);
+
+/* Encoder.forward in TRAIN mode (model/model.py:440-489 with the six nn.Dropout active).  Same outputs as
+ * zs_encoder_forward; the workspace keeps what the backward needs and must stay untouched until it ran.
+ *   dropout_p     Encoder(dp=...); 0 disables dropout
+ *   dropout_seed  counter-based masks: keep(seed, layer, b, c, t), reproduced by the backward
+ *   keep_masks    NULL, or six device pointers to explicit (B, c_h2, T_l) byte masks in the reference's layout
+ *                 (1 = keep) - lets a test replay the reference's own bernoulli draws */
+int zs_encoder_forward_train(zs_encoder* h, const float* x, int B, int T, const float* gumbel_noise,
+                             float dropout_p, uint64_t dropout_seed, const uint8_t* const* keep_masks,
+                             float* logits, float* act, int32_t* unit_ids,
+                             void* workspace, size_t workspace_bytes, void* stream);
+/* backward of the above: d_act (B, enc_size, T8) fp32 = (dLoss/d out_act) * d_act_scale; the same
+ * gumbel_noise / logits / dropout arguments as the forward call; gradients accumulate into `grads`. */
+int zs_encoder_backward(zs_encoder* h, const float* d_act, float d_act_scale, const float* gumbel_noise,
+                        const float* logits, int B, int T, float dropout_p, uint64_t dropout_seed,
+                        const uint8_t* const* keep_masks, float loss_scale, const zs_encoder_weights* grads,
+                        void* workspace, size_t workspace_bytes, void* stream);
+
+/* Decoder.forward in train mode (dense enc_act input so that it can take a gradient). */
+int zs_decoder_forward_train(zs_decoder* h, const float* enc_act, const int64_t* spk, int B, int T8, float* spec,
+                             void* workspace, size_t workspace_bytes, void* stream);
+/* backward: either `target` (B, c_out, T) is given - the L1 loss of trainer.py:327 is fused: *loss += mean|spec - target|
+ * (zero it first) - or `d_spec` (B, c_out, T) fp32 = dLoss/dspec (unscaled).  d_act (B, c_in, T8) fp32 receives
+ * (dLoss/d enc_act) * loss_scale. */
+int zs_decoder_backward(zs_decoder* h, const float* spec, const float* target, const float* d_spec,
+                        const int64_t* spk, int B, int T8, float loss_scale, float* loss,
+                        const zs_decoder_weights* grads, float* d_act,
+                        void* workspace, size_t workspace_bytes, void* stream);
+
+/* sum of squares of a flat fp32 gradient buffer: *out += sum g^2 (zero it first) */
+int zs_grad_sqnorm(const float* g, size_t n, float* out, void* stream);
+/* nn.utils.clip_grad_norm_(max_norm) over ONE network (utils.py:53-55) fused with torch.optim.Adam's update
+ * (trainer.py:64-66: lr, betas (0.5, 0.9), eps 1e-8, no weight decay): `sqnorm` is that network's squared
+ * gradient norm (device scalar) BEFORE `grad_mult`, a factor applied to every gradient first (1/world_size after a
+ * summing all-reduce); step = 1-based step count for the bias corrections.  When the norm is not
+ * finite nothing is updated and *skipped (device int, may be NULL) is set to 1. */
+int zs_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, size_t n,
+                 const float* sqnorm, float grad_mult, float max_norm, float lr, float beta1, float beta2, float eps,
+                 int step, int* skipped, void* stream);
 
 /* ---- measurement hooks (bench.py) --------------------------------------------------
  * Kernel classes: 0 = conv/linear implicit GEMM (tcgen05), 1 = GRU recurrence, 2 = everything else.
@@ -209,6 +265,20 @@ int zs_pack_nct(const float* x, int B, int C, int T, void* out, int rows, int pi
 int zs_gru_recurrence(const float* gx, const float* w_hh, const float* b_hh, int B, int T, int H,
                       void* out, int out_rows, int out_pitch, int out_halo, int out_choff,
                       int operand, int impl, void* stream);
+
+/* Weight-gradient GEMM of one conv / linear layer on channels-last fp16 buffers (tcgen05, MN-major operands):
+ *   grad[co][ci_off + ci][tap0 + j] += scale * sum_{b,t} dy[b][dy_row0 + t][dy_ch0 + co] * x[b][x_row0 + stride*t + j][x_ch0 + ci]
+ * for j < taps; grad is (c_out, c_in_total, k) fp32.  T in {8,16,32,64,128,...}: a power of two, or a multiple of 64.
+ * ps_c > 0: dy channel m = r*ps_c + c stands for conv output channel 2c + r. */
+typedef struct {
+    const void* dy; int32_t dy_rows, dy_pitch, dy_channels, dy_ch0, dy_row0, c_out;
+    const void* x; int32_t x_rows, x_pitch, x_channels, x_ch0, x_row0, c_in, stride;
+    int32_t B, T, taps;
+    float* grad; int32_t c_in_total, ci_off, k, tap0;
+    int32_t ps_c;
+    float scale;
+} zs_wgrad_desc;
+int zs_wgrad_cl(const zs_wgrad_desc* d, void* stream);
 
 #ifdef __cplusplus
 }

@@ -13,7 +13,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, 'csrc')
 SO_PATH = os.path.join(_HERE, 'libzsae.so')
 HEADER = os.path.join(os.path.dirname(_HERE), 'include', 'zs_ae.h')
-_SOURCES = ['zs_ae.cu', 'conv_gemm.cuh', 'kernels.cuh', 'gru_cluster.cuh', 'ptx.cuh']
+_SOURCES = ['zs_ae.cu', 'conv_gemm.cuh', 'kernels.cuh', 'gru_cluster.cuh', 'ptx.cuh', 'train_kernels.cuh',
+            'wgrad_gemm.cuh', 'zs_train.cuh']
 
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-Xcompiler', '-fPIC', '-shared']
@@ -49,7 +50,7 @@ def build(force=False, verbose=False):
 class EncoderCfg(C.Structure):
     _fields_ = [('c_in', C.c_int32), ('c_h1', C.c_int32), ('c_h2', C.c_int32), ('c_h3', C.c_int32),
                 ('enc_size', C.c_int32), ('enc_mode', C.c_int32), ('seg_len', C.c_int32), ('operand', C.c_int32),
-                ('ns', C.c_float)]
+                ('ns', C.c_float), ('train', C.c_int32)]
 
 
 class EncoderWeights(C.Structure):
@@ -61,7 +62,8 @@ class EncoderWeights(C.Structure):
 
 class DecoderCfg(C.Structure):
     _fields_ = [('c_in', C.c_int32), ('c_out', C.c_int32), ('c_h', C.c_int32), ('c_a', C.c_int32),
-                ('seg_len', C.c_int32), ('output_mask', C.c_int32), ('operand', C.c_int32), ('ns', C.c_float)]
+                ('seg_len', C.c_int32), ('output_mask', C.c_int32), ('operand', C.c_int32), ('ns', C.c_float),
+                ('train', C.c_int32)]
 
 
 class DecoderWeights(C.Structure):
@@ -82,6 +84,16 @@ class ConvDesc(C.Structure):
                 ('res_pitch', C.c_int32), ('res_halo', C.c_int32), ('act', C.c_int32), ('out_mode', C.c_int32),
                 ('out', C.c_void_p), ('out_rows', C.c_int32), ('out_pitch', C.c_int32), ('out_halo', C.c_int32),
                 ('out_choff', C.c_int32), ('accumulate', C.c_int32), ('operand', C.c_int32), ('nb_hint', C.c_int32)]
+
+
+class WgradDesc(C.Structure):
+    _fields_ = [('dy', C.c_void_p), ('dy_rows', C.c_int32), ('dy_pitch', C.c_int32), ('dy_channels', C.c_int32),
+                ('dy_ch0', C.c_int32), ('dy_row0', C.c_int32), ('c_out', C.c_int32),
+                ('x', C.c_void_p), ('x_rows', C.c_int32), ('x_pitch', C.c_int32), ('x_channels', C.c_int32),
+                ('x_ch0', C.c_int32), ('x_row0', C.c_int32), ('c_in', C.c_int32), ('stride', C.c_int32),
+                ('B', C.c_int32), ('T', C.c_int32), ('taps', C.c_int32),
+                ('grad', C.c_void_p), ('c_in_total', C.c_int32), ('ci_off', C.c_int32), ('k', C.c_int32),
+                ('tap0', C.c_int32), ('ps_c', C.c_int32), ('scale', C.c_float)]
 
 
 # every symbol include/zs_ae.h declares: name -> (restype, argtypes)
@@ -105,6 +117,22 @@ SYMBOLS = {
     'zs_conv1d_cl': (_i, [C.POINTER(ConvDesc), _vp]),
     'zs_pack_nct': (_i, [_vp, _i, _i, _i, _vp, _i, _i, _i, _i, _i, C.c_float, _i, _i, _vp]),
     'zs_gru_recurrence': (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    # pretrain_AE step
+    'zs_encoder_repack': (_i, [_vp, C.POINTER(EncoderWeights), _vp]),
+    'zs_decoder_repack': (_i, [_vp, C.POINTER(DecoderWeights), _vp]),
+    'zs_encoder_train_workspace_bytes': (_sz, [_vp, _i, _i]),
+    'zs_decoder_train_workspace_bytes': (_sz, [_vp, _i, _i]),
+    'zs_encoder_forward_train': (_i, [_vp, _vp, _i, _i, _vp, C.c_float, C.c_uint64, C.POINTER(_vp), _vp, _vp, _vp,
+                                      _vp, _sz, _vp]),
+    'zs_encoder_backward': (_i, [_vp, _vp, C.c_float, _vp, _vp, _i, _i, C.c_float, C.c_uint64, C.POINTER(_vp),
+                                 C.c_float, C.POINTER(EncoderWeights), _vp, _sz, _vp]),
+    'zs_decoder_forward_train': (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _sz, _vp]),
+    'zs_decoder_backward': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, C.c_float, _vp, C.POINTER(DecoderWeights), _vp,
+                                 _vp, _sz, _vp]),
+    'zs_grad_sqnorm': (_i, [_vp, _sz, _vp, _vp]),
+    'zs_adam_step': (_i, [_vp, _vp, _vp, _vp, _sz, _vp, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
+                          C.c_float, _i, _vp, _vp]),
+    'zs_wgrad_cl': (_i, [C.POINTER(WgradDesc), _vp]),
 }
 
 _LIB = None

@@ -63,6 +63,12 @@ struct alignas(64) GemmParams {
     int out_rows, out_pitch, out_halo, out_choff, accumulate;
     uint32_t idesc;
     int debug;   // timing experiments (results wrong): 1 = no TMA loads, 2 = no MMA issue, 4 = no epilogue stores/loads
+    // training extras
+    float* stats;             // InstanceNorm (mean, rstd) per (segment, channel): [B][bias_stride][2], or null
+    const float* post_emb;    // added after everything: post_emb[spk[b]][out channel] (speaker embedding of the NEXT layer's input)
+    const long long* post_spk;
+    int post_pitch, post_n;
+    int no_sat;               // gradient outputs: let fp16 overflow to inf (the loss-scale logic detects it) instead of clamping
 };
 
 template <typename OT>
@@ -97,9 +103,15 @@ __device__ __forceinline__ float tanh_f(float v) {
 // ---- epilogue building blocks ---------------------------------------------------------------------
 // One thread = one output channel = one TMEM lane; the frames of a segment are that lane's columns.
 
-struct ChanNorm {      // y = act(lrelu(acc + bias)) * scale + shift   (InstanceNorm folded into scale/shift)
-    float bias, scale, shift;
+struct ChanNorm {      // y = act(lrelu(acc + bias)) * scale + shift (+ residual) + post   (InstanceNorm folded into scale/shift)
+    float bias, scale, shift, post;
 };
+template <typename OT>
+__device__ __forceinline__ OT float_to_ot_nosat(float v);
+template <>
+__device__ __forceinline__ __half float_to_ot_nosat<__half>(float v) { return __float2half_rn(v); }
+template <>
+__device__ __forceinline__ __nv_bfloat16 float_to_ot_nosat<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
 
 // InstanceNorm statistics of one (segment, channel) in ONE pass over TMEM: sums are taken relative to the
 // first frame's value so the variance does not cancel catastrophically.
@@ -181,7 +193,8 @@ __device__ __forceinline__ void frames_to_staging(const GemmParams& p, uint32_t 
             if (lrelu) x = fmaxf(x, x * ns);
             x = fmaf(x, cn.scale, cn.shift);
             if (RES != RES_NONE) x += r[i];
-            y[i] = float_to_ot<OT>(x);
+            x += cn.post;
+            y[i] = p.no_sat ? float_to_ot_nosat<OT>(x) : float_to_ot<OT>(x);
         }
         OT* sp = stg + (c0 - f_lo) * (FSTEP * STG_PITCH);
 #pragma unroll
@@ -399,11 +412,20 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
                 }
                 cn.scale = 1.f;
                 cn.shift = 0.f;
+                cn.post = 0.f;
                 if (p.inorm) {
                     float mean, rstd;
                     chan_stats(t_seg, T, cn.bias, lrelu, ns, mean, rstd);
                     cn.scale = rstd;
                     cn.shift = -mean * rstd;
+                    if (p.stats != nullptr && ch_ok)
+                        *reinterpret_cast<float2*>(p.stats + (static_cast<size_t>(b) * p.bias_stride + ch) * 2) = make_float2(mean, rstd);
+                }
+                if (p.post_emb != nullptr) {
+                    long long sp = p.post_spk[b];
+                    sp = sp < 0 ? 0 : (sp >= p.post_n ? p.post_n - 1 : sp);
+                    const int oc = p.out_mode == OUT_PS ? (mt * 64 + (row & 63)) : ch;
+                    if (oc < p.post_pitch) cn.post = p.post_emb[static_cast<size_t>(sp) * p.post_pitch + oc];
                 }
                 return cn;
             };

@@ -104,6 +104,7 @@ struct GruParams {
     void* out;              // operand type [B][out_rows][out_pitch]
     int B, T, H, out_rows, out_pitch, out_halo, out_choff, fmt, debug;
     long long* dbg;        // debug bit 3: per-step clock64 stamps of cluster 0 / CTA 0 ([T][8])
+    void* gates;           // training: r, z, n, hn = W_hn h + b_hn per step, operand type [B][T][2][4][H]; null = not saved
 };
 
 template <typename OT>
@@ -267,6 +268,10 @@ __global__ void __launch_bounds__(GRU_THREADS, 1) gru_cluster_kernel(const GruPa
                 const float n = tanh_f(ot_to_float<OT>(gn[i]) + r * (hn[i] + b_n));
                 h[i] = (1.f - z) * n + z * h[i];
                 const OT y = float_to_ot<OT>(h[i]);
+                if (p.gates != nullptr && seq0 + i < p.B) {
+                    OT* g = reinterpret_cast<OT*>(p.gates) + ((static_cast<size_t>(seq0 + i) * p.T + tt) * 2 + dir) * 4 * H + unit;
+                    g[0] = float_to_ot<OT>(r); g[H] = float_to_ot<OT>(z); g[2 * H] = float_to_ot<OT>(n); g[3 * H] = float_to_ot<OT>(hn[i] + b_n);
+                }
                 const int s = 8 * hi + i;      // row of the state tile
                 *reinterpret_cast<OT*>(hnext + s * 128 + ((((u_loc >> 3) ^ (s & 7)) << 4) | ((u_loc & 7) << 1))) = y;
                 const int b = seq0 + i;

@@ -133,7 +133,7 @@ __global__ void bottleneck_misc_kernel(const float* __restrict__ logits, const f
 template <typename OT, int NBG>
 __global__ void gru_simple_kernel(const OT* __restrict__ gx, const float* __restrict__ whhT,
                                   const float* __restrict__ bhh, int B, int T, int H, OT* __restrict__ out,
-                                  int rows, int pitch, int halo, int choff) {
+                                  int rows, int pitch, int halo, int choff, OT* __restrict__ gates) {
     extern __shared__ float s_h[];  // [NBG][H]
     const int dir = blockIdx.y, b0 = blockIdx.x * NBG, j = threadIdx.x;
     const float* W = whhT + static_cast<size_t>(dir) * H * 3 * H;
@@ -172,6 +172,10 @@ __global__ void gru_simple_kernel(const OT* __restrict__ gx, const float* __rest
                 const float n = tanhf(ot_to_float<OT>(g[2 * H + j]) + r * (an[s] + bn));
                 h[s] = (1.f - z) * n + z * h[s];
                 s_h[s * H + j] = h[s];
+                if (gates != nullptr) {   // training: r, z, n, hn per step [B][T][2][4][H]
+                    OT* gs = gates + ((static_cast<size_t>(b) * T + t) * 2 + dir) * 4 * H + j;
+                    gs[0] = float_to_ot<OT>(r); gs[H] = float_to_ot<OT>(z); gs[2 * H] = float_to_ot<OT>(n); gs[3 * H] = float_to_ot<OT>(an[s] + bn);
+                }
                 out[(static_cast<size_t>(b) * rows + halo + t) * pitch + choff + dir * H + j] = float_to_ot<OT>(h[s]);
             }
         }

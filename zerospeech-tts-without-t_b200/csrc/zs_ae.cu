@@ -15,6 +15,8 @@
 #include "conv_gemm.cuh"
 #include "kernels.cuh"
 #include "gru_cluster.cuh"
+#include "train_kernels.cuh"
+#include "wgrad_gemm.cuh"
 
 using namespace zs;
 
@@ -134,7 +136,14 @@ static int make_map(CUtensorMap* m, int operand, void* base, int rank, const cuu
     return ZS_OK;
 }
 
-static int launch_conv(const zs_conv_desc* d, cudaStream_t stream) {
+struct ConvExtras {        // training-path additions to a layer launch (not part of the public descriptor)
+    float* stats = nullptr;
+    const float* post_emb = nullptr;
+    const int64_t* post_spk = nullptr;
+    int post_pitch = 0, post_n = 0, no_sat = 0;
+};
+
+static int launch_conv(const zs_conv_desc* d, cudaStream_t stream, const ConvExtras* ex = nullptr) {
     ZS_TRY(ensure_device());
     if (!d->w || !d->in || !d->out) return fail(ZS_ERR_ARG, "conv: null operand pointer");
     if (d->m_rows % BM || d->m_rows <= 0 || d->m_valid > d->m_rows) return fail(ZS_ERR_ARG, "conv: m_rows %d must be a multiple of 128 >= m_valid %d", d->m_rows, d->m_valid);
@@ -234,6 +243,11 @@ static int launch_conv(const zs_conv_desc* d, cudaStream_t stream) {
     p.out_halo = d->out_halo; p.out_choff = d->out_choff; p.accumulate = d->accumulate;
     p.idesc = umma_idesc_f16(d->operand == ZS_OPERAND_BF16 ? 1 : 0, p.N);
     { const char* dbg = getenv("ZS_GEMM_DEBUG"); p.debug = dbg ? atoi(dbg) : 0; }
+    if (ex) {
+        p.stats = ex->stats; p.post_emb = ex->post_emb; p.post_spk = reinterpret_cast<const long long*>(ex->post_spk);
+        p.post_pitch = ex->post_pitch; p.post_n = ex->post_n > 0 ? ex->post_n : 1; p.no_sat = ex->no_sat;
+        if (p.post_emb && !p.post_spk) return fail(ZS_ERR_ARG, "conv: post-add embedding needs speaker ids");
+    }
 
     const int grid = std::min(m_tiles * n_tiles, g_num_sms);
     const int which = d->operand == ZS_OPERAND_BF16 ? 1 : 0;
@@ -295,16 +309,16 @@ extern "C" int zs_bottleneck_one_hot(const float* logits, const float* noise, in
 }
 
 static int launch_gru(const void* gx, const float* whhT, const float* bhh, int B, int T, int H, void* out, int rows,
-                      int pitch, int halo, int choff, int operand, cudaStream_t st) {
+                      int pitch, int halo, int choff, int operand, cudaStream_t st, void* gates = nullptr) {
     if (H < 1 || H > 1024) return fail(ZS_ERR_ARG, "gru: hidden size %d outside [1, 1024]", H);
     constexpr int NBG = 4;
     dim3 grid((B + NBG - 1) / NBG, 2);
     const size_t smem = static_cast<size_t>(NBG) * H * 4;
     LaunchScope scope(st, KC_GRU, 2.0 * 2 * B * static_cast<double>(T) * 3 * H * H);
     if (operand == ZS_OPERAND_BF16)
-        gru_simple_kernel<__nv_bfloat16, NBG><<<grid, H, smem, st>>>(static_cast<const __nv_bfloat16*>(gx), whhT, bhh, B, T, H, static_cast<__nv_bfloat16*>(out), rows, pitch, halo, choff);
+        gru_simple_kernel<__nv_bfloat16, NBG><<<grid, H, smem, st>>>(static_cast<const __nv_bfloat16*>(gx), whhT, bhh, B, T, H, static_cast<__nv_bfloat16*>(out), rows, pitch, halo, choff, static_cast<__nv_bfloat16*>(gates));
     else
-        gru_simple_kernel<__half, NBG><<<grid, H, smem, st>>>(static_cast<const __half*>(gx), whhT, bhh, B, T, H, static_cast<__half*>(out), rows, pitch, halo, choff);
+        gru_simple_kernel<__half, NBG><<<grid, H, smem, st>>>(static_cast<const __half*>(gx), whhT, bhh, B, T, H, static_cast<__half*>(out), rows, pitch, halo, choff, static_cast<__half*>(gates));
     CUDA_TRY(cudaGetLastError());
     return ZS_OK;
 }
@@ -312,9 +326,10 @@ static int launch_gru(const void* gx, const float* whhT, const float* bhh, int B
 static bool gru_cluster_ok(int H) { return H % GRU_UNITS == 0 && H / GRU_UNITS >= 1 && H / GRU_UNITS <= 8; }
 
 static int launch_gru_cluster(const void* w_img, const float* bhh, const void* gx, int B, int T, int H, void* out, int rows,
-                              int pitch, int halo, int choff, int operand, cudaStream_t st) {
+                              int pitch, int halo, int choff, int operand, cudaStream_t st, void* gates = nullptr) {
     ZS_TRY(ensure_device());
     GruParams p;
+    p.gates = gates;
     p.w_img = w_img; p.bhh = bhh; p.gx = gx; p.out = out; p.B = B; p.T = T; p.H = H;
     p.out_rows = rows; p.out_pitch = pitch; p.out_halo = halo; p.out_choff = choff;
     p.fmt = operand == ZS_OPERAND_BF16 ? 1 : 0;
@@ -420,11 +435,15 @@ struct Layer {          // one GEMM's worth of packed weights
     void* w = nullptr;      // operand type [m_rows][w_taps * c_in_pad]
     float* bias = nullptr;  // [n_tab][m_rows]
     int m_rows = 0, m_valid = 0, taps = 1, w_taps = 1, c_in_pad = 0, c_in_valid = 0, per_spk = 0, ps = 0, n_tab = 1;
+    // training: transposed weights for the data-gradient GEMM, [t_rows][t_taps * t_kpad] fp16 (pack_weight_T_kernel)
+    void* wt = nullptr;
+    int t_rows = 0, t_valid = 0, t_taps = 1, t_kpad = 0, t_kvalid = 0;
 };
 
 struct DevPool {        // owns every device allocation of a handle
     std::vector<void*> ptrs;
     int alloc(void** p, size_t bytes, cudaStream_t st) {
+        if (*p) return ZS_OK;        // re-pack into the existing allocation
         CUDA_TRY(cudaMalloc(p, bytes));
         CUDA_TRY(cudaMemsetAsync(*p, 0, bytes, st));
         ptrs.push_back(*p);
@@ -461,6 +480,24 @@ static int pack_layer(DevPool& pool, Layer& L, int operand, const float* W, cons
     return ZS_OK;
 }
 
+// transposed weights of layer L for its data-gradient GEMM (training handles only).
+// mode 0: stride-1 conv / linear over input channels [0, ci_n); mode 1: stride-2 conv (pixel-shuffle-by-parity rows)
+static int pack_layer_T(DevPool& pool, Layer& L, const float* W, int C_out, int C_in, int k, int ci_n, int mode, int ps_c,
+                        cudaStream_t st) {
+    L.t_valid = mode == 1 ? 2 * ci_n : ci_n;
+    L.t_rows = round_up(L.t_valid, BM);
+    L.t_taps = mode == 1 ? k / 2 + 1 : k;
+    L.t_kpad = round_up(C_out, BK);
+    L.t_kvalid = C_out;
+    if (mode == 1 && ci_n % 64) return fail(ZS_ERR_ARG, "train: a stride-2 layer needs c_in %% 64 == 0 (got %d)", ci_n);
+    const long long k_total = static_cast<long long>(L.t_taps) * L.t_kpad;
+    ZS_TRY(pool.alloc(&L.wt, static_cast<size_t>(L.t_rows) * k_total * 2, st));
+    const long long total = static_cast<long long>(C_out) * ci_n * k;
+    pack_weight_T_kernel<<<static_cast<int>((total + 255) / 256), 256, 0, st>>>(W, static_cast<__half*>(L.wt), C_out, C_in, k, ci_n, k_total, L.t_kpad, mode, ps_c);
+    CUDA_TRY(cudaGetLastError());
+    return ZS_OK;
+}
+
 struct zs_encoder {
     zs_encoder_cfg cfg;
     DevPool pool;
@@ -474,6 +511,7 @@ struct zs_encoder {
     float* bhh = nullptr;   // [2][3H]
     void* whh_img = nullptr;  // cluster-kernel shared-memory images (H % 64 == 0)
     Layer linear;
+    const float* w_hh[2] = {nullptr, nullptr};   // training: the caller's fp32 W_hh (read by the BPTT kernel)
 };
 
 struct zs_decoder {
@@ -489,6 +527,8 @@ struct zs_decoder {
     void* whh_img = nullptr;
     Layer dense5;
     Layer linear;
+    const float* w_hh[2] = {nullptr, nullptr};   // training: the caller's fp32 parameters read directly by kernels
+    const float* emb[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 
 static int pack_gru(DevPool& pool, Layer& ih, float** whhT, float** bhh, void** whh_img, int operand, const float* const* w_ih,
@@ -522,51 +562,77 @@ static int pack_gru(DevPool& pool, Layer& ih, float** whhT, float** bhh, void** 
     return ZS_OK;
 }
 
+// W_ih of both directions, transposed: [C rows][6H] (K index = dir * 3H + gate row), for the GRU input's data gradient
+static int pack_gru_T(DevPool& pool, Layer& ih, const float* const* w_ih, int C, int H, cudaStream_t st) {
+    ih.t_valid = C; ih.t_rows = round_up(C, BM); ih.t_taps = 1; ih.t_kpad = round_up(6 * H, BK); ih.t_kvalid = 6 * H;
+    ZS_TRY(pool.alloc(&ih.wt, static_cast<size_t>(ih.t_rows) * ih.t_kpad * 2, st));
+    for (int dir = 0; dir < 2; ++dir) {
+        const long long total = static_cast<long long>(3) * H * C;
+        // mode 0, k = 1: dst[ci][kk] with kk = co; shift the destination by dir * 3H columns
+        pack_weight_T_kernel<<<static_cast<int>((total + 255) / 256), 256, 0, st>>>(w_ih[dir], static_cast<__half*>(ih.wt) + dir * 3 * H, 3 * H, C, 1, C, ih.t_kpad, ih.t_kpad, 0, 0);
+    }
+    CUDA_TRY(cudaGetLastError());
+    return ZS_OK;
+}
+
+static int encoder_fill(zs_encoder* h, const zs_encoder_weights* w, cudaStream_t st) {
+    const zs_encoder_cfg* cfg = &h->cfg;
+    const int op = cfg->operand, c_in = cfg->c_in, h1 = cfg->c_h1, h2 = cfg->c_h2, h3 = cfg->c_h3;
+    h->bank_merged = (h1 == BM);
+    if (h->bank_merged) {   // 7 kernels in one [896][7 taps][c_in_pad] matrix, kernel k at tap 3 - k/2
+        Layer& L = h->bank[0];
+        L.m_rows = 7 * BM; L.m_valid = 7 * BM; L.taps = 7; L.w_taps = 7; L.c_in_pad = round_up(c_in, BK); L.c_in_valid = c_in;
+        const long long k_total = 7LL * L.c_in_pad;
+        ZS_TRY(h->pool.alloc(&L.w, static_cast<size_t>(L.m_rows) * k_total * 2, st));
+        ZS_TRY(h->pool.alloc(reinterpret_cast<void**>(&L.bias), static_cast<size_t>(L.m_rows) * 4, st));
+        for (int i = 0; i < 7; ++i) {
+            const int k = i + 1;
+            const long long total = static_cast<long long>(h1) * c_in * k;
+            const int blocks = static_cast<int>((total + 255) / 256);
+            if (op == ZS_OPERAND_BF16)
+                pack_weight_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(w->conv1s_w[i], static_cast<__nv_bfloat16*>(L.w), h1, c_in, k, 0, c_in, k_total, L.c_in_pad, 3 - k / 2, i * BM, 0);
+            else
+                pack_weight_kernel<__half><<<blocks, 256, 0, st>>>(w->conv1s_w[i], static_cast<__half*>(L.w), h1, c_in, k, 0, c_in, k_total, L.c_in_pad, 3 - k / 2, i * BM, 0);
+            fold_bias_kernel<<<(h1 * 32 + 255) / 256, 256, 0, st>>>(w->conv1s_w[i], w->conv1s_b[i], nullptr, L.bias, h1, c_in, k, 0, 0, 1, L.m_rows, i * BM, 0);
+        }
+        CUDA_TRY(cudaGetLastError());
+    } else {
+        for (int i = 0; i < 7; ++i)
+            ZS_TRY(pack_layer(h->pool, h->bank[i], op, w->conv1s_w[i], w->conv1s_b[i], h1, c_in, i + 1, 0, c_in, 0, nullptr, 0, 0, 1, st));
+    }
+    ZS_TRY(pack_layer(h->pool, h->conv[0], op, w->conv_w[0], w->conv_b[0], h2, 7 * h1 + c_in, 1, 0, 7 * h1 + c_in, 0, nullptr, 0, 0, 1, st));
+    for (int i = 1; i < 7; ++i)
+        ZS_TRY(pack_layer(h->pool, h->conv[i], op, w->conv_w[i], w->conv_b[i], h2, h2, 5, 0, h2, 0, nullptr, 0, 0, 1, st));
+    for (int i = 0; i < 4; ++i)
+        ZS_TRY(pack_layer(h->pool, h->dense[i], op, w->dense_w[i], w->dense_b[i], h2, h2, 1, 0, h2, 0, nullptr, 0, 0, 1, st));
+    ZS_TRY(pack_gru(h->pool, h->gru_ih, &h->whhT, &h->bhh, &h->whh_img, op, w->gru_w_ih, w->gru_w_hh, w->gru_b_ih, w->gru_b_hh, h2, h3, nullptr, 1, st));
+    ZS_TRY(pack_layer(h->pool, h->linear, op, w->linear_w, w->linear_b, h->n_out, h2 + 2 * h3, 1, 0, h2 + 2 * h3, 0, nullptr, 0, 0, 1, st));
+    if (cfg->train) {   // data-gradient operands; the conv bank needs none (x takes no gradient)
+        ZS_TRY(pack_layer_T(h->pool, h->conv[0], w->conv_w[0], h2, 7 * h1 + c_in, 1, 7 * h1, 0, 0, st));   // bank channels only
+        for (int i = 1; i < 7; ++i)
+            ZS_TRY(pack_layer_T(h->pool, h->conv[i], w->conv_w[i], h2, h2, 5, h2, (i % 2 == 0) ? 1 : 0, 0, st));   // conv4/6/8 are stride 2
+        for (int i = 0; i < 4; ++i)
+            ZS_TRY(pack_layer_T(h->pool, h->dense[i], w->dense_w[i], h2, h2, 1, h2, 0, 0, st));
+        ZS_TRY(pack_gru_T(h->pool, h->gru_ih, w->gru_w_ih, h2, h3, st));
+        ZS_TRY(pack_layer_T(h->pool, h->linear, w->linear_w, h->n_out, h2 + 2 * h3, 1, h2 + 2 * h3, 0, 0, st));
+        for (int d = 0; d < 2; ++d) h->w_hh[d] = w->gru_w_hh[d];
+    }
+    return ZS_OK;
+}
+
 extern "C" int zs_encoder_pack(const zs_encoder_cfg* cfg, const zs_encoder_weights* w, void* stream, zs_encoder** out) {
     if (!cfg || !w || !out) return fail(ZS_ERR_ARG, "encoder_pack: null argument");
     ZS_TRY(ensure_device());
     if (cfg->seg_len < 64) return fail(ZS_ERR_ARG, "encoder: seg_len %d < 64 selects zero padding (model/model.py:38); only the reflect mode is implemented", cfg->seg_len);
     if (cfg->enc_mode < 0 || cfg->enc_mode > 3) return fail(ZS_ERR_ARG, "encoder: enc_mode %d not supported ('binary' needs an enc_size^2 projection)", cfg->enc_mode);
     if (cfg->c_h2 % 8 || cfg->c_h1 % 8 || cfg->c_h3 < 1) return fail(ZS_ERR_ARG, "encoder: c_h1/c_h2 must be multiples of 8");
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (cfg->train && cfg->operand != ZS_OPERAND_FP16) return fail(ZS_ERR_ARG, "encoder: the training path computes in fp16 operands (loss-scaled gradients)");
+    if (cfg->train && cfg->enc_mode != ZS_ENC_ONE_HOT) return fail(ZS_ERR_ARG, "encoder: the training path implements enc_mode 'one_hot' only");
+    if (cfg->train && (cfg->c_h2 % 64 || cfg->c_h3 % 8)) return fail(ZS_ERR_ARG, "encoder: training needs c_h2 %% 64 == 0 and c_h3 %% 8 == 0");
     zs_encoder* h = new zs_encoder();
     h->cfg = *cfg;
     h->n_out = cfg->enc_mode == ZS_ENC_MULTILABEL_BINARY ? 2 * cfg->enc_size : cfg->enc_size;
-    const int op = cfg->operand, c_in = cfg->c_in, h1 = cfg->c_h1, h2 = cfg->c_h2, h3 = cfg->c_h3;
-    int rc = ZS_OK;
-    auto run = [&]() -> int {
-        h->bank_merged = (h1 == BM);
-        if (h->bank_merged) {   // 7 kernels in one [896][7 taps][c_in_pad] matrix, kernel k at tap 3 - k/2
-            Layer& L = h->bank[0];
-            L.m_rows = 7 * BM; L.m_valid = 7 * BM; L.taps = 7; L.w_taps = 7; L.c_in_pad = round_up(c_in, BK); L.c_in_valid = c_in;
-            const long long k_total = 7LL * L.c_in_pad;
-            ZS_TRY(h->pool.alloc(&L.w, static_cast<size_t>(L.m_rows) * k_total * 2, st));
-            ZS_TRY(h->pool.alloc(reinterpret_cast<void**>(&L.bias), static_cast<size_t>(L.m_rows) * 4, st));
-            for (int i = 0; i < 7; ++i) {
-                const int k = i + 1;
-                const long long total = static_cast<long long>(h1) * c_in * k;
-                const int blocks = static_cast<int>((total + 255) / 256);
-                if (op == ZS_OPERAND_BF16)
-                    pack_weight_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(w->conv1s_w[i], static_cast<__nv_bfloat16*>(L.w), h1, c_in, k, 0, c_in, k_total, L.c_in_pad, 3 - k / 2, i * BM, 0);
-                else
-                    pack_weight_kernel<__half><<<blocks, 256, 0, st>>>(w->conv1s_w[i], static_cast<__half*>(L.w), h1, c_in, k, 0, c_in, k_total, L.c_in_pad, 3 - k / 2, i * BM, 0);
-                fold_bias_kernel<<<(h1 * 32 + 255) / 256, 256, 0, st>>>(w->conv1s_w[i], w->conv1s_b[i], nullptr, L.bias, h1, c_in, k, 0, 0, 1, L.m_rows, i * BM, 0);
-            }
-            CUDA_TRY(cudaGetLastError());
-        } else {
-            for (int i = 0; i < 7; ++i)
-                ZS_TRY(pack_layer(h->pool, h->bank[i], op, w->conv1s_w[i], w->conv1s_b[i], h1, c_in, i + 1, 0, c_in, 0, nullptr, 0, 0, 1, st));
-        }
-        ZS_TRY(pack_layer(h->pool, h->conv[0], op, w->conv_w[0], w->conv_b[0], h2, 7 * h1 + c_in, 1, 0, 7 * h1 + c_in, 0, nullptr, 0, 0, 1, st));
-        for (int i = 1; i < 7; ++i)
-            ZS_TRY(pack_layer(h->pool, h->conv[i], op, w->conv_w[i], w->conv_b[i], h2, h2, 5, 0, h2, 0, nullptr, 0, 0, 1, st));
-        for (int i = 0; i < 4; ++i)
-            ZS_TRY(pack_layer(h->pool, h->dense[i], op, w->dense_w[i], w->dense_b[i], h2, h2, 1, 0, h2, 0, nullptr, 0, 0, 1, st));
-        ZS_TRY(pack_gru(h->pool, h->gru_ih, &h->whhT, &h->bhh, &h->whh_img, op, w->gru_w_ih, w->gru_w_hh, w->gru_b_ih, w->gru_b_hh, h2, h3, nullptr, 1, st));
-        ZS_TRY(pack_layer(h->pool, h->linear, op, w->linear_w, w->linear_b, h->n_out, h2 + 2 * h3, 1, 0, h2 + 2 * h3, 0, nullptr, 0, 0, 1, st));
-        return ZS_OK;
-    };
-    rc = run();
+    const int rc = encoder_fill(h, w, static_cast<cudaStream_t>(stream));
     if (rc != ZS_OK) {
         h->pool.release();
         delete h;
@@ -574,6 +640,12 @@ extern "C" int zs_encoder_pack(const zs_encoder_cfg* cfg, const zs_encoder_weigh
     }
     *out = h;
     return ZS_OK;
+}
+
+/* refresh every packed buffer from the (updated) fp32 parameters; same pointers semantics as zs_encoder_pack */
+extern "C" int zs_encoder_repack(zs_encoder* h, const zs_encoder_weights* w, void* stream) {
+    if (!h || !w) return fail(ZS_ERR_ARG, "encoder_repack: null argument");
+    return encoder_fill(h, w, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" void zs_encoder_free(zs_encoder* h) {
@@ -582,38 +654,57 @@ extern "C" void zs_encoder_free(zs_encoder* h) {
     delete h;
 }
 
+static int decoder_fill(zs_decoder* h, const zs_decoder_weights* w, cudaStream_t st) {
+    const zs_decoder_cfg* cfg = &h->cfg;
+    const int op = cfg->operand, ch = cfg->c_h, ca = cfg->c_a;
+    const bool tr = cfg->train != 0;     // training: speaker embeddings are added to the activations, not folded
+    ZS_TRY(pack_layer(h->pool, h->input_emb, op, w->input_emb_w, w->input_emb_b, ch, cfg->c_in, 1, 0, cfg->c_in, 0, nullptr, 0, 0, 1, st));
+    ZS_TRY(h->pool.alloc(&h->emb_table, static_cast<size_t>(cfg->c_in) * ch * 2, st));
+    {
+        const long long total = static_cast<long long>(ch) * cfg->c_in;
+        const int blocks = static_cast<int>((total + 255) / 256);
+        if (op == ZS_OPERAND_BF16) transpose_emb_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(w->input_emb_w, static_cast<__nv_bfloat16*>(h->emb_table), ch, cfg->c_in);
+        else transpose_emb_kernel<__half><<<blocks, 256, 0, st>>>(w->input_emb_w, static_cast<__half*>(h->emb_table), ch, cfg->c_in);
+        CUDA_TRY(cudaGetLastError());
+    }
+    for (int i = 0; i < 6; ++i) {   // conv1,3,5: 2*c_h rows pixel-shuffle-permuted; block b uses emb[b] for both convs
+        const bool up = (i % 2 == 0);
+        ZS_TRY(pack_layer(h->pool, h->conv[i], op, w->conv_w[i], w->conv_b[i], up ? 2 * ch : ch, ch, 3, 0, ch, up ? 1 : 0, tr ? nullptr : w->emb[i / 2], 0, ch, ca, st));
+    }
+    for (int i = 0; i < 4; ++i)     // emb4 conditions all four dense layers (model/model.py:350-351)
+        ZS_TRY(pack_layer(h->pool, h->dense[i], op, w->dense_w[i], w->dense_b[i], ch, ch, 1, 0, ch, 0, tr ? nullptr : w->emb[3], 0, ch, ca, st));
+    ZS_TRY(pack_gru(h->pool, h->gru_ih, &h->whhT, &h->bhh, &h->whh_img, op, w->gru_w_ih, w->gru_w_hh, w->gru_b_ih, w->gru_b_hh, ch, ch / 2, tr ? nullptr : w->emb[4], ca, st));
+    // dense5 sees cat([out, rnn, emb5]): inference sends the first 2*c_h inputs through the GEMM and folds the last c_h
+    // into the bias; training keeps all 3*c_h as real input channels (append_emb materialised)
+    if (tr) ZS_TRY(pack_layer(h->pool, h->dense5, op, w->dense5_w, w->dense5_b, ch, 3 * ch, 1, 0, 3 * ch, 0, nullptr, 0, 0, 1, st));
+    else ZS_TRY(pack_layer(h->pool, h->dense5, op, w->dense5_w, w->dense5_b, ch, 3 * ch, 1, 0, 2 * ch, 0, w->emb[4], 2 * ch, ch, ca, st));
+    ZS_TRY(pack_layer(h->pool, h->linear, op, w->linear_w, w->linear_b, cfg->c_out, ch, 1, 0, ch, 0, nullptr, 0, 0, 1, st));
+    if (tr) {
+        ZS_TRY(pack_layer_T(h->pool, h->input_emb, w->input_emb_w, ch, cfg->c_in, 1, cfg->c_in, 0, 0, st));
+        for (int i = 0; i < 6; ++i) {
+            const bool up = (i % 2 == 0);
+            ZS_TRY(pack_layer_T(h->pool, h->conv[i], w->conv_w[i], up ? 2 * ch : ch, ch, 3, ch, 0, up ? ch : 0, st));
+        }
+        for (int i = 0; i < 4; ++i) ZS_TRY(pack_layer_T(h->pool, h->dense[i], w->dense_w[i], ch, ch, 1, ch, 0, 0, st));
+        ZS_TRY(pack_gru_T(h->pool, h->gru_ih, w->gru_w_ih, ch, ch / 2, st));
+        ZS_TRY(pack_layer_T(h->pool, h->dense5, w->dense5_w, ch, 3 * ch, 1, 3 * ch, 0, 0, st));
+        ZS_TRY(pack_layer_T(h->pool, h->linear, w->linear_w, cfg->c_out, ch, 1, ch, 0, 0, st));
+        for (int d = 0; d < 2; ++d) h->w_hh[d] = w->gru_w_hh[d];
+        for (int i = 0; i < 5; ++i) h->emb[i] = w->emb[i];
+    }
+    return ZS_OK;
+}
+
 extern "C" int zs_decoder_pack(const zs_decoder_cfg* cfg, const zs_decoder_weights* w, void* stream, zs_decoder** out) {
     if (!cfg || !w || !out) return fail(ZS_ERR_ARG, "decoder_pack: null argument");
     ZS_TRY(ensure_device());
     if (cfg->seg_len < 64) return fail(ZS_ERR_ARG, "decoder: seg_len %d < 64 selects zero padding (model/model.py:38); the speaker-embedding bias fold needs the reflect mode", cfg->seg_len);
     if (cfg->c_h % 64) return fail(ZS_ERR_ARG, "decoder: c_h %d must be a multiple of 64 (pixel-shuffle tile permutation)", cfg->c_h);
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (cfg->train && cfg->operand != ZS_OPERAND_FP16) return fail(ZS_ERR_ARG, "decoder: the training path computes in fp16 operands (loss-scaled gradients)");
+    if (cfg->train && cfg->c_in % 8) return fail(ZS_ERR_ARG, "decoder: training needs c_in %% 8 == 0");
     zs_decoder* h = new zs_decoder();
     h->cfg = *cfg;
-    const int op = cfg->operand, ch = cfg->c_h, ca = cfg->c_a;
-    auto run = [&]() -> int {
-        ZS_TRY(pack_layer(h->pool, h->input_emb, op, w->input_emb_w, w->input_emb_b, ch, cfg->c_in, 1, 0, cfg->c_in, 0, nullptr, 0, 0, 1, st));
-        ZS_TRY(h->pool.alloc(&h->emb_table, static_cast<size_t>(cfg->c_in) * ch * 2, st));
-        {
-            const long long total = static_cast<long long>(ch) * cfg->c_in;
-            const int blocks = static_cast<int>((total + 255) / 256);
-            if (op == ZS_OPERAND_BF16) transpose_emb_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(w->input_emb_w, static_cast<__nv_bfloat16*>(h->emb_table), ch, cfg->c_in);
-            else transpose_emb_kernel<__half><<<blocks, 256, 0, st>>>(w->input_emb_w, static_cast<__half*>(h->emb_table), ch, cfg->c_in);
-            CUDA_TRY(cudaGetLastError());
-        }
-        for (int i = 0; i < 6; ++i) {   // conv1,3,5: 2*c_h rows pixel-shuffle-permuted; block b uses emb[b] for both convs
-            const bool up = (i % 2 == 0);
-            ZS_TRY(pack_layer(h->pool, h->conv[i], op, w->conv_w[i], w->conv_b[i], up ? 2 * ch : ch, ch, 3, 0, ch, up ? 1 : 0, w->emb[i / 2], 0, ch, ca, st));
-        }
-        for (int i = 0; i < 4; ++i)     // emb4 conditions all four dense layers (model/model.py:350-351)
-            ZS_TRY(pack_layer(h->pool, h->dense[i], op, w->dense_w[i], w->dense_b[i], ch, ch, 1, 0, ch, 0, w->emb[3], 0, ch, ca, st));
-        ZS_TRY(pack_gru(h->pool, h->gru_ih, &h->whhT, &h->bhh, &h->whh_img, op, w->gru_w_ih, w->gru_w_hh, w->gru_b_ih, w->gru_b_hh, ch, ch / 2, w->emb[4], ca, st));
-        // dense5 sees cat([out, rnn, emb5]): the first 2*c_h inputs go through the GEMM, the last c_h fold into the bias
-        ZS_TRY(pack_layer(h->pool, h->dense5, op, w->dense5_w, w->dense5_b, ch, 3 * ch, 1, 0, 2 * ch, 0, w->emb[4], 2 * ch, ch, ca, st));
-        ZS_TRY(pack_layer(h->pool, h->linear, op, w->linear_w, w->linear_b, cfg->c_out, ch, 1, 0, ch, 0, nullptr, 0, 0, 1, st));
-        return ZS_OK;
-    };
-    int rc = run();
+    const int rc = decoder_fill(h, w, static_cast<cudaStream_t>(stream));
     if (rc != ZS_OK) {
         h->pool.release();
         delete h;
@@ -621,6 +712,11 @@ extern "C" int zs_decoder_pack(const zs_decoder_cfg* cfg, const zs_decoder_weigh
     }
     *out = h;
     return ZS_OK;
+}
+
+extern "C" int zs_decoder_repack(zs_decoder* h, const zs_decoder_weights* w, void* stream) {
+    if (!h || !w) return fail(ZS_ERR_ARG, "decoder_repack: null argument");
+    return decoder_fill(h, w, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" void zs_decoder_free(zs_decoder* h) {
@@ -719,6 +815,8 @@ struct ConvOpts {
         accumulate = 0, bank = 0, c_in_valid = -1;
     const Buf* res = nullptr;
     const int64_t* spk = nullptr;
+    int in_row0 = -1000;           // override (data-gradient GEMMs read zero-padded gradient buffers from row 0)
+    const ConvExtras* ex = nullptr;
 };
 // runs layer L on `in`, writing T_out frames per segment into `out` (a Buf, or raw fp32 (B, C, T) for NCT32)
 static int run_layer(const Layer& L, int operand, float ns, const Buf& in, int B, int T_out, const Buf* out, void* out_raw,
@@ -729,7 +827,7 @@ static int run_layer(const Layer& L, int operand, float ns, const Buf& in, int B
     d.bank = o.bank;
     d.in = in.p; d.in_rows = in.rows; d.in_pitch = in.pitch;
     const int pad_left = o.bank ? 3 : L.taps / 2;
-    d.in_row0 = in.halo - pad_left;
+    d.in_row0 = o.in_row0 != -1000 ? o.in_row0 : in.halo - pad_left;
     if (d.in_row0 < 0) return fail(ZS_ERR_ARG, "layer: input halo %d < pad %d", in.halo, pad_left);
     d.c_in_valid = o.c_in_valid >= 0 ? o.c_in_valid : L.c_in_valid;
     d.stride = o.stride; d.B = B; d.T_out = T_out;
@@ -742,7 +840,7 @@ static int run_layer(const Layer& L, int operand, float ns, const Buf& in, int B
     if (out) { d.out = out->p; d.out_rows = out->rows; d.out_pitch = out->pitch; d.out_halo = out->halo; }
     else { d.out = out_raw; d.out_rows = out_raw_rows; d.out_pitch = out_raw_pitch; d.out_halo = 0; }
     d.out_choff = o.out_choff; d.accumulate = o.accumulate; d.operand = operand; d.nb_hint = 0;
-    return launch_conv(&d, st);
+    return launch_conv(&d, st, o.ex);
 }
 
 extern "C" int zs_encoder_forward(zs_encoder* h, const float* x, int B, int T, const float* gumbel_noise, float* logits,
@@ -872,3 +970,5 @@ extern "C" int zs_decoder_forward(zs_decoder* h, const float* enc_act, const int
     }
     return ZS_OK;
 }
+
+#include "zs_train.cuh"

@@ -17,8 +17,10 @@ Differences from the reference, all deliberate:
     (`noise=`): the reference draws it inside forward from torch's CPU generator
     (model/model.py:96) - when `noise` is None this module draws it the same way
     (same generator, same shape, same call order) so seeding reproduces the reference;
-  * inference only: forward does not build an autograd graph (`torch.no_grad`
-    semantics); dropout (train mode) is not applied;
+  * `forward` is the inference path (no autograd graph, dropout not applied); the pretrain_AE training step
+    (trainer.py:321-332) runs through `forward_train` / `backward` below - driven by `zs_b200.train.PretrainAE`
+    or, for code that calls `loss.backward()` itself, by the autograd wrappers `zs_b200.train.encode_step /
+    decode_step`;
   * segments are limited to 9 <= T <= 256 frames (the range convert.py's chunking produces
     for seg_len = 128) and the reflect padding mode (hps seg_len >= 64);
   * errors are raised, never swallowed; there is no CPU path.
@@ -60,6 +62,10 @@ class _Packed(nn.Module):
         self._packed_key = None
         self._workspace = None
         self.operand = 'fp16'
+        # training handle (cfg.train = 1): re-packed in place after every optimiser step
+        self._thandle = None
+        self._tpacked_key = None
+        self._tworkspace = None
 
     def _param_key(self):
         return tuple((p.data_ptr(), p._version, str(p.device)) for p in self.parameters()) + (self.operand,)
@@ -73,10 +79,30 @@ class _Packed(nn.Module):
     def _ensure_packed(self, dev):
         key = self._param_key()
         if self._handle is None or key != self._packed_key:
-            self._free()
-            self._pack(dev)
+            self._free_eval()
+            self._handle = self._pack(dev, train=False)
             self._packed_key = key
         return self._handle
+
+    def _ensure_train_packed(self, dev):
+        if self.operand != 'fp16':
+            raise RuntimeError('the training path computes in fp16 operands')
+        key = self._param_key()
+        if self._thandle is None:
+            self._thandle = self._pack(dev, train=True)
+        elif key != self._tpacked_key:
+            self._repack(dev)
+        self._tpacked_key = key
+        return self._thandle
+
+    def mark_repacked(self):
+        self._tpacked_key = self._param_key()
+
+    def _get_train_workspace(self, nbytes, dev):
+        ws = self._tworkspace
+        if ws is None or ws.numel() < nbytes or ws.device != dev:
+            self._tworkspace = ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        return ws
 
     def _get_workspace(self, nbytes, dev):
         ws = self._workspace
@@ -126,40 +152,112 @@ class Encoder(_Packed):
         self.linear = nn.Linear(c_h2 + 2 * c_h3, n_out)
 
     # -- library handle ------------------------------------------------------------------
-    def _free(self):
+    def _free_eval(self):
         if self._handle is not None:
             _lib.lib().zs_encoder_free(self._handle)
             self._handle = None
 
-    def _pack(self, dev):
+    def _free(self):
+        self._free_eval()
+        if self._thandle is not None:
+            _lib.lib().zs_encoder_free(self._thandle)
+            self._thandle = None
+
+    def weight_table(self, tensors=None):
+        """`zs_encoder_weights` filled with the data pointers of the parameters, or of same-named tensors in
+        `tensors` (a dict name -> tensor shaped like the parameter: the gradient table of the backward pass)."""
+        get = (dict(self.named_parameters()) if tensors is None else tensors).__getitem__
+        w = _lib.EncoderWeights()
+        for i in range(7):
+            w.conv1s_w[i] = get(f'conv1s.{i}.weight').data_ptr()
+            w.conv1s_b[i] = get(f'conv1s.{i}.bias').data_ptr()
+            w.conv_w[i] = get(f'conv{i + 2}.weight').data_ptr()
+            w.conv_b[i] = get(f'conv{i + 2}.bias').data_ptr()
+        for i in range(4):
+            w.dense_w[i] = get(f'dense{i + 1}.weight').data_ptr()
+            w.dense_b[i] = get(f'dense{i + 1}.bias').data_ptr()
+        for i, sfx in enumerate(('', '_reverse')):
+            w.gru_w_ih[i] = get('RNN.weight_ih_l0' + sfx).data_ptr()
+            w.gru_w_hh[i] = get('RNN.weight_hh_l0' + sfx).data_ptr()
+            w.gru_b_ih[i] = get('RNN.bias_ih_l0' + sfx).data_ptr()
+            w.gru_b_hh[i] = get('RNN.bias_hh_l0' + sfx).data_ptr()
+        w.linear_w = get('linear.weight').data_ptr()
+        w.linear_b = get('linear.bias').data_ptr()
+        return w
+
+    def _pack(self, dev, train=False):
         lib = _lib.lib()
         cfg = _lib.EncoderCfg(self.c_in, self.c_h1, self.c_h2, self.c_h3, self.enc_size,
-                              _lib.ENC_MODES[self.enc_mode], self.seg_len, _lib.OPERANDS[self.operand], self.ns)
-        w = _lib.EncoderWeights()
+                              _lib.ENC_MODES[self.enc_mode], self.seg_len, _lib.OPERANDS[self.operand], self.ns,
+                              int(train))
         for p in self.parameters():
             if p.dtype != torch.float32 or not p.is_contiguous():
                 raise RuntimeError('Encoder parameters must be contiguous float32')
-        for i in range(7):
-            w.conv1s_w[i] = self.conv1s[i].weight.data_ptr()
-            w.conv1s_b[i] = self.conv1s[i].bias.data_ptr()
-            conv = getattr(self, f'conv{i + 2}')
-            w.conv_w[i] = conv.weight.data_ptr()
-            w.conv_b[i] = conv.bias.data_ptr()
-        for i in range(4):
-            d = getattr(self, f'dense{i + 1}')
-            w.dense_w[i] = d.weight.data_ptr()
-            w.dense_b[i] = d.bias.data_ptr()
-        for i, sfx in enumerate(('', '_reverse')):
-            w.gru_w_ih[i] = getattr(self.RNN, 'weight_ih_l0' + sfx).data_ptr()
-            w.gru_w_hh[i] = getattr(self.RNN, 'weight_hh_l0' + sfx).data_ptr()
-            w.gru_b_ih[i] = getattr(self.RNN, 'bias_ih_l0' + sfx).data_ptr()
-            w.gru_b_hh[i] = getattr(self.RNN, 'bias_hh_l0' + sfx).data_ptr()
-        w.linear_w = self.linear.weight.data_ptr()
-        w.linear_b = self.linear.bias.data_ptr()
+        w = self.weight_table()
         h = C.c_void_p()
         with torch.cuda.device(dev):
             _lib.check(lib.zs_encoder_pack(C.byref(cfg), C.byref(w), _stream(), C.byref(h)))
-        self._handle = h
+        return h
+
+    def _repack(self, dev):
+        w = self.weight_table()
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().zs_encoder_repack(self._thandle, C.byref(w), _stream()))
+
+    # -- training path (model/model.py:440-489 in train mode; trainer.py:246-249 encode_step) ----------
+    def forward_train(self, x, noise, dropout_seed=0, keep_masks=None):
+        """Train-mode forward.  `noise` = Gumbel noise (B, T8, enc_size) on the device; `keep_masks` = optional
+        list of six (B, c_h2, T_l) uint8 tensors replaying explicit Dropout draws.  Returns (act, logits, ids);
+        the activations the backward needs stay in the module's training workspace until `backward`."""
+        self._check_input(x, 'x')
+        B, _, T = x.shape
+        dev = x.device
+        x = x.detach().contiguous().float()
+        noise = noise.to(dev, torch.float32).contiguous()
+        if tuple(noise.shape) != (B, self.t8(T), self.enc_size):
+            raise RuntimeError(f'Encoder.forward_train: noise must be (B, T8, enc_size), got {tuple(noise.shape)}')
+        lib = _lib.lib()
+        with torch.cuda.device(dev):
+            h = self._ensure_train_packed(dev)
+            T8 = self.t8(T)
+            logits = torch.empty(B, self.n_out, T8, dtype=torch.float32, device=dev)
+            act = torch.empty(B, self.enc_size, T8, dtype=torch.float32, device=dev)
+            ids = torch.empty(B, T8, dtype=torch.int32, device=dev)
+            ws = self._get_train_workspace(lib.zs_encoder_train_workspace_bytes(h, B, T), dev)
+            km = self._mask_table(keep_masks)
+            _lib.check(lib.zs_encoder_forward_train(h, _ptr(x), B, T, _ptr(noise), float(self.dp), int(dropout_seed), km,
+                                                    _ptr(logits), _ptr(act), _ptr(ids), _ptr(ws), ws.numel(), _stream()))
+        self._train_ctx = (B, T, noise, logits, int(dropout_seed), keep_masks)
+        return act, logits, ids
+
+    @staticmethod
+    def _mask_table(keep_masks):
+        if keep_masks is None:
+            return None
+        if len(keep_masks) != 6:
+            raise RuntimeError('keep_masks must hold the six Dropout keep-masks')
+        arr = (C.c_void_p * 6)()
+        for i, m in enumerate(keep_masks):
+            if m.dtype != torch.uint8 or not m.is_cuda or not m.is_contiguous():
+                raise RuntimeError('keep_masks must be contiguous CUDA uint8 tensors')
+            arr[i] = m.data_ptr()
+        return arr
+
+    def backward(self, d_act, grads, loss_scale, d_act_scale=1.0):
+        """Backward of the last `forward_train`: `d_act` (B, enc_size, T8) fp32 = dLoss/d(out_act) * d_act_scale;
+        parameter gradients are ACCUMULATED into the tensors of `grads` (dict name -> fp32 tensor)."""
+        B, T, noise, logits, seed, keep_masks = self._train_ctx
+        dev = d_act.device
+        d_act = d_act.contiguous().float()
+        lib = _lib.lib()
+        with torch.cuda.device(dev):
+            h = self._thandle
+            ws = self._tworkspace
+            g = self.weight_table(grads)
+            km = self._mask_table(keep_masks)
+            _lib.check(lib.zs_encoder_backward(h, _ptr(d_act), float(d_act_scale), _ptr(noise), _ptr(logits), B, T,
+                                               float(self.dp), seed, km, float(loss_scale), C.byref(g), _ptr(ws),
+                                               ws.numel(), _stream()))
 
     @staticmethod
     def t8(T):
@@ -222,41 +320,97 @@ class Decoder(_Packed):
         for j in range(1, 6):
             setattr(self, f'emb{j}', nn.Embedding(c_a, c_h))
 
-    def _free(self):
+    def _free_eval(self):
         if self._handle is not None:
             _lib.lib().zs_decoder_free(self._handle)
             self._handle = None
 
-    def _pack(self, dev):
+    def _free(self):
+        self._free_eval()
+        if self._thandle is not None:
+            _lib.lib().zs_decoder_free(self._thandle)
+            self._thandle = None
+
+    def weight_table(self, tensors=None):
+        """`zs_decoder_weights` of the parameters, or of same-named tensors in `tensors` (gradient table)."""
+        get = (dict(self.named_parameters()) if tensors is None else tensors).__getitem__
+        w = _lib.DecoderWeights()
+        for i in range(6):
+            w.conv_w[i] = get(f'conv{i + 1}.weight').data_ptr()
+            w.conv_b[i] = get(f'conv{i + 1}.bias').data_ptr()
+        for i in range(4):
+            w.dense_w[i] = get(f'dense{i + 1}.weight').data_ptr()
+            w.dense_b[i] = get(f'dense{i + 1}.bias').data_ptr()
+        for i, sfx in enumerate(('', '_reverse')):
+            w.gru_w_ih[i] = get('RNN.weight_ih_l0' + sfx).data_ptr()
+            w.gru_w_hh[i] = get('RNN.weight_hh_l0' + sfx).data_ptr()
+            w.gru_b_ih[i] = get('RNN.bias_ih_l0' + sfx).data_ptr()
+            w.gru_b_hh[i] = get('RNN.bias_hh_l0' + sfx).data_ptr()
+        w.dense5_w, w.dense5_b = get('dense5.weight').data_ptr(), get('dense5.bias').data_ptr()
+        w.linear_w, w.linear_b = get('linear.weight').data_ptr(), get('linear.bias').data_ptr()
+        w.input_emb_w, w.input_emb_b = get('input_emb.weight').data_ptr(), get('input_emb.bias').data_ptr()
+        for i in range(5):
+            w.emb[i] = get(f'emb{i + 1}.weight').data_ptr()
+        return w
+
+    def _pack(self, dev, train=False):
         lib = _lib.lib()
         cfg = _lib.DecoderCfg(self.c_in, self.c_out, self.c_h, self.c_a, self.seg_len, int(bool(self.output_mask)),
-                              _lib.OPERANDS[self.operand], self.ns)
+                              _lib.OPERANDS[self.operand], self.ns, int(train))
         for p in self.parameters():
             if p.dtype != torch.float32 or not p.is_contiguous():
                 raise RuntimeError('Decoder parameters must be contiguous float32')
-        w = _lib.DecoderWeights()
-        for i in range(6):
-            conv = getattr(self, f'conv{i + 1}')
-            w.conv_w[i] = conv.weight.data_ptr()
-            w.conv_b[i] = conv.bias.data_ptr()
-        for i in range(4):
-            d = getattr(self, f'dense{i + 1}')
-            w.dense_w[i] = d.weight.data_ptr()
-            w.dense_b[i] = d.bias.data_ptr()
-        for i, sfx in enumerate(('', '_reverse')):
-            w.gru_w_ih[i] = getattr(self.RNN, 'weight_ih_l0' + sfx).data_ptr()
-            w.gru_w_hh[i] = getattr(self.RNN, 'weight_hh_l0' + sfx).data_ptr()
-            w.gru_b_ih[i] = getattr(self.RNN, 'bias_ih_l0' + sfx).data_ptr()
-            w.gru_b_hh[i] = getattr(self.RNN, 'bias_hh_l0' + sfx).data_ptr()
-        w.dense5_w, w.dense5_b = self.dense5.weight.data_ptr(), self.dense5.bias.data_ptr()
-        w.linear_w, w.linear_b = self.linear.weight.data_ptr(), self.linear.bias.data_ptr()
-        w.input_emb_w, w.input_emb_b = self.input_emb.weight.data_ptr(), self.input_emb.bias.data_ptr()
-        for i in range(5):
-            w.emb[i] = getattr(self, f'emb{i + 1}').weight.data_ptr()
+        w = self.weight_table()
         h = C.c_void_p()
         with torch.cuda.device(dev):
             _lib.check(lib.zs_decoder_pack(C.byref(cfg), C.byref(w), _stream(), C.byref(h)))
-        self._handle = h
+        return h
+
+    def _repack(self, dev):
+        w = self.weight_table()
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().zs_decoder_repack(self._thandle, C.byref(w), _stream()))
+
+    # -- training path (model/model.py:344-365; trainer.py:251-254 decode_step) -------------------------
+    def forward_train(self, x, c):
+        """Train-mode forward on dense activations x (B, c_in, T8); keeps what `backward` needs."""
+        self._check_input(x, 'x')
+        dev = x.device
+        x = x.detach().contiguous().float()
+        B, _, T8 = x.shape
+        c = c.to(dev, torch.int64).contiguous().view(-1)
+        if c.numel() != B:
+            raise RuntimeError(f'Decoder: {c.numel()} speaker ids for {B} segments')
+        lib = _lib.lib()
+        with torch.cuda.device(dev):
+            h = self._ensure_train_packed(dev)
+            spec = torch.empty(B, self.c_out, 8 * T8, dtype=torch.float32, device=dev)
+            ws = self._get_train_workspace(lib.zs_decoder_train_workspace_bytes(h, B, T8), dev)
+            _lib.check(lib.zs_decoder_forward_train(h, _ptr(x), _ptr(c), B, T8, _ptr(spec), _ptr(ws), ws.numel(), _stream()))
+        self._train_ctx = (B, T8, c, spec)
+        return spec
+
+    def backward(self, grads, loss_scale, target=None, d_spec=None, loss_out=None, want_d_act=True):
+        """Backward of the last `forward_train`.  Either `target` (B, c_out, T): the L1 loss of trainer.py:327 is fused
+        and added to `loss_out` (device fp32 scalar, zero it first), or `d_spec` = dLoss/dspec.  Parameter gradients
+        are ACCUMULATED into `grads`; returns d_act = dLoss/d(enc_act) * loss_scale, (B, c_in, T8) fp32."""
+        B, T8, c, spec = self._train_ctx
+        dev = spec.device
+        lib = _lib.lib()
+        if target is not None:
+            target = target.contiguous().float()
+            if tuple(target.shape) != tuple(spec.shape):
+                raise RuntimeError(f'Decoder.backward: target {tuple(target.shape)} vs output {tuple(spec.shape)}')
+        if d_spec is not None:
+            d_spec = d_spec.contiguous().float()
+        with torch.cuda.device(dev):
+            d_act = torch.empty(B, self.c_in, T8, dtype=torch.float32, device=dev) if want_d_act else None
+            g = self.weight_table(grads)
+            ws = self._tworkspace
+            _lib.check(lib.zs_decoder_backward(self._thandle, _ptr(spec), _ptr(target), _ptr(d_spec), _ptr(c), B, T8,
+                                               float(loss_scale), _ptr(loss_out), C.byref(g), _ptr(d_act), _ptr(ws),
+                                               ws.numel(), _stream()))
+        return d_act
 
     @torch.no_grad()
     def decode(self, x=None, c=None, unit_ids=None, out=None, accumulate=0):
