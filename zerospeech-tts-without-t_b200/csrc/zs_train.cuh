@@ -125,14 +125,16 @@ static int run_dgrad(const Layer& L, const Buf& dpre, int B, int T_out, const Bu
 
 // weight (+ bias) gradient of layer L: dy = `dpre` (frames at rows dy_halo..), x = the layer's forward input buffer
 struct WgradOpts {
-    int taps = 1, k = 1, tap0 = 0, stride = 1, x_row0 = 0, x_ch0 = 0, c_in = 0, c_in_total = 0, ci_off = 0, dy_ch0 = 0, c_out = 0, ps_c = 0;
+    int taps = 1, k = 1, tap0 = 0, stride = 1, x_ch0 = 0, c_in = 0, c_in_total = 0, ci_off = 0, dy_ch0 = 0, c_out = 0, ps_c = 0;
+    int pad_left = -1;    // frames of left padding the forward conv saw (default k / 2)
+    int x_shift = 0;      // extra row offset (GRU: h_{t-1} / h_{t+1})
 };
 static int run_wgrad(const Buf& dpre, const Buf& x, int B, int T, float* grad_w, float* grad_b, float inv_scale, const WgradOpts& o,
                      cudaStream_t st) {
     zs_wgrad_desc d;
     memset(&d, 0, sizeof(d));
     d.dy = dpre.p; d.dy_rows = dpre.rows; d.dy_pitch = dpre.pitch; d.dy_channels = dpre.pitch; d.dy_ch0 = o.dy_ch0; d.dy_row0 = dpre.halo; d.c_out = o.c_out;
-    d.x = x.p; d.x_rows = x.rows; d.x_pitch = x.pitch; d.x_channels = x.pitch; d.x_ch0 = o.x_ch0; d.x_row0 = o.x_row0; d.c_in = o.c_in; d.stride = o.stride;
+    d.x = x.p; d.x_rows = x.rows; d.x_pitch = x.pitch; d.x_channels = x.pitch; d.x_ch0 = o.x_ch0; d.x_row0 = x.halo - (o.pad_left >= 0 ? o.pad_left : o.k / 2) + o.x_shift; d.c_in = o.c_in; d.stride = o.stride;
     d.B = B; d.T = T; d.taps = o.taps; d.grad = grad_w; d.c_in_total = o.c_in_total ? o.c_in_total : o.c_in; d.ci_off = o.ci_off; d.k = o.k; d.tap0 = o.tap0;
     d.ps_c = o.ps_c; d.scale = inv_scale;
     ZS_TRY(launch_wgrad(&d, st));
@@ -173,7 +175,7 @@ static int gru_backward(const Buf& gates, const Buf& xin, int c_in, const Buf& h
     for (int d = 0; d < 2; ++d) {
         WgradOpts wi; wi.c_out = 3 * H; wi.dy_ch0 = d * 3 * H; wi.c_in = c_in;
         ZS_TRY(run_wgrad(dgx, xin, B, T, g_w_ih[d], g_b_ih[d], inv_scale, wi, st));
-        WgradOpts wh; wh.c_out = 3 * H; wh.dy_ch0 = d * 3 * H; wh.c_in = H; wh.x_ch0 = h_choff + d * H; wh.x_row0 = d ? 1 : -1;   // h_{t-1} / h_{t+1}
+        WgradOpts wh; wh.c_out = 3 * H; wh.dy_ch0 = d * 3 * H; wh.c_in = H; wh.x_ch0 = h_choff + d * H; wh.x_shift = d ? 1 : -1;   // h_{t-1} / h_{t+1}
         ZS_TRY(run_wgrad(dgh, hbuf, B, T, g_w_hh[d], g_b_hh[d], inv_scale, wh, st));
     }
     return ZS_OK;
@@ -408,7 +410,7 @@ extern "C" int zs_decoder_backward(zs_decoder* h, const float* spec, const float
         const float* e_next = grads->emb[blk < 2 ? blk + 1 : 3];
         // conv2/4/6: IN + lrelu, k = 3 on p (pixel-shuffle output + e)
         ZS_TRY(tail(next_a, gsrc_none(), next_r, &w.xh[blk], w.stats[blk], 1, nullptr, &w.dpre_c2[blk], &w.gsum_c[blk], G(e_next), 1, To, ch));
-        WgradOpts o2; o2.c_out = ch; o2.c_in = ch; o2.taps = 3; o2.k = 3; o2.x_row0 = 0;     // p has halo 1 = pad
+        WgradOpts o2; o2.c_out = ch; o2.c_in = ch; o2.taps = 3; o2.k = 3;
         ZS_TRY(run_wgrad(w.dpre_c2[blk], w.p[blk], B, To, G(grads->conv_w[2 * blk + 1]), G(grads->conv_b[2 * blk + 1]), inv, o2, st));
         ZS_TRY(run_dgrad(h->conv[2 * blk + 1], w.dpre_c2[blk], B, To + 2, &w.Gp_p[blk], nullptr, 0, ns, st));
         // conv1/3/5: lrelu, pixel shuffle, + e: the tail runs in pixel-shuffle space (To frames x ch channels)
@@ -416,7 +418,7 @@ extern "C" int zs_decoder_backward(zs_decoder* h, const float* spec, const float
                     G(grads->emb[blk]), 3, To, ch));
         const Buf dv = ps_view(w.dpre_c1[blk]);   // [Ti + 4][2 ch], zero halo 2
         const Buf& xe = blk == 0 ? w.x0e : w.ye[blk - 1];
-        WgradOpts o1; o1.c_out = 2 * ch; o1.c_in = ch; o1.taps = 3; o1.k = 3; o1.x_row0 = 0; o1.ps_c = ch;
+        WgradOpts o1; o1.c_out = 2 * ch; o1.c_in = ch; o1.taps = 3; o1.k = 3; o1.ps_c = ch;
         ZS_TRY(run_wgrad(dv, xe, B, Ti, G(grads->conv_w[2 * blk]), G(grads->conv_b[2 * blk]), inv, o1, st));
         ZS_TRY(run_dgrad(h->conv[2 * blk], dv, B, Ti + 2, &w.Gp_xe[blk], nullptr, 0, ns, st));
         next_a = gsrc(w.Gp_xe[blk], GS_PADDED, 1);
@@ -641,11 +643,11 @@ extern "C" int zs_encoder_backward(zs_encoder* h, const float* d_act, float d_ac
     for (int j = 2; j >= 0; --j) {
         const int Ti = w.T[j], To = w.T[j + 1];
         ZS_TRY(tail(next_a, gsrc_none(), next_r, &w.xh[j + 1], w.stats[j + 1], j + 1, &w.dpre_s2[j], &w.gs_a[j], To, h2));
-        WgradOpts o2; o2.c_out = h2; o2.c_in = h2; o2.taps = 5; o2.k = 5; o2.stride = 2; o2.x_row0 = 0;   // a[2j+1] has halo 2 = pad
+        WgradOpts o2; o2.c_out = h2; o2.c_in = h2; o2.taps = 5; o2.k = 5; o2.stride = 2;
         ZS_TRY(run_wgrad(w.dpre_s2[j], w.a[2 * j + 1], B, To, G(grads->conv_w[2 + 2 * j]), G(grads->conv_b[2 + 2 * j]), inv, o2, st));
         ZS_TRY(run_dgrad(h->conv[2 + 2 * j], w.dpre_s2[j], B, To + 2, &w.Gp_odd[j], nullptr, 1, ns, st));   // rows 2w'+r of the padded input
         ZS_TRY(tail(gsrc(w.Gp_odd[j], GS_PADDED, 2), gsrc_none(), gsrc_none(), &w.a[2 * j + 1], nullptr, -1, &w.dpre_c[j], nullptr, Ti, h2));
-        WgradOpts o1; o1.c_out = h2; o1.c_in = h2; o1.taps = 5; o1.k = 5; o1.x_row0 = 0;
+        WgradOpts o1; o1.c_out = h2; o1.c_in = h2; o1.taps = 5; o1.k = 5;
         ZS_TRY(run_wgrad(w.dpre_c[j], w.a[2 * j], B, Ti, G(grads->conv_w[1 + 2 * j]), G(grads->conv_b[1 + 2 * j]), inv, o1, st));
         ZS_TRY(run_dgrad(h->conv[1 + 2 * j], w.dpre_c[j], B, Ti + 4, &w.Gp_even[j], nullptr, 0, ns, st));
         next_a = gsrc(w.Gp_even[j], GS_PADDED, 2);
@@ -661,7 +663,7 @@ extern "C" int zs_encoder_backward(zs_encoder* h, const float* d_act, float d_ac
         ZS_TRY(tail(gsrc(w.G_cat, GS_PADDED), gsrc_none(), gsrc_none(), &w.cat, nullptr, -1, &w.dpre_bank, nullptr, T, 7 * g.c_h1));
         for (int i = 0; i < 7; ++i) {
             const int k = i + 1;
-            WgradOpts o; o.c_out = g.c_h1; o.dy_ch0 = i * g.c_h1; o.c_in = g.c_in; o.taps = k; o.k = k; o.x_row0 = 3 - k / 2;   // xp has halo 3
+            WgradOpts o; o.c_out = g.c_h1; o.dy_ch0 = i * g.c_h1; o.c_in = g.c_in; o.taps = k; o.k = k;   // xp has halo 3; kernel k pads k/2 on the left
             ZS_TRY(run_wgrad(w.dpre_bank, w.xp, B, T, G(grads->conv1s_w[i]), G(grads->conv1s_b[i]), inv, o, st));
         }
     }

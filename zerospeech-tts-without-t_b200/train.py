@@ -23,18 +23,20 @@ from .model import Decoder, Encoder, _ptr, _stream, gumbel_from_uniform
 
 def flatten_parameters(module):
     """Moves every parameter of `module` into ONE contiguous fp32 buffer (parameters become views of it, names and
-    shapes unchanged) and returns (flat_params, {name: (offset, numel)})."""
+    shapes unchanged; every tensor starts on a 256-byte boundary, the zero gaps are inert for the norm and Adam) and
+    returns (flat_params, {name: (offset, numel)})."""
     params = list(module.named_parameters())
     dev = params[0][1].device
-    total = sum(p.numel() for _, p in params)
-    flat = torch.empty(total, dtype=torch.float32, device=dev)
+    align = 64
+    total = sum((p.numel() + align - 1) // align * align for _, p in params)
+    flat = torch.zeros(total, dtype=torch.float32, device=dev)
     layout, off = {}, 0
     for name, p in params:
         n = p.numel()
         flat[off:off + n].copy_(p.data.reshape(-1))
         p.data = flat[off:off + n].view_as(p)
         layout[name] = (off, n)
-        off += n
+        off += (n + align - 1) // align * align
     return flat, layout
 
 
