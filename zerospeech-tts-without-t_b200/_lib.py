@@ -14,7 +14,7 @@ _CSRC = os.path.join(_HERE, 'csrc')
 SO_PATH = os.path.join(_HERE, 'libzsae.so')
 HEADER = os.path.join(os.path.dirname(_HERE), 'include', 'zs_ae.h')
 _SOURCES = ['zs_ae.cu', 'conv_gemm.cuh', 'kernels.cuh', 'gru_cluster.cuh', 'ptx.cuh', 'train_kernels.cuh',
-            'wgrad_gemm.cuh', 'zs_train.cuh']
+            'wgrad_gemm.cuh', 'zs_train.cuh', 'gru_bptt_cluster.cuh']
 
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-Xcompiler', '-fPIC', '-shared']

@@ -16,6 +16,7 @@
 #include "kernels.cuh"
 #include "gru_cluster.cuh"
 #include "train_kernels.cuh"
+#include "gru_bptt_cluster.cuh"
 #include "wgrad_gemm.cuh"
 
 using namespace zs;
@@ -511,7 +512,8 @@ struct zs_encoder {
     float* bhh = nullptr;   // [2][3H]
     void* whh_img = nullptr;  // cluster-kernel shared-memory images (H % 64 == 0)
     Layer linear;
-    const float* w_hh[2] = {nullptr, nullptr};   // training: the caller's fp32 W_hh (read by the BPTT kernel)
+    const float* w_hh[2] = {nullptr, nullptr};   // training: the caller's fp32 W_hh (read by the CUDA-core BPTT kernel)
+    void* whhT_img = nullptr;                    // training: streamed W_hh^T images of the cluster BPTT kernel
 };
 
 struct zs_decoder {
@@ -528,6 +530,7 @@ struct zs_decoder {
     Layer dense5;
     Layer linear;
     const float* w_hh[2] = {nullptr, nullptr};   // training: the caller's fp32 parameters read directly by kernels
+    void* whhT_img = nullptr;
     const float* emb[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 
@@ -559,6 +562,17 @@ static int pack_gru(DevPool& pool, Layer& ih, float** whhT, float** bhh, void** 
         ZS_TRY(pool.alloc(whh_img, static_cast<size_t>(2) * (H / GRU_UNITS) * gru_w_image_bytes(H), st));
         ZS_TRY(pack_gru_image(*whh_img, w_hh, nullptr, H, operand, st));
     }
+    return ZS_OK;
+}
+
+// streamed W_hh^T images of the cluster BPTT kernel (both directions), only when the cluster kernels apply
+static int pack_gru_bptt_image(DevPool& pool, void** img, const float* const* w_hh, int H, cudaStream_t st) {
+    if (!gru_cluster_ok(H)) return ZS_OK;
+    const size_t per_dir = static_cast<size_t>(H / 64) * gb_w_image_bytes(H);
+    ZS_TRY(pool.alloc(img, 2 * per_dir, st));
+    for (int dir = 0; dir < 2; ++dir)
+        gru_pack_whhT_kernel<<<(3 * H * H + 255) / 256, 256, 0, st>>>(w_hh[dir], reinterpret_cast<__half*>(static_cast<uint8_t*>(*img) + dir * per_dir), H);
+    CUDA_TRY(cudaGetLastError());
     return ZS_OK;
 }
 
@@ -614,6 +628,7 @@ static int encoder_fill(zs_encoder* h, const zs_encoder_weights* w, cudaStream_t
         for (int i = 0; i < 4; ++i)
             ZS_TRY(pack_layer_T(h->pool, h->dense[i], w->dense_w[i], h2, h2, 1, h2, 0, 0, st));
         ZS_TRY(pack_gru_T(h->pool, h->gru_ih, w->gru_w_ih, h2, h3, st));
+        ZS_TRY(pack_gru_bptt_image(h->pool, &h->whhT_img, w->gru_w_hh, h3, st));
         ZS_TRY(pack_layer_T(h->pool, h->linear, w->linear_w, h->n_out, h2 + 2 * h3, 1, h2 + 2 * h3, 0, 0, st));
         for (int d = 0; d < 2; ++d) h->w_hh[d] = w->gru_w_hh[d];
     }
@@ -687,6 +702,7 @@ static int decoder_fill(zs_decoder* h, const zs_decoder_weights* w, cudaStream_t
         }
         for (int i = 0; i < 4; ++i) ZS_TRY(pack_layer_T(h->pool, h->dense[i], w->dense_w[i], ch, ch, 1, ch, 0, 0, st));
         ZS_TRY(pack_gru_T(h->pool, h->gru_ih, w->gru_w_ih, ch, ch / 2, st));
+        ZS_TRY(pack_gru_bptt_image(h->pool, &h->whhT_img, w->gru_w_hh, ch / 2, st));
         ZS_TRY(pack_layer_T(h->pool, h->dense5, w->dense5_w, ch, 3 * ch, 1, 3 * ch, 0, 0, st));
         ZS_TRY(pack_layer_T(h->pool, h->linear, w->linear_w, cfg->c_out, ch, 1, ch, 0, 0, st));
         for (int d = 0; d < 2; ++d) h->w_hh[d] = w->gru_w_hh[d];

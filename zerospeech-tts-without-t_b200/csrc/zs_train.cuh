@@ -145,8 +145,37 @@ static int run_wgrad(const Buf& dpre, const Buf& x, int B, int T, float* grad_w,
 // -------------------------------------------------------------------------------------------------
 // GRU backward (CUDA-core BPTT) launcher
 // -------------------------------------------------------------------------------------------------
+static int launch_gru_bptt_cluster(const void* whhT_img, const Buf& gates, const Buf& hbuf, int h_choff, const Buf& dout, int do_choff, int B,
+                                   int T, int H, const Buf& dgx, const Buf& dgh, cudaStream_t st) {
+    GruBpttParams p;
+    p.w_img = whhT_img; p.gates = static_cast<const __half*>(gates.p);
+    p.hbuf = static_cast<const __half*>(hbuf.p); p.h_rows = hbuf.rows; p.h_pitch = hbuf.pitch; p.h_choff = h_choff;
+    p.dout = static_cast<const __half*>(dout.p); p.do_rows = dout.rows; p.do_pitch = dout.pitch; p.do_choff = do_choff;
+    p.dgx = static_cast<__half*>(dgx.p); p.dgh = static_cast<__half*>(dgh.p); p.B = B; p.T = T; p.H = H;
+    const int NC = H / GRU_UNITS, n_groups = (B + GRU_NSEQ - 1) / GRU_NSEQ, smem = gb_smem_bytes(H);
+    static int attr_set = 0;
+    if (attr_set < smem) {
+        CUDA_TRY(cudaFuncSetAttribute(gru_bptt_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_set = smem;
+    }
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(2 * n_groups * NC);
+    cfg.blockDim = dim3(GB_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = NC; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    LaunchScope scope(st, KC_GRU, 2.0 * 2 * B * static_cast<double>(T) * 3 * H * H);
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, gru_bptt_cluster_kernel, p));
+    return ZS_OK;
+}
+
 static int launch_gru_bptt(const Buf& gates, const Buf& hbuf, int h_choff, const Buf& dout, int do_choff, const float* const* w_hh,
-                           int B, int T, int H, const Buf& dgx, const Buf& dgh, cudaStream_t st) {
+                           int B, int T, int H, const Buf& dgx, const Buf& dgh, cudaStream_t st, const void* whhT_img = nullptr) {
+    if (whhT_img && !getenv("ZS_GRU_BPTT_SIMPLE")) return launch_gru_bptt_cluster(whhT_img, gates, hbuf, h_choff, dout, do_choff, B, T, H, dgx, dgh, st);
     if (H > 1024) return fail(ZS_ERR_ARG, "gru bptt: H %d > 1024", H);
     constexpr int NBG = 4;
     dim3 grid((B + NBG - 1) / NBG, 2);
@@ -170,8 +199,8 @@ static int run_gru_train(void* whh_img, const float* whhT, const float* bhh, con
 // `hbuf` holds h_t at channels [h_choff + dir*H, ...), `dout` the gradient of that same region.
 static int gru_backward(const Buf& gates, const Buf& xin, int c_in, const Buf& hbuf, int h_choff, const Buf& dout, const float* const* w_hh,
                         int B, int T, int H, const Buf& dgx, const Buf& dgh, float* const* g_w_ih, float* const* g_w_hh,
-                        float* const* g_b_ih, float* const* g_b_hh, float inv_scale, cudaStream_t st) {
-    ZS_TRY(launch_gru_bptt(gates, hbuf, h_choff, dout, h_choff, w_hh, B, T, H, dgx, dgh, st));
+                        float* const* g_b_ih, float* const* g_b_hh, float inv_scale, cudaStream_t st, const void* whhT_img) {
+    ZS_TRY(launch_gru_bptt(gates, hbuf, h_choff, dout, h_choff, w_hh, B, T, H, dgx, dgh, st, whhT_img));
     for (int d = 0; d < 2; ++d) {
         WgradOpts wi; wi.c_out = 3 * H; wi.dy_ch0 = d * 3 * H; wi.c_in = c_in;
         ZS_TRY(run_wgrad(dgx, xin, B, T, g_w_ih[d], g_b_ih[d], inv_scale, wi, st));
@@ -379,7 +408,7 @@ extern "C" int zs_decoder_backward(zs_decoder* h, const float* spec, const float
         float* gwh[2] = {G(grads->gru_w_hh[0]), G(grads->gru_w_hh[1])};
         float* gbi[2] = {G(grads->gru_b_ih[0]), G(grads->gru_b_ih[1])};
         float* gbh[2] = {G(grads->gru_b_hh[0]), G(grads->gru_b_hh[1])};
-        ZS_TRY(gru_backward(w.gates, w.yBe, ch, w.catr, ch, w.G2, h->w_hh, B, Tf, H, w.dgx, w.dgh, gwi, gwh, gbi, gbh, inv, st));
+        ZS_TRY(gru_backward(w.gates, w.yBe, ch, w.catr, ch, w.G2, h->w_hh, B, Tf, H, w.dgx, w.dgh, gwi, gwh, gbi, gbh, inv, st, h->whhT_img));
         ZS_TRY(run_dgrad(h->gru_ih, w.dgx, B, Tf, &w.G3, nullptr, 0, ns, st));
     }
     {   // dense block 2 (:351): out = IN(lrelu(dense4(lrelu(dense3(yA + e4)) + e4))) + yA
@@ -618,7 +647,7 @@ extern "C" int zs_encoder_backward(zs_encoder* h, const float* d_act, float d_ac
         float* gwh[2] = {G(grads->gru_w_hh[0]), G(grads->gru_w_hh[1])};
         float* gbi[2] = {G(grads->gru_b_ih[0]), G(grads->gru_b_ih[1])};
         float* gbh[2] = {G(grads->gru_b_hh[0]), G(grads->gru_b_hh[1])};
-        ZS_TRY(gru_backward(w.gates, w.catr, h2, w.catr, h2, w.G_catr, h->w_hh, B, T8, H, w.dgx, w.dgh, gwi, gwh, gbi, gbh, inv, st));
+        ZS_TRY(gru_backward(w.gates, w.catr, h2, w.catr, h2, w.G_catr, h->w_hh, B, T8, H, w.dgx, w.dgh, gwi, gwh, gbi, gbh, inv, st, h->whhT_img));
         ZS_TRY(run_dgrad(h->gru_ih, w.dgx, B, T8, &w.G3, nullptr, 0, ns, st));
     }
     WgradOpts od; od.c_out = h2; od.c_in = h2;
