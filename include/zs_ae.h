@@ -165,17 +165,20 @@ size_t zs_decoder_train_workspace_bytes(const zs_decoder* h, int B, int T8);
  * zs_encoder_forward; the workspace keeps what the backward needs and must stay untouched until it ran.
  *   dropout_p     Encoder(dp=...); 0 disables dropout
  *   dropout_seed  counter-based masks: keep(seed, layer, b, c, t), reproduced by the backward
+ *   dropout_seed_dev  NULL, or a device pointer the kernels read the seed from instead (a CUDA-graph replay of the
+ *                 step then changes the masks by updating that word, without re-capture)
  *   keep_masks    NULL, or six device pointers to explicit (B, c_h2, T_l) byte masks in the reference's layout
  *                 (1 = keep) - lets a test replay the reference's own bernoulli draws */
 int zs_encoder_forward_train(zs_encoder* h, const float* x, int B, int T, const float* gumbel_noise,
-                             float dropout_p, uint64_t dropout_seed, const uint8_t* const* keep_masks,
-                             float* logits, float* act, int32_t* unit_ids,
+                             float dropout_p, uint64_t dropout_seed, const uint64_t* dropout_seed_dev,
+                             const uint8_t* const* keep_masks, float* logits, float* act, int32_t* unit_ids,
                              void* workspace, size_t workspace_bytes, void* stream);
 /* backward of the above: d_act (B, enc_size, T8) fp32 = (dLoss/d out_act) * d_act_scale; the same
  * gumbel_noise / logits / dropout arguments as the forward call; gradients accumulate into `grads`. */
 int zs_encoder_backward(zs_encoder* h, const float* d_act, float d_act_scale, const float* gumbel_noise,
                         const float* logits, int B, int T, float dropout_p, uint64_t dropout_seed,
-                        const uint8_t* const* keep_masks, float loss_scale, const zs_encoder_weights* grads,
+                        const uint64_t* dropout_seed_dev, const uint8_t* const* keep_masks, float loss_scale,
+                        const zs_encoder_weights* grads,
                         void* workspace, size_t workspace_bytes, void* stream);
 
 /* Decoder.forward in train mode (dense enc_act input so that it can take a gradient). */
@@ -194,11 +197,12 @@ int zs_grad_sqnorm(const float* g, size_t n, float* out, void* stream);
 /* nn.utils.clip_grad_norm_(max_norm) over ONE network (utils.py:53-55) fused with torch.optim.Adam's update
  * (trainer.py:64-66: lr, betas (0.5, 0.9), eps 1e-8, no weight decay): `sqnorm` is that network's squared
  * gradient norm (device scalar) BEFORE `grad_mult`, a factor applied to every gradient first (1/world_size after a
- * summing all-reduce); step = 1-based step count for the bias corrections.  When the norm is not
+ * summing all-reduce); step = 1-based step count for the bias corrections - or bias_corr_dev = device pointer to
+ * {1 - beta1^step, sqrt(1 - beta2^step)} (CUDA-graph replays).  When the norm is not
  * finite nothing is updated and *skipped (device int, may be NULL) is set to 1. */
 int zs_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, size_t n,
                  const float* sqnorm, float grad_mult, float max_norm, float lr, float beta1, float beta2, float eps,
-                 int step, int* skipped, void* stream);
+                 int step, const float* bias_corr_dev, int* skipped, void* stream);
 
 /* ---- measurement hooks (bench.py) --------------------------------------------------
  * Kernel classes: 0 = conv/linear implicit GEMM (tcgen05), 1 = GRU recurrence, 2 = everything else.

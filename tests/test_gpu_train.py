@@ -252,7 +252,7 @@ def test_clip_adam_kernels():
         sq.zero_()
         _lib.check(lib.zs_grad_sqnorm(gh.ptr(gd), n, gh.ptr(sq), gh.stream()))
         _lib.check(lib.zs_adam_step(gh.ptr(pd), gh.ptr(gd), gh.ptr(md), gh.ptr(vd), n, gh.ptr(sq), 0.5, 5.0, 1e-3, 0.5, 0.9,
-                                    1e-8, t, gh.ptr(skipped), gh.stream()))
+                                    1e-8, t, None, gh.ptr(skipped), gh.stream()))
         torch.cuda.synchronize()
         assert abs(sq.sqrt().item() * 0.5 - norm.item()) <= 1e-4 * norm.item()
         assert (pd.cpu() - params['w']).abs().max().item() <= 2e-6
@@ -262,7 +262,7 @@ def test_clip_adam_kernels():
     sq.zero_()
     _lib.check(lib.zs_grad_sqnorm(gh.ptr(gd), n, gh.ptr(sq), gh.stream()))
     _lib.check(lib.zs_adam_step(gh.ptr(pd), gh.ptr(gd), gh.ptr(md), gh.ptr(vd), n, gh.ptr(sq), 0.5, 5.0, 1e-3, 0.5, 0.9, 1e-8, 4,
-                                gh.ptr(skipped), gh.stream()))
+                                None, gh.ptr(skipped), gh.stream()))
     torch.cuda.synchronize()
     assert int(skipped.item()) == 1 and torch.equal(pd, before)
 

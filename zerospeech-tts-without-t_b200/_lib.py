@@ -122,16 +122,16 @@ SYMBOLS = {
     'zs_decoder_repack': (_i, [_vp, C.POINTER(DecoderWeights), _vp]),
     'zs_encoder_train_workspace_bytes': (_sz, [_vp, _i, _i]),
     'zs_decoder_train_workspace_bytes': (_sz, [_vp, _i, _i]),
-    'zs_encoder_forward_train': (_i, [_vp, _vp, _i, _i, _vp, C.c_float, C.c_uint64, C.POINTER(_vp), _vp, _vp, _vp,
+    'zs_encoder_forward_train': (_i, [_vp, _vp, _i, _i, _vp, C.c_float, C.c_uint64, _vp, C.POINTER(_vp), _vp, _vp, _vp,
                                       _vp, _sz, _vp]),
-    'zs_encoder_backward': (_i, [_vp, _vp, C.c_float, _vp, _vp, _i, _i, C.c_float, C.c_uint64, C.POINTER(_vp),
+    'zs_encoder_backward': (_i, [_vp, _vp, C.c_float, _vp, _vp, _i, _i, C.c_float, C.c_uint64, _vp, C.POINTER(_vp),
                                  C.c_float, C.POINTER(EncoderWeights), _vp, _sz, _vp]),
     'zs_decoder_forward_train': (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _sz, _vp]),
     'zs_decoder_backward': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, C.c_float, _vp, C.POINTER(DecoderWeights), _vp,
                                  _vp, _sz, _vp]),
     'zs_grad_sqnorm': (_i, [_vp, _sz, _vp, _vp]),
     'zs_adam_step': (_i, [_vp, _vp, _vp, _vp, _sz, _vp, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
-                          C.c_float, _i, _vp, _vp]),
+                          C.c_float, _i, _vp, _vp, _vp]),
     'zs_wgrad_cl': (_i, [C.POINTER(WgradDesc), _vp]),
 }
 

@@ -21,17 +21,26 @@ __device__ __forceinline__ uint32_t mix64(unsigned long long z) {
     return static_cast<uint32_t>(z >> 32);
 }
 struct DropSpec {
-    float p;                    // 0 = no dropout
-    unsigned long long seed;    // already mixed with the layer index
-    const uint8_t* keep;        // explicit mask (B, C, T) or null
+    float p;                          // 0 = no dropout
+    unsigned long long seed;          // step seed (value) ...
+    const unsigned long long* seed_dev;   // ... or read from device memory (CUDA-graph replays change it without re-capture)
+    int layer;                        // Dropout layer index, mixed into the seed
+    const uint8_t* keep;              // explicit mask (B, C, T) or null
     int C, T;
 };
-__device__ __forceinline__ float drop_scale(const DropSpec& d, int b, int c, int t) {
+__device__ __forceinline__ unsigned long long drop_layer_seed(const DropSpec& d) {
+    unsigned long long z = (d.seed_dev ? *d.seed_dev : d.seed) + 0x9E3779B97F4A7C15ull * static_cast<unsigned long long>(d.layer + 1);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+// `ls` = drop_layer_seed(d), hoisted by the caller
+__device__ __forceinline__ float drop_scale(const DropSpec& d, unsigned long long ls, int b, int c, int t) {
     if (d.p <= 0.f) return 1.f;
     const size_t idx = (static_cast<size_t>(b) * d.C + c) * d.T + t;
     bool keep;
     if (d.keep) keep = d.keep[idx] != 0;
-    else keep = (mix64(d.seed ^ (idx * 0x2545F4914F6CDD1Dull)) >> 8) * (1.f / 16777216.f) >= d.p;
+    else keep = (mix64(ls ^ (idx * 0x2545F4914F6CDD1Dull)) >> 8) * (1.f / 16777216.f) >= d.p;
     return keep ? 1.f / (1.f - d.p) : 0.f;
 }
 
@@ -73,8 +82,9 @@ __global__ void combine_fwd_kernel(const CombineParams p) {
     const int c = static_cast<int>(i % c2) * 2, t = static_cast<int>((i / c2) % p.T), b = static_cast<int>(i / (static_cast<size_t>(c2) * p.T));
     float2 v = __half22float2(*reinterpret_cast<const __half2*>(cl_at(p.x, b, p.x.halo + t, c)));
     if (p.drop.p > 0.f) {
-        v.x *= drop_scale(p.drop, b, c, t);
-        v.y *= drop_scale(p.drop, b, c + 1, t);
+        const unsigned long long ls = drop_layer_seed(p.drop);
+        v.x *= drop_scale(p.drop, ls, b, c, t);
+        v.y *= drop_scale(p.drop, ls, b, c + 1, t);
     }
     if (p.res_mode == RES_SAME) {
         const float2 r = __half22float2(*reinterpret_cast<const __half2*>(cl_at(p.res, b, p.res.halo + t, c)));
@@ -286,6 +296,7 @@ __global__ void __launch_bounds__(256) act_bwd_kernel(const ActBwdParams p) {
     }
     const __half* fwd = p.fwd ? p.fwd + static_cast<size_t>(b) * p.f_rows * p.f_pitch + p.f_choff + c : nullptr;
     const bool need_pass1 = p.stats != nullptr || p.demb != nullptr;
+    const unsigned long long ls = p.drop.p > 0.f ? drop_layer_seed(p.drop) : 0ull;
     float s1x = 0.f, s1y = 0.f, s2x = 0.f, s2y = 0.f, ex = 0.f, ey = 0.f;
     if (need_pass1 && c_ok) {
         for (int t = tl; t < T; t += 8) {
@@ -296,7 +307,7 @@ __global__ void __launch_bounds__(256) act_bwd_kernel(const ActBwdParams p) {
             else if (p.demb_from == 3) { ex += gx; ey += gy; }
             if (p.stats) {
                 const float2 xh = ld_h2(fwd + static_cast<size_t>(p.f_halo + t) * p.f_pitch);
-                if (p.drop.p > 0.f) { gx *= drop_scale(p.drop, b, c, t); gy *= drop_scale(p.drop, b, c + 1, t); }
+                if (p.drop.p > 0.f) { gx *= drop_scale(p.drop, ls, b, c, t); gy *= drop_scale(p.drop, ls, b, c + 1, t); }
                 s1x += gx; s1y += gy;
                 s2x = fmaf(gx, xh.x, s2x); s2y = fmaf(gy, xh.y, s2y);
             }
@@ -333,7 +344,7 @@ __global__ void __launch_bounds__(256) act_bwd_kernel(const ActBwdParams p) {
         if (fwd) f = ld_h2(fwd + static_cast<size_t>(p.f_halo + t) * p.f_pitch);
         float ux, uy;   // sign carriers of the pre-activation
         if (p.stats) {
-            if (p.drop.p > 0.f) { gx *= drop_scale(p.drop, b, c, t); gy *= drop_scale(p.drop, b, c + 1, t); }
+            if (p.drop.p > 0.f) { gx *= drop_scale(p.drop, ls, b, c, t); gy *= drop_scale(p.drop, ls, b, c + 1, t); }
             gx = rstd0 * (gx - m1x - f.x * m2x);
             gy = rstd1 * (gy - m1y - f.y * m2y);
             ux = f.x + mean0 * rstd0;     // u = xhat / rstd + mean has the sign of xhat + mean * rstd
@@ -490,7 +501,9 @@ __global__ void sqnorm_kernel(const float* __restrict__ g, size_t n, float* __re
 // the norm is not finite - the step is then a no-op (dynamic loss scaling).
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, size_t n, const float* __restrict__ sq, float grad_mult, float max_norm,
-                            float lr, float beta1, float beta2, float eps, float bc1, float bc2_sqrt, int* __restrict__ skip) {
+                            float lr, float beta1, float beta2, float eps, float bc1, float bc2_sqrt, const float* __restrict__ bc_dev,
+                            int* __restrict__ skip) {
+    if (bc_dev) { bc1 = bc_dev[0]; bc2_sqrt = bc_dev[1]; }     // CUDA-graph replays: the step count lives in device memory
     const float norm = sqrtf(*sq) * grad_mult;
     if (!isfinite(norm)) {
         if (skip && blockIdx.x == 0 && threadIdx.x == 0) *skip = 1;

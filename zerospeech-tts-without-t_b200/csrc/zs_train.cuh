@@ -70,18 +70,13 @@ static GradSrc gsrc_none() { return GradSrc{nullptr, 0, 0, 0, 0, GS_NONE}; }
 static GradSrc gsrc(const Buf& b, int mode, int pad = 0, int choff = 0) {
     return GradSrc{static_cast<const __half*>(b.p), b.rows, b.pitch, choff, pad, mode};
 }
-static unsigned long long layer_seed(uint64_t seed, int layer) {
-    unsigned long long z = seed + 0x9E3779B97F4A7C15ull * static_cast<unsigned long long>(layer + 1);
-    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-    return z ^ (z >> 31);
-}
-static DropSpec drop_spec(float p, uint64_t seed, int layer, const uint8_t* const* keep, int C, int T) {
+static DropSpec drop_spec(float p, uint64_t seed, const uint64_t* seed_dev, int layer, const uint8_t* const* keep, int C, int T) {
     DropSpec d;
-    d.p = p; d.seed = layer_seed(seed, layer); d.keep = (p > 0.f && keep) ? keep[layer] : nullptr; d.C = C; d.T = T;
+    d.p = p; d.seed = seed; d.seed_dev = reinterpret_cast<const unsigned long long*>(seed_dev); d.layer = layer;
+    d.keep = (p > 0.f && keep) ? keep[layer] : nullptr; d.C = C; d.T = T;
     return d;
 }
-static DropSpec drop_none() { return DropSpec{0.f, 0ull, nullptr, 0, 0}; }
+static DropSpec drop_none() { return DropSpec{0.f, 0ull, nullptr, 0, nullptr, 0, 0}; }
 
 static int launch_combine(CombineParams& p, cudaStream_t st) {
     if (p.C % 2) return fail(ZS_ERR_ARG, "combine: odd channel count %d", p.C);
@@ -521,7 +516,7 @@ extern "C" size_t zs_encoder_train_workspace_bytes(const zs_encoder* h, int B, i
 }
 
 extern "C" int zs_encoder_forward_train(zs_encoder* h, const float* x, int B, int T, const float* gumbel_noise, float dropout_p,
-                                        uint64_t dropout_seed, const uint8_t* const* keep_masks, float* logits, float* act,
+                                        uint64_t dropout_seed, const uint64_t* dropout_seed_dev, const uint8_t* const* keep_masks, float* logits, float* act,
                                         int32_t* unit_ids, void* workspace, size_t workspace_bytes, void* stream) {
     if (!h || !x || !logits || !gumbel_noise) return fail(ZS_ERR_ARG, "encoder_forward_train: null argument");
     if (!h->cfg.train) return fail(ZS_ERR_ARG, "encoder_forward_train: handle was packed without cfg.train");
@@ -539,7 +534,7 @@ extern "C" int zs_encoder_forward_train(zs_encoder* h, const float* x, int B, in
         memset(&p, 0, sizeof(p));
         p.x = cl_view(xh); p.res = res ? cl_view(*res) : cl_none(); p.res_mode = res_mode;
         p.y = cl_view(y); p.ye = cl_none(); p.bc = cl_none();
-        p.drop = drop_spec(dropout_p, dropout_seed, layer, keep_masks, h2, Tl);
+        p.drop = drop_spec(dropout_p, dropout_seed, dropout_seed_dev, layer, keep_masks, h2, Tl);
         p.B = B; p.T = Tl; p.C = h2;
         return launch_combine(p, st);
     };
@@ -597,7 +592,7 @@ extern "C" int zs_encoder_forward_train(zs_encoder* h, const float* x, int B, in
 }
 
 extern "C" int zs_encoder_backward(zs_encoder* h, const float* d_act, float d_act_scale, const float* gumbel_noise, const float* logits, int B,
-                                   int T, float dropout_p, uint64_t dropout_seed, const uint8_t* const* keep_masks, float loss_scale,
+                                   int T, float dropout_p, uint64_t dropout_seed, const uint64_t* dropout_seed_dev, const uint8_t* const* keep_masks, float loss_scale,
                                    const zs_encoder_weights* grads, void* workspace, size_t workspace_bytes, void* stream) {
     if (!h || !d_act || !gumbel_noise || !logits || !grads) return fail(ZS_ERR_ARG, "encoder_backward: null argument");
     if (!h->cfg.train) return fail(ZS_ERR_ARG, "encoder_backward: handle was packed without cfg.train");
@@ -617,7 +612,7 @@ extern "C" int zs_encoder_backward(zs_encoder* h, const float* d_act, float d_ac
         p.a = a; p.b = b; p.r = r;
         if (fwd) { p.fwd = static_cast<const __half*>(fwd->p); p.f_rows = fwd->rows; p.f_pitch = fwd->pitch; p.f_halo = fwd->halo; p.f_choff = f_choff; }
         p.stats = stats; p.stat_pitch = round_up(h2, BM); p.lrelu = 1; p.ns = ns;
-        p.drop = drop_layer >= 0 ? drop_spec(dropout_p, dropout_seed, drop_layer, keep_masks, h2, Tl) : drop_none();
+        p.drop = drop_layer >= 0 ? drop_spec(dropout_p, dropout_seed, dropout_seed_dev, drop_layer, keep_masks, h2, Tl) : drop_none();
         if (dpre) { p.dpre = static_cast<__half*>(dpre->p); p.d_rows = dpre->rows; p.d_pitch = dpre->pitch; p.d_halo = dpre->halo; }
         if (gsum) { p.gsum = static_cast<__half*>(gsum->p); p.g_rows = gsum->rows; p.g_pitch = gsum->pitch; }
         p.B = B; p.T = Tl; p.C = C;
@@ -712,7 +707,8 @@ extern "C" int zs_grad_sqnorm(const float* g, size_t n, float* out, void* stream
     return ZS_OK;
 }
 extern "C" int zs_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, size_t n, const float* sqnorm,
-                            float grad_mult, float max_norm, float lr, float beta1, float beta2, float eps, int step, int* skipped, void* stream) {
+                            float grad_mult, float max_norm, float lr, float beta1, float beta2, float eps, int step, const float* bias_corr_dev,
+                            int* skipped, void* stream) {
     if (!params || !grads || !exp_avg || !exp_avg_sq || !sqnorm) return fail(ZS_ERR_ARG, "adam_step: null argument");
     if (step < 1) return fail(ZS_ERR_ARG, "adam_step: step %d must be >= 1", step);
     ZS_TRY(ensure_device());
@@ -720,7 +716,7 @@ extern "C" int zs_adam_step(float* params, const float* grads, float* exp_avg, f
     const float bc1 = 1.f - powf(beta1, static_cast<float>(step)), bc2 = sqrtf(1.f - powf(beta2, static_cast<float>(step)));
     LaunchScope scope(st, KC_OTHER);
     adam_kernel<<<std::min<size_t>(8 * g_num_sms, (n + 255) / 256), 256, 0, st>>>(params, grads, exp_avg, exp_avg_sq, n, sqnorm, grad_mult, max_norm, lr,
-                                                                                  beta1, beta2, eps, bc1, bc2, skipped);
+                                                                                  beta1, beta2, eps, bc1, bc2, bias_corr_dev, skipped);
     CUDA_TRY(cudaGetLastError());
     return ZS_OK;
 }

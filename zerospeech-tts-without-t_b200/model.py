@@ -205,7 +205,7 @@ class Encoder(_Packed):
             _lib.check(_lib.lib().zs_encoder_repack(self._thandle, C.byref(w), _stream()))
 
     # -- training path (model/model.py:440-489 in train mode; trainer.py:246-249 encode_step) ----------
-    def forward_train(self, x, noise, dropout_seed=0, keep_masks=None):
+    def forward_train(self, x, noise, dropout_seed=0, keep_masks=None, seed_dev=None):
         """Train-mode forward.  `noise` = Gumbel noise (B, T8, enc_size) on the device; `keep_masks` = optional
         list of six (B, c_h2, T_l) uint8 tensors replaying explicit Dropout draws.  Returns (act, logits, ids);
         the activations the backward needs stay in the module's training workspace until `backward`."""
@@ -225,9 +225,10 @@ class Encoder(_Packed):
             ids = torch.empty(B, T8, dtype=torch.int32, device=dev)
             ws = self._get_train_workspace(lib.zs_encoder_train_workspace_bytes(h, B, T), dev)
             km = self._mask_table(keep_masks)
-            _lib.check(lib.zs_encoder_forward_train(h, _ptr(x), B, T, _ptr(noise), float(self.dp), int(dropout_seed), km,
-                                                    _ptr(logits), _ptr(act), _ptr(ids), _ptr(ws), ws.numel(), _stream()))
-        self._train_ctx = (B, T, noise, logits, int(dropout_seed), keep_masks)
+            _lib.check(lib.zs_encoder_forward_train(h, _ptr(x), B, T, _ptr(noise), float(self.dp), int(dropout_seed) & (2 ** 64 - 1),
+                                                    _ptr(seed_dev), km, _ptr(logits), _ptr(act), _ptr(ids), _ptr(ws), ws.numel(),
+                                                    _stream()))
+        self._train_ctx = (B, T, noise, logits, int(dropout_seed) & (2 ** 64 - 1), keep_masks, seed_dev)
         return act, logits, ids
 
     @staticmethod
@@ -246,7 +247,7 @@ class Encoder(_Packed):
     def backward(self, d_act, grads, loss_scale, d_act_scale=1.0):
         """Backward of the last `forward_train`: `d_act` (B, enc_size, T8) fp32 = dLoss/d(out_act) * d_act_scale;
         parameter gradients are ACCUMULATED into the tensors of `grads` (dict name -> fp32 tensor)."""
-        B, T, noise, logits, seed, keep_masks = self._train_ctx
+        B, T, noise, logits, seed, keep_masks, seed_dev = self._train_ctx
         dev = d_act.device
         d_act = d_act.contiguous().float()
         lib = _lib.lib()
@@ -256,8 +257,8 @@ class Encoder(_Packed):
             g = self.weight_table(grads)
             km = self._mask_table(keep_masks)
             _lib.check(lib.zs_encoder_backward(h, _ptr(d_act), float(d_act_scale), _ptr(noise), _ptr(logits), B, T,
-                                               float(self.dp), seed, km, float(loss_scale), C.byref(g), _ptr(ws),
-                                               ws.numel(), _stream()))
+                                               float(self.dp), seed, _ptr(seed_dev), km, float(loss_scale), C.byref(g),
+                                               _ptr(ws), ws.numel(), _stream()))
 
     @staticmethod
     def t8(T):

@@ -62,7 +62,7 @@ class PretrainAE:
     """One object = the (Encoder, Decoder, ae_opt) triple of trainer.py:58-66 with `step()` = trainer.py:321-332."""
 
     def __init__(self, encoder: Encoder, decoder: Decoder, lr=1e-4, betas=(0.5, 0.9), eps=1e-8, max_grad_norm=5.0,
-                 loss_scale=None, process_group=None, cpu_noise=False):
+                 loss_scale=None, process_group=None, cpu_noise=False, use_graph=True):
         if encoder.enc_mode != 'one_hot':
             raise RuntimeError("PretrainAE: the training path implements enc_mode 'one_hot'")
         self.enc, self.dec = _Net(encoder), _Net(decoder)
@@ -80,6 +80,16 @@ class PretrainAE:
         self._skip_event = None
         self.side = torch.cuda.Stream(device=dev) if self.world > 1 else None
         self.n_skipped = 0
+        # CUDA-graph replay of the whole iteration (single rank; ~190 launches otherwise cost more host time than the
+        # GPU needs to run them).  What changes between replays lives in device memory, refreshed from `_meta_host`
+        # by a copy node at the head of the graph: the dropout seed and Adam's two bias corrections.
+        self.use_graph = bool(use_graph) and self.world == 1 and not cpu_noise and dev.type == 'cuda'
+        self._graph = None
+        self._graph_key = None
+        self._warm = 0
+        if dev.type == 'cuda':
+            self._meta_host = torch.zeros(4, dtype=torch.float32).pin_memory()      # [seed lo, seed hi (as raw bits), bc1, bc2]
+            self._meta_dev = torch.zeros(4, dtype=torch.float32, device=dev)
 
     # ---- pieces -----------------------------------------------------------------------------------------
     def _noise(self, B, T8, dev):
@@ -109,17 +119,17 @@ class PretrainAE:
         with torch.cuda.stream(stream):
             dist.all_reduce(net.grad, op=dist.ReduceOp.SUM, group=self.pg)
 
-    def _optim(self, net):
+    def _optim(self, net, bc_dev=None):
         lib = _lib.lib()
         n = net.flat.numel()
         net.sqnorm.zero_()
         _lib.check(lib.zs_grad_sqnorm(_ptr(net.grad), n, _ptr(net.sqnorm), _stream()))
         _lib.check(lib.zs_adam_step(_ptr(net.flat), _ptr(net.grad), _ptr(net.m), _ptr(net.v), n, _ptr(net.sqnorm),
                                     1.0 / self.world, self.max_grad_norm, self.lr, self.betas[0], self.betas[1], self.eps,
-                                    self.step_count, _ptr(self.skipped), _stream()))
+                                    max(self.step_count, 1), _ptr(bc_dev), _ptr(self.skipped), _stream()))
 
     # ---- the iteration ----------------------------------------------------------------------------------
-    def forward_backward(self, x, c, noise=None, dropout_seed=None, keep_masks=None):
+    def forward_backward(self, x, c, noise=None, dropout_seed=None, keep_masks=None, seed_dev=None):
         """encode_step -> decode_step -> L1 -> backward.  Leaves the (local) gradients in the flat buffers and
         returns (loss (device scalar), unit ids)."""
         enc, dec = self.enc.module, self.dec.module
@@ -134,7 +144,7 @@ class PretrainAE:
         self.enc.grad.zero_()
         self.dec.grad.zero_()
         self.loss.zero_()
-        act, _, ids = enc.forward_train(x, noise, dropout_seed, keep_masks)             # trainer.py:325
+        act, _, ids = enc.forward_train(x, noise, dropout_seed, keep_masks, seed_dev)   # trainer.py:325
         dec.forward_train(act, c)                                                        # :326
         d_act = dec.backward(self.dec.grad_views, self.loss_scale, target=x, loss_out=self.loss)   # :327-329
         if self.world > 1:                  # decoder gradients travel while the encoder backward runs
@@ -143,10 +153,56 @@ class PretrainAE:
         enc.backward(d_act, self.enc.grad_views, self.loss_scale, d_act_scale=self.loss_scale)
         return self.loss, ids
 
+    def _set_meta(self):
+        import struct
+        seed = (self.step_count * 0x9E3779B97F4A7C15 + 0x1234567) & (2 ** 64 - 1)
+        # NaN bit patterns would not survive a float round trip through python: write the raw words instead
+        self._meta_host.view(torch.int32)[0:2] = torch.tensor(struct.unpack('ii', struct.pack('Q', seed)), dtype=torch.int32)
+        self._meta_host[2] = 1.0 - self.betas[0] ** self.step_count
+        self._meta_host[3] = (1.0 - self.betas[1] ** self.step_count) ** 0.5
+
+    def _graph_body(self):
+        """The iteration on static buffers; everything here is captured into the CUDA graph."""
+        self._meta_dev.copy_(self._meta_host, non_blocking=True)
+        seed_dev = self._meta_dev[0:2].view(torch.int64)
+        loss, _ = self.forward_backward(self._x_static, self._c_static, None, 0, None, seed_dev)
+        dev = self._x_static.device
+        with torch.cuda.device(dev):
+            self._optim(self.enc, self._meta_dev[2:4])
+            self._optim(self.dec, self._meta_dev[2:4])
+            self.enc.module._repack(dev)
+            self.dec.module._repack(dev)
+
+    def _step_graph(self, x, c):
+        key = (tuple(x.shape), float(self.loss_scale) if self.loss_scale else None)
+        if self._graph is None or key != self._graph_key:
+            self._x_static = torch.empty_like(x)
+            self._c_static = torch.empty_like(c)
+            self._graph = torch.cuda.CUDAGraph()
+            self._x_static.copy_(x)
+            self._c_static.copy_(c)
+            self._set_meta()
+            torch.cuda.synchronize()
+            with torch.cuda.graph(self._graph):
+                self._graph_body()
+            self._graph_key = key
+        self._x_static.copy_(x, non_blocking=True)
+        self._c_static.copy_(c, non_blocking=True)
+        self._set_meta()
+        self._graph.replay()
+        self.enc.module._packed_key = self.dec.module._packed_key = None
+        return self.loss
+
     def step(self, x, c, noise=None, dropout_seed=None, keep_masks=None):
         """One pretrain_AE iteration (trainer.py:321-332).  Returns the loss as a device tensor (no host sync)."""
         self._poll_skip()
         self.step_count += 1
+        plain = noise is not None or dropout_seed is not None or keep_masks is not None
+        if self.use_graph and not plain and self._warm >= 2:     # two eager steps first: allocations, attributes, loss scale
+            loss = self._step_graph(x, c)
+            self._after_step()
+            return loss
+        self._warm += 1
         loss, _ = self.forward_backward(x, c, noise, dropout_seed, keep_masks)
         if self.world > 1:
             self.side.wait_stream(torch.cuda.current_stream())
@@ -159,11 +215,14 @@ class PretrainAE:
             self.enc.module._repack(x.device)
             self.dec.module._repack(x.device)
             self.enc.module._packed_key = self.dec.module._packed_key = None     # the eval handles are stale now
+        self._after_step()
+        return loss
+
+    def _after_step(self):
         if self._skipped_host is not None and self._skip_event is None:
             self._skipped_host.copy_(self.skipped, non_blocking=True)
             self._skip_event = torch.cuda.Event()
             self._skip_event.record()
-        return loss
 
     def grad_norms(self):
         """(encoder, decoder) gradient L2 norms of the last step, before clipping (host floats; synchronises)."""
