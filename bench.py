@@ -42,9 +42,10 @@ def parse():
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
-    ap.add_argument('--segments', type=int, default=256, help='128-frame segments per GPU per step')
-    ap.add_argument('--micro-batch', type=int, default=256, help='segments per library call (device-resident value)')
-    ap.add_argument('--e2e-micro-batch', type=int, default=128, help='segments per pipelined copy/compute stage (e2e)')
+    ap.add_argument('--segments', type=int, default=896, help='128-frame segments per GPU per step')
+    ap.add_argument('--micro-batch', type=int, default=224,
+                    help='segments per library call: 224 = 14 GRU clusters of 32 sequences, one wave of the 15 that fit a B200')
+    ap.add_argument('--e2e-micro-batch', type=int, default=224, help='segments per pipelined copy/compute stage (e2e)')
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--operand', default='fp16', choices=['fp16', 'bf16'])
     ap.add_argument('--cpu-sample', type=int, default=32, help='segments in the CPU baseline sample')

@@ -213,6 +213,10 @@ int zs_adam_step(float* params, const float* grads, float* exp_avg, float* exp_a
 void zs_profile_begin(void);
 int zs_profile_end(double* ms, double* flops, long long* launches);
 void zs_launch_counts(long long* launches);
+/* Per-launch detail of the spans recorded since zs_profile_begin(), in launch order (call BEFORE zs_profile_end;
+ * synchronises the events): fills up to `max` entries of milliseconds / algorithmic FLOPs / kernel class and
+ * returns the number of recorded launches. */
+int zs_profile_detail(double* ms, double* flops, int* cls, int max);
 
 /* ---- building blocks, exported for the unit tests -------------------------------- */
 

@@ -112,6 +112,7 @@ SYMBOLS = {
     'zs_decoder_forward': (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _i, _vp, _sz, _vp]),
     'zs_profile_begin': (None, []),
     'zs_profile_end': (_i, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
+    'zs_profile_detail': (_i, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int), _i]),
     'zs_launch_counts': (None, [C.POINTER(C.c_longlong)]),
     'zs_bottleneck_one_hot': (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
     'zs_conv1d_cl': (_i, [C.POINTER(ConvDesc), _vp]),

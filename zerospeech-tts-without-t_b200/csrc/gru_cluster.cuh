@@ -1,14 +1,18 @@
 // Bidirectional GRU recurrence (model/model.py:59-66, zero initial state) on tcgen05 tensor cores.
 //
-// One thread-block CLUSTER of NC = H/64 CTAs runs the T sequential steps of one (direction, group of 16
+// One thread-block CLUSTER of NC = H/64 CTAs runs the T sequential steps of one (direction, group of 32
 // sequences).  CTA r owns hidden units [64r, 64r+64): its 192 rows of W_hh (r|z|n gates of those units, all
 // K = H columns, fp16/bf16) stay resident in shared memory for the whole kernel as the A operand; the hidden
-// state of the 16 sequences is the B operand ([16 rows][H], K-major, 128-byte swizzled), double-buffered.
-// Per step:  D_rz[128 x 16] = W_rz h^T (M = 128),  D_n[64 x 16] = W_n h^T (M = 64)  -> TMEM;
-// the 4 epilogue warps read D, add the precomputed input projections gx (from the GEMM kernel) and b_hh,
-// apply the gates, keep h in fp32 registers, write h_t to the output buffer and publish their 64-unit slice of
-// the new state to every CTA of the cluster with one bulk shared->shared::cluster copy per peer that
-// completes on the peer's mbarrier (no cluster-wide barrier inside the time loop).
+// state of the 32 sequences is the B operand ([32 rows][H], K-major, 128-byte swizzled) in ONE buffer (W_hh
+// leaves room for no more at H = 512).
+// Per step:  D_rz[128 x 32] = W_rz h^T (M = 128),  D_n[64 x 32] = W_n h^T (M = 64)  -> TMEM;
+// the 8 gate warps (two per TMEM lane quadrant, 16 sequences each) read D, add the precomputed input
+// projections gx (from the GEMM kernel) and b_hh, apply the gates, keep h in fp32 registers, write h_t to the
+// output buffer and publish their 64-unit slice of the new state to every CTA of the cluster with one bulk
+// shared->shared::cluster copy per peer that completes on the peer's mbarrier (no cluster-wide barrier inside
+// the time loop).  The single state buffer may only be overwritten once EVERY CTA's MMAs of the step have read
+// it: each CTA's tcgen05.commit is multicast to a `consumed` mbarrier in all CTAs of the cluster, and the gate
+// warps wait for it (normally long complete - the gate math sits in between) before they store or send h_{t+1}.
 //
 // Row order of the A tiles is chosen so a unit's three gate pre-activations land in the same warp:
 //   tile RZ (M = 128): TMEM lane 32q + l  = r-gate of unit 16q + l (l < 16), z-gate of unit 16q + l - 16 (l >= 16)
@@ -22,14 +26,16 @@
 
 namespace zs {
 
-constexpr int GRU_NSEQ = 16;        // sequences per cluster (UMMA N)
+constexpr int GRU_NSEQ = 16;        // sequences per cluster of the BPTT kernel (gru_bptt_cluster.cuh)
+constexpr int GRU_FWD_NSEQ = 32;    // sequences per cluster of the forward recurrence (UMMA N)
 constexpr int GRU_UNITS = 64;       // hidden units per CTA
-constexpr int GRU_THREADS = 160;    // warps 0-3: gate math (one TMEM quadrant each), warp 4: MMA issue / control
+constexpr int GRU_GATE_WARPS = 8;   // warp w: TMEM quadrant w & 3, sequences 16 * (w >> 2) .. + 16
+constexpr int GRU_THREADS = 32 * (GRU_GATE_WARPS + 1);    // + warp 8: MMA issue / control
 constexpr int GRU_TMEM_COLS = 64;
 
 __host__ __device__ inline int gru_w_image_bytes(int H) { return 192 * H * 2; }
 __host__ __device__ inline int gru_smem_bytes(int H) {
-    return gru_w_image_bytes(H) + 2 * GRU_NSEQ * H * 2 + 1024 /*align*/ + 128 /*barriers*/;
+    return gru_w_image_bytes(H) + GRU_FWD_NSEQ * H * 2 + 1024 /*align*/ + 128 /*barriers*/;
 }
 
 // byte offset of element (row, k) inside a K-major tile of `rows` rows stored as K/64 consecutive chunks of
@@ -104,31 +110,41 @@ struct GruParams {
     void* out;              // operand type [B][out_rows][out_pitch]
     int B, T, H, out_rows, out_pitch, out_halo, out_choff, fmt, debug;
     long long* dbg;        // debug bit 3: per-step clock64 stamps of cluster 0 / CTA 0 ([T][8])
+    int fast_act;          // 1: sigmoid/tanh through tanh.approx.f32 (one MUFU each, 2^-11 relative error)
     void* gates;           // training: r, z, n, hn = W_hn h + b_hn per step, operand type [B][T][2][4][H]; null = not saved
 };
+
+__device__ __forceinline__ float tanh_mufu(float v) {
+    float r;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(r) : "f"(v));
+    return r;
+}
 
 template <typename OT>
 __global__ void __launch_bounds__(GRU_THREADS, 1) gru_cluster_kernel(const GruParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_addr = smem_u32(smem_raw);
     uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+    constexpr int NSEQ = GRU_FWD_NSEQ;
     const int H = p.H, KCH = H >> 6;
     const int NC = (p.debug & 1) ? 1 : KCH;      // debug bit 0: pretend to be alone (no exchange, no peer waits)
     uint8_t* sW = smem;                                   // [192 * H * 2]
-    uint8_t* sH = smem + gru_w_image_bytes(H);            // 2 x [KCH chunks][16 rows][128 B]
-    const int hbuf_bytes = GRU_NSEQ * H * 2;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sH + 2 * hbuf_bytes);
-    uint64_t* h_full = bars;          // [2]
-    uint64_t* mma_done = bars + 2;    // [1]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
+    uint8_t* sH = smem + gru_w_image_bytes(H);            // [KCH chunks][32 rows][128 B]
+    const int hbuf_bytes = NSEQ * H * 2;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sH + hbuf_bytes);
+    uint64_t* h_chunk = bars;         // [8] chunk c of the next state (the 64 units of CTA c) is in place
+    uint64_t* rz_done = bars + 8;     // my r|z-tile MMAs of this step are complete
+    uint64_t* mma_done = bars + 9;    // all my MMAs of this step are complete
+    uint64_t* consumed = bars + 10;   // all MMAs of this step are complete in EVERY CTA of the cluster
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
     const int cl = cluster_id_x();
-    const int n_groups = (p.B + GRU_NSEQ - 1) / GRU_NSEQ;
-    const int dir = cl / n_groups, b0 = (cl % n_groups) * GRU_NSEQ;
+    const int n_groups = (p.B + NSEQ - 1) / NSEQ;
+    const int dir = cl / n_groups, b0 = (cl % n_groups) * NSEQ;
 
-    // ---- one-time setup: W_hh slice -> smem, zero h buffers, barriers, TMEM ----
+    // ---- one-time setup: W_hh slice -> smem, zero state, barriers, TMEM ----
     {
         const uint4* src = reinterpret_cast<const uint4*>(static_cast<const uint8_t*>(p.w_img) +
                                                           (static_cast<size_t>(dir) * KCH + rank) * gru_w_image_bytes(H));
@@ -136,15 +152,16 @@ __global__ void __launch_bounds__(GRU_THREADS, 1) gru_cluster_kernel(const GruPa
         const int n16 = gru_w_image_bytes(H) / 16;
         for (int i = threadIdx.x; i < n16; i += GRU_THREADS) dst[i] = src[i];
         uint4* hz = reinterpret_cast<uint4*>(sH);
-        for (int i = threadIdx.x; i < 2 * hbuf_bytes / 16; i += GRU_THREADS) hz[i] = make_uint4(0, 0, 0, 0);
+        for (int i = threadIdx.x; i < hbuf_bytes / 16; i += GRU_THREADS) hz[i] = make_uint4(0, 0, 0, 0);
     }
     if (threadIdx.x == 0) {
-        mbar_init(&h_full[0], 2);
-        mbar_init(&h_full[1], 2);
+        for (int c = 0; c < 8; ++c) mbar_init(&h_chunk[c], 1);
+        mbar_init(rz_done, 1);
         mbar_init(mma_done, 1);
+        mbar_init(consumed, NC);
         fence_barrier_init();
     }
-    if (warp == 4) tmem_alloc<GRU_TMEM_COLS>(tmem_slot);
+    if (warp == GRU_GATE_WARPS) tmem_alloc<GRU_TMEM_COLS>(tmem_slot);
     fence_proxy_async_smem();          // generic-proxy smem writes -> visible to the tensor-core (async) proxy
     tc_fence_before();
     __syncthreads();
@@ -152,70 +169,72 @@ __global__ void __launch_bounds__(GRU_THREADS, 1) gru_cluster_kernel(const GruPa
     const uint32_t tmem_base = *tmem_slot;
     cluster_sync_all();                // every CTA's barriers are initialised before any peer signals them
 
-    const uint32_t slice_bytes = GRU_NSEQ * 128;          // one 64-unit chunk of the state: [16 rows][128 B]
-    const uint32_t peer_tx = (NC - 1) * slice_bytes;
+    const uint32_t slice_bytes = NSEQ * 128;              // one 64-unit chunk of the state: [32 rows][128 B]
 
-    if (warp == 4) {
+    if (warp == GRU_GATE_WARPS) {
         // ------------------------------ control / MMA issue (whole warp, elected lane issues) ----
-        {
-            const uint32_t idesc_rz = umma_idesc_f16_m(p.fmt, 128, GRU_NSEQ);
-            const uint32_t idesc_n = umma_idesc_f16_m(p.fmt, 64, GRU_NSEQ);
-            const uint32_t w_rz = smem_u32(sW), w_n = smem_u32(sW) + 128 * H * 2, hb = smem_u32(sH);
-            if (elect_one()) {
-                if (NC > 1) {              // arm the first use of each state buffer (steps 1 and 2)
-                    if (p.T > 1) mbar_expect_tx(&h_full[1], peer_tx);
-                    if (p.T > 2) mbar_expect_tx(&h_full[0], peer_tx);
-                } else {
-                    if (p.T > 1) mbar_arrive(&h_full[1]);
-                    if (p.T > 2) mbar_arrive(&h_full[0]);
-                }
-            }
-            __syncwarp();
-            for (int t = 0; t < p.T; ++t) {
-                const int pb = t & 1;
-                if (t > 0) {
-                    mbar_wait(&h_full[pb], ((t - 1) >> 1) & 1);
-                    if (t + 2 < p.T && elect_one()) {   // re-arm this buffer for step t + 2
-                        if (NC > 1) mbar_expect_tx(&h_full[pb], peer_tx);
-                        else mbar_arrive(&h_full[pb]);
-                    }
+        const uint32_t idesc_rz = umma_idesc_f16_m(p.fmt, 128, NSEQ);
+        const uint32_t idesc_n = umma_idesc_f16_m(p.fmt, 64, NSEQ);
+        const uint32_t w_rz = smem_u32(sW), w_n = smem_u32(sW) + 128 * H * 2, hb = smem_u32(sH);
+        const uint16_t all_ctas = NC > 1 ? static_cast<uint16_t>((1u << NC) - 1u) : static_cast<uint16_t>(1u << rank);
+        if (p.T > 1 && elect_one())                      // arm the arrival of the peers' slices of h_1
+            for (int c = 0; c < NC; ++c)
+                if (c != static_cast<int>(rank)) mbar_expect_tx(&h_chunk[c], slice_bytes);
+        __syncwarp();
+        for (int t = 0; t < p.T; ++t) {
+            const bool rec = (p.debug & 8) && p.dbg && blockIdx.x == 0 && lane == 0;
+            // r|z tile first, chunk by chunk in the order the slices land (mine, then the peers by ring distance):
+            // the MMAs of the early chunks run while the late ones are still in flight
+            if ((p.debug & 32) && t > 0 && NC > 1)            // experiment: no MMA before every slice has landed
+                for (int c = 0; c < KCH; ++c) mbar_wait(&h_chunk[c], (t - 1) & 1);
+            for (int j = 0; j < KCH; ++j) {
+                const int c = (static_cast<int>(rank) + KCH - j) % KCH;
+                if (t > 0 && (NC > 1 || j == 0)) {
+                    mbar_wait(&h_chunk[c], (t - 1) & 1);
+                    // re-arm for h_{t+1}: no peer sends it before it has seen my commit of this step
+                    if (c != static_cast<int>(rank) && t + 1 < p.T && elect_one()) mbar_expect_tx(&h_chunk[c], slice_bytes);
                     __syncwarp();
                 }
                 tc_fence_after();
-                const bool rec = (p.debug & 8) && p.dbg && blockIdx.x == 0 && lane == 0;
-                if (rec) p.dbg[t * 8 + 0] = clock64();
-                const uint32_t hcur = hb + pb * hbuf_bytes;
+                if (rec && j == 0) p.dbg[t * 8 + 0] = clock64();
                 if (elect_one()) {
-                    uint64_t da = umma_desc_sw128(w_rz), dn = umma_desc_sw128(w_n), db = umma_desc_sw128(hcur);
-                    for (int c = 0; c < KCH; ++c) {
+                    const uint64_t da = umma_desc_sw128(w_rz + c * (128 * 128)), db = umma_desc_sw128(hb + c * slice_bytes);
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            umma_f16(tmem_base, da + 2 * k, db + 2 * k, idesc_rz, (c | k) != 0);
-                            umma_f16(tmem_base + 32, dn + 2 * k, db + 2 * k, idesc_n, (c | k) != 0);
-                        }
-                        da += (128 * 128) >> 4;      // next 64-wide K chunk of each operand (address field is >> 4)
-                        dn += (64 * 128) >> 4;
-                        db += slice_bytes >> 4;
-                    }
-                    umma_commit(mma_done);
+                    for (int k = 0; k < 4; ++k) umma_f16(tmem_base, da + 2 * k, db + 2 * k, idesc_rz, (j | k) != 0);
                 }
                 __syncwarp();
-                if (rec) p.dbg[t * 8 + 1] = clock64();
             }
+            if (elect_one()) {
+                umma_commit(rz_done);
+                uint64_t dn = umma_desc_sw128(w_n), db = umma_desc_sw128(hb);
+                for (int c = 0; c < KCH; ++c) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) umma_f16(tmem_base + NSEQ, dn + 2 * k, db + 2 * k, idesc_n, (c | k) != 0);
+                    dn += (64 * 128) >> 4;       // next 64-wide K chunk of each operand (address field is >> 4)
+                    db += slice_bytes >> 4;
+                }
+                umma_commit(mma_done);
+                if (t + 1 < p.T) umma_commit_multicast(consumed, all_ctas);
+            }
+            __syncwarp();
+            if (rec) p.dbg[t * 8 + 1] = clock64();
         }
     } else {
-        // ------------------------------ gate math (warps 0..3) ------------------------------
-        const int q = warp, l = lane & 15, hi = lane >> 4;     // hi = 0: sequences 0..7, hi = 1: sequences 8..15
+        // ------------------------------ gate math (warps 0..7) ------------------------------
+        const int q = warp & 3, half = warp >> 2;
+        const int l = lane & 15, hi = lane >> 4;               // hi: which 8 of this warp's 16 sequences
         const int u_loc = 16 * q + l;                          // unit within this CTA's 64
         const int unit = rank * GRU_UNITS + u_loc;
         const float* bh = p.bhh + static_cast<size_t>(dir) * 3 * H;
         const float b_r = bh[unit], b_z = bh[H + unit], b_n = bh[2 * H + unit];
+        const bool fast = p.fast_act != 0;
         float h[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) h[i] = 0.f;
         OT* out = reinterpret_cast<OT*>(p.out);
-        const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(32 * q) << 16);
-        const int seq0 = b0 + 8 * hi;
+        const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(32 * q) << 16) + 16 * half;
+        const int row0 = 16 * half + 8 * hi;                   // first row of the state tile this thread writes
+        const int seq0 = b0 + row0;
         // input projections are prefetched one full step ahead (their HBM latency would otherwise sit on the
         // critical path of every step); they stay RAW in registers - converting them here would wait for the load
         OT gr[8], gz[8], gn[8], pr[8], pz[8], pn[8];
@@ -235,65 +254,102 @@ __global__ void __launch_bounds__(GRU_THREADS, 1) gru_cluster_kernel(const GruPa
         load_gx(0, pr, pz, pn);
         for (int t = 0; t < p.T; ++t) {
             const int tt = dir ? p.T - 1 - t : t;
-            const int pb = t & 1;
 #pragma unroll
             for (int i = 0; i < 8; ++i) { gr[i] = pr[i]; gz[i] = pz[i]; gn[i] = pn[i]; }
             load_gx(t + 1, pr, pz, pn);
             const bool rec = (p.debug & 8) && p.dbg && blockIdx.x == 0 && threadIdx.x == 0;
             if (rec) p.dbg[t * 8 + 2] = clock64();
-            mbar_wait(mma_done, t & 1);
+            // ---- r and z while the n-tile MMAs still run ----
+            mbar_wait(rz_done, t & 1);
             tc_fence_after();
             if (rec) p.dbg[t * 8 + 3] = clock64();
-            uint32_t a[16], nn[16];
-            tmem_ld16(t_addr, a);            // lanes 0-15: W_hr h, lanes 16-31: W_hz h   (16 sequences)
-            tmem_ld16(t_addr + 32, nn);      // lanes 0-15: W_hn h
-            tmem_ld_wait();
-            tc_fence_before();
-            if (rec) p.dbg[t * 8 + 4] = clock64();
-            float hr[8], hzv[8], hn[8];
+            float r[8], z[8];
+            {
+                uint32_t a[16];
+                tmem_ld16(t_addr, a);        // lanes 0-15: W_hr h, lanes 16-31: W_hz h   (this warp's 16 sequences)
+                tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const uint32_t send = hi ? a[i] : a[8 + i];
-                const uint32_t got = __shfl_xor_sync(0xffffffffu, send, 16);
-                const uint32_t gotn = __shfl_xor_sync(0xffffffffu, nn[8 + i], 16);
-                hr[i] = __uint_as_float(hi ? got : a[i]);
-                hzv[i] = __uint_as_float(hi ? a[8 + i] : got);
-                hn[i] = __uint_as_float(hi ? gotn : nn[i]);
-            }
-            uint8_t* hnext = sH + (pb ^ 1) * hbuf_bytes + rank * slice_bytes;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const float r = sigmoid_f(ot_to_float<OT>(gr[i]) + hr[i] + b_r);
-                const float z = sigmoid_f(ot_to_float<OT>(gz[i]) + hzv[i] + b_z);
-                const float n = tanh_f(ot_to_float<OT>(gn[i]) + r * (hn[i] + b_n));
-                h[i] = (1.f - z) * n + z * h[i];
-                const OT y = float_to_ot<OT>(h[i]);
-                if (p.gates != nullptr && seq0 + i < p.B) {
-                    OT* g = reinterpret_cast<OT*>(p.gates) + ((static_cast<size_t>(seq0 + i) * p.T + tt) * 2 + dir) * 4 * H + unit;
-                    g[0] = float_to_ot<OT>(r); g[H] = float_to_ot<OT>(z); g[2 * H] = float_to_ot<OT>(n); g[3 * H] = float_to_ot<OT>(hn[i] + b_n);
+                for (int i = 0; i < 8; ++i) {
+                    const uint32_t got = __shfl_xor_sync(0xffffffffu, hi ? a[i] : a[8 + i], 16);
+                    const float hr = __uint_as_float(hi ? got : a[i]);
+                    const float hz = __uint_as_float(hi ? a[8 + i] : got);
+                    const float xr = ot_to_float<OT>(gr[i]) + hr + b_r, xz = ot_to_float<OT>(gz[i]) + hz + b_z;
+                    if (fast) {
+                        r[i] = fmaf(0.5f, tanh_mufu(0.5f * xr), 0.5f);
+                        z[i] = fmaf(0.5f, tanh_mufu(0.5f * xz), 0.5f);
+                    } else {
+                        r[i] = sigmoid_f(xr);
+                        z[i] = sigmoid_f(xz);
+                    }
                 }
-                const int s = 8 * hi + i;      // row of the state tile
-                *reinterpret_cast<OT*>(hnext + s * 128 + ((((u_loc >> 3) ^ (s & 7)) << 4) | ((u_loc & 7) << 1))) = y;
-                const int b = seq0 + i;
-                if (b < p.B && !(p.debug & 4))
-                    out[(static_cast<size_t>(b) * p.out_rows + p.out_halo + tt) * p.out_pitch + p.out_choff + dir * H + unit] = y;
+            }
+            if (rec) p.dbg[t * 8 + 4] = clock64();
+            // ---- n and the new state ----
+            mbar_wait(mma_done, t & 1);
+            tc_fence_after();
+            OT y[8];
+            {
+                uint32_t nn[16];
+                tmem_ld16(t_addr + NSEQ, nn);    // lanes 0-15: W_hn h
+                tmem_ld_wait();
+                tc_fence_before();
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const uint32_t gotn = __shfl_xor_sync(0xffffffffu, nn[8 + i], 16);
+                    const float hn = __uint_as_float(hi ? gotn : nn[i]) + b_n;
+                    const float xn = fmaf(r[i], hn, ot_to_float<OT>(gn[i]));
+                    const float n = fast ? tanh_mufu(xn) : tanh_f(xn);
+                    h[i] = fmaf(z[i], h[i] - n, n);          // (1 - z) n + z h
+                    y[i] = float_to_ot<OT>(h[i]);
+                    const int b = seq0 + i;
+                    if (p.gates != nullptr && b < p.B) {
+                        OT* g = reinterpret_cast<OT*>(p.gates) + ((static_cast<size_t>(b) * p.T + tt) * 2 + dir) * 4 * H + unit;
+                        g[0] = float_to_ot<OT>(r[i]); g[H] = float_to_ot<OT>(z[i]); g[2 * H] = float_to_ot<OT>(n); g[3 * H] = float_to_ot<OT>(hn);
+                    }
+                }
             }
             if (rec) p.dbg[t * 8 + 5] = clock64();
+            if ((p.debug & 64) && !(p.debug & 4)) {           // experiment: output stores before the exchange
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int b = seq0 + i;
+                    if (b < p.B)
+                        out[(static_cast<size_t>(b) * p.out_rows + p.out_halo + tt) * p.out_pitch + p.out_choff + dir * H + unit] = y[i];
+                }
+            }
             if (t + 1 < p.T) {
+                // every CTA's MMAs of this step have read the state (and with them my previous outgoing copies have
+                // long landed): the buffer may now take h_{t+1}
+                mbar_wait(consumed, t & 1);
+                uint8_t* hnext = sH + rank * slice_bytes;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int s = row0 + i;      // row of the state tile
+                    *reinterpret_cast<OT*>(hnext + s * 128 + ((((u_loc >> 3) ^ (s & 7)) << 4) | ((u_loc & 7) << 1))) = y[i];
+                }
                 fence_proxy_async_smem();                       // my slice -> visible to the bulk-copy engine / MMA
-                asm volatile("bar.sync 1, 128;" ::: "memory");   // the 4 gate warps only
+                asm volatile("bar.sync 1, %0;" ::"n"(32 * GRU_GATE_WARPS) : "memory");   // the gate warps only
                 if (rec) p.dbg[t * 8 + 6] = clock64();
                 if (elect_one()) {      // each gate warp publishes the slice to its share of the peers
                     const uint32_t src = smem_u32(hnext);
-                    const uint32_t bar_local = smem_u32(&h_full[pb ^ 1]);
-                    for (uint32_t d = 1 + warp; d < static_cast<uint32_t>(NC); d += 4) {
+                    const uint32_t bar_local = smem_u32(&h_chunk[rank]);
+                    if (warp == 0) mbar_arrive(&h_chunk[rank]);   // my own slice is in place
+                    for (uint32_t d = 1 + warp; d < static_cast<uint32_t>(NC); d += GRU_GATE_WARPS) {
                         const uint32_t peer = (rank + d) % NC;
                         dsmem_bulk_copy(mapa_shared(src, peer), src, slice_bytes, mapa_shared(bar_local, peer));
                     }
-                    if (warp == 0) mbar_arrive(&h_full[pb ^ 1]);   // my own slice is in place
                 }
                 __syncwarp();
                 if (rec) p.dbg[t * 8 + 7] = clock64();
+            }
+            // h_t to the output buffer, off the exchange's critical path
+            if (!(p.debug & (4 | 64))) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int b = seq0 + i;
+                    if (b < p.B)
+                        out[(static_cast<size_t>(b) * p.out_rows + p.out_halo + tt) * p.out_pitch + p.out_choff + dir * H + unit] = y[i];
+                }
             }
         }
     }
@@ -301,7 +357,7 @@ __global__ void __launch_bounds__(GRU_THREADS, 1) gru_cluster_kernel(const GruPa
     tc_fence_before();
     __syncthreads();
     cluster_sync_all();                // nobody leaves while a peer may still be reading its slices
-    if (warp == 4) tmem_dealloc<GRU_TMEM_COLS>(tmem_base);
+    if (warp == GRU_GATE_WARPS) tmem_dealloc<GRU_TMEM_COLS>(tmem_base);
 }
 
 }  // namespace zs

@@ -115,6 +115,19 @@ extern "C" int zs_profile_end(double* ms, double* flops, long long* launches) {
     g_prof.clear();
     return ZS_OK;
 }
+extern "C" int zs_profile_detail(double* ms, double* flops, int* cls, int max) {
+    int n = 0;
+    for (auto& s : g_prof) {
+        if (n < max) {
+            if (cudaEventSynchronize(s.b) != cudaSuccess) return -1;
+            float t = 0.f;
+            if (cudaEventElapsedTime(&t, s.a, s.b) != cudaSuccess) return -1;
+            ms[n] = t; flops[n] = s.flops; cls[n] = s.cls;
+        }
+        ++n;
+    }
+    return n;
+}
 extern "C" void zs_launch_counts(long long* launches) {
     for (int i = 0; i < KC_COUNT; ++i) launches[i] = g_launches[i];
 }
@@ -331,6 +344,9 @@ static int launch_gru_cluster(const void* w_img, const float* bhh, const void* g
     ZS_TRY(ensure_device());
     GruParams p;
     p.gates = gates;
+    // gates through tanh.approx.f32 (one MUFU each; 2^-11 relative error, below the fp16 rounding of the state that
+    // feeds the next step's MMA) on the inference path; the training forward keeps the exp/rcp form
+    { const char* fa = getenv("ZS_GRU_FAST_ACT"); p.fast_act = fa ? atoi(fa) : (gates == nullptr ? 1 : 0); }
     p.w_img = w_img; p.bhh = bhh; p.gx = gx; p.out = out; p.B = B; p.T = T; p.H = H;
     p.out_rows = rows; p.out_pitch = pitch; p.out_halo = halo; p.out_choff = choff;
     p.fmt = operand == ZS_OPERAND_BF16 ? 1 : 0;
@@ -357,7 +373,7 @@ static int launch_gru_cluster(const void* w_img, const float* bhh, const void* g
             }
         }
     }
-    const int NC = H / GRU_UNITS, n_groups = (B + GRU_NSEQ - 1) / GRU_NSEQ;
+    const int NC = H / GRU_UNITS, n_groups = (B + GRU_FWD_NSEQ - 1) / GRU_FWD_NSEQ;
     const int smem = gru_smem_bytes(H);
     static int attr_set[2] = {0, 0};
     const int which = p.fmt;

@@ -183,16 +183,21 @@ class AutoencoderPath:
                 segs.append((u, j, e - s, spec[s:e]))
         return segs, keeps
 
-    def _run(self, specs, speakers, enc_only, decode, reference_noise_order):
+    def _run(self, specs, speakers, enc_only, decode, reference_noise_order, only=None):
+        """`only`: utterance indices this process is responsible for (multi-GPU sharding, shard.py); the noise of
+        every chunk is still drawn, in order, so the draws match a single-process run."""
         segs, keeps = self._segments(specs)
         enc_size = self.Encoder.enc_size
         # the reference draws the Gumbel noise per chunk, in call order, from the CPU generator
         noises = None
         if reference_noise_order and self.Encoder.enc_mode != 'continues':
             noises = [sample_gumbel(self.Encoder.noise_shape(1, T)) for (_, _, T, _) in segs]
+        wanted = range(len(specs)) if only is None else list(only)
+        want = set(wanted)
         by_len = {}
-        for i, (_, _, T, _) in enumerate(segs):
-            by_len.setdefault(T, []).append(i)
+        for i, (u, _, T, _) in enumerate(segs):
+            if u in want:
+                by_len.setdefault(T, []).append(i)
         units = [None] * len(segs)
         outs = [None] * len(segs)
         for T, idxs in by_len.items():
@@ -216,7 +221,7 @@ class AutoencoderPath:
                     if decode:
                         outs[i] = x_dec[n]
         res_units, res_specs = [], []
-        for u in range(len(specs)):
+        for u in wanted:
             mine = sorted((j, i) for i, (uu, j, _, _) in enumerate(segs) if uu == u)
             e = np.concatenate([units[i] for _, i in mine], axis=0)
             if keeps[u] is not None:
@@ -226,10 +231,10 @@ class AutoencoderPath:
                 res_specs.append(np.concatenate([outs[i] for _, i in mine], axis=0))
         return res_specs, res_units
 
-    def encode_utterances(self, specs, reference_noise_order=True):
+    def encode_utterances(self, specs, reference_noise_order=True, only=None):
         """encode() for a list of (L, 513) spectrograms -> list of (n_units, enc_size) arrays."""
-        return self._run(specs, None, True, False, reference_noise_order)[1]
+        return self._run(specs, None, True, False, reference_noise_order, only)[1]
 
-    def convert_utterances(self, specs, target_speakers, enc_only=True, reference_noise_order=True):
+    def convert_utterances(self, specs, target_speakers, enc_only=True, reference_noise_order=True, only=None):
         """convert() up to (not including) Griffin-Lim: -> (list of (L', 513) spectrograms, list of unit arrays)."""
-        return self._run(specs, list(target_speakers), enc_only, True, reference_noise_order)
+        return self._run(specs, list(target_speakers), enc_only, True, reference_noise_order, only)

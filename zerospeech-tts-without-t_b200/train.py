@@ -45,6 +45,15 @@ def views_like(flat, layout, module):
     return {n: flat[o:o + k].view(shapes[n]) for n, (o, k) in layout.items()}
 
 
+def reduce_gradients(flat_grad, group=None):
+    """The one collective of the training path: summing all-reduce of a network's flat fp32 gradient
+    over the data-parallel ranks (NCCL over NVLink on the GPUs, gloo in the CPU tests).  The sum is divided by the
+    world size where it is consumed (zs_adam_step's `grad_scale`), which makes the update that of the reference
+    step on the concatenated batch: mean-L1 over equal per-rank batches, no cross-sample statistics anywhere."""
+    dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM, group=group)
+    return flat_grad
+
+
 class _Net:
     """Flat parameter / gradient / Adam-moment storage of one network."""
 
@@ -117,7 +126,7 @@ class PretrainAE:
     def _allreduce(self, net, stream):
         """Summing all-reduce of one network's flat gradient on `stream` (zs_adam_step divides by the world size)."""
         with torch.cuda.stream(stream):
-            dist.all_reduce(net.grad, op=dist.ReduceOp.SUM, group=self.pg)
+            reduce_gradients(net.grad, self.pg)
 
     def _optim(self, net, bc_dev=None):
         lib = _lib.lib()
