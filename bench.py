@@ -42,10 +42,11 @@ def parse():
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
-    ap.add_argument('--segments', type=int, default=896, help='128-frame segments per GPU per step')
-    ap.add_argument('--micro-batch', type=int, default=224,
-                    help='segments per library call: 224 = 14 GRU clusters of 32 sequences, one wave of the 15 that fit a B200')
-    ap.add_argument('--e2e-micro-batch', type=int, default=224, help='segments per pipelined copy/compute stage (e2e)')
+    ap.add_argument('--segments', type=int, default=888, help='128-frame segments per GPU per step')
+    ap.add_argument('--micro-batch', type=int, default=222,
+                    help='segments per library call: 222 x 128 frames = 111 column tiles, x 8 row tiles = 6 x 148 CTAs exactly for the '
+                         '1024-channel layers, and 14 GRU clusters of 32 sequences (one wave of the 15 that fit a B200)')
+    ap.add_argument('--e2e-micro-batch', type=int, default=222, help='segments per pipelined copy/compute stage (e2e)')
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--operand', default='fp16', choices=['fp16', 'bf16'])
     ap.add_argument('--cpu-sample', type=int, default=32, help='segments in the CPU baseline sample')

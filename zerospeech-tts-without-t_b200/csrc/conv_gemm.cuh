@@ -7,8 +7,11 @@
 // B box, a stride-2 conv reads the buffer through a (channel, row parity, row pair, segment) view so the
 // box stays dense.
 // One CTA per SM, persistent over output tiles of 128 channels x (nb segments x Tt frames <= 256 columns).
-// Warp 0 = TMA producer, warp 1 = MMA issuer (one elected thread), warps 2..5 = epilogue.  Two fp32
-// accumulators of 256 TMEM columns each let the epilogue of tile i overlap the main loop of tile i+1.
+// Warp 0 = TMA producer, warp 1 = MMA issuer (one elected thread), warps 2..9 = epilogue in two SETS of four
+// (one warp per TMEM lane quadrant in each set); the sets take alternate segment groups of a tile, each with its
+// own staging tiles, residual barrier and TMA stores, so two epilogue warps per scheduler hide each other's
+// TMEM-load / shared-memory latency.  Two fp32 accumulators of 256 TMEM columns each let the epilogue of tile i
+// overlap the main loop of tile i+1.
 //
 // Epilogue (one thread = one output channel = one TMEM lane; the frames of a segment are its columns, so
 // InstanceNorm statistics never leave the thread): + bias[speaker] -> leaky-relu -> InstanceNorm ->
@@ -28,10 +31,13 @@ constexpr int MAX_BN = 256;
 constexpr int STAGES = 3;
 constexpr int A_STAGE_BYTES = BM * BK * 2;
 constexpr int B_STAGE_BYTES = MAX_BN * BK * 2;
-constexpr int GEMM_THREADS = 192;
+constexpr int EPI_SETS = 2;
+constexpr int GEMM_THREADS = 64 + EPI_SETS * 128;
 constexpr int TMEM_COLS = 512;
-constexpr int STAGING_BYTES = 65536;   // 2 epilogue staging tiles of 128 columns x 128 channels (or 256 x 64) x 2 B:
+constexpr int STAGING_BYTES = 65536;   // per epilogue set 2 staging tiles of 64 columns x 128 channels (or 128 x 64) x 2 B:
                                        // output double buffer, or output + residual tile
+constexpr int SET_STAGING_BYTES = STAGING_BYTES / EPI_SETS;
+constexpr int STG_TILE_BYTES = SET_STAGING_BYTES / 2;
 constexpr int GEMM_SMEM_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + STAGING_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 constexpr float IN_EPS = 1e-5f;
 
@@ -271,8 +277,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
     uint64_t* empty = full + STAGES;
     uint64_t* tfull = empty + STAGES;
     uint64_t* tempty = tfull + 2;
-    uint64_t* rbar = tempty + 2;   // residual tile landed in the staging buffer
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rbar + 1);
+    uint64_t* rbar = tempty + 2;   // [EPI_SETS] residual tile landed in the set's staging buffer
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rbar + EPI_SETS);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -284,9 +290,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tfull[i], 1);
-            mbar_init(&tempty[i], 4);
+            mbar_init(&tempty[i], 4 * EPI_SETS);
         }
-        mbar_init(rbar, 1);
+        for (int i = 0; i < EPI_SETS; ++i) mbar_init(&rbar[i], 1);
         fence_barrier_init();
         tma_prefetch_desc(&p.tmA);
         tma_prefetch_desc(&p.tmB);
@@ -383,11 +389,16 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
     } else {
         // ------------------------------ epilogue ----------------------------------
         const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+        const int eset = (warp - 2) >> 2;                    // epilogue set: warps 2..5 / 6..9
+        const bool set_lead = ((warp - 2) & 3) == 0;         // the set's TMA-issuing warp
+        const int set_bar = 1 + eset;                        // named barrier of the set's 128 threads
+        uint64_t* my_rbar = &rbar[eset];
         const int row = quad * 32 + lane;
         const bool lrelu = p.lrelu != 0;
         const float ns = p.ns;
         const int T = p.T;
-        OT* stage = reinterpret_cast<OT*>(sStage);
+        uint8_t* set_stage = sStage + eset * SET_STAGING_BYTES;
+        OT* stage = reinterpret_cast<OT*>(set_stage);
         int it = 0, rnd = 0;
         uint32_t res_phase = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
@@ -434,7 +445,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tempty[as]);
             } else if (p.out_mode == OUT_NCT32) {
-                for (int s = 0; s < p.nb; ++s) {
+                for (int s = eset; s < p.nb; s += EPI_SETS) {
                     const int b = nt * p.nb + s;
                     if (b >= p.B) break;
                     const uint32_t t_seg = t_lane + s * p.Tt;
@@ -457,19 +468,27 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
                 // residual rows per output frame: SAME 1, UP2 1/2, AVG2 2
                 const int res_rows_per_seg = p.res_mode == RES_UP2 ? p.rnd_rows / 2 : (p.res_mode == RES_AVG2 ? 2 * p.rnd_rows : p.rnd_rows);
                 ChanNorm cn_keep;
-                for (int s0 = 0; s0 < p.nb; s0 += p.rnd_ns) {
+                // segment groups alternate between the two sets; the last group of THIS set hands the accumulator back
+                const int n_groups = (p.nb + p.rnd_ns - 1) / p.rnd_ns;
+                const int my_last = ((n_groups - 1 - eset) & ~1) + eset;      // last group index with my parity (< 0: none)
+                if (my_last < 0 || eset >= n_groups) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tempty[as]);
+                }
+                for (int s0 = eset * p.rnd_ns; s0 < p.nb; s0 += EPI_SETS * p.rnd_ns) {
                     for (int h = 0; h < p.rnd_sub; ++h, ++rnd) {
                         const int f_lo = h * p.rnd_frames, f_hi = min(T, f_lo + p.rnd_frames);
                         // staging: with a residual, tile 0 = output and tile 1 = residual; otherwise the two tiles
                         // alternate as output buffers so a store's shared-memory read overlaps the next round
-                        OT* stage_out = stage + (has_res ? 0 : (rnd & 1) * (STAGING_BYTES / 4));
-                        const OT* stage_res = stage + STAGING_BYTES / 4;
+                        OT* stage_out = stage + (has_res ? 0 : (rnd & 1) * (STG_TILE_BYTES / 2));
+                        const OT* stage_res = stage + STG_TILE_BYTES / 2;
                         if (has_res) {
-                            if (warp == 2 && nt * p.nb + s0 < p.B && elect_one()) {
+                            if (set_lead && nt * p.nb + s0 < p.B && elect_one()) {
                                 // the previous round's readers passed the end-of-round barrier: tile 1 is free
-                                mbar_expect_tx(rbar, static_cast<uint32_t>(p.rnd_ns) * res_rows_per_seg * 256);
+                                mbar_expect_tx(my_rbar, static_cast<uint32_t>(p.rnd_ns) * res_rows_per_seg * 256);
                                 const int r_row = p.res_halo + (p.res_mode == RES_UP2 ? f_lo / 2 : (p.res_mode == RES_AVG2 ? 2 * f_lo : f_lo));
-                                tma_load_3d(&p.tmRes, sStage + STAGING_BYTES / 2, rbar, mt * BM, r_row, nt * p.nb + s0);
+                                tma_load_3d(&p.tmRes, set_stage + STG_TILE_BYTES, my_rbar, mt * BM, r_row, nt * p.nb + s0);
                             }
                             __syncwarp();
                         }
@@ -480,7 +499,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
                             const uint32_t t_seg = t_lane + s * p.Tt;
                             if (h == 0) cn_keep = chan_norm(b, t_seg);
                             if (has_res && !waited) {
-                                mbar_wait(rbar, res_phase);
+                                mbar_wait(my_rbar, res_phase);
                                 waited = true;
                             }
                             OT* stg = stage_out + static_cast<size_t>(s - s0) * p.rnd_rows * fstep * stg_row + stg_ch;
@@ -494,21 +513,21 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
                             else frames_to_staging<OT, RES_AVG2, false>(p, t_seg, f_lo, f_hi, T, cn_keep, lrelu, ns, stg, res_stg, out_s, 0, ch_ok);
                         }
                         if (has_res && nt * p.nb + s0 < p.B) res_phase ^= 1;
-                        const bool last = (s0 + p.rnd_ns >= p.nb) && (h + 1 == p.rnd_sub);
+                        const bool last = (s0 / p.rnd_ns == my_last) && (h + 1 == p.rnd_sub);
                         if (last) {   // every TMEM read of this tile is done: hand the accumulator back
                             tc_fence_before();
                             __syncwarp();
                             if (lane == 0) mbar_arrive(&tempty[as]);
                         }
                         fence_proxy_async();                              // staging writes -> visible to the TMA engine
-                        asm volatile("bar.sync 1, 128;" ::: "memory");
-                        if (warp == 2 && nt * p.nb + s0 < p.B && elect_one()) {
+                        asm volatile("bar.sync %0, 128;" ::"r"(set_bar) : "memory");
+                        if (set_lead && nt * p.nb + s0 < p.B && elect_one()) {
                             tma_store_3d(&p.tmOut, stage_out, ps ? mt * 64 : mt * BM, p.out_halo + fstep * f_lo, nt * p.nb + s0);
                             tma_store_commit();
                             if (has_res) tma_store_wait_read();            // single output tile: it must be free next round
                             else tma_store_wait_read1();                   // the other tile's store (2 rounds ago) is done
                         }
-                        asm volatile("bar.sync 1, 128;" ::: "memory");
+                        asm volatile("bar.sync %0, 128;" ::"r"(set_bar) : "memory");
                     }
                 }
             }

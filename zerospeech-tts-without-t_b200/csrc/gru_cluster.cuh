@@ -236,20 +236,36 @@ __global__ void __launch_bounds__(GRU_THREADS, 1) gru_cluster_kernel(const GruPa
         const int row0 = 16 * half + 8 * hi;                   // first row of the state tile this thread writes
         const int seq0 = b0 + row0;
         // input projections are prefetched one full step ahead (their HBM latency would otherwise sit on the
-        // critical path of every step); they stay RAW in registers - converting them here would wait for the load
+        // critical path of every step); they stay RAW in registers - converting them here would wait for the load.
+        // Per-sequence element offsets are kept in registers and stepped by a constant (no 64-bit address
+        // arithmetic inside the time loop); sequences past the batch are masked once.
         OT gr[8], gz[8], gn[8], pr[8], pz[8], pn[8];
-        auto load_gx = [&](int step, OT (&xr)[8], OT (&xz)[8], OT (&xn)[8]) {
-            const int ts = dir ? p.T - 1 - step : step;
+        const OT* gx_base = reinterpret_cast<const OT*>(p.gx);
+        const int gx_step = (dir ? -1 : 1) * 2 * 3 * H;              // elements between consecutive steps of a sequence
+        const int out_step = (dir ? -1 : 1) * p.out_pitch;
+        const int t_first = dir ? p.T - 1 : 0;
+        uint32_t live = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            if (seq0 + i < p.B) live |= 1u << i;
+        // element offsets of this thread's FIRST sequence at the current step (the launcher checks the 32-bit range);
+        // its other sequences follow at a constant stride
+        const int gx_seq = p.T * 6 * H, out_seq = p.out_rows * p.out_pitch;
+        int gx_off = ((seq0 * p.T + t_first) * 2 + dir) * 3 * H + unit;
+        int out_off = (seq0 * p.out_rows + p.out_halo + t_first) * p.out_pitch + p.out_choff + dir * H + unit;
+        const bool no_gx = (p.debug & 2) != 0;
+        auto load_gx = [&](int step, OT (&xr)[8], OT (&xz)[8], OT (&xn)[8]) {      // `step` must be the NEXT unread step
+            const bool ok = step < p.T && !no_gx;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                const int b = seq0 + i;
-                if (b < p.B && step < p.T && !(p.debug & 2)) {
-                    const OT* g = reinterpret_cast<const OT*>(p.gx) + ((static_cast<size_t>(b) * p.T + ts) * 2 + dir) * 3 * H + unit;
+                if (ok && (live >> i & 1)) {
+                    const OT* g = gx_base + (gx_off + i * gx_seq);
                     xr[i] = g[0]; xz[i] = g[H]; xn[i] = g[2 * H];
                 } else {
                     xr[i] = xz[i] = xn[i] = float_to_ot<OT>(0.f);
                 }
             }
+            gx_off += gx_step;
         };
         load_gx(0, pr, pz, pn);
         for (int t = 0; t < p.T; ++t) {
@@ -311,11 +327,8 @@ __global__ void __launch_bounds__(GRU_THREADS, 1) gru_cluster_kernel(const GruPa
             if (rec) p.dbg[t * 8 + 5] = clock64();
             if ((p.debug & 64) && !(p.debug & 4)) {           // experiment: output stores before the exchange
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int b = seq0 + i;
-                    if (b < p.B)
-                        out[(static_cast<size_t>(b) * p.out_rows + p.out_halo + tt) * p.out_pitch + p.out_choff + dir * H + unit] = y[i];
-                }
+                for (int i = 0; i < 8; ++i)
+                    if (live >> i & 1) out[out_off + i * out_seq] = y[i];
             }
             if (t + 1 < p.T) {
                 // every CTA's MMAs of this step have read the state (and with them my previous outgoing copies have
@@ -345,12 +358,10 @@ __global__ void __launch_bounds__(GRU_THREADS, 1) gru_cluster_kernel(const GruPa
             // h_t to the output buffer, off the exchange's critical path
             if (!(p.debug & (4 | 64))) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int b = seq0 + i;
-                    if (b < p.B)
-                        out[(static_cast<size_t>(b) * p.out_rows + p.out_halo + tt) * p.out_pitch + p.out_choff + dir * H + unit] = y[i];
-                }
+                for (int i = 0; i < 8; ++i)
+                    if (live >> i & 1) out[out_off + i * out_seq] = y[i];
             }
+            out_off += out_step;
         }
     }
 

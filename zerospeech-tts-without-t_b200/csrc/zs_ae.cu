@@ -216,9 +216,9 @@ static int launch_conv(const zs_conv_desc* d, cudaStream_t stream, const ConvExt
     }
     if (d->out_mode != OUT_NCT32) {   // epilogue rounds + the TMA store map of the channels-last output
         const bool ps = d->out_mode == OUT_PS;
-        // a round fills one 32 KB staging tile: 128 frames x 128 channels; avg-pool residual tiles have twice the
-        // rows of their output, so those layers run 64-frame rounds
-        const int rf = d->res_mode == RES_AVG2 ? 64 : 128;
+        // a round fills one 16 KB staging tile of its epilogue set: 64 frames x 128 channels; avg-pool residual tiles
+        // have twice the rows of their output, so those layers run 32-frame rounds
+        const int rf = d->res_mode == RES_AVG2 ? 32 : 64;
         p.rnd_frames = rf;
         p.rnd_rows = std::min(Tt, rf);
         p.rnd_sub = (Tt + rf - 1) / rf;
@@ -373,6 +373,8 @@ static int launch_gru_cluster(const void* w_img, const float* bhh, const void* g
             }
         }
     }
+    if (static_cast<long long>(B) * T * 6 * H >= (1ll << 31) || static_cast<long long>(B) * rows * pitch >= (1ll << 31))
+        return fail(ZS_ERR_ARG, "gru: %d sequences x %d steps exceed the 32-bit element offsets of the recurrence kernel", B, T);
     const int NC = H / GRU_UNITS, n_groups = (B + GRU_FWD_NSEQ - 1) / GRU_FWD_NSEQ;
     const int smem = gru_smem_bytes(H);
     static int attr_set[2] = {0, 0};
