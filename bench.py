@@ -215,24 +215,37 @@ def run_ours(args):
 
     streamer = StreamingResynthesizer(enc, dec, micro_batch=min(args.e2e_micro_batch, S), device=dev)
 
-    def step_e2e(i):     # public API: pinned host spectrograms/speakers/noise in, pinned host spectrograms/units out
+    # public API: pinned host spectrograms/speakers/noise in, pinned host spectrograms/units out.  Steps are issued
+    # back to back as a streaming server would (run_async): the upload of step i+1 overlaps the compute and download
+    # of step i; every step's results land in host memory inside the timed region (two alternating output buffers).
+    out_hosts = [(spec_host, ids_host), (torch.empty(S, 513, FRAMES).pin_memory(), torch.empty(S, 16, dtype=torch.int32).pin_memory())]
+    pending = []
+
+    def step_e2e(i):
         k = i % n_sets
-        streamer.run(xs_host[k], cs_host[k], spec_host, ids_host, nz_host[k])
+        sh, ih = out_hosts[i % 2]
+        if len(pending) >= 2:
+            pending.pop(0).synchronize()        # this output buffer's previous results are complete (and consumable)
+        pending.append(streamer.run_async(xs_host[k], cs_host[k], sh, ih, nz_host[k]))
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps, warmup):
+    def timed(fn, steps, warmup, finish=None):
         for i in range(warmup):
             fn(i)
+        if finish:
+            finish()
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
         e0.record()
         for i in range(steps):
             fn(warmup + i)
+        if finish:
+            finish()            # the timing stream waits for every step's download before the closing event
         e1.record()
         barrier()
         wall = time.perf_counter() - t0
@@ -262,7 +275,11 @@ def run_ours(args):
     gemm_ms, gemm_flops, gemm_launches = ms3[0] / 3, fl3[0] / 3, int(cnt[0]) // 3
     gru_ms, other_ms = ms3[1] / 3, ms3[2] / 3
 
-    t_e2e, _ = timed(step_e2e, args.steps, W)
+    def finish_e2e():
+        while pending:
+            torch.cuda.current_stream().wait_event(pending.pop(0))
+
+    t_e2e, _ = timed(step_e2e, args.steps, W, finish_e2e)
 
     frames_per_step = S * FRAMES * world
     value = frames_per_step * args.steps / t_dev
@@ -285,7 +302,9 @@ def run_ours(args):
             'clocks': clocks, 'gpu_launches': launches_per_step * args.steps,
             'e2e': {'value': e2e, 'unit': 'frames/s',
                     'h2d_bytes_per_step': S * (513 * FRAMES * 4 + 8 + 16 * ENC_SIZE * 4),
-                    'd2h_bytes_per_step': S * (513 * FRAMES * 4 + 16 * 4), 'ms_per_step': t_e2e / args.steps * 1e3},
+                    'd2h_bytes_per_step': S * (513 * FRAMES * 4 + 16 * 4), 'ms_per_step': t_e2e / args.steps * 1e3,
+                    'api': 'StreamingResynthesizer.run_async: pinned host in -> pinned host out, steps issued back to back '
+                           '(upload of step i+1 under compute/download of step i)'},
             'roofline': {'bound': 'tensor', 'kernel': 'conv_gemm_kernel (tcgen05 implicit GEMM, all conv/linear layers)',
                          'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak if peak else None,
                          'traffic': None, 'peak_source': peak_src, 'launches_per_step': gemm_launches,

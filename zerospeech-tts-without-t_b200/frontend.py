@@ -59,10 +59,13 @@ class StreamingResynthesizer:
         self.device = torch.device(device)
         self.s_in, self.s_cmp, self.s_out = (torch.cuda.Stream(self.device) for _ in range(3))
         self._bufs = None
+        self._issued = 0          # micro-batches issued over the life of the object (buffer sets rotate across calls)
 
     def _buffers(self, T, with_noise):
         key = (T, with_noise)
         if self._bufs is None or self._bufs[0] != key:
+            for st in (self.s_in, self.s_cmp, self.s_out):    # earlier calls may still be using the old buffers
+                st.synchronize()
             mb, dev, enc = self.mb, self.device, self.enc
             T8 = Encoder.t8(T)
             sets = []
@@ -71,27 +74,30 @@ class StreamingResynthesizer:
                     x=torch.empty(mb, enc.c_in, T, device=dev), c=torch.empty(mb, dtype=torch.int64, device=dev),
                     noise=torch.empty(enc.noise_shape(mb, T), device=dev) if with_noise else None,
                     spec=torch.empty(mb, self.dec.c_out, 8 * T8, device=dev),
-                    ids=torch.empty(mb, T8, dtype=torch.int32, device=dev),
+                    ids=torch.empty(mb, T8, dtype=torch.int32, device=dev), used=False,
                     loaded=torch.cuda.Event(), computed=torch.cuda.Event(), drained=torch.cuda.Event()))
             self._bufs = (key, sets)
         return self._bufs[1]
 
     @torch.no_grad()
-    def run(self, x_host, c_host, spec_host, ids_host=None, noise_host=None):
+    def run_async(self, x_host, c_host, spec_host, ids_host=None, noise_host=None):
         """x_host (S, c_in, T) fp32, c_host (S,) int64, optional noise_host (S, T8, enc_size) -> spec_host (S, c_out, T'),
-        ids_host (S, T8) int32.  Returns after everything has landed in the host tensors."""
+        ids_host (S, T8) int32.  Returns a CUDA event that completes when everything has landed in the host tensors;
+        nothing here waits on the host, and consecutive calls overlap (the upload of call k+1 runs under the compute
+        and download of call k), so the host tensors of a call must stay untouched until its event has completed."""
         S, _, T = x_host.shape
         sets = self._buffers(T, noise_host is not None)
-        cur = torch.cuda.current_stream(self.device)
-        for st in (self.s_in, self.s_cmp, self.s_out):
-            st.wait_stream(cur)
+        ready = torch.cuda.Event()
+        ready.record(torch.cuda.current_stream(self.device))      # whatever prepared the inputs on the caller's stream
+        self.s_in.wait_event(ready)
         n_mb = (S + self.mb - 1) // self.mb
         for i in range(n_mb):
             s0, s1 = i * self.mb, min(S, (i + 1) * self.mb)
             n = s1 - s0
-            b = sets[i % self.nbuf]
+            b = sets[self._issued % self.nbuf]
+            self._issued += 1
             with torch.cuda.stream(self.s_in):
-                if i >= self.nbuf:
+                if b['used']:
                     self.s_in.wait_event(b['computed'])       # the compute that last read this input set is done
                 b['x'][:n].copy_(x_host[s0:s1], non_blocking=True)
                 b['c'][:n].copy_(c_host[s0:s1], non_blocking=True)
@@ -100,7 +106,7 @@ class StreamingResynthesizer:
                 b['loaded'].record(self.s_in)
             with torch.cuda.stream(self.s_cmp):
                 self.s_cmp.wait_event(b['loaded'])
-                if i >= self.nbuf:
+                if b['used']:
                     self.s_cmp.wait_event(b['drained'])       # its previous outputs have left the device
                 noise = b['noise'][:n] if noise_host is not None else None
                 _, _, ids = self.enc.encode(b['x'][:n], noise)
@@ -113,9 +119,16 @@ class StreamingResynthesizer:
                 if ids_host is not None:
                     ids_host[s0:s1].copy_(b['ids'][:n], non_blocking=True)
                 b['drained'].record(self.s_out)
-        cur.wait_stream(self.s_out)
-        cur.wait_stream(self.s_cmp)
-        cur.wait_stream(self.s_in)
+            b['used'] = True
+        done = torch.cuda.Event()
+        done.record(self.s_out)          # downloads are issued in order on one stream: the last one closes the call
+        return done
+
+    def run(self, x_host, c_host, spec_host, ids_host=None, noise_host=None):
+        """`run_async` + the caller's stream waits for the results (stream-ordered, like a torch op)."""
+        done = self.run_async(x_host, c_host, spec_host, ids_host, noise_host)
+        torch.cuda.current_stream(self.device).wait_event(done)
+        return done
 
 
 class AutoencoderPath:
