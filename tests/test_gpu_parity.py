@@ -355,8 +355,9 @@ def test_streaming_host_to_host_overlapping_calls(full_models):
         spec = torch.zeros(S, 513, T).pin_memory()
         ids = torch.zeros(S, 16, dtype=torch.int32).pin_memory()
         calls.append((x, c, noise, spec, ids, st.run_async(x, c, spec, ids, noise)))     # no host wait in between
+    for call in calls:
+        call[-1].synchronize()       # a module handle takes ONE call in flight: finish the stream before the direct calls
     for x, c, noise, spec, ids, done in calls:
-        done.synchronize()
         _, _, ids_d = enc.encode(x.cuda(), noise.cuda())
         spec_d = dec.decode(None, c.cuda(), unit_ids=ids_d)
         assert torch.equal(ids, ids_d.cpu())

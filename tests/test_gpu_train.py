@@ -339,3 +339,55 @@ def test_autograd_wrappers_match_fused_step():
             assert p.grad is not None
             ref = fused[k]
             assert (p.grad - ref).norm().item() <= 5e-2 * ref.norm().item() + 1e-6, (net, k)   # different loss scales -> different fp16 roundings
+
+
+def test_reference_training_loop_runs_unchanged_on_the_modules():
+    """trainer.py:321-332 verbatim in shape: Encoder(x) / Decoder(enc_act, c) in train() mode carry an autograd graph,
+    `loss.backward()` fills `.grad`, clip_grad_norm_ per network, ONE torch Adam over both networks; the modules
+    notice the in-place parameter update and re-pack their tensor-core operands.  Checked against the oracle's step."""
+    g = load_train_golden('train_small_dp0')
+    m = g['meta']
+    enc_sd, dec_sd, x, c, u, keep = train_inputs(g)
+    enc, dec = build_train_models(m)
+    enc.dp = 0.0
+    params = list(enc.parameters()) + list(dec.parameters())
+    opt = torch.optim.Adam(params, lr=1e-4, betas=(0.5, 0.9))             # trainer.py:64-66
+    xd, cd = x.cuda().requires_grad_(True), c.cuda()                      # utils.py:43-45: to_var -> requires_grad
+    enc_act, enc_out = enc(xd, gumbel_from_uniform(u).cuda())             # :325 encode_step
+    x_dec = dec(enc_act, cd)                                              # :326 decode_step
+    loss_rec = torch.mean(torch.abs(x_dec - xd))                          # :327
+    for net in (enc, dec):                                                # :328 reset_grad
+        net.zero_grad()
+    loss_rec.backward()                                                   # :329
+    for net in (enc, dec):                                                # :330 grad_clip per network
+        torch.nn.utils.clip_grad_norm_(net.parameters(), 5)
+    opt.step()                                                            # :332
+    torch.cuda.synchronize()
+    assert abs(loss_rec.item() - float(g['loss'])) <= 1e-3 * float(g['loss'])
+    o_enc = {k: v.clone() for k, v in enc_sd.items()}
+    o_dec = {k: v.clone() for k, v in dec_sd.items()}
+    orc.pretrain_ae_step(o_enc, o_dec, {}, x, c, u, keep_masks=None, dp=0.0, ns=m['ns'], seg_len=m['seg_len'])
+    moved = agree = 0
+    for sd0, sd1, mod in ((enc_sd, o_enc, enc), (dec_sd, o_dec, dec)):
+        for k, p in mod.named_parameters():
+            want = (sd1[k] - sd0[k])                                      # the oracle's update of this tensor
+            got = p.detach().cpu() - sd0[k]
+            big = want.abs() > 0.5e-4                                     # first Adam step: |update| ~ lr where |g| >> eps
+            moved += int(big.sum())
+            agree += int((torch.sign(got[big]) == torch.sign(want[big])).sum())
+    # (kinks of |.| and leaky-relu make individual signs ill-conditioned on the toy fixture - see test_train_step_matches_reference)
+    assert moved > 1000 and agree >= 0.6 * moved, (agree, moved)
+    for mod in (enc, dec):
+        for k, p in mod.named_parameters():
+            assert p.grad is not None and torch.isfinite(p.grad).all(), k
+    # the eval path sees the updated weights: the oracle on the module's own (updated) parameters
+    enc.eval(); dec.eval()
+    with torch.no_grad():
+        _, logits2, _ = enc.encode(x.cuda(), gumbel_from_uniform(u).cuda())
+        ours = {k: v.detach().cpu() for k, v in enc.state_dict().items()}
+        rels = {}
+        for name, sd in (('updated', ours), ('original', enc_sd), ('oracle-updated', o_enc)):
+            l_o = orc.encoder_forward(sd, x, u, ns=m['ns'], seg_len=m['seg_len'], enc_size=m['enc_size'])[1]
+            rels[name] = ((logits2.cpu() - l_o).norm() / l_o.norm()).item()
+    print('eval logits rel-RMS vs oracle on', rels)
+    assert rels['updated'] < 3e-2, rels

@@ -301,6 +301,12 @@ class Encoder(_Packed):
         return act, logits, ids
 
     def forward(self, x, noise=None):
+        """model/model.py:440-489.  eval() / no_grad: the inference kernels.  train() with autograd enabled (the
+        reference's `encode_step`, trainer.py:246-249): the training forward behind a `torch.autograd.Function`, so
+        the reference's own loop (loss.backward(), grad_clip, ae_opt.step()) runs unchanged on these modules."""
+        if self.training and torch.is_grad_enabled():
+            from .train import encode_step
+            return encode_step(self, x, noise)
         act, logits, _ = self.encode(x, noise)
         return act, logits
 
@@ -451,4 +457,8 @@ class Decoder(_Packed):
         return out
 
     def forward(self, x, c):
+        """model/model.py:344-365; train() with autograd enabled = `decode_step` (trainer.py:251-254) with a graph."""
+        if self.training and torch.is_grad_enabled():
+            from .train import decode_step
+            return decode_step(self, x, c)
         return self.decode(x, c)
