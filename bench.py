@@ -298,6 +298,16 @@ def run_ours(args):
         peak_src = 'MEASURED_PEAKS.json bf16_tflops_sustained (fp16 and bf16 share the kind::f16 rate)' if peaks \
             else 'fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)'
         achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+        # DRAM traffic of the GEMM launches from the committed ncu --set full capture (same micro-batch size only)
+        traffic, traffic_note = None, None
+        try:
+            tr = json.load(open(os.path.join(ROOT, 'profiles', 'r01_gemm_traffic.json')))
+            if tr['micro_batch'] == MB and S % MB == 0:
+                traffic = (tr['dram_read_bytes'] + tr['dram_write_bytes']) * (S // MB)
+                traffic_note = (f"bytes per step over all {gemm_launches} GEMM launches = {S // MB} micro-batches x "
+                                f"{(tr['dram_read_bytes'] + tr['dram_write_bytes']) / 1e9:.2f} GB (ncu capture of one micro-batch, profiles/r01_ncu_full_conv_gemm_mb222.csv)")
+        except Exception:
+            pass
         line = {
             'metric': METRIC, 'value': value, 'unit': 'frames/s', 'n_gpus': world, 'steps': args.steps, 'warmup': W,
             'ms_per_step': t_dev / args.steps * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
@@ -310,7 +320,7 @@ def run_ours(args):
                            '(upload of step i+1 under compute/download of step i)'},
             'roofline': {'bound': 'tensor', 'kernel': 'conv_gemm_kernel (tcgen05 implicit GEMM, all conv/linear layers)',
                          'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak if peak else None,
-                         'traffic': None, 'peak_source': peak_src, 'launches_per_step': gemm_launches,
+                         'traffic': traffic, 'traffic_note': traffic_note, 'peak_source': peak_src, 'launches_per_step': gemm_launches,
                          'algorithmic_gflop_per_step': gemm_flops / 1e9, 'kernel_ms_per_step': gemm_ms,
                          'share_of_step': gemm_ms / (gemm_ms + gru_ms + other_ms) if gemm_ms else None,
                          'gru_ms_per_step': gru_ms, 'other_ms_per_step': other_ms},
