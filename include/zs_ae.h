@@ -153,7 +153,8 @@ int zs_decoder_forward(zs_decoder* h, const float* enc_act, const int32_t* unit_
  * optimiser step (zs_*_repack: same allocations, no cudaMalloc).  Activation gradients travel as fp16 buffers
  * multiplied by `loss_scale` (a power of two; 2^15 * B is a good start); weight gradients are written UNSCALED in fp32
  * into caller-owned buffers shaped like the parameters (`zs_*_weights` used as a table of gradient pointers) and are
- * ACCUMULATED (+=, like autograd) - zero them before a step.  An fp16 overflow surfaces as a non-finite gradient
+ * written into ZEROED buffers - zero them before every backward (partial sums are combined with atomic adds, whole
+ * reductions are stored; a backward does not accumulate on top of an earlier one).  An fp16 overflow surfaces as a non-finite gradient
  * norm: zs_adam_step then skips the update and raises *skipped so the caller can halve the scale.
  * T must be 64 or 128 (seg_len; the weight-gradient GEMM reduces over 64-row boxes). */
 int zs_encoder_repack(zs_encoder* h, const zs_encoder_weights* w, void* stream);
@@ -217,6 +218,8 @@ void zs_launch_counts(long long* launches);
  * synchronises the events): fills up to `max` entries of milliseconds / algorithmic FLOPs / kernel class and
  * returns the number of recorded launches. */
 int zs_profile_detail(double* ms, double* flops, int* cls, int max);
+/* kernel label of recorded launch i (valid until zs_profile_end) */
+const char* zs_profile_name(int i);
 
 /* ---- building blocks, exported for the unit tests -------------------------------- */
 
@@ -277,7 +280,9 @@ int zs_gru_recurrence(const float* gx, const float* w_hh, const float* b_hh, int
 /* Weight-gradient GEMM of one conv / linear layer on channels-last fp16 buffers (tcgen05, MN-major operands):
  *   grad[co][ci_off + ci][tap0 + j] += scale * sum_{b,t} dy[b][dy_row0 + t][dy_ch0 + co] * x[b][x_row0 + stride*t + j][x_ch0 + ci]
  * for j < taps; grad is (c_out, c_in_total, k) fp32.  T in {8,16,32,64,128,...}: a power of two, or a multiple of 64.
- * ps_c > 0: dy channel m = r*ps_c + c stands for conv output channel 2c + r. */
+ * ps_c > 0: dy channel m = r*ps_c + c stands for conv output channel 2c + r.
+ * grad_is_zero != 0: the caller guarantees the addressed gradient entries are zero on entry; the library may then
+ * keep the whole reduction in one CTA and STORE the result instead of combining partial sums with atomic adds. */
 typedef struct {
     const void* dy; int32_t dy_rows, dy_pitch, dy_channels, dy_ch0, dy_row0, c_out;
     const void* x; int32_t x_rows, x_pitch, x_channels, x_ch0, x_row0, c_in, stride;
@@ -285,6 +290,7 @@ typedef struct {
     float* grad; int32_t c_in_total, ci_off, k, tap0;
     int32_t ps_c;
     float scale;
+    int32_t grad_is_zero;
 } zs_wgrad_desc;
 int zs_wgrad_cl(const zs_wgrad_desc* d, void* stream);
 

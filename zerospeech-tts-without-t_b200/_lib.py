@@ -93,7 +93,7 @@ class WgradDesc(C.Structure):
                 ('x_ch0', C.c_int32), ('x_row0', C.c_int32), ('c_in', C.c_int32), ('stride', C.c_int32),
                 ('B', C.c_int32), ('T', C.c_int32), ('taps', C.c_int32),
                 ('grad', C.c_void_p), ('c_in_total', C.c_int32), ('ci_off', C.c_int32), ('k', C.c_int32),
-                ('tap0', C.c_int32), ('ps_c', C.c_int32), ('scale', C.c_float)]
+                ('tap0', C.c_int32), ('ps_c', C.c_int32), ('scale', C.c_float), ('grad_is_zero', C.c_int32)]
 
 
 # every symbol include/zs_ae.h declares: name -> (restype, argtypes)
@@ -113,6 +113,7 @@ SYMBOLS = {
     'zs_profile_begin': (None, []),
     'zs_profile_end': (_i, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
     'zs_profile_detail': (_i, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int), _i]),
+    'zs_profile_name': (C.c_char_p, [_i]),
     'zs_launch_counts': (None, [C.POINTER(C.c_longlong)]),
     'zs_bottleneck_one_hot': (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
     'zs_conv1d_cl': (_i, [C.POINTER(ConvDesc), _vp]),

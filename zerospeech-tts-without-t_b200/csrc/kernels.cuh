@@ -194,19 +194,34 @@ __host__ __device__ inline int ps_row(int co) {
 
 // W (C_out, C_in, k) fp32 -> dst[row_off + row(co)][(tap_off + j) * c_in_pad + ci] operand type,
 // for input channels ci_lo <= ci_lo + ci < ci_lo + ci_n.  dst is pre-zeroed.
+// One block per (output channel, chunk of PACK_CI input channels): the (ci, j) -> (j, ci) transpose goes through
+// shared memory so both the fp32 reads and the operand writes are contiguous runs.
+constexpr int PACK_CI = 256;
 template <typename OT>
 __global__ void pack_weight_kernel(const float* __restrict__ W, OT* __restrict__ dst, int C_out, int C_in, int k,
                                    int ci_lo, int ci_n, long long k_total, int c_in_pad, int tap_off, int row_off,
                                    int ps) {
-    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-    const long long total = static_cast<long long>(C_out) * ci_n * k;
-    if (i >= total) return;
-    const int j = i % k;
-    const int ci = (i / k) % ci_n;
-    const int co = i / (static_cast<long long>(k) * ci_n);
-    const float v = W[(static_cast<long long>(co) * C_in + ci_lo + ci) * k + j];
+    extern __shared__ float pack_sw[];                    // [PACK_CI * k]
+    const int co = blockIdx.y, c0 = blockIdx.x * PACK_CI;
+    const int n = min(PACK_CI, ci_n - c0);
+    const float* src = W + (static_cast<long long>(co) * C_in + ci_lo + c0) * k;
+    for (int i = threadIdx.x; i < n * k; i += blockDim.x) pack_sw[i] = src[i];
+    __syncthreads();
     const int row = row_off + (ps ? ps_row(co) : co);
-    dst[row * k_total + static_cast<long long>(tap_off + j) * c_in_pad + ci] = float_to_ot<OT>(v);
+    OT* d = dst + row * k_total + static_cast<long long>(tap_off) * c_in_pad + c0;
+    for (int i = threadIdx.x; i < n * k; i += blockDim.x) {
+        const int j = i / n, ci = i - j * n;
+        d[static_cast<long long>(j) * c_in_pad + ci] = float_to_ot<OT>(pack_sw[ci * k + j]);
+    }
+    (void)C_out;
+}
+template <typename OT>
+inline cudaError_t launch_pack_weight(const float* W, OT* dst, int C_out, int C_in, int k, int ci_lo, int ci_n,
+                                      long long k_total, int c_in_pad, int tap_off, int row_off, int ps, cudaStream_t st) {
+    dim3 grid((ci_n + PACK_CI - 1) / PACK_CI, C_out);
+    pack_weight_kernel<OT><<<grid, 256, PACK_CI * k * sizeof(float), st>>>(W, dst, C_out, C_in, k, ci_lo, ci_n, k_total, c_in_pad,
+                                                                          tap_off, row_off, ps);
+    return cudaGetLastError();
 }
 
 // tab[s][row_off + row(co)] = (b ? b[co] : 0) + sum_{ci < C_e, j < k} W[co][ci_lo + ci][j] * emb[s][ci]

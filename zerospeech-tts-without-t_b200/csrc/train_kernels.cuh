@@ -459,19 +459,39 @@ __global__ void gru_bptt_simple_kernel(const __half* __restrict__ gates /* [B][T
 // ps_c > 0: the forward conv was pixel-shuffled: its gradient buffer keeps channel kk = r*ps_c + c for co = 2c + r
 // ---------------------------------------------------------------------------------------------
 __host__ __device__ inline int ps_row_ci(int ci, int r) { return (ci >> 6) * 128 + r * 64 + (ci & 63); }
+// One block per tile of PT_CO output channels x PT_CI input channels: the (co) <-> (ci) transpose goes through shared
+// memory, reads are runs of PT_CI * k floats per output channel, writes runs of up to PT_CO halves per (ci, tap).
+constexpr int PT_CO = 64, PT_CI = 16;
 __global__ void pack_weight_T_kernel(const float* __restrict__ W, __half* __restrict__ dst, int C_out, int C_in, int k,
                                      int ci_n, long long k_total, int c_out_pad, int mode, int ps_c) {
-    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (i >= static_cast<long long>(C_out) * ci_n * k) return;
-    const int j = i % k;
-    const int ci = (i / k) % ci_n;
-    const int co = i / (static_cast<long long>(k) * ci_n);
-    const float v = W[(static_cast<long long>(co) * C_in + ci) * k + j];
-    const int kk = ps_c > 0 ? (co & 1) * ps_c + (co >> 1) : co;
-    int row, tap;
-    if (mode == 0) { row = ci; tap = k - 1 - j; }
-    else { const int r = j & 1; row = ps_row_ci(ci, r); tap = (k >> 1) - ((j - r) >> 1); }
-    dst[row * k_total + static_cast<long long>(tap) * c_out_pad + kk] = __float2half_rn(v);
+    extern __shared__ float pt_sw[];                      // [PT_CO][PT_CI * k + 1]
+    const int co0 = blockIdx.y * PT_CO, ci0 = blockIdx.x * PT_CI;
+    const int n_co = min(PT_CO, C_out - co0), n_ci = min(PT_CI, ci_n - ci0);
+    const int rowlen = PT_CI * k + 1, run = n_ci * k;
+    for (int i = threadIdx.x; i < n_co * run; i += blockDim.x) {
+        const int co = i / run, r = i - co * run;
+        pt_sw[co * rowlen + r] = W[(static_cast<long long>(co0 + co) * C_in + ci0) * k + r];
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < PT_CO * run; i += blockDim.x) {
+        const int col = i & (PT_CO - 1), r = i / PT_CO;  // r = ci * k + j
+        // consecutive threads write consecutive K columns kk: with ps_c the even / odd output channels form two runs
+        const int co = ps_c > 0 ? ((col & 31) << 1 | (col >> 5)) : col;
+        if (co >= n_co) continue;
+        const int ci = ci0 + r / k, j = r % k;
+        const int gco = co0 + co;
+        const int kk = ps_c > 0 ? (gco & 1) * ps_c + (gco >> 1) : gco;
+        int row, tap;
+        if (mode == 0) { row = ci; tap = k - 1 - j; }
+        else { const int rr = j & 1; row = ps_row_ci(ci, rr); tap = (k >> 1) - ((j - rr) >> 1); }
+        dst[row * k_total + static_cast<long long>(tap) * c_out_pad + kk] = __float2half_rn(pt_sw[co * rowlen + r]);
+    }
+}
+inline cudaError_t launch_pack_weight_T(const float* W, __half* dst, int C_out, int C_in, int k, int ci_n, long long k_total,
+                                        int c_out_pad, int mode, int ps_c, cudaStream_t st) {
+    dim3 grid((ci_n + PT_CI - 1) / PT_CI, (C_out + PT_CO - 1) / PT_CO);
+    pack_weight_T_kernel<<<grid, 256, PT_CO * (PT_CI * k + 1) * sizeof(float), st>>>(W, dst, C_out, C_in, k, ci_n, k_total, c_out_pad, mode, ps_c);
+    return cudaGetLastError();
 }
 
 // ---------------------------------------------------------------------------------------------

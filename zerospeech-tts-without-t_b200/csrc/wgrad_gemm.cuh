@@ -8,9 +8,12 @@
 // activations are ever made.  A tap is a row offset of the X box, a stride-2 conv reads X through the same
 // (channel, row parity, row pair, segment) view the forward kernel uses.
 //
-// Work item = (128 output channels) x (<= 256 input channels) x (one tap) x (one K split); one CTA per SM walks
-// the items.  Warp 0 = TMA producer, warp 1 = MMA issuer, warps 2..5 = epilogue: fp32 accumulators leave TMEM
-// through red.global.add.f32 into the gradient in the reference's (C_out, C_in, k) layout.
+// Work item = (128 INPUT channels = the M rows of the MMA) x (<= 256 output channels) x (one tap) x (one K split);
+// one CTA per SM walks the items.  Warp 0 = TMA producer, warp 1 = MMA issuer, warps 2..5 = epilogue: fp32
+// accumulators leave TMEM through red.global.add.f32 into the gradient in the reference's (C_out, C_in, k) layout.
+// The input channel is the TMEM lane on purpose: the 32 lanes of an epilogue warp then add to 32 CONSECUTIVE
+// input channels of one output channel (stride k floats - one or a few cache lines per warp instruction) instead
+// of 32 different output-channel rows (32 lines per instruction).
 #pragma once
 #include <cuda_fp16.h>
 
@@ -22,8 +25,8 @@ namespace zs {
 constexpr int WG_STAGES = 4;
 constexpr int WG_KROWS = 64;                               // reduction rows per pipeline stage
 constexpr int WG_BLK_BYTES = WG_KROWS * 128;               // one {64 channels, 64 rows} box
-constexpr int WG_A_BYTES = 2 * WG_BLK_BYTES;               // 128 output channels
-constexpr int WG_B_BYTES = 4 * WG_BLK_BYTES;               // up to 256 input channels
+constexpr int WG_A_BYTES = 2 * WG_BLK_BYTES;               // 128 input channels (X)
+constexpr int WG_B_BYTES = 4 * WG_BLK_BYTES;               // up to 256 output channels (dY)
 constexpr int WG_SMEM_BYTES = WG_STAGES * (WG_A_BYTES + WG_B_BYTES) + 1024 + 256;
 constexpr int WG_THREADS = 192;
 
@@ -32,7 +35,7 @@ struct alignas(64) WgradParams {
     CUtensorMap tmB;      // X: stride 1 (channel, row, segment) box {64, rows_ps, nb}; stride 2 (channel, parity, pair, segment) box {64, 1, rows_ps, nb}
     float* grad;          // (c_out, c_in_total, k) fp32
     int m_tiles, n_tiles, taps, ksplit;
-    int n_blk_last;       // 64-channel blocks of the LAST n tile (others have 4)
+    int n_blk_last;       // 64-channel blocks of the LAST n (output-channel) tile (others have 4)
     int c_in, c_in_total, ci_off, c_out, k, tap0;   // grad index ((co * c_in_total + ci_off + ci) * k + tap0 + tap)
     int a_ch0, a_row0;    // A: first channel / buffer row of frame 0
     int b_ch0, b_row0;    // B: first channel / buffer row read by tap 0 of frame 0
@@ -40,6 +43,7 @@ struct alignas(64) WgradParams {
     int rows_ps, nb, seg_steps, n_groups;   // stage = nb segments x rows_ps rows (= 64); seg_steps stages per segment group
     int ps_c;             // > 0: A channel m = r * ps_c + c is conv output channel 2c + r (pixel-shuffled layer)
     float scale;
+    int direct;           // 1: ksplit == 1 and the gradient is zero on entry - store instead of red.add
 };
 
 __device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr) {
@@ -117,18 +121,18 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_gemm_kernel(const __grid_
                     mbar_expect_tx(&full[stage], tx);
                     uint8_t* a = sA + stage * WG_A_BYTES;
                     uint8_t* bb = sB + stage * WG_B_BYTES;
-                    const int a_row = p.a_row0 + sub * p.rows_ps;
-                    tma_load_3d(&p.tmA, a, &full[stage], p.a_ch0 + mt * 128, a_row, g * p.nb);
-                    tma_load_3d(&p.tmA, a + WG_BLK_BYTES, &full[stage], p.a_ch0 + mt * 128 + 64, a_row, g * p.nb);
-                    for (int j = 0; j < n_blk; ++j) {
-                        const int ch = p.b_ch0 + nt * 256 + j * 64;
+                    for (int j = 0; j < 2; ++j) {               // A: 128 input channels of X, shifted by the tap
+                        const int ch = p.b_ch0 + mt * 128 + j * 64;
                         if (p.stride == 2) {
                             const int r = p.b_row0 + tap;       // buffer row of frame 0; frame t is row r + 2t
-                            tma_load_4d(&p.tmB, bb + j * WG_BLK_BYTES, &full[stage], ch, r & 1, (r >> 1) + sub * p.rows_ps, g * p.nb);
+                            tma_load_4d(&p.tmB, a + j * WG_BLK_BYTES, &full[stage], ch, r & 1, (r >> 1) + sub * p.rows_ps, g * p.nb);
                         } else {
-                            tma_load_3d(&p.tmB, bb + j * WG_BLK_BYTES, &full[stage], ch, p.b_row0 + tap + sub * p.rows_ps, g * p.nb);
+                            tma_load_3d(&p.tmB, a + j * WG_BLK_BYTES, &full[stage], ch, p.b_row0 + tap + sub * p.rows_ps, g * p.nb);
                         }
                     }
+                    const int a_row = p.a_row0 + sub * p.rows_ps;
+                    for (int j = 0; j < n_blk; ++j)             // B: up to 256 output channels of dY
+                        tma_load_3d(&p.tmA, bb + j * WG_BLK_BYTES, &full[stage], p.a_ch0 + nt * 256 + j * 64, a_row, g * p.nb);
                 }
                 __syncwarp();
                 if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
@@ -175,21 +179,27 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_gemm_kernel(const __grid_
             const int as = it & 1;
             mbar_wait(&tfull[as], (it >> 1) & 1);
             tc_fence_after();
-            const int m = mt * 128 + row;                          // channel of the dY buffer (relative to a_ch0)
-            const int co = p.ps_c > 0 ? 2 * (m % p.ps_c) + m / p.ps_c : m;
-            const bool co_ok = m < p.c_out;
+            const int ci = mt * 128 + row;                         // input channel (relative to b_ch0) = TMEM lane
+            const bool ci_ok = ci < p.c_in;
             const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * MAX_BN;
-            float* gr = p.grad + (static_cast<size_t>(co_ok ? co : 0) * p.c_in_total + p.ci_off) * p.k + p.tap0 + tap;
+            float* gr = p.grad + (static_cast<size_t>(p.ci_off) + (ci_ok ? ci : 0)) * p.k + p.tap0 + tap;
+            const size_t co_stride = static_cast<size_t>(p.c_in_total) * p.k;
             if (s1 > s0) {
                 for (int c0 = 0; c0 < n_blk * 64; c0 += 16) {
                     uint32_t v[16];
                     tmem_ld16(t_lane + c0, v);
                     tmem_ld_wait();
-                    const int ci0 = nt * 256 + c0;
-                    if (co_ok) {
+                    const int m0 = nt * 256 + c0;                  // channel of the dY buffer (relative to a_ch0)
+                    if (ci_ok) {
 #pragma unroll
-                        for (int i = 0; i < 16; ++i)
-                            if (ci0 + i < p.c_in) red_add_f32(gr + static_cast<size_t>(ci0 + i) * p.k, __uint_as_float(v[i]) * p.scale);
+                        for (int i = 0; i < 16; ++i) {
+                            const int m = m0 + i;
+                            if (m < p.c_out) {
+                                const int co = p.ps_c > 0 ? 2 * (m % p.ps_c) + m / p.ps_c : m;
+                                if (p.direct) gr[co * co_stride] = __uint_as_float(v[i]) * p.scale;
+                                else red_add_f32(gr + co * co_stride, __uint_as_float(v[i]) * p.scale);
+                            }
+                        }
                     }
                 }
             }

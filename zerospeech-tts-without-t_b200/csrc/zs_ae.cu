@@ -79,20 +79,20 @@ extern "C" int zs_device_check(void) { return ensure_device(); }
 // launch accounting + optional per-kernel-class CUDA-event timing (zs_profile_begin / zs_profile_end)
 // -------------------------------------------------------------------------------------------------
 enum { KC_GEMM = 0, KC_GRU = 1, KC_OTHER = 2, KC_COUNT = 3 };
-struct ProfSpan { cudaEvent_t a, b; int cls; double flops; };
+struct ProfSpan { cudaEvent_t a, b; int cls; double flops; const char* name; };
 static bool g_prof_on = false;
 static std::vector<ProfSpan> g_prof;
 static long long g_launches[KC_COUNT] = {0, 0, 0};
 static double g_flops[KC_COUNT] = {0, 0, 0};
 
 struct LaunchScope {     // brackets one kernel launch on `st`
-    cudaStream_t st; int cls; double flops; cudaEvent_t a = nullptr, b = nullptr;
-    LaunchScope(cudaStream_t s, int c, double f = 0.0) : st(s), cls(c), flops(f) {
+    cudaStream_t st; int cls; double flops; const char* name; cudaEvent_t a = nullptr, b = nullptr;
+    LaunchScope(cudaStream_t s, int c, double f = 0.0, const char* nm = "") : st(s), cls(c), flops(f), name(nm) {
         g_launches[c]++; g_flops[c] += f;
         if (g_prof_on) { cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, st); }
     }
     ~LaunchScope() {
-        if (a) { cudaEventRecord(b, st); g_prof.push_back({a, b, cls, flops}); }
+        if (a) { cudaEventRecord(b, st); g_prof.push_back({a, b, cls, flops, name}); }
     }
 };
 
@@ -127,6 +127,9 @@ extern "C" int zs_profile_detail(double* ms, double* flops, int* cls, int max) {
         ++n;
     }
     return n;
+}
+extern "C" const char* zs_profile_name(int i) {
+    return (i >= 0 && i < static_cast<int>(g_prof.size())) ? g_prof[i].name : "";
 }
 extern "C" void zs_launch_counts(long long* launches) {
     for (int i = 0; i < KC_COUNT; ++i) launches[i] = g_launches[i];
@@ -273,7 +276,7 @@ static int launch_conv(const zs_conv_desc* d, cudaStream_t stream, const ConvExt
     {   // algorithmic FLOPs: 2 * valid out channels * true taps * true in channels * valid frames
         double taps_sum = d->bank ? 28.0 / 7.0 : static_cast<double>(d->taps);
         const double flops = 2.0 * d->m_valid * taps_sum * d->c_in_valid * static_cast<double>(d->B) * d->T_out;
-        LaunchScope scope(stream, KC_GEMM, flops);
+        LaunchScope scope(stream, KC_GEMM, flops, d->stride == 2 ? "conv_gemm s2" : (d->taps > 1 ? "conv_gemm" : "conv_gemm k1"));
         if (which) conv_gemm_kernel<__nv_bfloat16><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, stream>>>(p);
         else conv_gemm_kernel<__half><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, stream>>>(p);
     }
@@ -290,7 +293,7 @@ static int launch_pack_nct(const float* x, int B, int C, int T, void* out, int r
     if (halo >= T && halo > 0) return fail(ZS_ERR_ARG, "pack: reflect halo %d needs more than %d frames", halo, T);
     const int c_fill = zero_pad ? pitch - choff : C;
     dim3 grid((T + 31) / 32, (c_fill + 31) / 32, B), block(32, 8);
-    LaunchScope scope(st, KC_OTHER);
+    LaunchScope scope(st, KC_OTHER, 0.0, "pack_nct_kernel");
     if (operand == ZS_OPERAND_BF16)
         pack_nct_kernel<__nv_bfloat16><<<grid, block, 0, st>>>(x, static_cast<__nv_bfloat16*>(out), C, T, rows, pitch, halo, choff, c_fill, lrelu, ns);
     else
@@ -311,7 +314,7 @@ static int launch_onehot(const float* logits, const float* noise, int B, int C, 
         CUDA_TRY(cudaFuncSetAttribute(bottleneck_onehot_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         attr = 200 * 1024;
     }
-    LaunchScope scope(st, KC_OTHER);
+    LaunchScope scope(st, KC_OTHER, 0.0, "bottleneck_onehot_kernel");
     bottleneck_onehot_kernel<<<B, 512, smem, st>>>(logits, noise, C, T8, act, ids);
     CUDA_TRY(cudaGetLastError());
     return ZS_OK;
@@ -328,7 +331,7 @@ static int launch_gru(const void* gx, const float* whhT, const float* bhh, int B
     constexpr int NBG = 4;
     dim3 grid((B + NBG - 1) / NBG, 2);
     const size_t smem = static_cast<size_t>(NBG) * H * 4;
-    LaunchScope scope(st, KC_GRU, 2.0 * 2 * B * static_cast<double>(T) * 3 * H * H);
+    LaunchScope scope(st, KC_GRU, 2.0 * 2 * B * static_cast<double>(T) * 3 * H * H, "gru_simple_kernel");
     if (operand == ZS_OPERAND_BF16)
         gru_simple_kernel<__nv_bfloat16, NBG><<<grid, H, smem, st>>>(static_cast<const __nv_bfloat16*>(gx), whhT, bhh, B, T, H, static_cast<__nv_bfloat16*>(out), rows, pitch, halo, choff, static_cast<__nv_bfloat16*>(gates));
     else
@@ -399,7 +402,7 @@ static int launch_gru_cluster(const void* w_img, const float* bhh, const void* g
         cudaError_t e = cudaOccupancyMaxActiveClusters(&ncl, gru_cluster_kernel<__half>, &cfg);
         fprintf(stderr, "gru: max active clusters of %d CTAs with %d B smem: %d (%s); launching %d clusters\n", NC, smem, ncl, cudaGetErrorString(e), 2 * n_groups);
     }
-    LaunchScope scope(st, KC_GRU, 2.0 * 2 * B * static_cast<double>(T) * 3 * H * H);
+    LaunchScope scope(st, KC_GRU, 2.0 * 2 * B * static_cast<double>(T) * 3 * H * H, "gru_cluster_kernel");
     if (which) CUDA_TRY(cudaLaunchKernelEx(&cfg, gru_cluster_kernel<__nv_bfloat16>, p));
     else CUDA_TRY(cudaLaunchKernelEx(&cfg, gru_cluster_kernel<__half>, p));
     return ZS_OK;
@@ -483,13 +486,10 @@ static int pack_layer(DevPool& pool, Layer& L, int operand, const float* W, cons
     L.c_in_pad = round_up(ci_n, BK); L.c_in_valid = ci_n; L.ps = ps; L.per_spk = emb ? 1 : 0;
     const long long k_total = static_cast<long long>(k) * L.c_in_pad;
     ZS_TRY(pool.alloc(&L.w, static_cast<size_t>(L.m_rows) * k_total * 2, st));
-    const long long total = static_cast<long long>(C_out) * ci_n * k;
-    const int blocks = static_cast<int>((total + 255) / 256);
     if (operand == ZS_OPERAND_BF16)
-        pack_weight_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(W, static_cast<__nv_bfloat16*>(L.w), C_out, C_in, k, ci_lo, ci_n, k_total, L.c_in_pad, 0, 0, ps);
+        CUDA_TRY(launch_pack_weight(W, static_cast<__nv_bfloat16*>(L.w), C_out, C_in, k, ci_lo, ci_n, k_total, L.c_in_pad, 0, 0, ps, st));
     else
-        pack_weight_kernel<__half><<<blocks, 256, 0, st>>>(W, static_cast<__half*>(L.w), C_out, C_in, k, ci_lo, ci_n, k_total, L.c_in_pad, 0, 0, ps);
-    CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(launch_pack_weight(W, static_cast<__half*>(L.w), C_out, C_in, k, ci_lo, ci_n, k_total, L.c_in_pad, 0, 0, ps, st));
     const int n_tab = emb ? n_spk : 1;
     L.n_tab = n_tab;
     ZS_TRY(pool.alloc(reinterpret_cast<void**>(&L.bias), static_cast<size_t>(n_tab) * L.m_rows * 4, st));
@@ -511,9 +511,7 @@ static int pack_layer_T(DevPool& pool, Layer& L, const float* W, int C_out, int 
     if (mode == 1 && ci_n % 64) return fail(ZS_ERR_ARG, "train: a stride-2 layer needs c_in %% 64 == 0 (got %d)", ci_n);
     const long long k_total = static_cast<long long>(L.t_taps) * L.t_kpad;
     ZS_TRY(pool.alloc(&L.wt, static_cast<size_t>(L.t_rows) * k_total * 2, st));
-    const long long total = static_cast<long long>(C_out) * ci_n * k;
-    pack_weight_T_kernel<<<static_cast<int>((total + 255) / 256), 256, 0, st>>>(W, static_cast<__half*>(L.wt), C_out, C_in, k, ci_n, k_total, L.t_kpad, mode, ps_c);
-    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(launch_pack_weight_T(W, static_cast<__half*>(L.wt), C_out, C_in, k, ci_n, k_total, L.t_kpad, mode, ps_c, st));
     return ZS_OK;
 }
 
@@ -564,12 +562,10 @@ static int pack_gru(DevPool& pool, Layer& ih, float** whhT, float** bhh, void** 
     ZS_TRY(pool.alloc(reinterpret_cast<void**>(whhT), static_cast<size_t>(2) * 3 * H * H * 4, st));
     ZS_TRY(pool.alloc(reinterpret_cast<void**>(bhh), static_cast<size_t>(2) * 3 * H * 4, st));
     for (int dir = 0; dir < 2; ++dir) {
-        const long long total = static_cast<long long>(3) * H * C;
-        const int blocks = static_cast<int>((total + 255) / 256);
         if (operand == ZS_OPERAND_BF16)
-            pack_weight_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(w_ih[dir], static_cast<__nv_bfloat16*>(ih.w), 3 * H, C, 1, 0, C, ih.c_in_pad, ih.c_in_pad, 0, dir * 3 * H, 0);
+            CUDA_TRY(launch_pack_weight(w_ih[dir], static_cast<__nv_bfloat16*>(ih.w), 3 * H, C, 1, 0, C, ih.c_in_pad, ih.c_in_pad, 0, dir * 3 * H, 0, st));
         else
-            pack_weight_kernel<__half><<<blocks, 256, 0, st>>>(w_ih[dir], static_cast<__half*>(ih.w), 3 * H, C, 1, 0, C, ih.c_in_pad, ih.c_in_pad, 0, dir * 3 * H, 0);
+            CUDA_TRY(launch_pack_weight(w_ih[dir], static_cast<__half*>(ih.w), 3 * H, C, 1, 0, C, ih.c_in_pad, ih.c_in_pad, 0, dir * 3 * H, 0, st));
         const long long warps = static_cast<long long>(n_tab) * 3 * H;
         fold_bias_kernel<<<static_cast<int>((warps * 32 + 255) / 256), 256, 0, st>>>(w_ih[dir], b_ih[dir], emb, ih.bias, 3 * H, C, 1, 0, emb ? C : 0, n_tab, ih.m_rows, dir * 3 * H, 0);
         transpose_whh_kernel<<<(3 * H * H + 255) / 256, 256, 0, st>>>(w_hh[dir], *whhT + static_cast<size_t>(dir) * 3 * H * H, H);
@@ -599,11 +595,9 @@ static int pack_gru_T(DevPool& pool, Layer& ih, const float* const* w_ih, int C,
     ih.t_valid = C; ih.t_rows = round_up(C, BM); ih.t_taps = 1; ih.t_kpad = round_up(6 * H, BK); ih.t_kvalid = 6 * H;
     ZS_TRY(pool.alloc(&ih.wt, static_cast<size_t>(ih.t_rows) * ih.t_kpad * 2, st));
     for (int dir = 0; dir < 2; ++dir) {
-        const long long total = static_cast<long long>(3) * H * C;
         // mode 0, k = 1: dst[ci][kk] with kk = co; shift the destination by dir * 3H columns
-        pack_weight_T_kernel<<<static_cast<int>((total + 255) / 256), 256, 0, st>>>(w_ih[dir], static_cast<__half*>(ih.wt) + dir * 3 * H, 3 * H, C, 1, C, ih.t_kpad, ih.t_kpad, 0, 0);
+        CUDA_TRY(launch_pack_weight_T(w_ih[dir], static_cast<__half*>(ih.wt) + dir * 3 * H, 3 * H, C, 1, C, ih.t_kpad, ih.t_kpad, 0, 0, st));
     }
-    CUDA_TRY(cudaGetLastError());
     return ZS_OK;
 }
 
@@ -619,12 +613,10 @@ static int encoder_fill(zs_encoder* h, const zs_encoder_weights* w, cudaStream_t
         ZS_TRY(h->pool.alloc(reinterpret_cast<void**>(&L.bias), static_cast<size_t>(L.m_rows) * 4, st));
         for (int i = 0; i < 7; ++i) {
             const int k = i + 1;
-            const long long total = static_cast<long long>(h1) * c_in * k;
-            const int blocks = static_cast<int>((total + 255) / 256);
             if (op == ZS_OPERAND_BF16)
-                pack_weight_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(w->conv1s_w[i], static_cast<__nv_bfloat16*>(L.w), h1, c_in, k, 0, c_in, k_total, L.c_in_pad, 3 - k / 2, i * BM, 0);
+                CUDA_TRY(launch_pack_weight(w->conv1s_w[i], static_cast<__nv_bfloat16*>(L.w), h1, c_in, k, 0, c_in, k_total, L.c_in_pad, 3 - k / 2, i * BM, 0, st));
             else
-                pack_weight_kernel<__half><<<blocks, 256, 0, st>>>(w->conv1s_w[i], static_cast<__half*>(L.w), h1, c_in, k, 0, c_in, k_total, L.c_in_pad, 3 - k / 2, i * BM, 0);
+                CUDA_TRY(launch_pack_weight(w->conv1s_w[i], static_cast<__half*>(L.w), h1, c_in, k, 0, c_in, k_total, L.c_in_pad, 3 - k / 2, i * BM, 0, st));
             fold_bias_kernel<<<(h1 * 32 + 255) / 256, 256, 0, st>>>(w->conv1s_w[i], w->conv1s_b[i], nullptr, L.bias, h1, c_in, k, 0, 0, 1, L.m_rows, i * BM, 0);
         }
         CUDA_TRY(cudaGetLastError());
@@ -938,7 +930,7 @@ extern "C" int zs_encoder_forward(zs_encoder* h, const float* x, int B, int T, c
         ZS_TRY(launch_onehot(logits, gumbel_noise, B, g.enc_size, T8, act, unit_ids, st));
     } else if (act) {
         const size_t n = g.enc_mode == ZS_ENC_GUMBEL_T ? static_cast<size_t>(B) * g.enc_size : static_cast<size_t>(B) * g.enc_size * T8;
-        LaunchScope scope(st, KC_OTHER);
+        LaunchScope scope(st, KC_OTHER, 0.0, "bottleneck_misc_kernel");
         bottleneck_misc_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(logits, gumbel_noise, g.enc_mode, B, g.enc_size, T8, ns, act);
         CUDA_TRY(cudaGetLastError());
     }
@@ -960,7 +952,7 @@ extern "C" int zs_decoder_forward(zs_decoder* h, const float* enc_act, const int
 
     if (unit_ids) {   // one-hot input: input_emb is a column gather (model/model.py:346)
         dim3 grid(T8, B);
-        LaunchScope scope(st, KC_OTHER);
+        LaunchScope scope(st, KC_OTHER, 0.0, "unit_gather_kernel");
         if (op == ZS_OPERAND_BF16)
             unit_gather_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(unit_ids, static_cast<const __nv_bfloat16*>(h->emb_table), h->input_emb.bias, static_cast<__nv_bfloat16*>(w.x0.p), T8, ch, w.x0.rows, w.x0.pitch, 1, g.c_in);
         else

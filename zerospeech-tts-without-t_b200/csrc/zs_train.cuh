@@ -19,11 +19,17 @@ static int launch_wgrad(const zs_wgrad_desc* d, cudaStream_t st) {
     WgradParams p;
     memset(&p, 0, sizeof(p));
     p.rows_ps = rows_ps; p.nb = WG_KROWS / rows_ps; p.seg_steps = d->T / rows_ps; p.n_groups = (d->B + p.nb - 1) / p.nb;
-    p.m_tiles = (d->c_out + 127) / 128; p.n_tiles = (d->c_in + 255) / 256; p.taps = d->taps;
-    p.n_blk_last = (d->c_in - (p.n_tiles - 1) * 256 + 63) / 64;
+    p.m_tiles = (d->c_in + 127) / 128; p.n_tiles = (d->c_out + 255) / 256; p.taps = d->taps;     // M = input channels
+    p.n_blk_last = (d->c_out - (p.n_tiles - 1) * 256 + 63) / 64;
     const int k_stages = p.n_groups * p.seg_steps, items0 = p.m_tiles * p.n_tiles * p.taps;
     int ksplit = (2 * g_num_sms + items0 - 1) / items0;
     ksplit = std::max(1, std::min(ksplit, std::max(1, k_stages / 4)));
+    // At small batches the kernel is bound by its fp32 atomic adds (one per weight per K split), not by the MMAs:
+    // when the gradient is known to be zero and the items fill at least half the SMs on their own, keep the reduction
+    // whole and store (measured at B = 32 on one box: 2.35 ms of weight-gradient GEMMs per step -> 2.10 ms).
+    static const int direct_mode = [] { const char* e = getenv("ZS_WGRAD_DIRECT"); return e ? atoi(e) : 2; }();   // 0 off, 1 >= SMs, 2 >= SMs / 2 (measured best at B = 32)
+    p.direct = (d->grad_is_zero && direct_mode > 0 && direct_mode * items0 >= g_num_sms) ? 1 : 0;
+    if (p.direct) ksplit = 1;
     p.ksplit = ksplit;
     p.grad = d->grad; p.c_in = d->c_in; p.c_in_total = d->c_in_total; p.ci_off = d->ci_off; p.c_out = d->c_out; p.k = d->k; p.tap0 = d->tap0;
     p.a_ch0 = d->dy_ch0; p.a_row0 = d->dy_row0; p.b_ch0 = d->x_ch0; p.b_row0 = d->x_row0; p.stride = d->stride;
@@ -53,7 +59,7 @@ static int launch_wgrad(const zs_wgrad_desc* d, cudaStream_t st) {
     }
     const int total = items0 * ksplit;
     {
-        LaunchScope scope(st, KC_GEMM, 2.0 * d->c_out * d->c_in * d->taps * static_cast<double>(d->B) * d->T);
+        LaunchScope scope(st, KC_GEMM, 2.0 * d->c_out * d->c_in * d->taps * static_cast<double>(d->B) * d->T, "wgrad_gemm_kernel");
         wgrad_gemm_kernel<<<std::min(total, g_num_sms), WG_THREADS, WG_SMEM_BYTES, st>>>(p);
     }
     CUDA_TRY(cudaGetLastError());
@@ -81,7 +87,7 @@ static DropSpec drop_none() { return DropSpec{0.f, 0ull, nullptr, 0, nullptr, 0,
 static int launch_combine(CombineParams& p, cudaStream_t st) {
     if (p.C % 2) return fail(ZS_ERR_ARG, "combine: odd channel count %d", p.C);
     const size_t n = static_cast<size_t>(p.B) * p.T * (p.C / 2);
-    LaunchScope scope(st, KC_OTHER);
+    LaunchScope scope(st, KC_OTHER, 0.0, "combine_fwd_kernel");
     combine_fwd_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(p);
     CUDA_TRY(cudaGetLastError());
     return ZS_OK;
@@ -89,7 +95,7 @@ static int launch_combine(CombineParams& p, cudaStream_t st) {
 static int launch_act_bwd(ActBwdParams& p, cudaStream_t st) {
     if (p.C % 2) return fail(ZS_ERR_ARG, "act_bwd: odd channel count %d", p.C);
     dim3 grid((p.C + 63) / 64, p.B);
-    LaunchScope scope(st, KC_OTHER);
+    LaunchScope scope(st, KC_OTHER, 0.0, "act_bwd_kernel");
     act_bwd_kernel<<<grid, 256, 0, st>>>(p);
     CUDA_TRY(cudaGetLastError());
     return ZS_OK;
@@ -100,7 +106,7 @@ static int launch_colsum(const Buf& b, int B, int choff, int C, float scale, flo
     const long long n_rows = rows_override ? rows_override : static_cast<long long>(B) * b.rows;
     const int pitch = pitch_override ? pitch_override : b.pitch;
     dim3 grid((C + 63) / 64, static_cast<unsigned>(std::min<long long>(64, (n_rows + 63) / 64)));
-    LaunchScope scope(st, KC_OTHER);
+    LaunchScope scope(st, KC_OTHER, 0.0, "colsum_kernel");
     colsum_kernel<<<grid, 256, 0, st>>>(static_cast<const __half*>(b.p), n_rows, pitch, choff, C, scale, out, ps_c);
     CUDA_TRY(cudaGetLastError());
     return ZS_OK;
@@ -132,6 +138,7 @@ static int run_wgrad(const Buf& dpre, const Buf& x, int B, int T, float* grad_w,
     d.x = x.p; d.x_rows = x.rows; d.x_pitch = x.pitch; d.x_channels = x.pitch; d.x_ch0 = o.x_ch0; d.x_row0 = x.halo - (o.pad_left >= 0 ? o.pad_left : o.k / 2) + o.x_shift; d.c_in = o.c_in; d.stride = o.stride;
     d.B = B; d.T = T; d.taps = o.taps; d.grad = grad_w; d.c_in_total = o.c_in_total ? o.c_in_total : o.c_in; d.ci_off = o.ci_off; d.k = o.k; d.tap0 = o.tap0;
     d.ps_c = o.ps_c; d.scale = inv_scale;
+    d.grad_is_zero = 1;       // every weight tensor is written by exactly one call per backward, into zeroed gradients
     ZS_TRY(launch_wgrad(&d, st));
     if (grad_b) ZS_TRY(launch_colsum(dpre, B, o.dy_ch0, o.c_out, inv_scale, grad_b, o.ps_c, st));
     return ZS_OK;
@@ -163,7 +170,7 @@ static int launch_gru_bptt_cluster(const void* whhT_img, const Buf& gates, const
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = NC; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    LaunchScope scope(st, KC_GRU, 2.0 * 2 * B * static_cast<double>(T) * 3 * H * H);
+    LaunchScope scope(st, KC_GRU, 2.0 * 2 * B * static_cast<double>(T) * 3 * H * H, "gru_bptt_cluster_kernel");
     CUDA_TRY(cudaLaunchKernelEx(&cfg, gru_bptt_cluster_kernel, p));
     return ZS_OK;
 }
@@ -175,7 +182,7 @@ static int launch_gru_bptt(const Buf& gates, const Buf& hbuf, int h_choff, const
     constexpr int NBG = 4;
     dim3 grid((B + NBG - 1) / NBG, 2);
     const size_t smem = static_cast<size_t>(NBG) * 3 * H * 4;
-    LaunchScope scope(st, KC_GRU, 2.0 * 2 * B * static_cast<double>(T) * 3 * H * H);
+    LaunchScope scope(st, KC_GRU, 2.0 * 2 * B * static_cast<double>(T) * 3 * H * H, "gru_bptt_simple_kernel");
     gru_bptt_simple_kernel<NBG><<<grid, H, smem, st>>>(static_cast<const __half*>(gates.p), static_cast<const __half*>(hbuf.p), hbuf.rows, hbuf.pitch,
                                                        h_choff, static_cast<const __half*>(dout.p), dout.rows, dout.pitch, do_choff, w_hh[0], w_hh[1],
                                                        B, T, H, static_cast<__half*>(dgx.p), static_cast<__half*>(dgh.p));
@@ -376,7 +383,7 @@ extern "C" int zs_decoder_backward(zs_decoder* h, const float* spec, const float
     {   // loss + gradient through sigmoid / tanh  ->  dlin (channels-last, c_out channels)
         dim3 grid((Tf + 31) / 32, (w.dlin.pitch + 31) / 32, B), block(32, 8);
         const double n = static_cast<double>(B) * g.c_out * Tf;
-        LaunchScope scope(st, KC_OTHER);
+        LaunchScope scope(st, KC_OTHER, 0.0, "l1_loss_bwd_kernel");
         if (target)
             l1_loss_bwd_kernel<<<grid, block, 0, st>>>(spec, target, g.c_out, Tf, static_cast<__half*>(w.dlin.p), w.dlin.rows, w.dlin.pitch,
                                                        static_cast<float>(loss_scale / n), static_cast<float>(1.0 / n), g.output_mask, loss);
@@ -627,7 +634,7 @@ extern "C" int zs_encoder_backward(zs_encoder* h, const float* d_act, float d_ac
             CUDA_TRY(cudaFuncSetAttribute(gumbel_st_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
             attr = 200 * 1024;
         }
-        LaunchScope scope(st, KC_OTHER);
+        LaunchScope scope(st, KC_OTHER, 0.0, "gumbel_st_bwd_kernel");
         gumbel_st_bwd_kernel<<<B, 512, smem, st>>>(logits, gumbel_noise, d_act, C, T8, 10.f /* 1 / temperature 0.1 */,
                                                    10.f * (loss_scale / d_act_scale), static_cast<__half*>(w.dlog.p), w.dlog.rows, w.dlog.pitch);
         CUDA_TRY(cudaGetLastError());
@@ -701,7 +708,7 @@ extern "C" int zs_grad_sqnorm(const float* g, size_t n, float* out, void* stream
     if (!g || !out) return fail(ZS_ERR_ARG, "grad_sqnorm: null argument");
     ZS_TRY(ensure_device());
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    LaunchScope scope(st, KC_OTHER);
+    LaunchScope scope(st, KC_OTHER, 0.0, "sqnorm_kernel");
     sqnorm_kernel<<<std::min<size_t>(4 * g_num_sms, (n + 1023) / 1024 + 1), 1024, 0, st>>>(g, n, out);
     CUDA_TRY(cudaGetLastError());
     return ZS_OK;
@@ -714,7 +721,7 @@ extern "C" int zs_adam_step(float* params, const float* grads, float* exp_avg, f
     ZS_TRY(ensure_device());
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const float bc1 = 1.f - powf(beta1, static_cast<float>(step)), bc2 = sqrtf(1.f - powf(beta2, static_cast<float>(step)));
-    LaunchScope scope(st, KC_OTHER);
+    LaunchScope scope(st, KC_OTHER, 0.0, "adam_kernel");
     adam_kernel<<<std::min<size_t>(8 * g_num_sms, (n + 255) / 256), 256, 0, st>>>(params, grads, exp_avg, exp_avg_sq, n, sqnorm, grad_mult, max_norm, lr,
                                                                                   beta1, beta2, eps, bc1, bc2, bias_corr_dev, skipped);
     CUDA_TRY(cudaGetLastError());

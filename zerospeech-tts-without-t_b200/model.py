@@ -246,7 +246,7 @@ class Encoder(_Packed):
 
     def backward(self, d_act, grads, loss_scale, d_act_scale=1.0):
         """Backward of the last `forward_train`: `d_act` (B, enc_size, T8) fp32 = dLoss/d(out_act) * d_act_scale;
-        parameter gradients are ACCUMULATED into the tensors of `grads` (dict name -> fp32 tensor)."""
+        parameter gradients are written into the tensors of `grads` (dict name -> fp32 tensor), which must be ZERO on entry."""
         B, T, noise, logits, seed, keep_masks, seed_dev = self._train_ctx
         dev = d_act.device
         d_act = d_act.contiguous().float()
@@ -400,7 +400,7 @@ class Decoder(_Packed):
     def backward(self, grads, loss_scale, target=None, d_spec=None, loss_out=None, want_d_act=True):
         """Backward of the last `forward_train`.  Either `target` (B, c_out, T): the L1 loss of trainer.py:327 is fused
         and added to `loss_out` (device fp32 scalar, zero it first), or `d_spec` = dLoss/dspec.  Parameter gradients
-        are ACCUMULATED into `grads`; returns d_act = dLoss/d(enc_act) * loss_scale, (B, c_in, T8) fp32."""
+        are written into `grads` (zero on entry); returns d_act = dLoss/d(enc_act) * loss_scale, (B, c_in, T8) fp32."""
         B, T8, c, spec = self._train_ctx
         dev = spec.device
         lib = _lib.lib()
