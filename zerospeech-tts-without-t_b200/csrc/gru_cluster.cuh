@@ -27,15 +27,16 @@
 namespace zs {
 
 constexpr int GRU_NSEQ = 16;        // sequences per cluster of the BPTT kernel (gru_bptt_cluster.cuh)
-constexpr int GRU_FWD_NSEQ = 32;    // sequences per cluster of the forward recurrence (UMMA N)
+constexpr int GRU_FWD_NSEQ = 32;    // sequences per cluster of the forward recurrence (UMMA N): throughput shape
+constexpr int GRU_FWD_NSEQ_SMALL = 16;   // latency shape for batches whose 16-sequence clusters fit one wave
 constexpr int GRU_UNITS = 64;       // hidden units per CTA
-constexpr int GRU_GATE_WARPS = 8;   // warp w: TMEM quadrant w & 3, sequences 16 * (w >> 2) .. + 16
+constexpr int GRU_GATE_WARPS = 8;   // warp w: TMEM quadrant w & 3, sequences (NSEQ/2) * (w >> 2) .. + NSEQ/2
 constexpr int GRU_THREADS = 32 * (GRU_GATE_WARPS + 1);    // + warp 8: MMA issue / control
 constexpr int GRU_TMEM_COLS = 64;
 
 __host__ __device__ inline int gru_w_image_bytes(int H) { return 192 * H * 2; }
-__host__ __device__ inline int gru_smem_bytes(int H) {
-    return gru_w_image_bytes(H) + GRU_FWD_NSEQ * H * 2 + 1024 /*align*/ + 128 /*barriers*/;
+__host__ __device__ inline int gru_smem_bytes(int H, int nseq = GRU_FWD_NSEQ) {
+    return gru_w_image_bytes(H) + nseq * H * 2 + 1024 /*align*/ + 128 /*barriers*/;
 }
 
 // byte offset of element (row, k) inside a K-major tile of `rows` rows stored as K/64 consecutive chunks of
@@ -120,12 +121,13 @@ __device__ __forceinline__ float tanh_mufu(float v) {
     return r;
 }
 
-template <typename OT>
+template <typename OT, int NSEQ>
 __global__ void __launch_bounds__(GRU_THREADS, 1) gru_cluster_kernel(const GruParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_addr = smem_u32(smem_raw);
     uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
-    constexpr int NSEQ = GRU_FWD_NSEQ;
+    constexpr int CPW = NSEQ / 2;      // TMEM columns (sequences) per gate warp
+    constexpr int SPT = NSEQ / 4;      // sequences per gate thread
     const int H = p.H, KCH = H >> 6;
     const int NC = (p.debug & 1) ? 1 : KCH;      // debug bit 0: pretend to be alone (no exchange, no peer waits)
     uint8_t* sW = smem;                                   // [192 * H * 2]
@@ -222,31 +224,31 @@ __global__ void __launch_bounds__(GRU_THREADS, 1) gru_cluster_kernel(const GruPa
     } else {
         // ------------------------------ gate math (warps 0..7) ------------------------------
         const int q = warp & 3, half = warp >> 2;
-        const int l = lane & 15, hi = lane >> 4;               // hi: which 8 of this warp's 16 sequences
+        const int l = lane & 15, hi = lane >> 4;               // hi: which half of this warp's CPW sequences
         const int u_loc = 16 * q + l;                          // unit within this CTA's 64
         const int unit = rank * GRU_UNITS + u_loc;
         const float* bh = p.bhh + static_cast<size_t>(dir) * 3 * H;
         const float b_r = bh[unit], b_z = bh[H + unit], b_n = bh[2 * H + unit];
         const bool fast = p.fast_act != 0;
-        float h[8];
+        float h[SPT];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) h[i] = 0.f;
+        for (int i = 0; i < SPT; ++i) h[i] = 0.f;
         OT* out = reinterpret_cast<OT*>(p.out);
-        const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(32 * q) << 16) + 16 * half;
-        const int row0 = 16 * half + 8 * hi;                   // first row of the state tile this thread writes
+        const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(32 * q) << 16) + CPW * half;
+        const int row0 = CPW * half + SPT * hi;                   // first row of the state tile this thread writes
         const int seq0 = b0 + row0;
         // input projections are prefetched one full step ahead (their HBM latency would otherwise sit on the
         // critical path of every step); they stay RAW in registers - converting them here would wait for the load.
         // Per-sequence element offsets are kept in registers and stepped by a constant (no 64-bit address
         // arithmetic inside the time loop); sequences past the batch are masked once.
-        OT gr[8], gz[8], gn[8], pr[8], pz[8], pn[8];
+        OT gr[SPT], gz[SPT], gn[SPT], pr[SPT], pz[SPT], pn[SPT];
         const OT* gx_base = reinterpret_cast<const OT*>(p.gx);
         const int gx_step = (dir ? -1 : 1) * 2 * 3 * H;              // elements between consecutive steps of a sequence
         const int out_step = (dir ? -1 : 1) * p.out_pitch;
         const int t_first = dir ? p.T - 1 : 0;
         uint32_t live = 0;
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
+        for (int i = 0; i < SPT; ++i)
             if (seq0 + i < p.B) live |= 1u << i;
         // element offsets of this thread's FIRST sequence at the current step (the launcher checks the 32-bit range);
         // its other sequences follow at a constant stride
@@ -254,10 +256,10 @@ __global__ void __launch_bounds__(GRU_THREADS, 1) gru_cluster_kernel(const GruPa
         int gx_off = ((seq0 * p.T + t_first) * 2 + dir) * 3 * H + unit;
         int out_off = (seq0 * p.out_rows + p.out_halo + t_first) * p.out_pitch + p.out_choff + dir * H + unit;
         const bool no_gx = (p.debug & 2) != 0;
-        auto load_gx = [&](int step, OT (&xr)[8], OT (&xz)[8], OT (&xn)[8]) {      // `step` must be the NEXT unread step
+        auto load_gx = [&](int step, OT (&xr)[SPT], OT (&xz)[SPT], OT (&xn)[SPT]) {      // `step` must be the NEXT unread step
             const bool ok = step < p.T && !no_gx;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
+            for (int i = 0; i < SPT; ++i) {
                 if (ok && (live >> i & 1)) {
                     const OT* g = gx_base + (gx_off + i * gx_seq);
                     xr[i] = g[0]; xz[i] = g[H]; xn[i] = g[2 * H];
@@ -271,7 +273,7 @@ __global__ void __launch_bounds__(GRU_THREADS, 1) gru_cluster_kernel(const GruPa
         for (int t = 0; t < p.T; ++t) {
             const int tt = dir ? p.T - 1 - t : t;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) { gr[i] = pr[i]; gz[i] = pz[i]; gn[i] = pn[i]; }
+            for (int i = 0; i < SPT; ++i) { gr[i] = pr[i]; gz[i] = pz[i]; gn[i] = pn[i]; }
             load_gx(t + 1, pr, pz, pn);
             const bool rec = (p.debug & 8) && p.dbg && blockIdx.x == 0 && threadIdx.x == 0;
             if (rec) p.dbg[t * 8 + 2] = clock64();
@@ -279,16 +281,16 @@ __global__ void __launch_bounds__(GRU_THREADS, 1) gru_cluster_kernel(const GruPa
             mbar_wait(rz_done, t & 1);
             tc_fence_after();
             if (rec) p.dbg[t * 8 + 3] = clock64();
-            float r[8], z[8];
+            float r[SPT], z[SPT];
             {
-                uint32_t a[16];
-                tmem_ld16(t_addr, a);        // lanes 0-15: W_hr h, lanes 16-31: W_hz h   (this warp's 16 sequences)
+                uint32_t a[CPW];
+                tmem_ld_cols(t_addr, a);        // lanes 0-15: W_hr h, lanes 16-31: W_hz h   (this warp's 16 sequences)
                 tmem_ld_wait();
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const uint32_t got = __shfl_xor_sync(0xffffffffu, hi ? a[i] : a[8 + i], 16);
+                for (int i = 0; i < SPT; ++i) {
+                    const uint32_t got = __shfl_xor_sync(0xffffffffu, hi ? a[i] : a[SPT + i], 16);
                     const float hr = __uint_as_float(hi ? got : a[i]);
-                    const float hz = __uint_as_float(hi ? a[8 + i] : got);
+                    const float hz = __uint_as_float(hi ? a[SPT + i] : got);
                     const float xr = ot_to_float<OT>(gr[i]) + hr + b_r, xz = ot_to_float<OT>(gz[i]) + hz + b_z;
                     if (fast) {
                         r[i] = fmaf(0.5f, tanh_mufu(0.5f * xr), 0.5f);
@@ -303,15 +305,15 @@ __global__ void __launch_bounds__(GRU_THREADS, 1) gru_cluster_kernel(const GruPa
             // ---- n and the new state ----
             mbar_wait(mma_done, t & 1);
             tc_fence_after();
-            OT y[8];
+            OT y[SPT];
             {
-                uint32_t nn[16];
-                tmem_ld16(t_addr + NSEQ, nn);    // lanes 0-15: W_hn h
+                uint32_t nn[CPW];
+                tmem_ld_cols(t_addr + NSEQ, nn);    // lanes 0-15: W_hn h
                 tmem_ld_wait();
                 tc_fence_before();
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const uint32_t gotn = __shfl_xor_sync(0xffffffffu, nn[8 + i], 16);
+                for (int i = 0; i < SPT; ++i) {
+                    const uint32_t gotn = __shfl_xor_sync(0xffffffffu, nn[SPT + i], 16);
                     const float hn = __uint_as_float(hi ? gotn : nn[i]) + b_n;
                     const float xn = fmaf(r[i], hn, ot_to_float<OT>(gn[i]));
                     const float n = fast ? tanh_mufu(xn) : tanh_f(xn);
@@ -327,7 +329,7 @@ __global__ void __launch_bounds__(GRU_THREADS, 1) gru_cluster_kernel(const GruPa
             if (rec) p.dbg[t * 8 + 5] = clock64();
             if ((p.debug & 64) && !(p.debug & 4)) {           // experiment: output stores before the exchange
 #pragma unroll
-                for (int i = 0; i < 8; ++i)
+                for (int i = 0; i < SPT; ++i)
                     if (live >> i & 1) out[out_off + i * out_seq] = y[i];
             }
             if (t + 1 < p.T) {
@@ -336,7 +338,7 @@ __global__ void __launch_bounds__(GRU_THREADS, 1) gru_cluster_kernel(const GruPa
                 mbar_wait(consumed, t & 1);
                 uint8_t* hnext = sH + rank * slice_bytes;
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
+                for (int i = 0; i < SPT; ++i) {
                     const int s = row0 + i;      // row of the state tile
                     *reinterpret_cast<OT*>(hnext + s * 128 + ((((u_loc >> 3) ^ (s & 7)) << 4) | ((u_loc & 7) << 1))) = y[i];
                 }
@@ -358,7 +360,7 @@ __global__ void __launch_bounds__(GRU_THREADS, 1) gru_cluster_kernel(const GruPa
             // h_t to the output buffer, off the exchange's critical path
             if (!(p.debug & (4 | 64))) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i)
+                for (int i = 0; i < SPT; ++i)
                     if (live >> i & 1) out[out_off + i * out_seq] = y[i];
             }
             out_off += out_step;

@@ -378,14 +378,21 @@ static int launch_gru_cluster(const void* w_img, const float* bhh, const void* g
     }
     if (static_cast<long long>(B) * T * 6 * H >= (1ll << 31) || static_cast<long long>(B) * rows * pitch >= (1ll << 31))
         return fail(ZS_ERR_ARG, "gru: %d sequences x %d steps exceed the 32-bit element offsets of the recurrence kernel", B, T);
-    const int NC = H / GRU_UNITS, n_groups = (B + GRU_FWD_NSEQ - 1) / GRU_FWD_NSEQ;
-    const int smem = gru_smem_bytes(H);
-    static int attr_set[2] = {0, 0};
+    // 32 sequences per cluster is the throughput shape; when the batch fits one wave of 16-sequence clusters (15 eight-CTA
+    // clusters are resident on a B200) the smaller shape halves the per-step exchange and gate math: lower latency
+    const int NC = H / GRU_UNITS;
+    int nseq = (2 * ((B + GRU_FWD_NSEQ_SMALL - 1) / GRU_FWD_NSEQ_SMALL) * NC <= 120) ? GRU_FWD_NSEQ_SMALL : GRU_FWD_NSEQ;
+    { const char* e = getenv("ZS_GRU_NSEQ"); if (e && (atoi(e) == 16 || atoi(e) == 32)) nseq = atoi(e); }
+    const int n_groups = (B + nseq - 1) / nseq;
+    const int smem = gru_smem_bytes(H, nseq);
+    using KernelT = void (*)(const GruParams);
     const int which = p.fmt;
-    if (attr_set[which] < smem) {
-        if (which) CUDA_TRY(cudaFuncSetAttribute(gru_cluster_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        else CUDA_TRY(cudaFuncSetAttribute(gru_cluster_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr_set[which] = smem;
+    KernelT kern = nseq == 16 ? (which ? gru_cluster_kernel<__nv_bfloat16, 16> : gru_cluster_kernel<__half, 16>)
+                              : (which ? gru_cluster_kernel<__nv_bfloat16, 32> : gru_cluster_kernel<__half, 32>);
+    static int attr_set[2][2] = {{0, 0}, {0, 0}};
+    if (attr_set[which][nseq == 16] < smem) {
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_set[which][nseq == 16] = smem;
     }
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
@@ -399,12 +406,11 @@ static int launch_gru_cluster(const void* w_img, const float* bhh, const void* g
     cfg.attrs = attr; cfg.numAttrs = 1;
     if (p.debug & 16) {
         int ncl = 0;
-        cudaError_t e = cudaOccupancyMaxActiveClusters(&ncl, gru_cluster_kernel<__half>, &cfg);
-        fprintf(stderr, "gru: max active clusters of %d CTAs with %d B smem: %d (%s); launching %d clusters\n", NC, smem, ncl, cudaGetErrorString(e), 2 * n_groups);
+        cudaError_t e = cudaOccupancyMaxActiveClusters(&ncl, kern, &cfg);
+        fprintf(stderr, "gru: max active clusters of %d CTAs with %d B smem: %d (%s); launching %d clusters of %d sequences\n", NC, smem, ncl, cudaGetErrorString(e), 2 * n_groups, nseq);
     }
     LaunchScope scope(st, KC_GRU, 2.0 * 2 * B * static_cast<double>(T) * 3 * H * H, "gru_cluster_kernel");
-    if (which) CUDA_TRY(cudaLaunchKernelEx(&cfg, gru_cluster_kernel<__nv_bfloat16>, p));
-    else CUDA_TRY(cudaLaunchKernelEx(&cfg, gru_cluster_kernel<__half>, p));
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, p));
     return ZS_OK;
 }
 
