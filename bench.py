@@ -27,6 +27,7 @@ import time
 
 import torch
 
+os.environ['NCCL_DEBUG'] = os.environ.get('ZS_NCCL_DEBUG', 'WARN')     # NCCL's version banner goes to stdout: keep the JSON line alone
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
@@ -123,6 +124,36 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------
+# host placement: pinned buffers on the GPU's own NUMA node
+# ------------------------------------------------------------------------------------------------
+def bind_to_gpu_numa(index):
+    """Restricts this process to the CPUs local to GPU `index` BEFORE the pinned host buffers are allocated, so that
+    first-touch puts them on the GPU's NUMA node (with 8 ranks streaming ~55 GB/s each, remote-socket buffers halve the
+    host-to-host rate).  Returns a short description, or None when the topology is not exposed."""
+    try:
+        bdf = subprocess.run(['nvidia-smi', '--query-gpu=pci.bus_id', '--format=csv,noheader', '-i', str(index)],
+                             capture_output=True, text=True, timeout=10).stdout.strip().lower()
+        if bdf.startswith('0000'):
+            bdf = bdf[4:]                      # nvidia-smi prints an 8-digit domain, sysfs a 4-digit one
+        base = f'/sys/bus/pci/devices/{bdf}'
+        node = int(open(base + '/numa_node').read())
+        cpus = open(base + '/local_cpulist').read().strip()
+        if node < 0 or not cpus:
+            return None
+        ids = set()
+        for part in cpus.split(','):
+            lo, _, hi = part.partition('-')
+            ids.update(range(int(lo), int(hi or lo) + 1))
+        ids &= os.sched_getaffinity(0)
+        if not ids:
+            return None
+        os.sched_setaffinity(0, ids)
+        return f'numa node {node}, {len(ids)} cpus'
+    except Exception:
+        return None
+
+
+# ------------------------------------------------------------------------------------------------
 # clocks
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
@@ -179,6 +210,7 @@ def run_ours(args):
     local = int(os.environ.get('LOCAL_RANK', 0))
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
+    numa = bind_to_gpu_numa(local) if world > 1 else None
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
 
@@ -316,6 +348,7 @@ def run_ours(args):
             'e2e': {'value': e2e, 'unit': 'frames/s',
                     'h2d_bytes_per_step': S * (513 * FRAMES * 4 + 8 + 16 * ENC_SIZE * 4),
                     'd2h_bytes_per_step': S * (513 * FRAMES * 4 + 16 * 4), 'ms_per_step': t_e2e / args.steps * 1e3,
+                    'host_placement': numa,
                     'api': 'StreamingResynthesizer.run_async: pinned host in -> pinned host out, steps issued back to back '
                            '(upload of step i+1 under compute/download of step i)'},
             'roofline': {'bound': 'tensor', 'kernel': 'conv_gemm_kernel (tcgen05 implicit GEMM, all conv/linear layers)',

@@ -89,6 +89,24 @@ def main():
     if rank == 0:
         print(f'(3) B={per}/rank x {world}: {t_dp:.3f} ms/step with the NCCL all-reduce (221 MB fp32), '
               f'{t_alone:.3f} ms/step eager without exchange -> {per * 128 * world / t_dp * 1e3:.0f} frames/s')
+    # (4) sharded inference == one process: utterance shards, reference-order noise, ordered gather
+    import numpy as np
+    from zs_b200.frontend import AutoencoderPath
+    from zs_b200.shard import ShardedPath
+    enc_i, dec_i = nets(0.5)
+    enc_i.eval(); dec_i.eval()
+    path = AutoencoderPath(enc_i, dec_i, seg_len=128, max_batch=64)
+    rng = np.random.Generator(np.random.PCG64(3))
+    specs = [np.clip(rng.random((int(n), 513), dtype=np.float32), 1e-8, 1) for n in (5, 300, 128, 1000, 77, 640, 2000, 131)]
+    spk = [int(i) % 102 for i in range(len(specs))]
+    torch.manual_seed(11)
+    out_s, units_s = ShardedPath(path).convert_utterances(specs, spk)
+    torch.manual_seed(11)
+    out_1, units_1 = path.convert_utterances(specs, spk)
+    same = all(np.array_equal(a, b) for a, b in zip(units_s, units_1)) and all(np.array_equal(a, b) for a, b in zip(out_s, out_1))
+    assert same, 'sharded inference differs from the single-process run'
+    if rank == 0:
+        print(f'(4) sharded convert_utterances over {world} ranks == single process, bit for bit ({len(specs)} utterances)')
     dist.barrier()
     dist.destroy_process_group()
 
