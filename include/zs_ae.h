@@ -36,8 +36,8 @@ extern "C" {
 #define ZS_ERR_CUDA 2     /* CUDA runtime / driver error */
 #define ZS_ERR_WORKSPACE 3 /* workspace too small */
 
-/* Encoder.enc_mode (model/model.py:457-487); 'binary' is not supported. */
-enum { ZS_ENC_CONTINUES = 0, ZS_ENC_ONE_HOT = 1, ZS_ENC_MULTILABEL_BINARY = 2, ZS_ENC_GUMBEL_T = 3 };
+/* Encoder.enc_mode (model/model.py:457-487).  'binary' projects to enc_size^2 channels (model/model.py:466-472): enc_size <= 128. */
+enum { ZS_ENC_CONTINUES = 0, ZS_ENC_ONE_HOT = 1, ZS_ENC_MULTILABEL_BINARY = 2, ZS_ENC_GUMBEL_T = 3, ZS_ENC_BINARY = 4 };
 /* tensor-core operand type of activations/weights (accumulation is always fp32) */
 enum { ZS_OPERAND_FP16 = 0, ZS_OPERAND_BF16 = 1 };
 
@@ -125,7 +125,7 @@ size_t zs_decoder_workspace_bytes(const zs_decoder* h, int B, int T8);
 
 /* Encoder.forward in eval mode (model/model.py:440-489; trainer.py:197, 227).
  *   x            (B, c_in, T) fp32
- *   gumbel_noise one_hot: (B, T8, enc_size); multilabel_binary: (B, T8, enc_size, 2);
+ *   gumbel_noise one_hot: (B, T8, enc_size); multilabel_binary: (B, T8, enc_size, 2); binary: (B, T8, enc_size, enc_size);
  *                gumbel_t: (B, enc_size, T8) - the value of _sample_gumbel() (model/model.py:95-98);
  *                NULL for `continues`
  *   logits       (B, n_out, T8) fp32  - the reference's second return value `out`

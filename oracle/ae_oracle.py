@@ -153,7 +153,7 @@ def encoder_forward(sd, x, uniform=None, ns=0.01, seg_len=128, enc_mode='one_hot
     """Encoder.forward in eval mode: returns (out_act, out, unit_ids or None).
 
     `uniform` is the torch.rand draw of gumbel_softmax (shape (B,T8,enc) for one_hot,
-    (B,T8,enc,2) for multilabel_binary, (B,enc,T8) for gumbel_t)."""
+    (B,T8,enc,2) for multilabel_binary, (B,T8,enc,enc) for binary, (B,enc,T8) for gumbel_t)."""
     logits = encoder_trunk(sd, x, ns, seg_len, keep_masks, dp)
     ids = None
     if enc_mode == 'continues':                               # :457-459
@@ -166,6 +166,12 @@ def encoder_forward(sd, x, uniform=None, ns=0.01, seg_len=128, enc_mode='one_hot
         proj = logits.permute(0, 2, 1).reshape(B, T8, C2 // 2, 2)
         hard, _ = gumbel_hard(proj, uniform)
         act = hard[..., 0].permute(0, 2, 1).contiguous()
+    elif enc_mode == 'binary':                                # :466-472
+        B, C2, T8 = logits.shape
+        E = int(round(C2 ** 0.5))
+        proj = logits.permute(0, 2, 1).reshape(B, T8, E, E)
+        hard, _ = gumbel_hard(proj, uniform)
+        act = torch.clamp(hard.sum(2), min=0, max=1).permute(0, 2, 1).contiguous()
     elif enc_mode == 'gumbel_t':                              # :482-484 (softmax over time)
         act, _ = gumbel_hard(logits, uniform)
     else:

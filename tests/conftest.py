@@ -22,7 +22,7 @@ def load_golden(name):
     return d
 
 
-GOLDEN_CASES = ['small_onehot', 'small_onehot_odd', 'small_mbv', 'small_continues', 'small_gumbel_t',
+GOLDEN_CASES = ['small_onehot', 'small_onehot_odd', 'small_mbv', 'small_continues', 'small_gumbel_t', 'small_binary',
                 'small_zeropad', 'full_b2_t128', 'full_b1_t207', 'full_b1_t9', 'full_b1_mbv', 'full_b1_e512']
 
 

@@ -56,7 +56,7 @@ def _run_case(ref, name, *, B, T, enc_size, enc_mode, emb_size, n_spk, c_h=(128,
     c = syn.speaker_ids(B, n_spk, seed)
     T8 = (((T + 1) // 2 + 1) // 2 + 1) // 2
     ushape = {'one_hot': (B, T8, enc_size), 'multilabel_binary': (B, T8, enc_size, 2),
-              'gumbel_t': (B, enc_size, T8), 'continues': None}[enc_mode]
+              'gumbel_t': (B, enc_size, T8), 'binary': (B, T8, enc_size, enc_size), 'continues': None}[enc_mode]
     out = {}
     with torch.no_grad():
         torch.manual_seed(1234 + seed)
@@ -67,7 +67,7 @@ def _run_case(ref, name, *, B, T, enc_size, enc_mode, emb_size, n_spk, c_h=(128,
         spec = dec(act, c)
         out['logits'] = logits.numpy()
         out['act_argmax'] = act.argmax(dim=1).numpy().astype(np.int32)
-        if enc_mode in ('multilabel_binary', 'gumbel_t'):
+        if enc_mode in ('multilabel_binary', 'gumbel_t', 'binary'):
             out['act'] = act.numpy().astype(np.uint8)
         if enc_mode == 'continues':
             out['act'] = act.numpy()
@@ -135,11 +135,15 @@ def main():
     torch.set_num_threads(os.cpu_count())
     ref = _load_ref_model()
     small = dict(emb_size=64, n_spk=5, c_h=(16, 64, 16), c_in=33)
+    if len(sys.argv) > 1 and sys.argv[1] == 'binary':      # added later: only this fixture (the others stay byte-identical)
+        _run_case(ref, 'small_binary', B=2, T=48, enc_size=16, enc_mode='binary', **small)
+        return
     _run_case(ref, 'small_onehot', B=3, T=40, enc_size=32, enc_mode='one_hot', patch=True, **small)
     _run_case(ref, 'small_onehot_odd', B=2, T=77, enc_size=32, enc_mode='one_hot', **small)
     _run_case(ref, 'small_mbv', B=2, T=48, enc_size=32, enc_mode='multilabel_binary', **small)
     _run_case(ref, 'small_continues', B=2, T=48, enc_size=32, enc_mode='continues', **small)
     _run_case(ref, 'small_gumbel_t', B=2, T=64, enc_size=32, enc_mode='gumbel_t', **small)
+    _run_case(ref, 'small_binary', B=2, T=48, enc_size=16, enc_mode='binary', **small)
     _run_case(ref, 'small_zeropad', B=2, T=40, enc_size=32, enc_mode='one_hot', seg_len=32, **small)
     full = dict(emb_size=1024, n_spk=102)
     _run_case(ref, 'full_b2_t128', B=2, T=128, enc_size=1024, enc_mode='one_hot', patch=True, **full)

@@ -72,9 +72,14 @@ def test_state_dict_contract(enc_mode):
     assert sum(p.numel() for p in dec.parameters()) == 42488321
 
 
-def test_binary_mode_rejected():
+def test_binary_mode_contract():
+    """enc_mode 'binary' (model/model.py:398-399, 466-472): an enc_size^2 projection; supported up to enc_size 128."""
+    enc = Encoder(enc_size=16, enc_mode='binary')
+    assert tuple(enc.linear.weight.shape) == (256, 768) and enc.noise_shape(2, 128) == (2, 16, 16, 16)
+    want = syn.encoder_shapes(enc_size=16, enc_mode='binary')
+    assert {k: tuple(v.shape) for k, v in enc.state_dict().items()} == {k: s for k, (s, _) in want.items()}
     with pytest.raises(NotImplementedError):
-        Encoder(enc_mode='binary')
+        Encoder(enc_size=1024, enc_mode='binary')          # 1 M output channels: rejected loudly
     with pytest.raises(NotImplementedError):
         Encoder(enc_mode='nonsense')
 

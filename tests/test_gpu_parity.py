@@ -159,7 +159,7 @@ def test_gru_recurrence_matches_oracle(H, B, T, impl):
 # ------------------------------------------------------------------------------------------------
 # whole path vs golden fixtures of the live reference
 # ------------------------------------------------------------------------------------------------
-GOLDEN_GPU = ['small_onehot', 'small_onehot_odd', 'small_mbv', 'small_continues', 'small_gumbel_t',
+GOLDEN_GPU = ['small_onehot', 'small_onehot_odd', 'small_mbv', 'small_continues', 'small_gumbel_t', 'small_binary',
               'full_b2_t128', 'full_b1_t207', 'full_b1_mbv', 'full_b1_e512']
 
 

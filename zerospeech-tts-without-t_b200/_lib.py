@@ -19,7 +19,7 @@ _SOURCES = ['zs_ae.cu', 'conv_gemm.cuh', 'kernels.cuh', 'gru_cluster.cuh', 'ptx.
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-Xcompiler', '-fPIC', '-shared']
 
-ENC_MODES = {'continues': 0, 'one_hot': 1, 'multilabel_binary': 2, 'gumbel_t': 3}
+ENC_MODES = {'continues': 0, 'one_hot': 1, 'multilabel_binary': 2, 'gumbel_t': 3, 'binary': 4}
 OPERANDS = {'fp16': 0, 'bf16': 1}
 
 

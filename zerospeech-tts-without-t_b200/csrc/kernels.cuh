@@ -90,7 +90,7 @@ __global__ void bottleneck_onehot_kernel(const float* __restrict__ logits, const
     }
 }
 
-// continues / multilabel_binary / gumbel_t epilogues of Encoder.forward (model/model.py:457-484)
+// continues / multilabel_binary / gumbel_t / binary epilogues of Encoder.forward (model/model.py:457-484)
 __global__ void bottleneck_misc_kernel(const float* __restrict__ logits, const float* __restrict__ noise, int mode,
                                        int B, int E, int T8, float ns, float* __restrict__ act) {
     const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -106,6 +106,23 @@ __global__ void bottleneck_misc_kernel(const float* __restrict__ logits, const f
             const float* nz = noise + ((static_cast<size_t>(b) * T8 + t) * E + e) * 2;
             const float v0 = lb[(2 * e) * T8 + t] + nz[0], v1 = lb[(2 * e + 1) * T8 + t] + nz[1];
             act[i] = (v0 >= v1) ? 1.f : 0.f;
+        }
+    } else if (mode == 4) {  // binary (model/model.py:466-472): channel r*E + c; every row r picks one column c (argmax of
+                             // logits + noise, first index on ties), act[c] = 1 if ANY row picked c.  act is pre-zeroed.
+        if (i < static_cast<size_t>(B) * T8 * E) {
+            const int r = i % E, t = (i / E) % T8, b = i / (static_cast<size_t>(E) * T8);
+            const float* lb = logits + (static_cast<size_t>(b) * E * E + static_cast<size_t>(r) * E) * T8 + t;
+            const float* nz = noise + ((static_cast<size_t>(b) * T8 + t) * E + r) * E;
+            float best = lb[0] + nz[0];
+            int bi = 0;
+            for (int c = 1; c < E; ++c) {
+                const float v = lb[static_cast<size_t>(c) * T8] + nz[c];
+                if (v > best) {
+                    best = v;
+                    bi = c;
+                }
+            }
+            act[(static_cast<size_t>(b) * E + bi) * T8 + t] = 1.f;
         }
     } else {  // gumbel_t: one-hot over the TIME axis of each (segment, unit) row
         if (i < static_cast<size_t>(B) * E) {

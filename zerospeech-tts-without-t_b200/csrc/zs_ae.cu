@@ -655,14 +655,15 @@ extern "C" int zs_encoder_pack(const zs_encoder_cfg* cfg, const zs_encoder_weigh
     if (!cfg || !w || !out) return fail(ZS_ERR_ARG, "encoder_pack: null argument");
     ZS_TRY(ensure_device());
     if (cfg->seg_len < 64) return fail(ZS_ERR_ARG, "encoder: seg_len %d < 64 selects zero padding (model/model.py:38); only the reflect mode is implemented", cfg->seg_len);
-    if (cfg->enc_mode < 0 || cfg->enc_mode > 3) return fail(ZS_ERR_ARG, "encoder: enc_mode %d not supported ('binary' needs an enc_size^2 projection)", cfg->enc_mode);
+    if (cfg->enc_mode < 0 || cfg->enc_mode > 4) return fail(ZS_ERR_ARG, "encoder: enc_mode %d not supported", cfg->enc_mode);
+    if (cfg->enc_mode == ZS_ENC_BINARY && cfg->enc_size > 128) return fail(ZS_ERR_ARG, "encoder: enc_mode 'binary' projects to enc_size^2 channels; enc_size %d > 128", cfg->enc_size);
     if (cfg->c_h2 % 8 || cfg->c_h1 % 8 || cfg->c_h3 < 1) return fail(ZS_ERR_ARG, "encoder: c_h1/c_h2 must be multiples of 8");
     if (cfg->train && cfg->operand != ZS_OPERAND_FP16) return fail(ZS_ERR_ARG, "encoder: the training path computes in fp16 operands (loss-scaled gradients)");
     if (cfg->train && cfg->enc_mode != ZS_ENC_ONE_HOT) return fail(ZS_ERR_ARG, "encoder: the training path implements enc_mode 'one_hot' only");
     if (cfg->train && (cfg->c_h2 % 64 || cfg->c_h3 % 8)) return fail(ZS_ERR_ARG, "encoder: training needs c_h2 %% 64 == 0 and c_h3 %% 8 == 0");
     zs_encoder* h = new zs_encoder();
     h->cfg = *cfg;
-    h->n_out = cfg->enc_mode == ZS_ENC_MULTILABEL_BINARY ? 2 * cfg->enc_size : cfg->enc_size;
+    h->n_out = cfg->enc_mode == ZS_ENC_MULTILABEL_BINARY ? 2 * cfg->enc_size : (cfg->enc_mode == ZS_ENC_BINARY ? cfg->enc_size * cfg->enc_size : cfg->enc_size);
     const int rc = encoder_fill(h, w, static_cast<cudaStream_t>(stream));
     if (rc != ZS_OK) {
         h->pool.release();
@@ -936,6 +937,7 @@ extern "C" int zs_encoder_forward(zs_encoder* h, const float* x, int B, int T, c
         ZS_TRY(launch_onehot(logits, gumbel_noise, B, g.enc_size, T8, act, unit_ids, st));
     } else if (act) {
         const size_t n = g.enc_mode == ZS_ENC_GUMBEL_T ? static_cast<size_t>(B) * g.enc_size : static_cast<size_t>(B) * g.enc_size * T8;
+        if (g.enc_mode == ZS_ENC_BINARY) CUDA_TRY(cudaMemsetAsync(act, 0, n * sizeof(float), st));
         LaunchScope scope(st, KC_OTHER, 0.0, "bottleneck_misc_kernel");
         bottleneck_misc_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(logits, gumbel_noise, g.enc_mode, B, g.enc_size, T8, ns, act);
         CUDA_TRY(cudaGetLastError());

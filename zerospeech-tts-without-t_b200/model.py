@@ -144,8 +144,10 @@ class Encoder(_Packed):
         elif enc_mode in ('continues', 'one_hot', 'gumbel_t'):
             assert enc_size % 2 == 0
             n_out = enc_size
-        elif enc_mode == 'binary':
-            raise NotImplementedError("enc_mode 'binary' (enc_size^2 projection) is not implemented on the B200 path")
+        elif enc_mode == 'binary':         # model/model.py:398-399: an enc_size x enc_size projection per frame
+            if enc_size > 128:
+                raise NotImplementedError("enc_mode 'binary' projects to enc_size^2 channels: supported up to enc_size 128")
+            n_out = enc_size * enc_size
         else:
             raise NotImplementedError('Invalid encoding mode!')
         self.n_out = n_out
@@ -267,7 +269,8 @@ class Encoder(_Packed):
     def noise_shape(self, B, T):
         T8 = self.t8(T)
         return {'one_hot': (B, T8, self.enc_size), 'multilabel_binary': (B, T8, self.enc_size, 2),
-                'gumbel_t': (B, self.enc_size, T8), 'continues': None}[self.enc_mode]
+                'gumbel_t': (B, self.enc_size, T8), 'binary': (B, T8, self.enc_size, self.enc_size),
+                'continues': None}[self.enc_mode]
 
     @torch.no_grad()
     def encode(self, x, noise=None):
