@@ -73,7 +73,7 @@ def test_state_dict_contract(enc_mode):
 
 
 def test_binary_mode_contract():
-    """enc_mode 'binary' (model/model.py:398-399, 466-472): an enc_size^2 projection; supported up to enc_size 128."""
+    """enc_mode 'binary' (model/model.py:391-392, 466-472): an enc_size^2 projection; supported up to enc_size 128."""
     enc = Encoder(enc_size=16, enc_mode='binary')
     assert tuple(enc.linear.weight.shape) == (256, 768) and enc.noise_shape(2, 128) == (2, 16, 16, 16)
     want = syn.encoder_shapes(enc_size=16, enc_mode='binary')

@@ -144,7 +144,7 @@ class Encoder(_Packed):
         elif enc_mode in ('continues', 'one_hot', 'gumbel_t'):
             assert enc_size % 2 == 0
             n_out = enc_size
-        elif enc_mode == 'binary':         # model/model.py:398-399: an enc_size x enc_size projection per frame
+        elif enc_mode == 'binary':         # model/model.py:391-392: an enc_size x enc_size projection per frame
             if enc_size > 128:
                 raise NotImplementedError("enc_mode 'binary' projects to enc_size^2 channels: supported up to enc_size 128")
             n_out = enc_size * enc_size
