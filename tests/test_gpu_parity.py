@@ -159,7 +159,7 @@ def test_gru_recurrence_matches_oracle(H, B, T, impl):
 # ------------------------------------------------------------------------------------------------
 # whole path vs golden fixtures of the live reference
 # ------------------------------------------------------------------------------------------------
-GOLDEN_GPU = ['small_onehot', 'small_onehot_odd', 'small_mbv', 'small_continues', 'small_gumbel_t', 'small_binary',
+GOLDEN_GPU = ['small_onehot', 'small_onehot_odd', 'small_mbv', 'small_continues', 'small_gumbel_t', 'small_binary', 'small_zeropad',
               'full_b2_t128', 'full_b1_t207', 'full_b1_mbv', 'full_b1_e512']
 
 
@@ -335,9 +335,9 @@ def test_errors_are_loud(full_models):
         enc(torch.rand(1, 100, 128, device='cuda'))        # wrong channel count
     with pytest.raises(RuntimeError):
         dec(torch.rand(1, 1024, 16, device='cuda'), torch.tensor([102]))   # speaker out of range (host ids)
-    with pytest.raises(RuntimeError):
-        e = Encoder(ns=0.01, enc_size=32, seg_len=32, enc_mode='one_hot', c_in=33, c_h1=16, c_h2=64, c_h3=16).cuda()
-        e(torch.rand(1, 33, 40, device='cuda'))            # zero-pad mode (seg_len < 64) is rejected, not approximated
+    with pytest.raises(RuntimeError):                       # zero-padding mode (seg_len < 64) is inference-only
+        e = Encoder(ns=0.01, enc_size=32, seg_len=32, enc_mode='one_hot', c_in=33, c_h1=16, c_h2=64, c_h3=16).cuda().train()
+        e.forward_train(torch.rand(1, 33, 40, device='cuda'), torch.zeros(1, 5, 32, device='cuda'))
 
 
 def test_streaming_host_to_host_overlapping_calls(full_models):

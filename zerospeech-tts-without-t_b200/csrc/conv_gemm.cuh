@@ -75,6 +75,11 @@ struct alignas(64) GemmParams {
     const long long* post_spk;
     int post_pitch, post_n;
     int no_sat;               // gradient outputs: let fp16 overflow to inf (the loss-scale logic detects it) instead of clamping
+    // zero-padding mode (model/model.py:36-38, seg_len < 64): halo rows are zeros, and a layer whose speaker embedding is
+    // folded into the bias loses the taps that fall into the padding: frame 0 gets -edge_lo, frame T-1 gets -edge_hi
+    int zero_halo;
+    const float* edge_lo;     // [n_spk][bias_stride] = W_0 . e   (null: reflect mode or no folded embedding)
+    const float* edge_hi;     // [n_spk][bias_stride] = W_{k-1} . e
 };
 
 template <typename OT>
@@ -111,7 +116,19 @@ __device__ __forceinline__ float tanh_f(float v) {
 
 struct ChanNorm {      // y = act(lrelu(acc + bias)) * scale + shift (+ residual) + post   (InstanceNorm folded into scale/shift)
     float bias, scale, shift, post;
+    int edge_off;             // zero-padding mode: index into the edge tables (subtracted from frame 0 / frame T-1), -1 = none
 };
+// zero-padding mode: the accumulators of a 16-frame chunk starting at frame c0, corrected at the segment's two edges
+// (the two table reads happen twice per segment and pass, so they are not kept in registers)
+__device__ __forceinline__ void apply_edges(const GemmParams& p, uint32_t (&v)[16], int c0, int T, const ChanNorm& cn) {
+    if (c0 == 0) v[0] = __float_as_uint(__uint_as_float(v[0]) - p.edge_lo[cn.edge_off]);
+    if (T - 1 >= c0 && T - 1 < c0 + 16) {
+        const float e = p.edge_hi[cn.edge_off];
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+            if (c0 + i == T - 1) v[i] = __float_as_uint(__uint_as_float(v[i]) - e);
+    }
+}
 template <typename OT>
 __device__ __forceinline__ OT float_to_ot_nosat(float v);
 template <>
@@ -121,13 +138,15 @@ __device__ __forceinline__ __nv_bfloat16 float_to_ot_nosat<__nv_bfloat16>(float 
 
 // InstanceNorm statistics of one (segment, channel) in ONE pass over TMEM: sums are taken relative to the
 // first frame's value so the variance does not cancel catastrophically.
-__device__ __forceinline__ void chan_stats(uint32_t t_seg, int T, float bias, bool lrelu, float ns, float& mean,
-                                           float& rstd) {
+template <bool ZP>
+__device__ __forceinline__ void chan_stats(const GemmParams& p, uint32_t t_seg, int T, float bias, bool lrelu, float ns,
+                                           const ChanNorm& cn, float& mean, float& rstd) {
     float s1 = 0.f, s2 = 0.f, x0 = 0.f;
     for (int c0 = 0; c0 < T; c0 += 16) {
         uint32_t v[16];
         tmem_ld16(t_seg + c0, v);
         tmem_ld_wait();
+        if (ZP && cn.edge_off >= 0) apply_edges(p, v, c0, T, cn);
         if (c0 == 0) {
             x0 = __uint_as_float(v[0]) + bias;
             if (lrelu) x0 = fmaxf(x0, x0 * ns);
@@ -163,7 +182,7 @@ __device__ __forceinline__ void chan_stats(uint32_t t_seg, int T, float bias, bo
 //   stg      : staging slot of (frame f_lo, this thread's channel); frame stride = STG_PITCH elements
 //   res_stg  : residual tile in shared memory (TMA-loaded), slot of (first residual row of this sub-round, channel)
 //   out_s    : output buffer at (this segment, row 0, this thread's output channel) - for the halo rows only
-template <typename OT, int RES, bool PS>
+template <typename OT, int RES, bool PS, bool ZP>
 __device__ __forceinline__ void frames_to_staging(const GemmParams& p, uint32_t t_seg, int f_lo, int f_hi, int T,
                                                   const ChanNorm& cn, bool lrelu, float ns, OT* __restrict__ stg,
                                                   const OT* __restrict__ res_stg, OT* __restrict__ out_s, int ps_r,
@@ -176,6 +195,7 @@ __device__ __forceinline__ void frames_to_staging(const GemmParams& p, uint32_t 
     tmem_ld16(t_seg + f_lo, v);
     for (int c0 = f_lo; c0 < f_hi; c0 += 16) {
         tmem_ld_wait();
+        if (ZP && cn.edge_off >= 0) apply_edges(p, v, c0, T, cn);
         const bool more = c0 + 16 < f_hi;
         if (more) tmem_ld16(t_seg + c0 + 16, vn);       // next chunk's accumulators while this one is processed
         float r[16];
@@ -212,8 +232,9 @@ __device__ __forceinline__ void frames_to_staging(const GemmParams& p, uint32_t 
                 const int t = c0 + i;
                 if (t < T) {
                     const int f = PS ? 2 * t + ps_r : t;
-                    if (f >= 1 && f <= halo) out_s[(halo - f) * p.out_pitch] = y[i];
-                    if (f >= T_out - 1 - halo && f <= T_out - 2) out_s[(halo + 2 * (T_out - 1) - f) * p.out_pitch] = y[i];
+                    const OT hv = ZP ? float_to_ot<OT>(0.f) : y[i];
+                    if (f >= 1 && f <= halo) out_s[(halo - f) * p.out_pitch] = hv;
+                    if (f >= T_out - 1 - halo && f <= T_out - 2) out_s[(halo + 2 * (T_out - 1) - f) * p.out_pitch] = hv;
                 }
             }
             __syncwarp();
@@ -226,7 +247,7 @@ __device__ __forceinline__ void frames_to_staging(const GemmParams& p, uint32_t 
 }
 
 // Frames of one (segment, channel) -> the reference's (B, C, T) fp32 layout, 16 contiguous floats per chunk.
-template <typename OT>
+template <typename OT, bool ZP>
 __device__ __forceinline__ void frames_to_nct(const GemmParams& p, uint32_t t_seg, int T, const ChanNorm& cn,
                                               bool lrelu, float ns, float* __restrict__ nct, bool ch_ok) {
     const bool vec4 = (T & 3) == 0 && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0;
@@ -240,6 +261,7 @@ __device__ __forceinline__ void frames_to_nct(const GemmParams& p, uint32_t t_se
             for (int i = 0; i < 16; ++i) r[i] = (ch_ok && c0 + i < T) ? nct[c0 + i] : 0.f;
         }
         tmem_ld_wait();
+        if (ZP && cn.edge_off >= 0) apply_edges(p, v, c0, T, cn);
         float x[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
@@ -265,7 +287,8 @@ __device__ __forceinline__ void frames_to_nct(const GemmParams& p, uint32_t t_se
     }
 }
 
-template <typename OT>
+// ZP: zero-padding mode (seg_len < 64) - a separate instantiation so the reflect-mode kernel carries none of its code
+template <typename OT, bool ZP>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid_constant__ GemmParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_addr = smem_u32(smem_raw);
@@ -412,6 +435,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
             auto chan_norm = [&](int b, uint32_t t_seg) {
                 ChanNorm cn;
                 cn.bias = 0.f;
+                cn.edge_off = -1;
                 if (p.bias != nullptr) {  // tables are padded to m_tiles * 128 rows
                     size_t off = 0;
                     if (p.spk) {
@@ -420,13 +444,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
                         off = static_cast<size_t>(sp) * p.bias_stride;
                     }
                     cn.bias = p.bias[off + ch];
+                    if (ZP && p.edge_lo != nullptr) cn.edge_off = static_cast<int>(off) + ch;
                 }
                 cn.scale = 1.f;
                 cn.shift = 0.f;
                 cn.post = 0.f;
                 if (p.inorm) {
                     float mean, rstd;
-                    chan_stats(t_seg, T, cn.bias, lrelu, ns, mean, rstd);
+                    chan_stats<ZP>(p, t_seg, T, cn.bias, lrelu, ns, cn, mean, rstd);
                     cn.scale = rstd;
                     cn.shift = -mean * rstd;
                     if (p.stats != nullptr && ch_ok)
@@ -450,7 +475,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
                     if (b >= p.B) break;
                     const uint32_t t_seg = t_lane + s * p.Tt;
                     const ChanNorm cn = chan_norm(b, t_seg);
-                    frames_to_nct<OT>(p, t_seg, T, cn, lrelu, ns,
+                    frames_to_nct<OT, ZP>(p, t_seg, T, cn, lrelu, ns,
                                       reinterpret_cast<float*>(p.out) + (static_cast<size_t>(b) * p.m_valid + ch) * T, ch_ok);
                 }
                 tc_fence_before();
@@ -506,11 +531,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
                             const OT* res_stg = stage_res + static_cast<size_t>(s - s0) * res_rows_per_seg * 128 + row;
                             OT* out_s = reinterpret_cast<OT*>(p.out) + static_cast<size_t>(b) * p.out_rows * p.out_pitch +
                                         p.out_choff + out_ch;
-                            if (ps) frames_to_staging<OT, RES_NONE, true>(p, t_seg, f_lo, f_hi, T, cn_keep, lrelu, ns, stg, res_stg, out_s, ps_r, ch_ok);
-                            else if (p.res_mode == RES_NONE) frames_to_staging<OT, RES_NONE, false>(p, t_seg, f_lo, f_hi, T, cn_keep, lrelu, ns, stg, res_stg, out_s, 0, ch_ok);
-                            else if (p.res_mode == RES_SAME) frames_to_staging<OT, RES_SAME, false>(p, t_seg, f_lo, f_hi, T, cn_keep, lrelu, ns, stg, res_stg, out_s, 0, ch_ok);
-                            else if (p.res_mode == RES_UP2) frames_to_staging<OT, RES_UP2, false>(p, t_seg, f_lo, f_hi, T, cn_keep, lrelu, ns, stg, res_stg, out_s, 0, ch_ok);
-                            else frames_to_staging<OT, RES_AVG2, false>(p, t_seg, f_lo, f_hi, T, cn_keep, lrelu, ns, stg, res_stg, out_s, 0, ch_ok);
+                            if (ps) frames_to_staging<OT, RES_NONE, true, ZP>(p, t_seg, f_lo, f_hi, T, cn_keep, lrelu, ns, stg, res_stg, out_s, ps_r, ch_ok);
+                            else if (p.res_mode == RES_NONE) frames_to_staging<OT, RES_NONE, false, ZP>(p, t_seg, f_lo, f_hi, T, cn_keep, lrelu, ns, stg, res_stg, out_s, 0, ch_ok);
+                            else if (p.res_mode == RES_SAME) frames_to_staging<OT, RES_SAME, false, ZP>(p, t_seg, f_lo, f_hi, T, cn_keep, lrelu, ns, stg, res_stg, out_s, 0, ch_ok);
+                            else if (p.res_mode == RES_UP2) frames_to_staging<OT, RES_UP2, false, ZP>(p, t_seg, f_lo, f_hi, T, cn_keep, lrelu, ns, stg, res_stg, out_s, 0, ch_ok);
+                            else frames_to_staging<OT, RES_AVG2, false, ZP>(p, t_seg, f_lo, f_hi, T, cn_keep, lrelu, ns, stg, res_stg, out_s, 0, ch_ok);
                         }
                         if (has_res && nt * p.nb + s0 < p.B) res_phase ^= 1;
                         const bool last = (s0 / p.rnd_ns == my_last) && (h + 1 == p.rnd_sub);

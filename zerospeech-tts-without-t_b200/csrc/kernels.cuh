@@ -10,12 +10,13 @@
 namespace zs {
 
 // ---------------------------------------------------------------------------------------------
-// (B, C, T) fp32  ->  channels-last operand buffer [B][rows][pitch] with reflected halo rows.
+// (B, C, T) fp32  ->  channels-last operand buffer [B][rows][pitch] with reflected halo rows (zero_halo: zero rows,
+// the 'constant' padding mode model/model.py:36-38 selects for seg_len < 64).
 // 32x32 tile transpose through shared memory: reads coalesced along T, writes coalesced along C.
 // ---------------------------------------------------------------------------------------------
 template <typename OT>
 __global__ void pack_nct_kernel(const float* __restrict__ x, OT* __restrict__ out, int C, int T, int rows, int pitch,
-                                int halo, int choff, int c_fill, int lrelu, float ns) {
+                                int halo, int choff, int c_fill, int lrelu, float ns, int zero_halo) {
     __shared__ float tile[32][33];
     const int t0 = blockIdx.x * 32, c0 = blockIdx.y * 32, b = blockIdx.z;
     const int tx = threadIdx.x, ty = threadIdx.y;
@@ -37,8 +38,9 @@ __global__ void pack_nct_kernel(const float* __restrict__ x, OT* __restrict__ ou
         const OT y = float_to_ot<OT>(v);
         ob[static_cast<size_t>(halo + t) * pitch + c] = y;
         if (halo > 0) {
-            if (t >= 1 && t <= halo) ob[static_cast<size_t>(halo - t) * pitch + c] = y;
-            if (t >= T - 1 - halo && t <= T - 2) ob[static_cast<size_t>(halo + 2 * (T - 1) - t) * pitch + c] = y;
+            const OT hv = zero_halo ? float_to_ot<OT>(0.f) : y;
+            if (t >= 1 && t <= halo) ob[static_cast<size_t>(halo - t) * pitch + c] = hv;
+            if (t >= T - 1 - halo && t <= T - 2) ob[static_cast<size_t>(halo + 2 * (T - 1) - t) * pitch + c] = hv;
         }
     }
 }
@@ -243,9 +245,10 @@ inline cudaError_t launch_pack_weight(const float* W, OT* dst, int C_out, int C_
 
 // tab[s][row_off + row(co)] = (b ? b[co] : 0) + sum_{ci < C_e, j < k} W[co][ci_lo + ci][j] * emb[s][ci]
 // one warp per (speaker, out channel).  C_e = 0 gives the plain (padded, permuted) bias vector.
+// j_only >= 0: only tap j_only enters the sum (edge-correction tables of the zero-padding mode).
 __global__ void fold_bias_kernel(const float* __restrict__ W, const float* __restrict__ b,
                                  const float* __restrict__ emb, float* __restrict__ tab, int C_out, int C_in, int k,
-                                 int ci_lo, int C_e, int n_spk, int m_rows, int row_off, int ps) {
+                                 int ci_lo, int C_e, int n_spk, int m_rows, int row_off, int ps, int j_only = -1) {
     const long long w = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (w >= static_cast<long long>(n_spk) * C_out) return;
@@ -253,7 +256,8 @@ __global__ void fold_bias_kernel(const float* __restrict__ W, const float* __res
     float acc = 0.f;
     const float* wr = W + (static_cast<long long>(co) * C_in + ci_lo) * k;
     const float* e = emb + static_cast<long long>(s) * C_e;
-    for (int i = lane; i < C_e * k; i += 32) acc = fmaf(wr[i], e[i / k], acc);
+    for (int i = lane; i < C_e * k; i += 32)
+        if (j_only < 0 || i % k == j_only) acc = fmaf(wr[i], e[i / k], acc);
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
     if (lane == 0) tab[static_cast<long long>(s) * m_rows + row_off + (ps ? ps_row(co) : co)] = acc + (b ? b[co] : 0.f);
@@ -286,7 +290,7 @@ __global__ void transpose_emb_kernel(const float* __restrict__ W, OT* __restrict
 template <typename OT>
 __global__ void unit_gather_kernel(const int* __restrict__ ids, const OT* __restrict__ WT,
                                    const float* __restrict__ bias, OT* __restrict__ out, int T8, int c_h, int rows,
-                                   int pitch, int halo, int n_units) {
+                                   int pitch, int halo, int n_units, int zero_halo) {
     const int t = blockIdx.x, b = blockIdx.y;
     int id = ids[b * T8 + t];
     id = min(max(id, 0), n_units - 1);
@@ -295,8 +299,9 @@ __global__ void unit_gather_kernel(const int* __restrict__ ids, const OT* __rest
         const OT y = float_to_ot<OT>(ot_to_float<OT>(WT[static_cast<size_t>(id) * c_h + c]) + bias[c]);
         ob[static_cast<size_t>(halo + t) * pitch + c] = y;
         if (halo > 0) {
-            if (t >= 1 && t <= halo) ob[static_cast<size_t>(halo - t) * pitch + c] = y;
-            if (t >= T8 - 1 - halo && t <= T8 - 2) ob[static_cast<size_t>(halo + 2 * (T8 - 1) - t) * pitch + c] = y;
+            const OT hv = zero_halo ? float_to_ot<OT>(0.f) : y;
+            if (t >= 1 && t <= halo) ob[static_cast<size_t>(halo - t) * pitch + c] = hv;
+            if (t >= T8 - 1 - halo && t <= T8 - 2) ob[static_cast<size_t>(halo + 2 * (T8 - 1) - t) * pitch + c] = hv;
         }
     }
 }

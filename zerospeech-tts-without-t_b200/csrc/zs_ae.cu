@@ -54,7 +54,6 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 static PFN_encodeTiled g_encode = nullptr;
 static int g_num_sms = 0;
-static bool g_attr_set[2] = {false, false};
 
 static int ensure_device() {
     if (g_encode && g_num_sms) return ZS_OK;
@@ -158,7 +157,13 @@ struct ConvExtras {        // training-path additions to a layer launch (not par
     const float* post_emb = nullptr;
     const int64_t* post_spk = nullptr;
     int post_pitch = 0, post_n = 0, no_sat = 0;
+    // zero-padding mode (seg_len < 64): zero halo rows + the edge corrections of a folded speaker embedding
+    int zero_halo = 0;
+    const float* edge_lo = nullptr;
+    const float* edge_hi = nullptr;
 };
+// padding mode of the forward pass being issued on this host thread (set by zs_*_forward from cfg.seg_len)
+static thread_local int t_zero_pad = 0;
 
 static int launch_conv(const zs_conv_desc* d, cudaStream_t stream, const ConvExtras* ex = nullptr) {
     ZS_TRY(ensure_device());
@@ -263,22 +268,26 @@ static int launch_conv(const zs_conv_desc* d, cudaStream_t stream, const ConvExt
     if (ex) {
         p.stats = ex->stats; p.post_emb = ex->post_emb; p.post_spk = reinterpret_cast<const long long*>(ex->post_spk);
         p.post_pitch = ex->post_pitch; p.post_n = ex->post_n > 0 ? ex->post_n : 1; p.no_sat = ex->no_sat;
+        p.zero_halo = ex->zero_halo; p.edge_lo = ex->edge_lo; p.edge_hi = ex->edge_hi;
         if (p.post_emb && !p.post_spk) return fail(ZS_ERR_ARG, "conv: post-add embedding needs speaker ids");
     }
 
     const int grid = std::min(m_tiles * n_tiles, g_num_sms);
     const int which = d->operand == ZS_OPERAND_BF16 ? 1 : 0;
-    if (!g_attr_set[which]) {
-        if (which) CUDA_TRY(cudaFuncSetAttribute(conv_gemm_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
-        else CUDA_TRY(cudaFuncSetAttribute(conv_gemm_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
-        g_attr_set[which] = true;
+    const int zp = p.zero_halo ? 1 : 0;
+    using KernelT = void (*)(const GemmParams);
+    KernelT kern = zp ? (which ? conv_gemm_kernel<__nv_bfloat16, true> : conv_gemm_kernel<__half, true>)
+                      : (which ? conv_gemm_kernel<__nv_bfloat16, false> : conv_gemm_kernel<__half, false>);
+    static bool attr_set[2][2] = {{false, false}, {false, false}};
+    if (!attr_set[which][zp]) {
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+        attr_set[which][zp] = true;
     }
     {   // algorithmic FLOPs: 2 * valid out channels * true taps * true in channels * valid frames
         double taps_sum = d->bank ? 28.0 / 7.0 : static_cast<double>(d->taps);
         const double flops = 2.0 * d->m_valid * taps_sum * d->c_in_valid * static_cast<double>(d->B) * d->T_out;
         LaunchScope scope(stream, KC_GEMM, flops, d->stride == 2 ? "conv_gemm s2" : (d->taps > 1 ? "conv_gemm" : "conv_gemm k1"));
-        if (which) conv_gemm_kernel<__nv_bfloat16><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, stream>>>(p);
-        else conv_gemm_kernel<__half><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, stream>>>(p);
+        kern<<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, stream>>>(p);
     }
     CUDA_TRY(cudaGetLastError());
     return ZS_OK;
@@ -290,19 +299,20 @@ extern "C" int zs_conv1d_cl(const zs_conv_desc* d, void* stream) { return launch
 // -------------------------------------------------------------------------------------------------
 static int launch_pack_nct(const float* x, int B, int C, int T, void* out, int rows, int pitch, int halo, int choff,
                            int lrelu, float ns, int operand, int zero_pad, cudaStream_t st) {
-    if (halo >= T && halo > 0) return fail(ZS_ERR_ARG, "pack: reflect halo %d needs more than %d frames", halo, T);
+    if (halo >= T && halo > 0) return fail(ZS_ERR_ARG, "pack: halo %d needs more than %d frames", halo, T);
     const int c_fill = zero_pad ? pitch - choff : C;
     dim3 grid((T + 31) / 32, (c_fill + 31) / 32, B), block(32, 8);
     LaunchScope scope(st, KC_OTHER, 0.0, "pack_nct_kernel");
     if (operand == ZS_OPERAND_BF16)
-        pack_nct_kernel<__nv_bfloat16><<<grid, block, 0, st>>>(x, static_cast<__nv_bfloat16*>(out), C, T, rows, pitch, halo, choff, c_fill, lrelu, ns);
+        pack_nct_kernel<__nv_bfloat16><<<grid, block, 0, st>>>(x, static_cast<__nv_bfloat16*>(out), C, T, rows, pitch, halo, choff, c_fill, lrelu, ns, t_zero_pad);
     else
-        pack_nct_kernel<__half><<<grid, block, 0, st>>>(x, static_cast<__half*>(out), C, T, rows, pitch, halo, choff, c_fill, lrelu, ns);
+        pack_nct_kernel<__half><<<grid, block, 0, st>>>(x, static_cast<__half*>(out), C, T, rows, pitch, halo, choff, c_fill, lrelu, ns, t_zero_pad);
     CUDA_TRY(cudaGetLastError());
     return ZS_OK;
 }
 extern "C" int zs_pack_nct(const float* x, int B, int C, int T, void* out, int rows, int pitch, int halo, int choff,
                            int lrelu, float ns, int operand, int zero_pad_channels, void* stream) {
+    t_zero_pad = 0;
     return launch_pack_nct(x, B, C, T, out, rows, pitch, halo, choff, lrelu, ns, operand, zero_pad_channels, static_cast<cudaStream_t>(stream));
 }
 
@@ -462,6 +472,7 @@ extern "C" int zs_gru_recurrence(const float* gx, const float* w_hh, const float
 struct Layer {          // one GEMM's worth of packed weights
     void* w = nullptr;      // operand type [m_rows][w_taps * c_in_pad]
     float* bias = nullptr;  // [n_tab][m_rows]
+    float* edge_lo = nullptr, *edge_hi = nullptr;   // zero-padding mode, folded embedding, k > 1: [n_tab][m_rows] = W_0 . e, W_{k-1} . e
     int m_rows = 0, m_valid = 0, taps = 1, w_taps = 1, c_in_pad = 0, c_in_valid = 0, per_spk = 0, ps = 0, n_tab = 1;
     // training: transposed weights for the data-gradient GEMM, [t_rows][t_taps * t_kpad] fp16 (pack_weight_T_kernel)
     void* wt = nullptr;
@@ -487,7 +498,7 @@ struct DevPool {        // owns every device allocation of a handle
 // emb != null folds  sum_{j, ci} W[co][ci_emb_lo + ci][j] * emb[s][ci]  into a per-speaker bias table.
 static int pack_layer(DevPool& pool, Layer& L, int operand, const float* W, const float* b, int C_out, int C_in, int k,
                       int ci_lo, int ci_n, int ps, const float* emb, int emb_ci_lo, int C_e, int n_spk,
-                      cudaStream_t st) {
+                      cudaStream_t st, int zero_pad = 0) {
     L.m_rows = round_up(C_out, BM); L.m_valid = C_out; L.taps = k; L.w_taps = k;
     L.c_in_pad = round_up(ci_n, BK); L.c_in_valid = ci_n; L.ps = ps; L.per_spk = emb ? 1 : 0;
     const long long k_total = static_cast<long long>(k) * L.c_in_pad;
@@ -502,6 +513,17 @@ static int pack_layer(DevPool& pool, Layer& L, int operand, const float* W, cons
     const long long warps = static_cast<long long>(n_tab) * C_out;
     fold_bias_kernel<<<static_cast<int>((warps * 32 + 255) / 256), 256, 0, st>>>(W, b, emb, L.bias, C_out, C_in, k, emb_ci_lo, emb ? C_e : 0, n_tab, L.m_rows, 0, ps);
     CUDA_TRY(cudaGetLastError());
+    if (zero_pad && emb && k > 1) {
+        // zero padding is applied AFTER the embedding was added (model/model.py:319-325: pad_layer(x + emb)), so the
+        // taps that fall into the padding at the two ends of a segment must not see it: frame 0 loses W_0 . e, frame
+        // T-1 loses W_{k-1} . e (k = 3 on this path)
+        if (k != 3) return fail(ZS_ERR_ARG, "zero-padding mode: a folded speaker embedding is implemented for kernel size 3 (got %d)", k);
+        ZS_TRY(pool.alloc(reinterpret_cast<void**>(&L.edge_lo), static_cast<size_t>(n_tab) * L.m_rows * 4, st));
+        ZS_TRY(pool.alloc(reinterpret_cast<void**>(&L.edge_hi), static_cast<size_t>(n_tab) * L.m_rows * 4, st));
+        fold_bias_kernel<<<static_cast<int>((warps * 32 + 255) / 256), 256, 0, st>>>(W, nullptr, emb, L.edge_lo, C_out, C_in, k, emb_ci_lo, C_e, n_tab, L.m_rows, 0, ps, 0);
+        fold_bias_kernel<<<static_cast<int>((warps * 32 + 255) / 256), 256, 0, st>>>(W, nullptr, emb, L.edge_hi, C_out, C_in, k, emb_ci_lo, C_e, n_tab, L.m_rows, 0, ps, k - 1);
+        CUDA_TRY(cudaGetLastError());
+    }
     return ZS_OK;
 }
 
@@ -654,7 +676,7 @@ static int encoder_fill(zs_encoder* h, const zs_encoder_weights* w, cudaStream_t
 extern "C" int zs_encoder_pack(const zs_encoder_cfg* cfg, const zs_encoder_weights* w, void* stream, zs_encoder** out) {
     if (!cfg || !w || !out) return fail(ZS_ERR_ARG, "encoder_pack: null argument");
     ZS_TRY(ensure_device());
-    if (cfg->seg_len < 64) return fail(ZS_ERR_ARG, "encoder: seg_len %d < 64 selects zero padding (model/model.py:38); only the reflect mode is implemented", cfg->seg_len);
+    if (cfg->seg_len < 64 && cfg->train) return fail(ZS_ERR_ARG, "encoder: seg_len %d < 64 selects zero padding (model/model.py:38); the training path implements the reflect mode", cfg->seg_len);
     if (cfg->enc_mode < 0 || cfg->enc_mode > 4) return fail(ZS_ERR_ARG, "encoder: enc_mode %d not supported", cfg->enc_mode);
     if (cfg->enc_mode == ZS_ENC_BINARY && cfg->enc_size > 128) return fail(ZS_ERR_ARG, "encoder: enc_mode 'binary' projects to enc_size^2 channels; enc_size %d > 128", cfg->enc_size);
     if (cfg->c_h2 % 8 || cfg->c_h1 % 8 || cfg->c_h3 < 1) return fail(ZS_ERR_ARG, "encoder: c_h1/c_h2 must be multiples of 8");
@@ -701,7 +723,7 @@ static int decoder_fill(zs_decoder* h, const zs_decoder_weights* w, cudaStream_t
     }
     for (int i = 0; i < 6; ++i) {   // conv1,3,5: 2*c_h rows pixel-shuffle-permuted; block b uses emb[b] for both convs
         const bool up = (i % 2 == 0);
-        ZS_TRY(pack_layer(h->pool, h->conv[i], op, w->conv_w[i], w->conv_b[i], up ? 2 * ch : ch, ch, 3, 0, ch, up ? 1 : 0, tr ? nullptr : w->emb[i / 2], 0, ch, ca, st));
+        ZS_TRY(pack_layer(h->pool, h->conv[i], op, w->conv_w[i], w->conv_b[i], up ? 2 * ch : ch, ch, 3, 0, ch, up ? 1 : 0, tr ? nullptr : w->emb[i / 2], 0, ch, ca, st, cfg->seg_len < 64));
     }
     for (int i = 0; i < 4; ++i)     // emb4 conditions all four dense layers (model/model.py:350-351)
         ZS_TRY(pack_layer(h->pool, h->dense[i], op, w->dense_w[i], w->dense_b[i], ch, ch, 1, 0, ch, 0, tr ? nullptr : w->emb[3], 0, ch, ca, st));
@@ -731,7 +753,7 @@ static int decoder_fill(zs_decoder* h, const zs_decoder_weights* w, cudaStream_t
 extern "C" int zs_decoder_pack(const zs_decoder_cfg* cfg, const zs_decoder_weights* w, void* stream, zs_decoder** out) {
     if (!cfg || !w || !out) return fail(ZS_ERR_ARG, "decoder_pack: null argument");
     ZS_TRY(ensure_device());
-    if (cfg->seg_len < 64) return fail(ZS_ERR_ARG, "decoder: seg_len %d < 64 selects zero padding (model/model.py:38); the speaker-embedding bias fold needs the reflect mode", cfg->seg_len);
+    if (cfg->seg_len < 64 && cfg->train) return fail(ZS_ERR_ARG, "decoder: seg_len %d < 64 selects zero padding (model/model.py:38); the training path implements the reflect mode", cfg->seg_len);
     if (cfg->c_h % 64) return fail(ZS_ERR_ARG, "decoder: c_h %d must be a multiple of 64 (pixel-shuffle tile permutation)", cfg->c_h);
     if (cfg->train && cfg->operand != ZS_OPERAND_FP16) return fail(ZS_ERR_ARG, "decoder: the training path computes in fp16 operands (loss-scaled gradients)");
     if (cfg->train && cfg->c_in % 8) return fail(ZS_ERR_ARG, "decoder: training needs c_in %% 8 == 0");
@@ -873,7 +895,10 @@ static int run_layer(const Layer& L, int operand, float ns, const Buf& in, int B
     if (out) { d.out = out->p; d.out_rows = out->rows; d.out_pitch = out->pitch; d.out_halo = out->halo; }
     else { d.out = out_raw; d.out_rows = out_raw_rows; d.out_pitch = out_raw_pitch; d.out_halo = 0; }
     d.out_choff = o.out_choff; d.accumulate = o.accumulate; d.operand = operand; d.nb_hint = 0;
-    return launch_conv(&d, st, o.ex);
+    if (!t_zero_pad) return launch_conv(&d, st, o.ex);
+    ConvExtras ex = o.ex ? *o.ex : ConvExtras();
+    ex.zero_halo = 1; ex.edge_lo = L.edge_lo; ex.edge_hi = L.edge_hi;
+    return launch_conv(&d, st, &ex);
 }
 
 extern "C" int zs_encoder_forward(zs_encoder* h, const float* x, int B, int T, const float* gumbel_noise, float* logits,
@@ -883,6 +908,7 @@ extern "C" int zs_encoder_forward(zs_encoder* h, const float* x, int B, int T, c
     if (T < 9 || T > 256) return fail(ZS_ERR_ARG, "encoder_forward: T %d outside [9, 256] (convert.py MIN_LEN=9; segments are < 2*seg_len frames)", T);
     const zs_encoder_cfg& g = h->cfg;
     if (g.enc_mode != ZS_ENC_CONTINUES && !gumbel_noise) return fail(ZS_ERR_ARG, "encoder_forward: enc_mode %d needs the Gumbel noise tensor", g.enc_mode);
+    t_zero_pad = g.seg_len < 64;           // model/model.py:36-38: 'constant' padding below seg_len 64
     EncWs w = carve_encoder(h, workspace, B, T);
     if (!workspace || workspace_bytes < w.bytes) return fail(ZS_ERR_WORKSPACE, "encoder_forward: workspace %zu < %zu bytes", workspace_bytes, w.bytes);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -952,6 +978,7 @@ extern "C" int zs_decoder_forward(zs_decoder* h, const float* enc_act, const int
     if (B < 1 || T8 < 2 || T8 > 32) return fail(ZS_ERR_ARG, "decoder_forward: B %d, T8 %d (T8 must be in [2, 32])", B, T8);
     if (accumulate < 0 || accumulate > 2) return fail(ZS_ERR_ARG, "decoder_forward: accumulate %d", accumulate);
     const zs_decoder_cfg& g = h->cfg;
+    t_zero_pad = g.seg_len < 64;           // model/model.py:36-38: 'constant' padding below seg_len 64
     DecWs w = carve_decoder(h, workspace, B, T8);
     if (!workspace || workspace_bytes < w.bytes) return fail(ZS_ERR_WORKSPACE, "decoder_forward: workspace %zu < %zu bytes", workspace_bytes, w.bytes);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -962,9 +989,9 @@ extern "C" int zs_decoder_forward(zs_decoder* h, const float* enc_act, const int
         dim3 grid(T8, B);
         LaunchScope scope(st, KC_OTHER, 0.0, "unit_gather_kernel");
         if (op == ZS_OPERAND_BF16)
-            unit_gather_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(unit_ids, static_cast<const __nv_bfloat16*>(h->emb_table), h->input_emb.bias, static_cast<__nv_bfloat16*>(w.x0.p), T8, ch, w.x0.rows, w.x0.pitch, 1, g.c_in);
+            unit_gather_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(unit_ids, static_cast<const __nv_bfloat16*>(h->emb_table), h->input_emb.bias, static_cast<__nv_bfloat16*>(w.x0.p), T8, ch, w.x0.rows, w.x0.pitch, 1, g.c_in, t_zero_pad);
         else
-            unit_gather_kernel<__half><<<grid, 256, 0, st>>>(unit_ids, static_cast<const __half*>(h->emb_table), h->input_emb.bias, static_cast<__half*>(w.x0.p), T8, ch, w.x0.rows, w.x0.pitch, 1, g.c_in);
+            unit_gather_kernel<__half><<<grid, 256, 0, st>>>(unit_ids, static_cast<const __half*>(h->emb_table), h->input_emb.bias, static_cast<__half*>(w.x0.p), T8, ch, w.x0.rows, w.x0.pitch, 1, g.c_in, t_zero_pad);
         CUDA_TRY(cudaGetLastError());
     } else {
         ZS_TRY(launch_pack_nct(enc_act, B, g.c_in, T8, w.actp.p, w.actp.rows, w.actp.pitch, 0, 0, 0, ns, op, 0, st));

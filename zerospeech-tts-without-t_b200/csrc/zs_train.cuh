@@ -277,6 +277,7 @@ static Buf ps_view(const Buf& b) {     // [B][rows][pitch] in pixel-shuffle spac
 
 extern "C" int zs_decoder_forward_train(zs_decoder* h, const float* enc_act, const int64_t* spk, int B, int T8, float* spec,
                                         void* workspace, size_t workspace_bytes, void* stream) {
+    t_zero_pad = 0;          // the training path is reflect-mode only (checked at pack time)
     if (!h || !enc_act || !spk || !spec) return fail(ZS_ERR_ARG, "decoder_forward_train: null argument");
     if (!h->cfg.train) return fail(ZS_ERR_ARG, "decoder_forward_train: handle was packed without cfg.train");
     if (B < 1) return fail(ZS_ERR_ARG, "decoder_forward_train: B %d", B);
@@ -349,6 +350,7 @@ extern "C" int zs_decoder_forward_train(zs_decoder* h, const float* enc_act, con
 extern "C" int zs_decoder_backward(zs_decoder* h, const float* spec, const float* target, const float* d_spec, const int64_t* spk,
                                    int B, int T8, float loss_scale, float* loss, const zs_decoder_weights* grads, float* d_act,
                                    void* workspace, size_t workspace_bytes, void* stream) {
+    t_zero_pad = 0;          // the training path is reflect-mode only (checked at pack time)
     if (!h || !spec || !spk || !grads || (!target && !d_spec)) return fail(ZS_ERR_ARG, "decoder_backward: null argument");
     if (target && !loss) return fail(ZS_ERR_ARG, "decoder_backward: the fused L1 loss needs a `loss` output");
     if (!h->cfg.train) return fail(ZS_ERR_ARG, "decoder_backward: handle was packed without cfg.train");
@@ -525,6 +527,7 @@ extern "C" size_t zs_encoder_train_workspace_bytes(const zs_encoder* h, int B, i
 extern "C" int zs_encoder_forward_train(zs_encoder* h, const float* x, int B, int T, const float* gumbel_noise, float dropout_p,
                                         uint64_t dropout_seed, const uint64_t* dropout_seed_dev, const uint8_t* const* keep_masks, float* logits, float* act,
                                         int32_t* unit_ids, void* workspace, size_t workspace_bytes, void* stream) {
+    t_zero_pad = 0;          // the training path is reflect-mode only (checked at pack time)
     if (!h || !x || !logits || !gumbel_noise) return fail(ZS_ERR_ARG, "encoder_forward_train: null argument");
     if (!h->cfg.train) return fail(ZS_ERR_ARG, "encoder_forward_train: handle was packed without cfg.train");
     if (B < 1) return fail(ZS_ERR_ARG, "encoder_forward_train: B %d", B);
@@ -601,6 +604,7 @@ extern "C" int zs_encoder_forward_train(zs_encoder* h, const float* x, int B, in
 extern "C" int zs_encoder_backward(zs_encoder* h, const float* d_act, float d_act_scale, const float* gumbel_noise, const float* logits, int B,
                                    int T, float dropout_p, uint64_t dropout_seed, const uint64_t* dropout_seed_dev, const uint8_t* const* keep_masks, float loss_scale,
                                    const zs_encoder_weights* grads, void* workspace, size_t workspace_bytes, void* stream) {
+    t_zero_pad = 0;          // the training path is reflect-mode only (checked at pack time)
     if (!h || !d_act || !gumbel_noise || !logits || !grads) return fail(ZS_ERR_ARG, "encoder_backward: null argument");
     if (!h->cfg.train) return fail(ZS_ERR_ARG, "encoder_backward: handle was packed without cfg.train");
     if (!(loss_scale > 0.f) || !(d_act_scale > 0.f)) return fail(ZS_ERR_ARG, "encoder_backward: scales must be positive");

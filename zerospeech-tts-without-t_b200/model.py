@@ -22,7 +22,8 @@ Differences from the reference, all deliberate:
     or, for code that calls `loss.backward()` itself, by the autograd wrappers `zs_b200.train.encode_step /
     decode_step`;
   * segments are limited to 9 <= T <= 256 frames (the range convert.py's chunking produces
-    for seg_len = 128) and the reflect padding mode (hps seg_len >= 64);
+    for seg_len = 128); both padding modes of pad_layer (reflect for hps seg_len >= 64, zero below - the latter
+    inference only);
   * errors are raised, never swallowed; there is no CPU path.
 """
 import ctypes as C
