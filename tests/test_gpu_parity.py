@@ -368,3 +368,24 @@ def test_streaming_host_to_host_overlapping_calls(full_models):
     st.run(x, c, spec, ids, noise)
     torch.cuda.current_stream().synchronize()
     assert float(spec.min()) > 0.0
+
+
+def test_zero_padding_mode_edges():
+    """seg_len < 64 selects 'constant' padding (model/model.py:36-38).  The speaker embedding is folded into per-speaker
+    bias tables, which under zero padding needs the edge corrections -W_0.e / -W_2.e at the first / last frame of every
+    k = 3 decoder conv: check the segment edges specifically, and that they are where the two padding modes differ."""
+    g = load_golden('small_zeropad')
+    m = g['meta']
+    assert m['seg_len'] < 64
+    enc, dec, enc_sd, dec_sd = build_models(m)
+    c = syn.speaker_ids(m['B'], m['n_spk'], m['seed'])
+    ref_act = torch.zeros(m['B'], m['enc_size'], g['act_argmax'].shape[1]).scatter_(
+        1, torch.from_numpy(g['act_argmax']).long().unsqueeze(1), 1.0)
+    spec = dec(ref_act.cuda(), c.cuda()).cpu()
+    ref = torch.from_numpy(g['spec'])                         # the live reference, zero padding
+    with torch.no_grad():
+        reflect = orc.decoder_forward(dec_sd, ref_act, c, ns=m['ns'], seg_len=128)
+    edge = [0, 1, 2, 3, -4, -3, -2, -1]
+    assert (reflect[:, :, edge] - ref[:, :, edge]).abs().max().item() > 5e-2      # the modes really differ at the edges
+    assert (spec[:, :, edge] - ref[:, :, edge]).abs().max().item() < SPEC_MAXABS
+    assert relrms(spec[:, :, edge], ref[:, :, edge]) < SPEC_RELRMS
