@@ -389,3 +389,44 @@ def test_zero_padding_mode_edges():
     assert (reflect[:, :, edge] - ref[:, :, edge]).abs().max().item() > 5e-2      # the modes really differ at the edges
     assert (spec[:, :, edge] - ref[:, :, edge]).abs().max().item() < SPEC_MAXABS
     assert relrms(spec[:, :, edge], ref[:, :, edge]) < SPEC_RELRMS
+
+
+@pytest.mark.parametrize('enc_size', [512, 1024])
+def test_long_utterance_with_patcher(enc_size):
+    """BASELINE config 5: AE + TTS patcher (second Decoder, g_mode 'targeted', trainer.py:200-209) on a 2000-frame
+    utterance -> chunks 14 x 128 + 1 x 207 (convert.py:154-165), enc_size 512 and 1024, against the oracle's
+    test_step chunk by chunk with the reference's noise order."""
+    m = dict(FULL, enc_size=enc_size)
+    enc, dec, enc_sd, dec_sd = build_models(m)
+    gen_sd = syn.decoder_state_dict(7, c_in=enc_size, c_out=513, c_h=1024, c_a=2)
+    gen = Decoder(c_in=enc_size, c_out=513, c_h=1024, c_a=2, ns=0.01, seg_len=128)
+    gen.load_state_dict(gen_sd)
+    path = AutoencoderPath(enc, dec, gen, g_mode='targeted', n_speakers=102, n_target_speakers=2, seg_len=128, max_batch=16)
+    rng = np.random.Generator(np.random.PCG64(11))
+    spec = np.clip(rng.random((2000, 513), dtype=np.float32), 1e-8, 1)
+    _, plan, _ = segment_plan(2000, 128)
+    assert [e - s for s, e in plan] == [128] * 14 + [207]
+    torch.manual_seed(5)
+    outs, units = path.convert_utterances([spec], [101], enc_only=False, reference_noise_order=True)
+    assert outs[0].shape == (14 * 128 + 8 * Encoder.t8(207), 513) and units[0].shape == (14 * 16 + Encoder.t8(207), enc_size)
+    torch.manual_seed(5)
+    noises = [torch.rand(1, Encoder.t8(e - s), enc_size) for s, e in plan]
+    got_units = torch.from_numpy(units[0]).argmax(1)
+    row = urow = 0
+    agree, n_units = 0, 0
+    with torch.no_grad():
+        for (s, e), un in list(zip(plan, noises))[::5] + [(plan[-1], noises[-1])]:      # every 5th chunk + the 207-frame tail
+            k = plan.index((s, e))
+            urow, row = sum(Encoder.t8(b - a) for a, b in plan[:k]), sum(8 * Encoder.t8(b - a) for a, b in plan[:k])
+            xs = torch.from_numpy(spec[s:e]).t().unsqueeze(0)
+            T8 = Encoder.t8(e - s)
+            _, _, o_ids = orc.encoder_forward(enc_sd, xs, un, enc_size=enc_size)
+            ours = got_units[urow:urow + T8]
+            agree += int((ours == o_ids[0]).sum()); n_units += T8
+            # decoder + patcher on OUR units (isolates the decoder/patcher error from unit flips)
+            act = torch.zeros(1, enc_size, T8).scatter_(1, ours.view(1, 1, T8), 1.0)
+            c = torch.tensor([101])
+            want = orc.decoder_forward(dec_sd, act, c) + orc.decoder_forward(gen_sd, act, c - 100)     # trainer.py:209
+            got = torch.from_numpy(outs[0][row:row + 8 * T8]).t().unsqueeze(0)
+            assert relrms(got, want) < SPEC_RELRMS and (got - want).abs().max().item() < 2 * SPEC_MAXABS
+    assert agree >= 0.95 * n_units, (agree, n_units)
