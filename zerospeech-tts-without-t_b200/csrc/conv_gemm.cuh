@@ -54,6 +54,8 @@ struct alignas(64) GemmParams {
     int rnd_ns, rnd_rows, rnd_sub, rnd_frames;
     int m_tiles, n_tiles, nb, Tt, T, B, N;
     int kc, taps, bank, stride, in_row0, c_in_pad;
+    int last_mmas;       // K = 16 MMAs of the LAST 64-channel chunk of a tap that hold valid input channels (1..4)
+    int pdl;             // launched with programmatic stream serialization: wait for the producer grid before touching its data
     int m_valid;
     const float* bias;
     const long long* spk;
@@ -327,6 +329,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (p.pdl) {
+        // programmatic dependent launch: the next kernel of the stream may be scheduled as SMs free up (its prologue
+        // then overlaps this grid's tail); everything above touched no data of the producer grid - from here on it does
+        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+    }
 
     const int total_tiles = p.m_tiles * p.n_tiles;
     const uint32_t stage_tx = A_STAGE_BYTES + static_cast<uint32_t>(p.N) * (BK * 2);
@@ -384,17 +392,21 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
                 mbar_wait(&tempty[as], ((it >> 1) & 1) ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + as * MAX_BN;
+                int kc_pos = 0;                      // chunk index within the current tap
                 for (int ks = 0; ks < ksteps; ++ks) {
                     mbar_wait(&full[stage], phase);
                     tc_fence_after();
                     const uint64_t da = umma_desc_sw128(a0 + stage * A_STAGE_BYTES);
                     const uint64_t db = umma_desc_sw128(b0 + stage * B_STAGE_BYTES);
+                    // the zero-padded tail of the input channels (513 -> 576, 1409 -> 1472) needs no MMAs
+                    const int n_mma = (++kc_pos == p.kc) ? p.last_mmas : BK / 16;
+                    if (kc_pos == p.kc) kc_pos = 0;
                     if (elect_one()) {
                         if (!(p.debug & 2)) {
 #pragma unroll
                             for (int k = 0; k < BK / 16; ++k) {
                                 // advance 16 elements (32 B) along K inside the swizzle row: +2 in the >>4 address field
-                                umma_f16(d_tmem, da + 2 * k, db + 2 * k, p.idesc, (ks | k) != 0);
+                                if (k < n_mma) umma_f16(d_tmem, da + 2 * k, db + 2 * k, p.idesc, (ks | k) != 0);
                             }
                         }
                         umma_commit(&empty[stage]);

@@ -258,6 +258,10 @@ static int launch_conv(const zs_conv_desc* d, cudaStream_t stream, const ConvExt
     p.m_tiles = m_tiles; p.n_tiles = n_tiles; p.nb = nb; p.Tt = Tt; p.T = d->T_out; p.B = d->B; p.N = nb * Tt;
     p.kc = d->c_in_pad / BK; p.taps = d->taps; p.bank = d->bank; p.stride = d->stride; p.in_row0 = d->in_row0;
     p.c_in_pad = d->c_in_pad; p.m_valid = d->m_valid;
+    {   // MMAs of a tap's last chunk that still cover valid channels (c_in_valid need not be a multiple of 64)
+        const int tail = d->c_in_valid - (p.kc - 1) * BK;
+        p.last_mmas = tail >= BK ? BK / 16 : std::max(1, (tail + 15) / 16);
+    }
     p.bias = d->bias; p.spk = reinterpret_cast<const long long*>(d->spk); p.bias_stride = d->m_rows; p.n_spk = d->n_spk > 0 ? d->n_spk : 1;
     p.lrelu = d->lrelu; p.ns = d->ns; p.inorm = d->inorm;
     p.res_mode = d->res_mode; p.res = d->res; p.res_rows = d->res_rows; p.res_pitch = d->res_pitch; p.res_halo = d->res_halo;
@@ -287,7 +291,18 @@ static int launch_conv(const zs_conv_desc* d, cudaStream_t stream, const ConvExt
         double taps_sum = d->bank ? 28.0 / 7.0 : static_cast<double>(d->taps);
         const double flops = 2.0 * d->m_valid * taps_sum * d->c_in_valid * static_cast<double>(d->B) * d->T_out;
         LaunchScope scope(stream, KC_GEMM, flops, d->stride == 2 ? "conv_gemm s2" : (d->taps > 1 ? "conv_gemm" : "conv_gemm k1"));
-        kern<<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, stream>>>(p);
+        // programmatic dependent launch (ZS_PDL=1): measured neutral on this path (9.505 vs 9.514 ms per step) - the
+        // kernels run back to back without host gaps and every CTA needs a whole SM, so only prologues could overlap
+        static const int use_pdl = [] { const char* e = getenv("ZS_PDL"); return e ? atoi(e) : 0; }();
+        p.pdl = use_pdl;
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(GEMM_THREADS); cfg.dynamicSmemBytes = GEMM_SMEM_BYTES; cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr; cfg.numAttrs = use_pdl ? 1 : 0;
+        CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, p));
     }
     CUDA_TRY(cudaGetLastError());
     return ZS_OK;
