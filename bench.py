@@ -44,10 +44,11 @@ def parse():
     ap.add_argument('--steps', type=int, default=50)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--segments', type=int, default=888, help='128-frame segments per GPU per step')
-    ap.add_argument('--micro-batch', type=int, default=222,
-                    help='segments per library call: 222 x 128 frames = 111 column tiles, x 8 row tiles = 6 x 148 CTAs exactly for the '
-                         '1024-channel layers, and 14 GRU clusters of 32 sequences (one wave of the 15 that fit a B200)')
-    ap.add_argument('--e2e-micro-batch', type=int, default=222, help='segments per pipelined copy/compute stage (e2e)')
+    ap.add_argument('--micro-batch', type=int, default=888,
+                    help='segments per library call: 888 x 128 frames = 444 column tiles, x 8 row tiles = 24 x 148 CTAs exactly for the '
+                         '1024-channel layers (12 / 24 exact waves on the 2048-channel up-convs too), and 56 GRU clusters of 32 '
+                         'sequences = 4 waves of the 14-15 that fit a B200')
+    ap.add_argument('--e2e-micro-batch', type=int, default=444, help='segments per pipelined copy/compute stage (e2e)')
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--operand', default='fp16', choices=['fp16', 'bf16'])
     ap.add_argument('--cpu-sample', type=int, default=32, help='segments in the CPU baseline sample')
@@ -334,10 +335,11 @@ def run_ours(args):
         traffic, traffic_note = None, None
         try:
             tr = json.load(open(os.path.join(ROOT, 'profiles', 'r01_gemm_traffic.json')))
-            if tr['micro_batch'] == MB and S % MB == 0:
-                traffic = (tr['dram_read_bytes'] + tr['dram_write_bytes']) * (S // MB)
-                traffic_note = (f"bytes per step over all {gemm_launches} GEMM launches = {S // MB} micro-batches x "
-                                f"{(tr['dram_read_bytes'] + tr['dram_write_bytes']) / 1e9:.2f} GB (ncu capture of one micro-batch, profiles/r01_ncu_full_conv_gemm_mb222.csv)")
+            if S % tr['micro_batch'] == 0 and MB % tr['micro_batch'] == 0:     # activation traffic scales with the segments
+                n_cap = S // tr['micro_batch']
+                traffic = (tr['dram_read_bytes'] + tr['dram_write_bytes']) * n_cap
+                traffic_note = (f"bytes per step over all {gemm_launches} GEMM launches = {n_cap} x "
+                                f"{(tr['dram_read_bytes'] + tr['dram_write_bytes']) / 1e9:.2f} GB (ncu capture of 222 segments, profiles/r01_ncu_full_conv_gemm_mb222.csv; weights are re-read once per call)")
         except Exception:
             pass
         line = {
