@@ -82,7 +82,60 @@ __global__ void __launch_bounds__(128, 1) test(float* D_out, int M_total) {
     if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;" ::"r"(tm) : "memory");
 }
 
+// issue cost: `n_mma` back-to-back MMAs of the given shape on the same operands, leader-side clock from first issue to commit arrival
+__global__ void __launch_bounds__(128, 1) bench2(long long* cyc, int M_total, int n_mma) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t slot;
+    const uint32_t rank = ctarank();
+    uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    for (int i = threadIdx.x; i < (16384 + 8192) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem_raw + (base - smem_u32(smem_raw)))[i] = 0;
+    if (threadIdx.x == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
+    if (threadIdx.x < 32) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&slot)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    tc_fence_before(); __syncthreads(); tc_fence_after();
+    cluster_sync();
+    const uint32_t tm = slot;
+    if (rank == 0 && threadIdx.x < 32) {
+        long long t0 = clock64();
+        if (elect_one()) {
+            const uint32_t id = idesc_f16(M_total, N);
+            const uint64_t da = umma_desc_sw128(base), db = umma_desc_sw128(base + 16384);
+            for (int i = 0; i < n_mma; ++i) umma_f16_2cta(tm + 64 * (i & 3), da + 2 * (i & 3), db + 2 * (i & 3), id, i >= 4 ? 1u : 0u);
+            asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                         ::"r"(smem_u32(&bar)), "h"((uint16_t)3) : "memory");
+        }
+        __syncwarp();
+        long long t1 = clock64();
+        mbar_wait(&bar, 0);
+        long long t2 = clock64();
+        if (threadIdx.x == 0) { cyc[0] = t1 - t0; cyc[1] = t2 - t0; }
+    } else {
+        mbar_wait(&bar, 0);
+    }
+    tc_fence_before(); __syncthreads();
+    cluster_sync();
+    if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;" ::"r"(tm) : "memory");
+}
+
 int main() {
+    {
+        long long* c; cudaMalloc(&c, 16);
+        cudaFuncSetAttribute(bench2, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+        for (int M_total : {256, 128}) for (int n_mma : {32, 64, 96}) {
+            cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof(cfg));
+            cfg.gridDim = dim3(2); cfg.blockDim = dim3(128); cfg.dynamicSmemBytes = 64 * 1024;
+            cudaLaunchAttribute at[1]; at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            cfg.attrs = at; cfg.numAttrs = 1;
+            cudaLaunchKernelEx(&cfg, bench2, c, M_total, n_mma);
+            cudaError_t e = cudaDeviceSynchronize();
+            long long hc[2]; cudaMemcpy(hc, c, 16, cudaMemcpyDeviceToHost);
+            printf("cta_group::2 M=%d N=%d: %d MMAs: issue %lld cycles, complete %lld cycles (%.1f / MMA) %s\n", M_total, N, n_mma, hc[0], hc[1], (double)hc[1] / n_mma, cudaGetErrorString(e));
+        }
+    }
     float* d;
     cudaMalloc(&d, 2 * 128 * N * 4);
     cudaFuncSetAttribute(test, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
