@@ -8,9 +8,11 @@
 // Per step:  D_rz[128 x 32] = W_rz h^T (M = 128),  D_n[64 x 32] = W_n h^T (M = 64)  -> TMEM;
 // the 8 gate warps (two per TMEM lane quadrant, 16 sequences each) read D, add the precomputed input
 // projections gx (from the GEMM kernel) and b_hh, apply the gates, keep h in fp32 registers, write h_t to the
-// output buffer and publish their 64-unit slice of the new state to every CTA of the cluster with one bulk
-// shared->shared::cluster copy per peer that completes on the peer's mbarrier (no cluster-wide barrier inside
-// the time loop).  The single state buffer may only be overwritten once EVERY CTA's MMAs of the step have read
+// output buffer and publish their 64-unit slice of the new state to every CTA of the cluster: one bulk store to an
+// L2-resident scratch and one MULTICAST bulk load back into the same shared-memory offset of all peers, completing on
+// each peer's per-source mbarrier (the direct alternative - one shared->shared::cluster bulk copy per peer - is bound by
+// the ~17 B/clk SM-to-SM port: 28 KB out + 28 KB in per CTA and step; through L2 the CTA sends 4 KB).  No cluster-wide
+// barrier inside the time loop.  The single state buffer may only be overwritten once EVERY CTA's MMAs of the step have read
 // it: each CTA's tcgen05.commit is multicast to a `consumed` mbarrier in all CTAs of the cluster, and the gate
 // warps wait for it (normally long complete - the gate math sits in between) before they store or send h_{t+1}.
 //
@@ -92,6 +94,23 @@ __device__ __forceinline__ void dsmem_bulk_copy(uint32_t dst_cluster_addr, uint3
         "r"(src_cta_addr), "r"(bytes), "r"(mbar_cluster_addr)
         : "memory");
 }
+// The same slice to EVERY peer through L2: one bulk store shared -> global scratch, then one multicast bulk load
+// global -> the same shared-memory offset of every CTA in `cta_mask`, completing (bytes) on each destination's mbarrier.
+// Per step a CTA then moves 4 KB out + 28 KB in through the L2 path instead of 28 KB out + 28 KB in through the
+// SM-to-SM port (measured ~17 B/clk per SM, the bound of the direct exchange).
+__device__ __forceinline__ void bulk_store_smem_to_global(void* gdst, uint32_t src_cta_addr, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(src_cta_addr), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");       // the write is complete (not only the source read)
+}
+__device__ __forceinline__ void bulk_load_multicast(uint32_t dst_cta_addr, const void* gsrc, uint32_t bytes, uint32_t mbar_cta_addr,
+                                                    uint16_t cta_mask) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(
+            dst_cta_addr),
+        "l"(gsrc), "r"(bytes), "r"(mbar_cta_addr), "h"(cta_mask)
+        : "memory");
+}
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 __host__ __device__ inline uint32_t umma_idesc_f16_m(int fmt, int m, int n) {
@@ -112,6 +131,7 @@ struct GruParams {
     int B, T, H, out_rows, out_pitch, out_halo, out_choff, fmt, debug;
     long long* dbg;        // debug bit 3: per-step clock64 stamps of cluster 0 / CTA 0 ([T][8])
     int fast_act;          // 1: sigmoid/tanh through tanh.approx.f32 (one MUFU each, 2^-11 relative error)
+    uint8_t* xchg;         // non-null: exchange the state slices through this L2-resident scratch ([clusters][NC][slice]) by multicast
     void* gates;           // training: r, z, n, hn = W_hn h + b_hn per step, operand type [B][T][2][4][H]; null = not saved
 };
 
@@ -349,9 +369,18 @@ __global__ void __launch_bounds__(GRU_THREADS, 1) gru_cluster_kernel(const GruPa
                     const uint32_t src = smem_u32(hnext);
                     const uint32_t bar_local = smem_u32(&h_chunk[rank]);
                     if (warp == 0) mbar_arrive(&h_chunk[rank]);   // my own slice is in place
-                    for (uint32_t d = 1 + warp; d < static_cast<uint32_t>(NC); d += GRU_GATE_WARPS) {
-                        const uint32_t peer = (rank + d) % NC;
-                        dsmem_bulk_copy(mapa_shared(src, peer), src, slice_bytes, mapa_shared(bar_local, peer));
+                    if (p.xchg != nullptr) {
+                        if (warp == 0 && NC > 1) {
+                            uint8_t* g = p.xchg + (static_cast<size_t>(cl) * KCH + rank) * slice_bytes;
+                            bulk_store_smem_to_global(g, src, slice_bytes);
+                            const uint16_t peers = static_cast<uint16_t>(((1u << NC) - 1u) & ~(1u << rank));
+                            bulk_load_multicast(src, g, slice_bytes, bar_local, peers);
+                        }
+                    } else {
+                        for (uint32_t d = 1 + warp; d < static_cast<uint32_t>(NC); d += GRU_GATE_WARPS) {
+                            const uint32_t peer = (rank + d) % NC;
+                            dsmem_bulk_copy(mapa_shared(src, peer), src, slice_bytes, mapa_shared(bar_local, peer));
+                        }
                     }
                 }
                 __syncwarp();

@@ -368,7 +368,7 @@ static int launch_gru(const void* gx, const float* whhT, const float* bhh, int B
 static bool gru_cluster_ok(int H) { return H % GRU_UNITS == 0 && H / GRU_UNITS >= 1 && H / GRU_UNITS <= 8; }
 
 static int launch_gru_cluster(const void* w_img, const float* bhh, const void* gx, int B, int T, int H, void* out, int rows,
-                              int pitch, int halo, int choff, int operand, cudaStream_t st, void* gates = nullptr) {
+                              int pitch, int halo, int choff, int operand, cudaStream_t st, void* gates = nullptr, void* xchg = nullptr, size_t xchg_bytes = 0) {
     ZS_TRY(ensure_device());
     GruParams p;
     p.gates = gates;
@@ -434,6 +434,12 @@ static int launch_gru_cluster(const void* w_img, const float* bhh, const void* g
         cudaError_t e = cudaOccupancyMaxActiveClusters(&ncl, kern, &cfg);
         fprintf(stderr, "gru: max active clusters of %d CTAs with %d B smem: %d (%s); launching %d clusters of %d sequences\n", NC, smem, ncl, cudaGetErrorString(e), 2 * n_groups, nseq);
     }
+    {   // state exchange through L2 + multicast (ZS_GRU_XCHG=0: direct SM-to-SM bulk copies)
+        static const int xmode = [] { const char* e = getenv("ZS_GRU_XCHG"); return e ? atoi(e) : 1; }();
+        p.xchg = nullptr;
+        const size_t need = static_cast<size_t>(2) * n_groups * NC * nseq * 128;     // one slice per CTA of every cluster
+        if (xmode && NC > 1 && xchg && need <= xchg_bytes) p.xchg = static_cast<uint8_t*>(xchg);
+    }
     LaunchScope scope(st, KC_GRU, 2.0 * 2 * B * static_cast<double>(T) * 3 * H * H, "gru_cluster_kernel");
     CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, p));
     return ZS_OK;
@@ -468,7 +474,11 @@ extern "C" int zs_gru_recurrence(const float* gx, const float* w_hh, const float
         const size_t bytes = static_cast<size_t>(2) * (H / GRU_UNITS) * gru_w_image_bytes(H);
         CUDA_TRY(cudaMallocAsync(&img, bytes, st));
         int r = pack_gru_image(img, nullptr, w_hh, H, operand, st);
-        if (r == ZS_OK) r = launch_gru_cluster(img, b_hh, gx_ot, B, T, H, out, out_rows, out_pitch, out_halo, out_choff, operand, st);
+        void* xch = nullptr;
+        const size_t xch_bytes = static_cast<size_t>(2) * round_up(B, 32) * H * 2;      // state-exchange scratch (L2 multicast path)
+        CUDA_TRY(cudaMallocAsync(&xch, xch_bytes, st));
+        if (r == ZS_OK) r = launch_gru_cluster(img, b_hh, gx_ot, B, T, H, out, out_rows, out_pitch, out_halo, out_choff, operand, st, nullptr, xch, xch_bytes);
+        cudaFreeAsync(xch, st);
         cudaFreeAsync(img, st);
         return r;
     }
@@ -820,7 +830,7 @@ struct Carver {
 };
 
 struct EncWs {
-    Buf xp, cat, a[7], d[3], catr, gx;
+    Buf xp, cat, a[7], d[3], catr, gx, xch;
     int T[4];
     size_t bytes;
 };
@@ -841,6 +851,7 @@ static EncWs carve_encoder(const zs_encoder* h, void* ws, int B, int T) {
     for (int i = 0; i < 3; ++i) w.d[i] = c.act(B, w.T[3], 0, g.c_h2);
     w.catr = c.act(B, w.T[3], 0, g.c_h2 + 2 * g.c_h3);
     w.gx = c.act(B, w.T[3], 0, 6 * g.c_h3, true);   // the recurrence indexes it as a dense [B][T][2][3H] array
+    w.xch = c.act(round_up(B, 32), 2, 0, g.c_h3);   // GRU state exchange scratch: one H-wide fp16 row per (direction, sequence)
     w.bytes = c.off;
     return w;
 }
@@ -850,7 +861,7 @@ extern "C" size_t zs_encoder_workspace_bytes(const zs_encoder* h, int B, int T) 
 }
 
 struct DecWs {
-    Buf actp, x0, p[3], y[3], d[3], catr, d5, gx;
+    Buf actp, x0, p[3], y[3], d[3], catr, d5, gx, xch;
     size_t bytes;
 };
 static DecWs carve_decoder(const zs_decoder* h, void* ws, int B, int T8) {
@@ -869,6 +880,7 @@ static DecWs carve_decoder(const zs_decoder* h, void* ws, int B, int T8) {
     w.catr = c.act(B, Tf, 0, 2 * ch);
     w.d5 = c.act(B, Tf, 0, ch);
     w.gx = c.act(B, Tf, 0, 3 * ch, true);
+    w.xch = c.act(round_up(B, 32), 2, 0, ch / 2);   // GRU state exchange scratch
     w.bytes = c.off;
     return w;
 }
@@ -967,7 +979,7 @@ extern "C" int zs_encoder_forward(zs_encoder* h, const float* x, int B, int T, c
     {   // :454-455 bi-GRU: input projection on tensor cores, then the recurrence
         ConvOpts o; o.lrelu = 0; o.c_in_valid = g.c_h2;
         ZS_TRY(run_layer(h->gru_ih, op, ns, w.catr, B, T8, &w.gx, nullptr, 0, 0, o, st));
-        if (h->whh_img) ZS_TRY(launch_gru_cluster(h->whh_img, h->bhh, w.gx.p, B, T8, g.c_h3, w.catr.p, w.catr.rows, w.catr.pitch, 0, g.c_h2, op, st));
+        if (h->whh_img) ZS_TRY(launch_gru_cluster(h->whh_img, h->bhh, w.gx.p, B, T8, g.c_h3, w.catr.p, w.catr.rows, w.catr.pitch, 0, g.c_h2, op, st, nullptr, w.xch.p, static_cast<size_t>(w.xch.rows) * w.xch.pitch * 2 * round_up(B, 32)));
         else ZS_TRY(launch_gru(w.gx.p, h->whhT, h->bhh, B, T8, g.c_h3, w.catr.p, w.catr.rows, w.catr.pitch, 0, g.c_h2, op, st));
     }
     {   // linear -> logits in the reference's (B, n_out, T8) fp32 layout
@@ -1035,7 +1047,7 @@ extern "C" int zs_decoder_forward(zs_decoder* h, const float* enc_act, const int
     {   // :352-355 bi-GRU on out + emb5
         ConvOpts o; o.lrelu = 0; o.c_in_valid = ch; o.spk = spk;
         ZS_TRY(run_layer(h->gru_ih, op, ns, w.catr, B, Tf, &w.gx, nullptr, 0, 0, o, st));
-        if (h->whh_img) ZS_TRY(launch_gru_cluster(h->whh_img, h->bhh, w.gx.p, B, Tf, ch / 2, w.catr.p, w.catr.rows, w.catr.pitch, 0, ch, op, st));
+        if (h->whh_img) ZS_TRY(launch_gru_cluster(h->whh_img, h->bhh, w.gx.p, B, Tf, ch / 2, w.catr.p, w.catr.rows, w.catr.pitch, 0, ch, op, st, nullptr, w.xch.p, static_cast<size_t>(w.xch.rows) * w.xch.pitch * 2 * round_up(B, 32)));
         else ZS_TRY(launch_gru(w.gx.p, h->whhT, h->bhh, B, Tf, ch / 2, w.catr.p, w.catr.rows, w.catr.pitch, 0, ch, op, st));
     }
     {   // :356-364 dense5 on cat([out, rnn, emb5]) -> lrelu -> linear -> sigmoid | tanh
