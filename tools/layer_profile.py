@@ -12,7 +12,7 @@ import zs_b200  # noqa: E402
 from zs_b200 import _lib, synthetic as syn  # noqa: E402
 from zs_b200.model import Decoder, Encoder, gumbel_from_uniform  # noqa: E402
 
-NAMES = ['pack x', 'pack x(bank in)', 'bank', 'conv2 IN', 'conv3', 'conv4 s2 IN+avg', 'conv5', 'conv6 s2 IN+avg', 'conv7',
+NAMES = ['pack x (bank in + cat)', 'bank', 'conv2 IN', 'conv3', 'conv4 s2 IN+avg', 'conv5', 'conv6 s2 IN+avg', 'conv7',
          'conv8 s2 IN+avg', 'dense1', 'dense2 IN+res', 'dense3', 'dense4 IN+res', 'gx', 'GRU enc', 'linear', 'bottleneck',
          'unit gather', 'd.conv1 PS', 'd.conv2 IN+up2', 'd.conv3 PS', 'd.conv4 IN+up2', 'd.conv5 PS', 'd.conv6 IN+up2',
          'd.dense1', 'd.dense2 IN+res', 'd.dense3', 'd.dense4 IN+res', 'd.gx', 'GRU dec', 'd.dense5', 'd.linear']

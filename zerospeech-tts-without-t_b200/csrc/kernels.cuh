@@ -1,6 +1,7 @@
 // HBM-bound companion kernels of the autoencoder path: layout packing, the discrete bottleneck,
 // the GRU recurrence, weight packing and speaker-embedding bias folding.
 #pragma once
+#include <type_traits>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <stdint.h>
@@ -41,6 +42,55 @@ __global__ void pack_nct_kernel(const float* __restrict__ x, OT* __restrict__ ou
             const OT hv = zero_halo ? float_to_ot<OT>(0.f) : y;
             if (t >= 1 && t <= halo) ob[static_cast<size_t>(halo - t) * pitch + c] = hv;
             if (t >= T - 1 - halo && t <= T - 2) ob[static_cast<size_t>(halo + 2 * (T - 1) - t) * pitch + c] = hv;
+        }
+    }
+}
+
+// The encoder's two views of its input in ONE pass over x (model/model.py:441-446): the conv bank reads x with a
+// 3-frame halo (`bank`, no activation), and conv2 reads cat([bank outputs, x]) after a leaky-relu (`cat`, channel offset
+// `cat_choff`, no halo).  Tiles of 64 channels x 32 frames: 128-byte reads along T, 128-byte half2 writes along C.
+template <typename OT>
+__global__ void __launch_bounds__(256) pack_x_dual_kernel(const float* __restrict__ x, int C, int T,
+                                                          OT* __restrict__ bank, int bank_rows, int bank_pitch, int bank_halo,
+                                                          OT* __restrict__ cat, int cat_rows, int cat_pitch, int cat_choff, int cat_fill,
+                                                          float ns, int zero_halo) {
+    __shared__ float tile[64][33];
+    const int t0 = blockIdx.x * 32, c0 = blockIdx.y * 64, b = blockIdx.z;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int c = c0 + ty + 8 * i, t = t0 + tx;
+        tile[ty + 8 * i][tx] = (c < C && t < T) ? x[(static_cast<size_t>(b) * C + c) * T + t] : 0.f;
+    }
+    __syncthreads();
+    OT* bb = bank + static_cast<size_t>(b) * bank_rows * bank_pitch;
+    OT* cb = cat + static_cast<size_t>(b) * cat_rows * cat_pitch + cat_choff;
+    const int c = c0 + 2 * tx;                       // this lane's channel pair
+    using OT2 = typename std::conditional<std::is_same<OT, __half>::value, __half2, __nv_bfloat162>::type;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int t = t0 + ty + 8 * i;
+        if (t >= T) continue;
+        const float v0 = tile[2 * tx][ty + 8 * i], v1 = tile[2 * tx + 1][ty + 8 * i];
+        if (c < bank_pitch) {                        // channels >= C are the zero padding of the K dimension
+            OT2 y; y.x = float_to_ot<OT>(v0); y.y = float_to_ot<OT>(v1);
+            OT2 hv = y;
+            if (zero_halo) { hv.x = float_to_ot<OT>(0.f); hv.y = hv.x; }
+            *reinterpret_cast<OT2*>(bb + static_cast<size_t>(bank_halo + t) * bank_pitch + c) = y;
+            if (t >= 1 && t <= bank_halo) *reinterpret_cast<OT2*>(bb + static_cast<size_t>(bank_halo - t) * bank_pitch + c) = hv;
+            if (t >= T - 1 - bank_halo && t <= T - 2)
+                *reinterpret_cast<OT2*>(bb + static_cast<size_t>(bank_halo + 2 * (T - 1) - t) * bank_pitch + c) = hv;
+        }
+        if (c < cat_fill) {
+            const float l0 = fmaxf(v0, v0 * ns), l1 = fmaxf(v1, v1 * ns);
+            OT* dst = cb + static_cast<size_t>(t) * cat_pitch + c;
+            if (((cat_choff + c) & 1) == 0 && c + 1 < cat_fill) {
+                OT2 y; y.x = float_to_ot<OT>(l0); y.y = float_to_ot<OT>(l1);
+                *reinterpret_cast<OT2*>(dst) = y;
+            } else {
+                dst[0] = float_to_ot<OT>(l0);
+                if (c + 1 < cat_fill) dst[1] = float_to_ot<OT>(l1);
+            }
         }
     }
 }

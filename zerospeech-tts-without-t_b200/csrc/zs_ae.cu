@@ -325,6 +325,22 @@ static int launch_pack_nct(const float* x, int B, int C, int T, void* out, int r
     CUDA_TRY(cudaGetLastError());
     return ZS_OK;
 }
+// x -> (bank input with halo, leaky-relu'd copy inside the concat buffer) in one pass
+static int launch_pack_x_dual(const float* x, int B, int C, int T, void* bank_p, int bank_rows, int bank_pitch, int bank_halo, void* cat_p,
+                              int cat_rows, int cat_pitch, int cat_choff, float ns, int operand, cudaStream_t st) {
+    if (bank_halo >= T) return fail(ZS_ERR_ARG, "pack: halo %d needs more than %d frames", bank_halo, T);
+    if ((cat_choff & 1) || (bank_pitch & 1)) return fail(ZS_ERR_ARG, "pack: channel offsets / pitches must be even");
+    dim3 grid((T + 31) / 32, (C + 63) / 64, B);
+    LaunchScope scope(st, KC_OTHER, 0.0, "pack_x_dual_kernel");
+    if (operand == ZS_OPERAND_BF16)
+        pack_x_dual_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(x, C, T, static_cast<__nv_bfloat16*>(bank_p), bank_rows, bank_pitch, bank_halo,
+                                                                static_cast<__nv_bfloat16*>(cat_p), cat_rows, cat_pitch, cat_choff, C, ns, t_zero_pad);
+    else
+        pack_x_dual_kernel<__half><<<grid, 256, 0, st>>>(x, C, T, static_cast<__half*>(bank_p), bank_rows, bank_pitch, bank_halo,
+                                                         static_cast<__half*>(cat_p), cat_rows, cat_pitch, cat_choff, C, ns, t_zero_pad);
+    CUDA_TRY(cudaGetLastError());
+    return ZS_OK;
+}
 extern "C" int zs_pack_nct(const float* x, int B, int C, int T, void* out, int rows, int pitch, int halo, int choff,
                            int lrelu, float ns, int operand, int zero_pad_channels, void* stream) {
     t_zero_pad = 0;
@@ -943,8 +959,7 @@ extern "C" int zs_encoder_forward(zs_encoder* h, const float* x, int B, int T, c
     const float ns = g.ns;
 
     // model/model.py:441-446: conv bank on x, concatenated with x, leaky-relu
-    ZS_TRY(launch_pack_nct(x, B, g.c_in, T, w.xp.p, w.xp.rows, w.xp.pitch, 3, 0, 0, ns, op, 0, st));
-    ZS_TRY(launch_pack_nct(x, B, g.c_in, T, w.cat.p, w.cat.rows, w.cat.pitch, 0, 7 * g.c_h1, 1, ns, op, 0, st));
+    ZS_TRY(launch_pack_x_dual(x, B, g.c_in, T, w.xp.p, w.xp.rows, w.xp.pitch, 3, w.cat.p, w.cat.rows, w.cat.pitch, 7 * g.c_h1, ns, op, st));
     if (h->bank_merged) {
         ConvOpts o; o.bank = 1;
         ZS_TRY(run_layer(h->bank[0], op, ns, w.xp, B, T, &w.cat, nullptr, 0, 0, o, st));

@@ -548,8 +548,7 @@ extern "C" int zs_encoder_forward_train(zs_encoder* h, const float* x, int B, in
         p.B = B; p.T = Tl; p.C = h2;
         return launch_combine(p, st);
     };
-    ZS_TRY(launch_pack_nct(x, B, g.c_in, T, w.xp.p, w.xp.rows, w.xp.pitch, 3, 0, 0, ns, op, 0, st));
-    ZS_TRY(launch_pack_nct(x, B, g.c_in, T, w.cat.p, w.cat.rows, w.cat.pitch, 0, 7 * g.c_h1, 1, ns, op, 0, st));
+    ZS_TRY(launch_pack_x_dual(x, B, g.c_in, T, w.xp.p, w.xp.rows, w.xp.pitch, 3, w.cat.p, w.cat.rows, w.cat.pitch, 7 * g.c_h1, ns, op, st));
     if (h->bank_merged) {
         ConvOpts o; o.bank = 1;
         ZS_TRY(run_layer(h->bank[0], op, ns, w.xp, B, T, &w.cat, nullptr, 0, 0, o, st));
