@@ -43,12 +43,12 @@ def parse():
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=50)
     ap.add_argument('--warmup', type=int, default=3)
-    ap.add_argument('--segments', type=int, default=888, help='128-frame segments per GPU per step')
-    ap.add_argument('--micro-batch', type=int, default=888,
-                    help='segments per library call: 888 x 128 frames = 444 column tiles, x 8 row tiles = 24 x 148 CTAs exactly for the '
-                         '1024-channel layers (12 / 24 exact waves on the 2048-channel up-convs too), and 56 GRU clusters of 32 '
-                         'sequences = 4 waves of the 14-15 that fit a B200')
-    ap.add_argument('--e2e-micro-batch', type=int, default=444, help='segments per pipelined copy/compute stage (e2e)')
+    ap.add_argument('--segments', type=int, default=960, help='128-frame segments per GPU per step')
+    ap.add_argument('--micro-batch', type=int, default=960,
+                    help='segments per library call: 960 x 128 frames = 480 column tiles, x 8 row tiles = 3840 tiles = 25.95 waves of 148 '
+                         'CTAs on the 1024-channel layers (same on the 2048-channel up-convs), and 60 GRU clusters of 32 sequences = '
+                         'exactly 4 waves of the 15 eight-CTA clusters that fit a B200')
+    ap.add_argument('--e2e-micro-batch', type=int, default=480, help='segments per pipelined copy/compute stage (e2e)')
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--operand', default='fp16', choices=['fp16', 'bf16'])
     ap.add_argument('--cpu-sample', type=int, default=32, help='segments in the CPU baseline sample')
@@ -335,10 +335,10 @@ def run_ours(args):
         traffic, traffic_note = None, None
         try:
             tr = json.load(open(os.path.join(ROOT, 'profiles', 'r01_gemm_traffic.json')))
-            if S % tr['micro_batch'] == 0 and MB % tr['micro_batch'] == 0:     # activation traffic scales with the segments
-                n_cap = S // tr['micro_batch']
+            if MB >= 444:     # saturating calls: the traffic is activation traffic and scales with the segments
+                n_cap = S / tr['micro_batch']
                 traffic = (tr['dram_read_bytes'] + tr['dram_write_bytes']) * n_cap
-                traffic_note = (f"bytes per step over all {gemm_launches} GEMM launches = {n_cap} x "
+                traffic_note = (f"bytes per step over all {gemm_launches} GEMM launches = {n_cap:.3f} x "
                                 f"{(tr['dram_read_bytes'] + tr['dram_write_bytes']) / 1e9:.2f} GB (ncu --set full capture of one {tr['micro_batch']}-segment call, profiles/r01_ncu_full_conv_gemm_mb888.csv)")
         except Exception:
             pass

@@ -51,11 +51,11 @@ class StreamingResynthesizer:
     The per-chunk reference loop pays one H2D, one launch train and one D2H *sync* per segment
     (convert.py:70-76, trainer.py:221).  Here segments go through in micro-batches on three CUDA streams:
     H2D of micro-batch i+1 and D2H of micro-batch i-1 run on the two copy engines while micro-batch i computes.
-    Host tensors must be pinned for the copies to be asynchronous.  Micro-batches of 444 / 888 segments of 128 frames
-    tile the B200 exactly (multiples of 148 CTAs on the wide layers, whole waves of GRU clusters): 13.1 / 13.5 M frames/s
-    against 12.1 M at 222 (4.4 MB of workspace per segment)."""
+    Host tensors must be pinned for the copies to be asynchronous.  Micro-batches of 480 / 960 segments of 128 frames
+    tile the B200 (25.95 waves of 148 CTAs on the wide layers, exactly 2 / 4 waves of 15 GRU clusters): large calls run at
+    ~14 M frames/s against 12 M at 222 segments (4.4 MB of workspace per segment)."""
 
-    def __init__(self, encoder: Encoder, decoder: Decoder, micro_batch=444, n_buffers=3, device='cuda'):
+    def __init__(self, encoder: Encoder, decoder: Decoder, micro_batch=480, n_buffers=3, device='cuda'):
         self.enc, self.dec = encoder, decoder
         self.mb, self.nbuf = micro_batch, n_buffers
         self.device = torch.device(device)
@@ -140,7 +140,7 @@ class AutoencoderPath:
     `encode_utterances` / `convert_utterances` that replace the per-chunk Python loops of convert.py."""
 
     def __init__(self, encoder: Encoder, decoder: Decoder, generator: Decoder = None, g_mode='targeted',
-                 n_speakers=102, n_target_speakers=2, seg_len=128, max_batch=888, device='cuda'):
+                 n_speakers=102, n_target_speakers=2, seg_len=128, max_batch=960, device='cuda'):
         self.Encoder, self.Decoder, self.Generator = encoder, decoder, generator
         self.g_mode, self.seg_len, self.max_batch = g_mode, seg_len, max_batch
         self.shift = n_speakers - n_target_speakers        # trainer.py:181 testing_shift_c
