@@ -339,7 +339,7 @@ def run_ours(args):
                 n_cap = S / tr['micro_batch']
                 traffic = (tr['dram_read_bytes'] + tr['dram_write_bytes']) * n_cap
                 traffic_note = (f"bytes per step over all {gemm_launches} GEMM launches = {n_cap:.3f} x "
-                                f"{(tr['dram_read_bytes'] + tr['dram_write_bytes']) / 1e9:.2f} GB (ncu --set full capture of one {tr['micro_batch']}-segment call, profiles/r01_ncu_full_conv_gemm_mb888.csv)")
+                                f"{(tr['dram_read_bytes'] + tr['dram_write_bytes']) / 1e9:.2f} GB (ncu --set full capture of one {tr['micro_batch']}-segment call, profiles/r01_ncu_full_conv_gemm_mb960.csv)")
         except Exception:
             pass
         line = {
