@@ -430,3 +430,44 @@ def test_long_utterance_with_patcher(enc_size):
             got = torch.from_numpy(outs[0][row:row + 8 * T8]).t().unsqueeze(0)
             assert relrms(got, want) < SPEC_RELRMS and (got - want).abs().max().item() < 2 * SPEC_MAXABS
     assert agree >= 0.95 * n_units, (agree, n_units)
+
+
+@pytest.mark.parametrize('g_mode', ['naive', 'targeted', 'targeted_residual'])
+def test_trainer_test_step_surface(full_models, g_mode):
+    """`AutoencoderPath.test_step / encoder_test_step` = Trainer.test_step / encoder_test_step (trainer.py:194-228): same
+    argument layout ((B, T, 513) in), numpy out, the three Decoder-as-patcher combine rules (trainer.py:206-211) fused into
+    the generator's output epilogue, and the target-speaker guard (trainer.py:202-203)."""
+    enc, dec, enc_sd, dec_sd = full_models
+    residual = g_mode == 'targeted_residual'
+    n_gen = 102 if g_mode == 'naive' else 2
+    gen_sd = syn.decoder_state_dict(9, c_in=1024, c_out=513, c_h=1024, c_a=n_gen)
+    gen = Decoder(c_in=1024, c_out=513, c_h=1024, c_a=n_gen, ns=0.01, seg_len=128, output_mask=residual)
+    gen.load_state_dict(gen_sd)
+    path = AutoencoderPath(enc, dec, gen, g_mode=g_mode, n_speakers=102, n_target_speakers=2, seg_len=128)
+    B, T = 2, 128
+    x = syn.spectrogram_batch(B, T, 31).permute(0, 2, 1).contiguous()           # (B, T, 513) as convert_x hands it over
+    c = torch.tensor([100, 101])
+    u = syn.gumbel_uniform((B, 16, 1024), 31)
+    noise = gumbel_from_uniform(u)
+    x_dec, enc_np = path.test_step(x, c, enc_only=False, noise=noise)
+    assert isinstance(x_dec, np.ndarray) and x_dec.shape == (B, 513, T) and enc_np.shape == (B, 1024, 16)
+    enc_only, _ = path.test_step(x, c, enc_only=True, noise=noise)
+    assert np.array_equal(path.encoder_test_step(x, noise=noise), enc_np)
+    ids = torch.from_numpy(enc_np).argmax(1)
+    with torch.no_grad():
+        act = torch.zeros(B, 1024, 16).scatter_(1, ids.unsqueeze(1), 1.0)           # our units: isolates the decoders' error
+        base = orc.decoder_forward(dec_sd, act, c)
+        if g_mode == 'naive':
+            want = base + orc.decoder_forward(gen_sd, act, c)
+        elif g_mode == 'targeted':
+            want = base + orc.decoder_forward(gen_sd, act, c - 100)
+        else:
+            want = base + base * orc.decoder_forward(gen_sd, act, c - 100, output_mask=True)
+        o_ids = orc.encoder_forward(enc_sd, x.permute(0, 2, 1), u)[2]
+    assert (ids == o_ids).float().mean().item() >= 0.95
+    assert relrms(torch.from_numpy(enc_only), base) < SPEC_RELRMS
+    assert relrms(torch.from_numpy(x_dec), want) < SPEC_RELRMS
+    assert (torch.from_numpy(x_dec) - want).abs().max().item() < 2 * SPEC_MAXABS
+    if g_mode != 'naive':
+        with pytest.raises(RuntimeError):
+            path.test_step(x, torch.tensor([3, 101]), enc_only=False, noise=noise)   # not a target speaker
