@@ -27,7 +27,11 @@ import time
 
 import torch
 
-os.environ['NCCL_DEBUG'] = os.environ.get('ZS_NCCL_DEBUG', 'WARN')     # NCCL's version banner goes to stdout: keep the JSON line alone
+# NCCL prints its version banner to STDOUT at any NCCL_DEBUG level from VERSION up: keep the JSON line alone on stdout
+if os.environ.get('ZS_NCCL_DEBUG'):
+    os.environ['NCCL_DEBUG'] = os.environ['ZS_NCCL_DEBUG']
+else:
+    os.environ.pop('NCCL_DEBUG', None)
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
