@@ -42,6 +42,27 @@ METRIC = 'spectrogram frames/s, AE encode+decode'
 MFLOP_PER_FRAME = 60.033
 
 
+class stdout_to_stderr:
+    """fd-level redirect: native libraries (NCCL's version banner) must not write into the JSON-only stdout."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self._saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def __exit__(self, *a):
+        sys.stdout.flush()
+        os.dup2(self._saved, 1)
+        os.close(self._saved)
+
+
+def init_distributed(dev):
+    import torch.distributed as dist
+    with stdout_to_stderr():
+        dist.init_process_group('nccl', device_id=dev)
+        dist.barrier()                       # communicator creation happens here at the latest
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -217,7 +238,7 @@ def run_ours(args):
     dev = torch.device('cuda', local)
     numa = bind_to_gpu_numa(local) if world > 1 else None
     if world > 1:
-        dist.init_process_group('nccl', device_id=dev)
+        init_distributed(dev)
 
     lib = _lib.lib()
     enc = Encoder(ns=0.01, dp=0.5, enc_size=ENC_SIZE, seg_len=128, enc_mode='one_hot')
@@ -397,7 +418,7 @@ def run_train(args):
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     if world > 1:
-        dist.init_process_group('nccl', device_id=dev)
+        init_distributed(dev)
     B = args.train_batch
     enc = Encoder(ns=0.01, dp=0.5, enc_size=ENC_SIZE, seg_len=128, enc_mode='one_hot')
     dec = Decoder(ns=0.01, c_in=ENC_SIZE, c_h=EMB_SIZE, c_a=N_SPK, seg_len=128)
