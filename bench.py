@@ -74,6 +74,7 @@ def parse():
                          'CTAs on the 1024-channel layers (same on the 2048-channel up-convs), and 60 GRU clusters of 32 sequences = '
                          'exactly 4 waves of the 15 eight-CTA clusters that fit a B200')
     ap.add_argument('--e2e-micro-batch', type=int, default=480, help='segments per pipelined copy/compute stage (e2e)')
+    ap.add_argument('--e2e-buffers', type=int, default=4, help='device buffer sets of the host-to-host pipeline')
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--operand', default='fp16', choices=['fp16', 'bf16'])
     ap.add_argument('--cpu-sample', type=int, default=32, help='segments in the CPU baseline sample')
@@ -274,7 +275,7 @@ def run_ours(args):
             dec.decode(None, cs[k][s0:s1], unit_ids=ids, out=spec_out[s0:s1])
             ids_out[s0:s1] = ids
 
-    streamer = StreamingResynthesizer(enc, dec, micro_batch=min(args.e2e_micro_batch, S), device=dev)
+    streamer = StreamingResynthesizer(enc, dec, micro_batch=min(args.e2e_micro_batch, S), n_buffers=args.e2e_buffers, device=dev)
 
     # public API: pinned host spectrograms/speakers/noise in, pinned host spectrograms/units out.  Steps are issued
     # back to back as a streaming server would (run_async): the upload of step i+1 overlaps the compute and download

@@ -55,7 +55,7 @@ class StreamingResynthesizer:
     tile the B200 (25.95 waves of 148 CTAs on the wide layers, exactly 2 / 4 waves of 15 GRU clusters): large calls run at
     ~14 M frames/s against 12 M at 222 segments (4.4 MB of workspace per segment)."""
 
-    def __init__(self, encoder: Encoder, decoder: Decoder, micro_batch=480, n_buffers=3, device='cuda'):
+    def __init__(self, encoder: Encoder, decoder: Decoder, micro_batch=480, n_buffers=4, device='cuda'):
         self.enc, self.dec = encoder, decoder
         self.mb, self.nbuf = micro_batch, n_buffers
         self.device = torch.device(device)
