@@ -71,9 +71,9 @@ def parse():
     ap.add_argument('--segments', type=int, default=960, help='128-frame segments per GPU per step')
     ap.add_argument('--micro-batch', type=int, default=960,
                     help='segments per library call: 960 x 128 frames = 480 column tiles, x 8 row tiles = 3840 tiles = 25.95 waves of 148 '
-                         'CTAs on the 1024-channel layers (same on the 2048-channel up-convs), and 60 GRU clusters of 32 sequences = '
-                         'exactly 4 waves of the 15 eight-CTA clusters that fit a B200')
-    ap.add_argument('--e2e-micro-batch', type=int, default=480, help='segments per pipelined copy/compute stage (e2e)')
+                         'CTAs on the 1024-channel layers (same on the 2048-channel up-convs), and 30 decoder-GRU clusters of 64 sequences = '
+                         'exactly 2 waves of the 15 eight-CTA clusters that fit a B200')
+    ap.add_argument('--e2e-micro-batch', type=int, default=960, help='segments per pipelined copy/compute stage (e2e)')
     ap.add_argument('--e2e-buffers', type=int, default=4, help='device buffer sets of the host-to-host pipeline')
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--operand', default='fp16', choices=['fp16', 'bf16'])

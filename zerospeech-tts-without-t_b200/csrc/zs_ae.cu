@@ -15,6 +15,7 @@
 #include "conv_gemm.cuh"
 #include "kernels.cuh"
 #include "gru_cluster.cuh"
+#include "gru_wide.cuh"
 #include "train_kernels.cuh"
 #include "gru_bptt_cluster.cuh"
 #include "wgrad_gemm.cuh"
@@ -383,6 +384,15 @@ static int launch_gru(const void* gx, const float* whhT, const float* bhh, int B
 
 static bool gru_cluster_ok(int H) { return H % GRU_UNITS == 0 && H / GRU_UNITS >= 1 && H / GRU_UNITS <= 8; }
 
+// GRU weight images of both directions: the swizzled shared-memory images of the cluster kernels, followed by the plain
+// r|z rows the wide kernel loads into TMEM
+static size_t gru_images_bytes(int H) {
+    const size_t NC = H / GRU_UNITS;
+    return 2 * NC * (static_cast<size_t>(gru_w_image_bytes(H)) + static_cast<size_t>(128) * H * 2);
+}
+static const void* gru_wrz_part(const void* img, int H) {
+    return static_cast<const uint8_t*>(img) + static_cast<size_t>(2) * (H / GRU_UNITS) * gru_w_image_bytes(H);
+}
 static int launch_gru_cluster(const void* w_img, const float* bhh, const void* gx, int B, int T, int H, void* out, int rows,
                               int pitch, int halo, int choff, int operand, cudaStream_t st, void* gates = nullptr, void* xchg = nullptr, size_t xchg_bytes = 0) {
     ZS_TRY(ensure_device());
@@ -419,6 +429,39 @@ static int launch_gru_cluster(const void* w_img, const float* bhh, const void* g
     }
     if (static_cast<long long>(B) * T * 6 * H >= (1ll << 31) || static_cast<long long>(B) * rows * pitch >= (1ll << 31))
         return fail(ZS_ERR_ARG, "gru: %d sequences x %d steps exceed the 32-bit element offsets of the recurrence kernel", B, T);
+    {   // 64 sequences per cluster with the r|z rows of W_hh in TMEM (gru_wide.cuh): the shape for batches that need more than
+        // one wave of 32-sequence clusters anyway.  ZS_GRU_WIDE=0 disables, =1 forces (where its preconditions hold).
+        static const int wide_mode = [] { const char* e = getenv("ZS_GRU_WIDE"); return e ? atoi(e) : 2; }();
+        const int NCw = H / GRU_UNITS, groups64 = (B + GRU_WIDE_NSEQ - 1) / GRU_WIDE_NSEQ;
+        const size_t need = static_cast<size_t>(2) * groups64 * NCw * GRU_WIDE_NSEQ * 128;
+        const bool can = !gates && xchg && need <= xchg_bytes && NCw >= 2 && NCw <= 8 && H % 64 == 0;
+        const bool want = wide_mode == 1 || (wide_mode == 2 && 2 * ((B + GRU_FWD_NSEQ - 1) / GRU_FWD_NSEQ) * NCw > 120);
+        if (can && want && wide_mode != 0) {
+            GruWideParams wp;
+            memset(&wp, 0, sizeof(wp));
+            wp.wrz = gru_wrz_part(w_img, H); wp.w_img = w_img; wp.bhh = bhh; wp.gx = gx; wp.out = out; wp.xchg = static_cast<uint8_t*>(xchg);
+            wp.B = B; wp.T = T; wp.H = H; wp.out_rows = rows; wp.out_pitch = pitch; wp.out_halo = halo; wp.out_choff = choff;
+            wp.fmt = operand == ZS_OPERAND_BF16 ? 1 : 0;
+            const int smem_w = gru_wide_smem_bytes(H);
+            using WideT = void (*)(const GruWideParams);
+            WideT wk = wp.fmt ? gru_wide_kernel<__nv_bfloat16> : gru_wide_kernel<__half>;
+            static int wattr[2] = {0, 0};
+            if (wattr[wp.fmt] < smem_w) {
+                CUDA_TRY(cudaFuncSetAttribute(wk, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_w));
+                wattr[wp.fmt] = smem_w;
+            }
+            cudaLaunchConfig_t wc;
+            memset(&wc, 0, sizeof(wc));
+            wc.gridDim = dim3(2 * groups64 * NCw); wc.blockDim = dim3(GRU_THREADS); wc.dynamicSmemBytes = smem_w; wc.stream = st;
+            cudaLaunchAttribute wa[1];
+            wa[0].id = cudaLaunchAttributeClusterDimension;
+            wa[0].val.clusterDim.x = NCw; wa[0].val.clusterDim.y = 1; wa[0].val.clusterDim.z = 1;
+            wc.attrs = wa; wc.numAttrs = 1;
+            LaunchScope scope(st, KC_GRU, 2.0 * 2 * B * static_cast<double>(T) * 3 * H * H, "gru_wide_kernel");
+            CUDA_TRY(cudaLaunchKernelEx(&wc, wk, wp));
+            return ZS_OK;
+        }
+    }
     // 32 sequences per cluster is the throughput shape; when the batch fits one wave of 16-sequence clusters (15 eight-CTA
     // clusters are resident on a B200) the smaller shape halves the per-step exchange and gate math: lower latency
     const int NC = H / GRU_UNITS;
@@ -469,6 +512,10 @@ static int pack_gru_image(void* img, const float* const* w_hh_dirs, const float*
         const int blocks = (3 * H * H + 255) / 256;
         if (operand == ZS_OPERAND_BF16) gru_pack_whh_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(W, static_cast<__nv_bfloat16*>(dst), H);
         else gru_pack_whh_kernel<__half><<<blocks, 256, 0, st>>>(W, static_cast<__half*>(dst), H);
+        void* plain = const_cast<uint8_t*>(static_cast<const uint8_t*>(gru_wrz_part(img, H))) + static_cast<size_t>(dir) * NC * 128 * H * 2;
+        const int blocks2 = (2 * H * H + 255) / 256;
+        if (operand == ZS_OPERAND_BF16) gru_pack_wrz_plain_kernel<__nv_bfloat16><<<blocks2, 256, 0, st>>>(W, static_cast<__nv_bfloat16*>(plain), H);
+        else gru_pack_wrz_plain_kernel<__half><<<blocks2, 256, 0, st>>>(W, static_cast<__half*>(plain), H);
     }
     CUDA_TRY(cudaGetLastError());
     return ZS_OK;
@@ -487,11 +534,11 @@ extern "C" int zs_gru_recurrence(const float* gx, const float* w_hh, const float
     if (impl == 2 && !gru_cluster_ok(H)) return fail(ZS_ERR_ARG, "gru: the cluster kernel needs H %% 64 == 0 and H <= 512 (H = %d)", H);
     if (impl == 2 || (impl == 0 && gru_cluster_ok(H))) {
         void* img = nullptr;
-        const size_t bytes = static_cast<size_t>(2) * (H / GRU_UNITS) * gru_w_image_bytes(H);
+        const size_t bytes = gru_images_bytes(H);
         CUDA_TRY(cudaMallocAsync(&img, bytes, st));
         int r = pack_gru_image(img, nullptr, w_hh, H, operand, st);
         void* xch = nullptr;
-        const size_t xch_bytes = static_cast<size_t>(2) * round_up(B, 32) * H * 2;      // state-exchange scratch (L2 multicast path)
+        const size_t xch_bytes = static_cast<size_t>(2) * round_up(B, 64) * H * 2;      // state-exchange scratch (L2 multicast path)
         CUDA_TRY(cudaMallocAsync(&xch, xch_bytes, st));
         if (r == ZS_OK) r = launch_gru_cluster(img, b_hh, gx_ot, B, T, H, out, out_rows, out_pitch, out_halo, out_choff, operand, st, nullptr, xch, xch_bytes);
         cudaFreeAsync(xch, st);
@@ -642,7 +689,7 @@ static int pack_gru(DevPool& pool, Layer& ih, float** whhT, float** bhh, void** 
     }
     CUDA_TRY(cudaGetLastError());
     if (gru_cluster_ok(H)) {
-        ZS_TRY(pool.alloc(whh_img, static_cast<size_t>(2) * (H / GRU_UNITS) * gru_w_image_bytes(H), st));
+        ZS_TRY(pool.alloc(whh_img, gru_images_bytes(H), st));
         ZS_TRY(pack_gru_image(*whh_img, w_hh, nullptr, H, operand, st));
     }
     return ZS_OK;
@@ -867,7 +914,7 @@ static EncWs carve_encoder(const zs_encoder* h, void* ws, int B, int T) {
     for (int i = 0; i < 3; ++i) w.d[i] = c.act(B, w.T[3], 0, g.c_h2);
     w.catr = c.act(B, w.T[3], 0, g.c_h2 + 2 * g.c_h3);
     w.gx = c.act(B, w.T[3], 0, 6 * g.c_h3, true);   // the recurrence indexes it as a dense [B][T][2][3H] array
-    w.xch = c.act(round_up(B, 32), 2, 0, g.c_h3);   // GRU state exchange scratch: one H-wide fp16 row per (direction, sequence)
+    w.xch = c.act(round_up(B, 64), 2, 0, g.c_h3);   // GRU state exchange scratch: one H-wide fp16 row per (direction, sequence)
     w.bytes = c.off;
     return w;
 }
@@ -896,7 +943,7 @@ static DecWs carve_decoder(const zs_decoder* h, void* ws, int B, int T8) {
     w.catr = c.act(B, Tf, 0, 2 * ch);
     w.d5 = c.act(B, Tf, 0, ch);
     w.gx = c.act(B, Tf, 0, 3 * ch, true);
-    w.xch = c.act(round_up(B, 32), 2, 0, ch / 2);   // GRU state exchange scratch
+    w.xch = c.act(round_up(B, 64), 2, 0, ch / 2);   // GRU state exchange scratch
     w.bytes = c.off;
     return w;
 }
@@ -994,7 +1041,7 @@ extern "C" int zs_encoder_forward(zs_encoder* h, const float* x, int B, int T, c
     {   // :454-455 bi-GRU: input projection on tensor cores, then the recurrence
         ConvOpts o; o.lrelu = 0; o.c_in_valid = g.c_h2;
         ZS_TRY(run_layer(h->gru_ih, op, ns, w.catr, B, T8, &w.gx, nullptr, 0, 0, o, st));
-        if (h->whh_img) ZS_TRY(launch_gru_cluster(h->whh_img, h->bhh, w.gx.p, B, T8, g.c_h3, w.catr.p, w.catr.rows, w.catr.pitch, 0, g.c_h2, op, st, nullptr, w.xch.p, static_cast<size_t>(w.xch.rows) * w.xch.pitch * 2 * round_up(B, 32)));
+        if (h->whh_img) ZS_TRY(launch_gru_cluster(h->whh_img, h->bhh, w.gx.p, B, T8, g.c_h3, w.catr.p, w.catr.rows, w.catr.pitch, 0, g.c_h2, op, st, nullptr, w.xch.p, static_cast<size_t>(w.xch.rows) * w.xch.pitch * 2 * round_up(B, 64)));
         else ZS_TRY(launch_gru(w.gx.p, h->whhT, h->bhh, B, T8, g.c_h3, w.catr.p, w.catr.rows, w.catr.pitch, 0, g.c_h2, op, st));
     }
     {   // linear -> logits in the reference's (B, n_out, T8) fp32 layout
@@ -1062,7 +1109,7 @@ extern "C" int zs_decoder_forward(zs_decoder* h, const float* enc_act, const int
     {   // :352-355 bi-GRU on out + emb5
         ConvOpts o; o.lrelu = 0; o.c_in_valid = ch; o.spk = spk;
         ZS_TRY(run_layer(h->gru_ih, op, ns, w.catr, B, Tf, &w.gx, nullptr, 0, 0, o, st));
-        if (h->whh_img) ZS_TRY(launch_gru_cluster(h->whh_img, h->bhh, w.gx.p, B, Tf, ch / 2, w.catr.p, w.catr.rows, w.catr.pitch, 0, ch, op, st, nullptr, w.xch.p, static_cast<size_t>(w.xch.rows) * w.xch.pitch * 2 * round_up(B, 32)));
+        if (h->whh_img) ZS_TRY(launch_gru_cluster(h->whh_img, h->bhh, w.gx.p, B, Tf, ch / 2, w.catr.p, w.catr.rows, w.catr.pitch, 0, ch, op, st, nullptr, w.xch.p, static_cast<size_t>(w.xch.rows) * w.xch.pitch * 2 * round_up(B, 64)));
         else ZS_TRY(launch_gru(w.gx.p, h->whhT, h->bhh, B, Tf, ch / 2, w.catr.p, w.catr.rows, w.catr.pitch, 0, ch, op, st));
     }
     {   // :356-364 dense5 on cat([out, rnn, emb5]) -> lrelu -> linear -> sigmoid | tanh

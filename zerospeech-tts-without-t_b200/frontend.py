@@ -51,11 +51,11 @@ class StreamingResynthesizer:
     The per-chunk reference loop pays one H2D, one launch train and one D2H *sync* per segment
     (convert.py:70-76, trainer.py:221).  Here segments go through in micro-batches on three CUDA streams:
     H2D of micro-batch i+1 and D2H of micro-batch i-1 run on the two copy engines while micro-batch i computes.
-    Host tensors must be pinned for the copies to be asynchronous.  Micro-batches of 480 / 960 segments of 128 frames
-    tile the B200 (25.95 waves of 148 CTAs on the wide layers, exactly 2 / 4 waves of 15 GRU clusters): large calls run at
-    ~14 M frames/s against 12 M at 222 segments (4.4 MB of workspace per segment)."""
+    Host tensors must be pinned for the copies to be asynchronous.  Micro-batches of 960 segments of 128 frames tile the
+    B200 (25.95 waves of 148 CTAs on the wide layers, exactly 2 waves of 15 sixty-four-sequence GRU clusters): such calls
+    run at ~15 M frames/s against 12 M at 222 segments (4.4 MB of workspace per segment)."""
 
-    def __init__(self, encoder: Encoder, decoder: Decoder, micro_batch=480, n_buffers=4, device='cuda'):
+    def __init__(self, encoder: Encoder, decoder: Decoder, micro_batch=960, n_buffers=4, device='cuda'):
         self.enc, self.dec = encoder, decoder
         self.mb, self.nbuf = micro_batch, n_buffers
         self.device = torch.device(device)
