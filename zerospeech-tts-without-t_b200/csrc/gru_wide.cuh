@@ -14,12 +14,12 @@
 
 namespace zs {
 
-constexpr int GRU_WIDE_NSEQ = 64;
+constexpr int GRU_WIDE_NSEQ = 64;       // sequences per cluster with 2 gate passes (NPASS = 4: 128)
 
 __host__ __device__ inline int gru_wide_wn_bytes(int H) { return 64 * H * 2; }               // n-gate rows, swizzled image
-__host__ __device__ inline int gru_wide_state_bytes(int H) { return GRU_WIDE_NSEQ * H * 2; }
-__host__ __device__ inline int gru_wide_smem_bytes(int H) {
-    return gru_wide_wn_bytes(H) + gru_wide_state_bytes(H) + 2 * 8 * 256 * 4 /* fp32 state of both passes */ + 1024 + 128;
+__host__ __device__ inline int gru_wide_state_bytes(int H, int npass) { return 32 * npass * H * 2; }
+__host__ __device__ inline int gru_wide_smem_bytes(int H, int npass) {
+    return gru_wide_wn_bytes(H) + gru_wide_state_bytes(H, npass) + npass * 8 * 256 * 4 /* fp32 state of every pass */ + 1024 + 128;
 }
 
 // W_hh (3H, H) fp32 of one direction -> plain r|z rows [NC][128 rows][H] operand type, rows ordered like the TMEM lanes of the
@@ -59,17 +59,17 @@ struct GruWideParams {
     int B, T, H, out_rows, out_pitch, out_halo, out_choff, fmt;
 };
 
-template <typename OT>
+template <typename OT, int NPASS>
 __global__ void __launch_bounds__(GRU_THREADS, 1) gru_wide_kernel(const GruWideParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_addr = smem_u32(smem_raw);
     uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
-    constexpr int NSEQ = GRU_WIDE_NSEQ;
+    constexpr int NSEQ = 32 * NPASS;
     const int H = p.H, KCH = H >> 6, NC = KCH;
     uint8_t* sWn = smem;                                        // [KCH chunks][64 rows][128 B]
-    uint8_t* sH = smem + gru_wide_wn_bytes(H);                  // [KCH chunks][64 rows][128 B]
-    float* sState = reinterpret_cast<float*>(sH + gru_wide_state_bytes(H));     // [2 passes][8][256 threads]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sState) + 2 * 8 * 256 * 4);
+    uint8_t* sH = smem + gru_wide_wn_bytes(H);                  // [KCH chunks][NSEQ rows][128 B]
+    float* sState = reinterpret_cast<float*>(sH + gru_wide_state_bytes(H, NPASS));     // [NPASS][8][256 threads]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sState) + NPASS * 8 * 256 * 4);
     uint64_t* h_chunk = bars;         // [8]
     uint64_t* rz_done = bars + 8;
     uint64_t* mma_done = bars + 9;
@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(GRU_THREADS, 1) gru_wide_kernel(const GruWideP
         const int n16 = gru_wide_wn_bytes(H) / 16;
         for (int i = threadIdx.x; i < n16; i += GRU_THREADS) dst[i] = src[i];
         uint4* hz = reinterpret_cast<uint4*>(sH);
-        for (int i = threadIdx.x; i < (gru_wide_state_bytes(H) + 2 * 8 * 256 * 4) / 16; i += GRU_THREADS) hz[i] = make_uint4(0, 0, 0, 0);
+        for (int i = threadIdx.x; i < (gru_wide_state_bytes(H, NPASS) + NPASS * 8 * 256 * 4) / 16; i += GRU_THREADS) hz[i] = make_uint4(0, 0, 0, 0);
     }
     if (threadIdx.x == 0) {
         for (int c = 0; c < 8; ++c) mbar_init(&h_chunk[c], 1);
@@ -106,8 +106,8 @@ __global__ void __launch_bounds__(GRU_THREADS, 1) gru_wide_kernel(const GruWideP
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t t_wrz = tmem_base;                          // columns [0, H/2): the r|z rows of W_hh
-    const uint32_t t_drz = tmem_base + (H >> 1);               // 64 columns
-    const uint32_t t_dn = t_drz + NSEQ;                        // 64 columns
+    const uint32_t t_drz = tmem_base + (H >> 1);               // NSEQ columns
+    const uint32_t t_dn = t_drz + NSEQ;                        // NSEQ columns (H/2 + 2 NSEQ <= 512)
     if (warp < GRU_GATE_WARPS) {
         // W_rz -> TMEM: this warp's quadrant (lane = row), its half of the K columns
         const int q = warp & 3, part = warp >> 2;
@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(GRU_THREADS, 1) gru_wide_kernel(const GruWideP
     tc_fence_after();
     cluster_sync_all();
 
-    const uint32_t slice_bytes = NSEQ * 128;                   // [64 rows][128 B]
+    const uint32_t slice_bytes = NSEQ * 128;                   // [NSEQ rows][128 B]
 
     if (warp == GRU_GATE_WARPS) {
         // ------------------------------ control / MMA issue ------------------------------
@@ -185,10 +185,10 @@ __global__ void __launch_bounds__(GRU_THREADS, 1) gru_wide_kernel(const GruWideP
         const int t_first = dir ? p.T - 1 : 0;
         const int gx_seq = p.T * 6 * H, out_seq = p.out_rows * p.out_pitch;
         // rows of the state tile / sequences of this thread: pass ps -> rows 32 ps + 16 half + 8 hi + i
-        int row0[2], gx_off[2], out_off[2];
-        uint32_t live[2];
+        int row0[NPASS], gx_off[NPASS], out_off[NPASS];
+        uint32_t live[NPASS];
 #pragma unroll
-        for (int ps = 0; ps < 2; ++ps) {
+        for (int ps = 0; ps < NPASS; ++ps) {
             row0[ps] = 32 * ps + 16 * half + 8 * hi;
             const int seq0 = b0 + row0[ps];
             live[ps] = 0;
@@ -215,11 +215,11 @@ __global__ void __launch_bounds__(GRU_THREADS, 1) gru_wide_kernel(const GruWideP
         uint8_t* hnext = sH + rank * slice_bytes;
         for (int t = 0; t < p.T; ++t) {
 #pragma unroll
-            for (int ps = 0; ps < 2; ++ps) {
+            for (int ps = 0; ps < NPASS; ++ps) {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) { gr[i] = pr[i]; gz[i] = pz[i]; gn[i] = pn[i]; }
-                // prefetch the other pass: pass 1 of this step, or pass 0 of the next one
-                if (ps == 0) load_gx(1, true, pr, pz, pn);
+                // prefetch the next pass: of this step, or pass 0 of the next one
+                if (ps + 1 < NPASS) load_gx(ps + 1, true, pr, pz, pn);
                 else load_gx(0, t + 1 < p.T, pr, pz, pn);
                 if (ps == 0) {
                     mbar_wait(rz_done, t & 1);
@@ -248,7 +248,7 @@ __global__ void __launch_bounds__(GRU_THREADS, 1) gru_wide_kernel(const GruWideP
                     uint32_t nn[16];
                     tmem_ld16(t_dn + lane_addr + 32 * ps + 16 * half, nn);
                     tmem_ld_wait();
-                    if (ps == 1) tc_fence_before();
+                    if (ps == NPASS - 1) tc_fence_before();
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
                         const uint32_t gotn = __shfl_xor_sync(0xffffffffu, nn[8 + i], 16);

@@ -432,8 +432,19 @@ static int launch_gru_cluster(const void* w_img, const float* bhh, const void* g
     {   // 64 sequences per cluster with the r|z rows of W_hh in TMEM (gru_wide.cuh): the shape for batches that need more than
         // one wave of 32-sequence clusters anyway.  ZS_GRU_WIDE=0 disables, =1 forces (where its preconditions hold).
         static const int wide_mode = [] { const char* e = getenv("ZS_GRU_WIDE"); return e ? atoi(e) : 2; }();
-        const int NCw = H / GRU_UNITS, groups64 = (B + GRU_WIDE_NSEQ - 1) / GRU_WIDE_NSEQ;
-        const size_t need = static_cast<size_t>(2) * groups64 * NCw * GRU_WIDE_NSEQ * 128;
+        const int NCw = H / GRU_UNITS;
+        // 64 sequences per cluster (2 gate passes), or 128 (4 passes) when the 64-sequence clusters would need a second wave and
+        // the state of 128 sequences fits (H <= 512: 64 KB of n rows + 128 KB of state; H/2 + 256 TMEM columns)
+        int npass = 2;
+        if (gru_wide_smem_bytes(H, 4) <= 232448 && (H >> 1) + 256 <= 512) {
+            // waves of resident clusters x cycles per step (MMAs + exchange ~5 000, ~1 900 per gate pass - measured)
+            const int per_wave = std::max(1, 120 / NCw);
+            auto cost = [&](int np) { const int cls = 2 * ((B + 32 * np - 1) / (32 * np)); return ((cls + per_wave - 1) / per_wave) * (5000 + 1900 * np); };
+            if (cost(4) < cost(2)) npass = 4;
+        }
+        { const char* e = getenv("ZS_GRU_NPASS"); if (e && (atoi(e) == 2 || atoi(e) == 4)) npass = atoi(e); }
+        const int nseq_w = 32 * npass, groups64 = (B + nseq_w - 1) / nseq_w;
+        const size_t need = static_cast<size_t>(2) * groups64 * NCw * nseq_w * 128;
         const bool can = !gates && xchg && need <= xchg_bytes && NCw >= 2 && NCw <= 8 && H % 64 == 0;
         const bool want = wide_mode == 1 || (wide_mode == 2 && 2 * ((B + GRU_FWD_NSEQ - 1) / GRU_FWD_NSEQ) * NCw > 120);
         if (can && want && wide_mode != 0) {
@@ -442,13 +453,14 @@ static int launch_gru_cluster(const void* w_img, const float* bhh, const void* g
             wp.wrz = gru_wrz_part(w_img, H); wp.w_img = w_img; wp.bhh = bhh; wp.gx = gx; wp.out = out; wp.xchg = static_cast<uint8_t*>(xchg);
             wp.B = B; wp.T = T; wp.H = H; wp.out_rows = rows; wp.out_pitch = pitch; wp.out_halo = halo; wp.out_choff = choff;
             wp.fmt = operand == ZS_OPERAND_BF16 ? 1 : 0;
-            const int smem_w = gru_wide_smem_bytes(H);
+            const int smem_w = gru_wide_smem_bytes(H, npass);
             using WideT = void (*)(const GruWideParams);
-            WideT wk = wp.fmt ? gru_wide_kernel<__nv_bfloat16> : gru_wide_kernel<__half>;
-            static int wattr[2] = {0, 0};
-            if (wattr[wp.fmt] < smem_w) {
+            WideT wk = npass == 4 ? (wp.fmt ? gru_wide_kernel<__nv_bfloat16, 4> : gru_wide_kernel<__half, 4>)
+                                  : (wp.fmt ? gru_wide_kernel<__nv_bfloat16, 2> : gru_wide_kernel<__half, 2>);
+            static int wattr[2][2] = {{0, 0}, {0, 0}};
+            if (wattr[wp.fmt][npass == 4] < smem_w) {
                 CUDA_TRY(cudaFuncSetAttribute(wk, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_w));
-                wattr[wp.fmt] = smem_w;
+                wattr[wp.fmt][npass == 4] = smem_w;
             }
             cudaLaunchConfig_t wc;
             memset(&wc, 0, sizeof(wc));
@@ -538,7 +550,7 @@ extern "C" int zs_gru_recurrence(const float* gx, const float* w_hh, const float
         CUDA_TRY(cudaMallocAsync(&img, bytes, st));
         int r = pack_gru_image(img, nullptr, w_hh, H, operand, st);
         void* xch = nullptr;
-        const size_t xch_bytes = static_cast<size_t>(2) * round_up(B, 64) * H * 2;      // state-exchange scratch (L2 multicast path)
+        const size_t xch_bytes = static_cast<size_t>(2) * round_up(B, 128) * H * 2;      // state-exchange scratch (L2 multicast path)
         CUDA_TRY(cudaMallocAsync(&xch, xch_bytes, st));
         if (r == ZS_OK) r = launch_gru_cluster(img, b_hh, gx_ot, B, T, H, out, out_rows, out_pitch, out_halo, out_choff, operand, st, nullptr, xch, xch_bytes);
         cudaFreeAsync(xch, st);
@@ -914,7 +926,7 @@ static EncWs carve_encoder(const zs_encoder* h, void* ws, int B, int T) {
     for (int i = 0; i < 3; ++i) w.d[i] = c.act(B, w.T[3], 0, g.c_h2);
     w.catr = c.act(B, w.T[3], 0, g.c_h2 + 2 * g.c_h3);
     w.gx = c.act(B, w.T[3], 0, 6 * g.c_h3, true);   // the recurrence indexes it as a dense [B][T][2][3H] array
-    w.xch = c.act(round_up(B, 64), 2, 0, g.c_h3);   // GRU state exchange scratch: one H-wide fp16 row per (direction, sequence)
+    w.xch = c.act(round_up(B, 128), 2, 0, g.c_h3);   // GRU state exchange scratch: one H-wide fp16 row per (direction, sequence)
     w.bytes = c.off;
     return w;
 }
@@ -943,7 +955,7 @@ static DecWs carve_decoder(const zs_decoder* h, void* ws, int B, int T8) {
     w.catr = c.act(B, Tf, 0, 2 * ch);
     w.d5 = c.act(B, Tf, 0, ch);
     w.gx = c.act(B, Tf, 0, 3 * ch, true);
-    w.xch = c.act(round_up(B, 64), 2, 0, ch / 2);   // GRU state exchange scratch
+    w.xch = c.act(round_up(B, 128), 2, 0, ch / 2);   // GRU state exchange scratch
     w.bytes = c.off;
     return w;
 }
@@ -1041,7 +1053,7 @@ extern "C" int zs_encoder_forward(zs_encoder* h, const float* x, int B, int T, c
     {   // :454-455 bi-GRU: input projection on tensor cores, then the recurrence
         ConvOpts o; o.lrelu = 0; o.c_in_valid = g.c_h2;
         ZS_TRY(run_layer(h->gru_ih, op, ns, w.catr, B, T8, &w.gx, nullptr, 0, 0, o, st));
-        if (h->whh_img) ZS_TRY(launch_gru_cluster(h->whh_img, h->bhh, w.gx.p, B, T8, g.c_h3, w.catr.p, w.catr.rows, w.catr.pitch, 0, g.c_h2, op, st, nullptr, w.xch.p, static_cast<size_t>(w.xch.rows) * w.xch.pitch * 2 * round_up(B, 64)));
+        if (h->whh_img) ZS_TRY(launch_gru_cluster(h->whh_img, h->bhh, w.gx.p, B, T8, g.c_h3, w.catr.p, w.catr.rows, w.catr.pitch, 0, g.c_h2, op, st, nullptr, w.xch.p, static_cast<size_t>(w.xch.rows) * w.xch.pitch * 2 * round_up(B, 128)));
         else ZS_TRY(launch_gru(w.gx.p, h->whhT, h->bhh, B, T8, g.c_h3, w.catr.p, w.catr.rows, w.catr.pitch, 0, g.c_h2, op, st));
     }
     {   // linear -> logits in the reference's (B, n_out, T8) fp32 layout
@@ -1109,7 +1121,7 @@ extern "C" int zs_decoder_forward(zs_decoder* h, const float* enc_act, const int
     {   // :352-355 bi-GRU on out + emb5
         ConvOpts o; o.lrelu = 0; o.c_in_valid = ch; o.spk = spk;
         ZS_TRY(run_layer(h->gru_ih, op, ns, w.catr, B, Tf, &w.gx, nullptr, 0, 0, o, st));
-        if (h->whh_img) ZS_TRY(launch_gru_cluster(h->whh_img, h->bhh, w.gx.p, B, Tf, ch / 2, w.catr.p, w.catr.rows, w.catr.pitch, 0, ch, op, st, nullptr, w.xch.p, static_cast<size_t>(w.xch.rows) * w.xch.pitch * 2 * round_up(B, 64)));
+        if (h->whh_img) ZS_TRY(launch_gru_cluster(h->whh_img, h->bhh, w.gx.p, B, Tf, ch / 2, w.catr.p, w.catr.rows, w.catr.pitch, 0, ch, op, st, nullptr, w.xch.p, static_cast<size_t>(w.xch.rows) * w.xch.pitch * 2 * round_up(B, 128)));
         else ZS_TRY(launch_gru(w.gx.p, h->whhT, h->bhh, B, Tf, ch / 2, w.catr.p, w.catr.rows, w.catr.pitch, 0, ch, op, st));
     }
     {   // :356-364 dense5 on cat([out, rnn, emb5]) -> lrelu -> linear -> sigmoid | tanh
