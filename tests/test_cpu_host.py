@@ -132,3 +132,23 @@ def test_synthetic_is_deterministic():
     assert all(torch.equal(a[k], b[k]) for k in a)
     x = syn.spectrogram_batch(2, 16, 0)
     assert x.shape == (2, 513, 16) and float(x.min()) >= 1e-8 and float(x.max()) <= 1.0
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU arm the driver runs next to ours): ONE JSON line on stdout with the contract's
+    keys, on a bounded sample, without touching a GPU."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, 'bench.py'), '--impl', 'reference', '--steps', '1', '--cpu-sample', '2'],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, lines
+    d = json.loads(lines[0])
+    assert d['impl'] == 'reference' and d['unit'] == 'frames/s' and d['higher_is_better'] is True and d['value'] > 0
+    assert d['metric'] == 'spectrogram frames/s, AE encode+decode' and d['vs_baseline'] is None
+    assert d['cpu_baseline']['kind'] == 'port' and d['cpu_baseline']['cores'] >= 1 and d['cpu_baseline']['value'] == d['value']
+    assert d['e2e'] == {'value': d['value'], 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
+    assert 'workload' in d['config'] and 'model' not in d['config']
