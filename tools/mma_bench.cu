@@ -8,12 +8,6 @@ __host__ __device__ inline uint32_t idesc_mn(int m, int n) {
     uint32_t d = 0; d |= 1u << 4; d |= (uint32_t)(n >> 3) << 17; d |= (uint32_t)(m >> 4) << 24; return d;
 }
 
-__device__ __forceinline__ bool elect_one() {
-    uint32_t pred;
-    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(pred));
-    return pred != 0;
-}
-
 __device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
