@@ -109,6 +109,13 @@ int zs_version(void);
 /* 0 when the current CUDA device is sm_100 class and the driver entry points resolve */
 int zs_device_check(void);
 
+/* fp16 operands carry a TF32-class mantissa but only +-65504 of range.  Every GEMM epilogue clamps its fp16 outputs to
+ * that range and COUNTS the epilogue threads that had to (nothing on the reference's value ranges comes close: the
+ * activations are O(1) after InstanceNorm).  Returns that count for the current device since the last reset after
+ * synchronising `stream`; a non-zero count means results are degraded and the checkpoint needs operand = bf16.  The
+ * Python front-end raises on it (the reference has no counterpart: it computes in fp32, model/model.py:20-110). */
+int zs_saturation_count(void* stream, unsigned long long* count, int reset);
+
 /* Packs fp32 parameters (device pointers) into tensor-core operand layout (fp16/bf16,
  * K-major rows of [taps][c_in padded to 64]) and, for the decoder, folds the five speaker
  * embeddings into per-(speaker, layer) fp32 bias tables (valid because a time-constant
@@ -135,6 +142,23 @@ size_t zs_decoder_workspace_bytes(const zs_decoder* h, int B, int T8);
 int zs_encoder_forward(zs_encoder* h, const float* x, int B, int T, const float* gumbel_noise,
                        float* logits, float* act, int32_t* unit_ids,
                        void* workspace, size_t workspace_bytes, void* stream);
+
+/* zs_encoder_forward for the batched front-end (replaces the per-chunk upload + permute of convert.py:70-83 and
+ * trainer.py:196, 226): the same computation with
+ *   x_dtype   ZS_X_F32, or ZS_X_F16 - an fp16 upload halves the host-to-device bytes; the path rounds its input to fp16
+ *             operands first thing anyway, so the results are bit-identical to the fp32 upload (fp16 operands only);
+ *   x_layout  ZS_X_NCT (B, c_in, T) as Encoder.forward receives it, or ZS_X_NTC (B, T, c_in) as Trainer.test_step receives
+ *             it BEFORE its permute (the layout of the HDF5 features, dataloader.py:74) - no transpose copy needed;
+ *   gumbel_noise NULL in one_hot mode: the noise is generated on the device from `noise_seeds` ((B,) uint64 on the device,
+ *             one counter-based stream per segment, so a segment's draw does not depend on the batch it rides in; same
+ *             distribution as model/model.py:95-98 but not the reference's CPU generator stream - a throughput mode that
+ *             saves 4 KB of upload per unit frame; pass the tensor for reference-exact draws);
+ *   logits / act  may be NULL when the caller only wants the unit ids (one_hot). */
+enum { ZS_X_F32 = 0, ZS_X_F16 = 1 };
+enum { ZS_X_NCT = 0, ZS_X_NTC = 1 };
+int zs_encoder_forward_x(zs_encoder* h, const void* x, int x_dtype, int x_layout, int B, int T, const float* gumbel_noise,
+                         const uint64_t* noise_seeds, float* logits, float* act, int32_t* unit_ids,
+                         void* workspace, size_t workspace_bytes, void* stream);
 
 /* Decoder.forward (model/model.py:344-365; trainer.py:199, 253).
  *   enc_act  (B, c_in, T8) fp32 dense activations, or NULL when unit_ids is given
@@ -200,10 +224,25 @@ int zs_grad_sqnorm(const float* g, size_t n, float* out, void* stream);
  * gradient norm (device scalar) BEFORE `grad_mult`, a factor applied to every gradient first (1/world_size after a
  * summing all-reduce); step = 1-based step count for the bias corrections - or bias_corr_dev = device pointer to
  * {1 - beta1^step, sqrt(1 - beta2^step)} (CUDA-graph replays).  When the norm is not
- * finite nothing is updated and *skipped (device int, may be NULL) is set to 1. */
+ * finite nothing is updated and *skipped (device int, may be NULL) is set to 1.
+ * bias_corr_dev, when given, is words [2..4] of a zs_train_meta block: {float bc1, float bc2_sqrt, int32 apply} - with
+ * apply == 0 the call updates nothing (another network of the same optimiser overflowed: trainer.py:64-66 builds ONE
+ * Adam over both networks, so they step together or not at all). */
 int zs_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, size_t n,
                  const float* sqnorm, float grad_mult, float max_norm, float lr, float beta1, float beta2, float eps,
                  int step, const float* bias_corr_dev, int* skipped, void* stream);
+
+/* Device-resident step state of the training iteration: 8 x 32-bit words
+ *   [0,1] dropout seed (uint64) | [2] 1 - beta1^n | [3] sqrt(1 - beta2^n) | [4] apply | [5] n = applied optimiser steps |
+ *   [6,7] iterations started (uint64).  Zero-initialise once.  Everything advances ON THE STREAM, so a CUDA-graph replay of
+ * the iteration needs no host writes (a pinned-host "meta" word could be overwritten while an earlier replay still reads it).
+ *   zs_train_meta_begin : iterations += 1; seed = splitmix64(iterations, seed_salt)  (salt = rank-dependent constant, so
+ *                         data-parallel ranks draw different dropout masks like the reference step on the concatenated batch)
+ *   zs_train_meta_commit: apply = every given squared gradient norm is finite; if so n += 1 and the bias corrections of
+ *                         step n are stored, else *skipped = 1 and n stays (only applied steps count, trainer.py:332). */
+int zs_train_meta_begin(void* meta, uint64_t seed_salt, void* stream);
+int zs_train_meta_commit(void* meta, const float* sqnorm_a, const float* sqnorm_b, float beta1, float beta2, int* skipped,
+                         void* stream);
 
 /* ---- measurement hooks (bench.py) --------------------------------------------------
  * Kernel classes: 0 = conv/linear implicit GEMM (tcgen05), 1 = GRU recurrence, 2 = everything else.

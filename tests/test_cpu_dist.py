@@ -79,6 +79,12 @@ def _sharded_encode(rank, world, tmp):
     torch.manual_seed(7)                                       # the reference's RNG contract: one CPU stream
     local = _oracle_units(specs, mine, enc_sd)
     everything = shard.gather_in_order(local, mine, len(specs))
+    # the tensor-collective gather the product uses: int32 unit ids in one flat buffer per rank, shapes known from the lengths
+    shards = shard.shard_utterances([len(s) for s in specs], world, SEG)
+    n_units = [shard.output_lengths(len(s), SEG)[0] for s in specs]
+    ids = shard.gather_arrays([a.argmax(1).astype(np.int32) for a in local], shards, [(n,) for n in n_units], np.int32)
+    for a, i in zip(everything, ids):
+        assert np.array_equal(a.argmax(1), i) and a.shape[0] == i.shape[0]
     if rank == 0:
         torch.manual_seed(7)
         single = _oracle_units(specs, list(range(len(specs))), enc_sd)
@@ -123,6 +129,20 @@ def _dp_step(rank, world, tmp):
 def test_gradient_allreduce_equals_full_batch_step(tmp_path):
     _spawn(_dp_step, 2, str(tmp_path))
     assert os.path.exists(tmp_path / 'ok_dp')
+
+
+def test_output_lengths_follow_the_chunk_plan():
+    # convert.py:139-168: L = 2000, seg_len 128 -> 14 chunks of 128 + one of 207 (its last frame dropped) -> 208 frames out
+    assert shard.output_lengths(2000, 128) == (14 * 16 + 26, 14 * 128 + 208)
+    assert shard.output_lengths(5, 128) == (1, 16)            # padded to MIN_LEN = 9: 2 unit frames, 1 kept
+    assert shard.output_lengths(128, 128) == (16, 128)
+
+
+def test_gather_arrays_single_process_and_size_check():
+    out = shard.gather_arrays([np.arange(3, dtype=np.int32), np.arange(2, dtype=np.int32)], [[1, 0]], [(2,), (3,)], np.int32)
+    assert np.array_equal(out[1], [0, 1, 2]) and np.array_equal(out[0], [0, 1])
+    with pytest.raises(RuntimeError):
+        shard.gather_arrays([np.arange(3, dtype=np.int32)], [[0]], [(2,)], np.int32)
 
 
 def test_gather_detects_missing_and_duplicate():

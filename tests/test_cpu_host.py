@@ -141,7 +141,7 @@ def test_bench_reference_arm_contract():
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    out = subprocess.run([sys.executable, os.path.join(root, 'bench.py'), '--impl', 'reference', '--steps', '1', '--cpu-sample', '2'],
+    out = subprocess.run([sys.executable, os.path.join(root, 'bench.py'), '--impl', 'reference', '--steps', '2', '--warmup', '1', '--cpu-sample', '2'],
                          capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stderr[-2000:]
     lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
@@ -152,3 +152,17 @@ def test_bench_reference_arm_contract():
     assert d['cpu_baseline']['kind'] == 'port' and d['cpu_baseline']['cores'] >= 1 and d['cpu_baseline']['value'] == d['value']
     assert d['e2e'] == {'value': d['value'], 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
     assert 'workload' in d['config'] and 'model' not in d['config']
+    # the record says what ran: --steps / --warmup honoured, the bounded sample and the port named
+    assert d['steps'] == 2 and d['warmup'] == 1
+    assert '2 segments' in d['config']['reference_sample'] and 'port' in d['config']['reference_sample']
+
+
+def test_bench_has_single_definitions():
+    """a botched paste once left every helper of bench.py defined twice (the later, older copy winning)."""
+    import ast
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    tree = ast.parse(open(os.path.join(root, 'bench.py')).read())
+    names = [n.name for n in tree.body if isinstance(n, (ast.FunctionDef, ast.ClassDef))]
+    assert len(names) == len(set(names)), sorted(n for n in names if names.count(n) > 1)
+    src = open(os.path.join(root, 'bench.py')).read()
+    assert 'environ.pop' not in src and "environ['NCCL_DEBUG']" not in src       # the driver reads NCCL's own log: leave it on

@@ -215,8 +215,7 @@ def test_train_step_matches_reference(name):
           f'(intrinsic fp16-weight-rounding floor of the oracle there: {w[1]:.2f})')
 
     # clip + Adam: gradient norms and the parameters after the update against the reference's
-    step._optim(step.enc)
-    step._optim(step.dec)
+    step._optim()
     torch.cuda.synchronize()
     n_enc, n_dec = step.grad_norms()
     assert abs(n_enc - float(g['norm_enc'])) <= 0.3 * float(g['norm_enc'])     # kink noise, see the docstring
@@ -318,6 +317,79 @@ def test_training_reduces_loss_and_eval_sees_updates():
         s_o = orc.decoder_forward(sd_d, act.cpu(), c.cpu())
     assert ((logits.cpu() - l_o).norm() / l_o.norm()).item() < 2e-2
     assert ((spec.cpu() - s_o).norm() / s_o.norm()).item() < 1e-2
+
+
+def test_train_mode_forward_draws_new_dropout_masks_every_call():
+    """the drop-in loop (Encoder(x) in train() mode) must not reuse one dropout mask forever.  Two consecutive
+    train-mode forwards with the same input and the same Gumbel noise differ (dp > 0); with dp = 0 they are identical; and
+    torch.manual_seed pins the masks."""
+    m = dict(seed=0, c_in=513, c_h=[128, 512, 128], enc_size=1024, emb_size=1024, n_spk=102, ns=0.01, seg_len=128, dp=0.5)
+    enc, _ = build_train_models(m)
+    x = syn.spectrogram_batch(4, 128, 5).cuda()
+    noise = gumbel_from_uniform(syn.gumbel_uniform((4, 16, 1024), 5)).cuda()
+    torch.manual_seed(7)
+    l1 = enc(x, noise)[1].clone()
+    l2 = enc(x, noise)[1].clone()
+    torch.manual_seed(7)
+    l3 = enc(x, noise)[1].clone()
+    assert not torch.equal(l1, l2), 'two train-mode forwards used identical dropout masks'
+    assert torch.equal(l1, l3), 'torch.manual_seed must pin the dropout masks'
+    enc.dp = 0.0
+    assert torch.equal(enc(x, noise)[1], enc(x, noise)[1])
+
+
+def test_pretrain_ae_ranks_and_steps_draw_different_masks():
+    """The device-resident seed changes every iteration and with the rank salt (zs_train_meta_begin)."""
+    lib = _lib.lib()
+    seeds = []
+    for salt in (1, 2):
+        meta = torch.zeros(8, dtype=torch.int32, device='cuda')
+        for _ in range(3):
+            _lib.check(lib.zs_train_meta_begin(gh.ptr(meta), salt, None))
+            seeds.append(int(meta[0:2].view(torch.int64).item()))
+        assert int(meta[6:8].view(torch.int64).item()) == 3
+    assert len(set(seeds)) == 6, seeds
+
+
+def test_overflow_skips_both_networks_and_does_not_count():
+    """zs_train_meta_commit: a non-finite norm of EITHER network leaves both untouched and the applied-step count alone."""
+    lib = _lib.lib()
+    n = 4096
+    meta = torch.zeros(8, dtype=torch.int32, device='cuda')
+    skipped = torch.zeros(1, dtype=torch.int32, device='cuda')
+    p = torch.randn(n, device='cuda'); p0 = p.clone()
+    g = torch.randn(n, device='cuda'); mm = torch.zeros(n, device='cuda'); vv = torch.zeros(n, device='cuda')
+    sq_ok = (g * g).sum().reshape(1)
+    sq_bad = torch.full((1,), float('inf'), device='cuda')
+    bc = C.c_void_p(meta.data_ptr() + 8)
+    for sq_b, applied in ((sq_bad, 0), (sq_ok, 1), (sq_ok, 2)):
+        _lib.check(lib.zs_train_meta_commit(gh.ptr(meta), gh.ptr(sq_ok), gh.ptr(sq_b), 0.5, 0.9, gh.ptr(skipped), None))
+        _lib.check(lib.zs_adam_step(gh.ptr(p), gh.ptr(g), gh.ptr(mm), gh.ptr(vv), n, gh.ptr(sq_ok), 1.0, 5.0, 1e-3, 0.5, 0.9, 1e-8,
+                                    1, bc, gh.ptr(skipped), None))
+        torch.cuda.synchronize()
+        assert int(meta[5].item()) == applied
+        if applied == 0:
+            assert torch.equal(p, p0) and int(skipped.item()) == 1
+        else:
+            assert not torch.equal(p, p0)
+            want_bc1 = 1 - 0.5 ** applied
+            assert abs(meta[2:3].view(torch.float32).item() - want_bc1) < 1e-6
+
+
+def test_autograd_wrappers_refuse_a_stale_backward():
+    """the module keeps ONE set of saved activations; a backward of an older forward must raise, not
+    silently differentiate the newer forward."""
+    g = load_train_golden('train_small_dp0')
+    m = g['meta']
+    enc_sd, dec_sd, x, c, u, keep = train_inputs(g)
+    enc, dec = build_train_models(m)
+    xd, cd, noise = x.cuda(), c.cuda(), gumbel_from_uniform(u).cuda()
+    act, _ = zt.encode_step(enc, xd, noise)
+    y1 = zt.decode_step(dec, act, cd)
+    y2 = zt.decode_step(dec, act.detach(), cd)        # second forward of the same module before the first backward
+    with pytest.raises(RuntimeError, match='another training forward'):
+        y1.abs().mean().backward()
+    y2.abs().mean().backward()                        # the latest forward is fine
 
 
 def test_autograd_wrappers_match_fused_step():

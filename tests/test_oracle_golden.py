@@ -142,3 +142,25 @@ def test_oracle_train_step_matches_reference(name):
             # update direction is summation-order noise, so those elements only have to stay within one lr
             tol = np.where(np.abs(g[f'g:{net}:{k}']) > 1e-6, 2e-5, 1.1 * m['lr'])
             assert (np.abs(got - g[f'p:{net}:{k}']) <= tol).all(), f'{net}:{k}'
+
+
+def test_torch_module_baseline_matches_the_oracle():
+    """oracle/torch_modules.py (stock nn.Conv1d / nn.GRU / ... modules: bench.py's eager-CUDA bar) computes what the
+    functional oracle computes, on the CPU, sharing one reference-layout state_dict (strict load)."""
+    from oracle.torch_modules import TorchDecoder, TorchEncoder
+    from zs_b200 import synthetic as syn
+    for T in (77, 128):
+        esd = syn.encoder_state_dict(3, enc_size=64, enc_mode='one_hot', c_h1=16, c_h2=64, c_h3=16, c_in=33)
+        dsd = syn.decoder_state_dict(3, c_in=64, c_h=64, c_a=5, c_out=33)
+        te = TorchEncoder(33, 16, 64, 16, 0.01, 64, 128).eval()
+        td = TorchDecoder(64, 33, 64, 5, 0.01, 128).eval()
+        te.load_state_dict(esd, strict=True)
+        td.load_state_dict(dsd, strict=True)
+        x, c = syn.spectrogram_batch(3, T, 1, c_in=33), syn.speaker_ids(3, 5, 1)
+        u = syn.gumbel_uniform((3, (T + 7) // 8, 64), 1)
+        with torch.no_grad():
+            act, logits = te(x, orc.gumbel_noise(u))
+            spec = td(act, c)
+            o_act, o_logits, _ = orc.encoder_forward(esd, x, u)
+            o_spec = orc.decoder_forward(dsd, o_act, c)
+        assert (logits - o_logits).abs().max() < 1e-4 and torch.equal(act, o_act) and (spec - o_spec).abs().max() < 1e-5

@@ -13,8 +13,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, 'csrc')
 SO_PATH = os.path.join(_HERE, 'libzsae.so')
 HEADER = os.path.join(os.path.dirname(_HERE), 'include', 'zs_ae.h')
-_SOURCES = ['zs_ae.cu', 'conv_gemm.cuh', 'kernels.cuh', 'gru_cluster.cuh', 'ptx.cuh', 'train_kernels.cuh',
-            'wgrad_gemm.cuh', 'zs_train.cuh', 'gru_bptt_cluster.cuh']
+import glob
+
 
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-Xcompiler', '-fPIC', '-shared']
@@ -27,7 +27,7 @@ def _stale():
     if not os.path.exists(SO_PATH):
         return True
     t = os.path.getmtime(SO_PATH)
-    deps = [os.path.join(_CSRC, s) for s in _SOURCES] + [HEADER]
+    deps = glob.glob(os.path.join(_CSRC, '*.cu')) + glob.glob(os.path.join(_CSRC, '*.cuh')) + [HEADER]
     return any(os.path.exists(d) and os.path.getmtime(d) > t for d in deps)
 
 
@@ -38,7 +38,10 @@ def build(force=False, verbose=False):
     nvcc = shutil.which('nvcc') or '/usr/local/cuda/bin/nvcc'
     if not os.path.exists(nvcc):
         raise RuntimeError('nvcc not found: libzsae.so cannot be built')
-    cmd = [nvcc] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-o', SO_PATH, os.path.join(_CSRC, 'zs_ae.cu')]
+    # ZS_BUILD_EXPERIMENTS=1 compiles the timing-experiment knobs in (tools/gemm_dbg.sh, tools/gru_probe.py); the default
+    # library reads no environment variables and carries no result-changing debug paths
+    extra = ['-DZS_EXPERIMENTS'] if os.environ.get('ZS_BUILD_EXPERIMENTS') == '1' else []
+    cmd = [nvcc] + NVCC_FLAGS + extra + (['-Xptxas', '-v'] if verbose else []) + ['-o', SO_PATH, os.path.join(_CSRC, 'zs_ae.cu')]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError('nvcc failed:\n' + res.stdout + res.stderr)
@@ -102,6 +105,7 @@ SYMBOLS = {
     'zs_last_error': (C.c_char_p, []),
     'zs_version': (_i, []),
     'zs_device_check': (_i, []),
+    'zs_saturation_count': (_i, [_vp, C.POINTER(C.c_ulonglong), _i]),
     'zs_encoder_pack': (_i, [C.POINTER(EncoderCfg), C.POINTER(EncoderWeights), _vp, C.POINTER(_vp)]),
     'zs_decoder_pack': (_i, [C.POINTER(DecoderCfg), C.POINTER(DecoderWeights), _vp, C.POINTER(_vp)]),
     'zs_encoder_free': (None, [_vp]),
@@ -109,6 +113,7 @@ SYMBOLS = {
     'zs_encoder_workspace_bytes': (_sz, [_vp, _i, _i]),
     'zs_decoder_workspace_bytes': (_sz, [_vp, _i, _i]),
     'zs_encoder_forward': (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    'zs_encoder_forward_x': (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     'zs_decoder_forward': (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _i, _vp, _sz, _vp]),
     'zs_profile_begin': (None, []),
     'zs_profile_end': (_i, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
@@ -135,6 +140,8 @@ SYMBOLS = {
     'zs_adam_step': (_i, [_vp, _vp, _vp, _vp, _sz, _vp, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
                           C.c_float, _i, _vp, _vp, _vp]),
     'zs_wgrad_cl': (_i, [C.POINTER(WgradDesc), _vp]),
+    'zs_train_meta_begin': (_i, [_vp, C.c_uint64, _vp]),
+    'zs_train_meta_commit': (_i, [_vp, _vp, _vp, C.c_float, C.c_float, _vp, _vp]),
 }
 
 _LIB = None
@@ -154,6 +161,13 @@ def lib():
             fn.argtypes = args
         _LIB = handle
     return _LIB
+
+
+def saturation_count(stream=None, reset=True):
+    """fp16 values the GEMM epilogues had to clamp to +-65504 on the current device since the last reset (synchronises)."""
+    n = C.c_ulonglong(0)
+    check(lib().zs_saturation_count(C.c_void_p(stream or 0), C.byref(n), int(reset)))
+    return int(n.value)
 
 
 def check(rc):

@@ -41,6 +41,13 @@ constexpr int STG_TILE_BYTES = SET_STAGING_BYTES / 2;
 constexpr int GEMM_SMEM_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + STAGING_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 constexpr float IN_EPS = 1e-5f;
 
+// timing-experiment bits (results are wrong with any bit set) exist only in -DZS_EXPERIMENTS builds
+#ifdef ZS_EXPERIMENTS
+#define ZS_DBG(p) ((p).debug)
+#else
+#define ZS_DBG(p) 0
+#endif
+
 enum { RES_NONE = 0, RES_SAME = 1, RES_AVG2 = 2, RES_UP2 = 3 };
 enum { ACT_NONE = 0, ACT_SIGMOID = 1, ACT_TANH = 2 };
 enum { OUT_CL = 0, OUT_PS = 1, OUT_NCT32 = 2 };
@@ -70,13 +77,14 @@ struct alignas(64) GemmParams {
     void* out;
     int out_rows, out_pitch, out_halo, out_choff, accumulate;
     uint32_t idesc;
-    int debug;   // timing experiments (results wrong): 1 = no TMA loads, 2 = no MMA issue, 4 = no epilogue stores/loads
+    int debug;   // -DZS_EXPERIMENTS builds only (results wrong): 1 = no TMA loads, 2 = no MMA issue, 4 = no epilogue stores/loads
     // training extras
     float* stats;             // InstanceNorm (mean, rstd) per (segment, channel): [B][bias_stride][2], or null
     const float* post_emb;    // added after everything: post_emb[spk[b]][out channel] (speaker embedding of the NEXT layer's input)
     const long long* post_spk;
     int post_pitch, post_n;
     int no_sat;               // gradient outputs: let fp16 overflow to inf (the loss-scale logic detects it) instead of clamping
+    unsigned int* sat_count;  // device word, += 1 per epilogue thread that clamped an fp16 output to +-65504 (never silent)
     // zero-padding mode (model/model.py:36-38, seg_len < 64): halo rows are zeros, and a layer whose speaker embedding is
     // folded into the bias loses the taps that fall into the padding: frame 0 gets -edge_lo, frame T-1 gets -edge_hi
     int zero_halo;
@@ -94,8 +102,11 @@ template <typename OT>
 __device__ __forceinline__ OT float_to_ot(float v);
 template <>
 __device__ __forceinline__ __half float_to_ot<__half>(float v) {
-    // saturate instead of overflowing to inf: fp16 operands carry tf32-class mantissa but less range
-    return __float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f));
+    // saturate instead of overflowing to inf (one F2FP.SATFINITE): fp16 operands carry tf32-class mantissa but less
+    // range; the GEMM epilogue counts the values it had to clamp (GemmParams::sat_count -> zs_saturation_count)
+    unsigned short h;
+    asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(h) : "f"(v));
+    return __ushort_as_half(h);
 }
 template <>
 __device__ __forceinline__ __nv_bfloat16 float_to_ot<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
@@ -131,6 +142,8 @@ __device__ __forceinline__ void apply_edges(const GemmParams& p, uint32_t (&v)[1
             if (c0 + i == T - 1) v[i] = __float_as_uint(__uint_as_float(v[i]) - e);
     }
 }
+template <typename OT> struct IS_BF16 { static constexpr bool value = false; };
+template <> struct IS_BF16<__nv_bfloat16> { static constexpr bool value = true; };
 template <typename OT>
 __device__ __forceinline__ OT float_to_ot_nosat(float v);
 template <>
@@ -188,7 +201,7 @@ template <typename OT, int RES, bool PS, bool ZP>
 __device__ __forceinline__ void frames_to_staging(const GemmParams& p, uint32_t t_seg, int f_lo, int f_hi, int T,
                                                   const ChanNorm& cn, bool lrelu, float ns, OT* __restrict__ stg,
                                                   const OT* __restrict__ res_stg, OT* __restrict__ out_s, int ps_r,
-                                                  bool ch_ok) {
+                                                  bool ch_ok, bool& sat) {
     constexpr int STG_PITCH = PS ? 64 : 128;          // channels per staging row
     constexpr int FSTEP = PS ? 2 : 1;                 // staging rows per input frame
     const int T_out = PS ? 2 * T : T;
@@ -222,6 +235,7 @@ __device__ __forceinline__ void frames_to_staging(const GemmParams& p, uint32_t 
             x = fmaf(x, cn.scale, cn.shift);
             if (RES != RES_NONE) x += r[i];
             x += cn.post;
+            if (sizeof(OT) == 2 && !IS_BF16<OT>::value) sat |= fabsf(x) > 65504.f;
             y[i] = p.no_sat ? float_to_ot_nosat<OT>(x) : float_to_ot<OT>(x);
         }
         OT* sp = stg + (c0 - f_lo) * (FSTEP * STG_PITCH);
@@ -356,7 +370,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
                     const int row_b = p.in_row0 + tap;
                     for (int c = 0; c < p.kc; ++c) {
                         mbar_wait(&empty[stage], phase ^ 1);
-                        if (p.debug & 1) {
+                        if (ZS_DBG(p) & 1) {
                             if (elect_one()) mbar_arrive(&full[stage]);
                         } else if (elect_one()) {
                             mbar_expect_tx(&full[stage], stage_tx);
@@ -402,7 +416,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
                     const int n_mma = (++kc_pos == p.kc) ? p.last_mmas : BK / 16;
                     if (kc_pos == p.kc) kc_pos = 0;
                     if (elect_one()) {
-                        if (!(p.debug & 2)) {
+                        if (!(ZS_DBG(p) & 2)) {
 #pragma unroll
                             for (int k = 0; k < BK / 16; ++k) {
                                 // advance 16 elements (32 B) along K inside the swizzle row: +2 in the >>4 address field
@@ -436,6 +450,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
         OT* stage = reinterpret_cast<OT*>(set_stage);
         int it = 0, rnd = 0;
         uint32_t res_phase = 0;
+        bool sat = false;           // this thread clamped an fp16 output (reported once per thread and launch)
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
             const int mt = tile % p.m_tiles, nt = tile / p.m_tiles;
             const int as = it & 1;
@@ -477,7 +492,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
                 }
                 return cn;
             };
-            if (p.debug & 4) {            // timing experiment: main loop only
+            if (ZS_DBG(p) & 4) {            // timing experiment: main loop only
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tempty[as]);
@@ -543,11 +558,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
                             const OT* res_stg = stage_res + static_cast<size_t>(s - s0) * res_rows_per_seg * 128 + row;
                             OT* out_s = reinterpret_cast<OT*>(p.out) + static_cast<size_t>(b) * p.out_rows * p.out_pitch +
                                         p.out_choff + out_ch;
-                            if (ps) frames_to_staging<OT, RES_NONE, true, ZP>(p, t_seg, f_lo, f_hi, T, cn_keep, lrelu, ns, stg, res_stg, out_s, ps_r, ch_ok);
-                            else if (p.res_mode == RES_NONE) frames_to_staging<OT, RES_NONE, false, ZP>(p, t_seg, f_lo, f_hi, T, cn_keep, lrelu, ns, stg, res_stg, out_s, 0, ch_ok);
-                            else if (p.res_mode == RES_SAME) frames_to_staging<OT, RES_SAME, false, ZP>(p, t_seg, f_lo, f_hi, T, cn_keep, lrelu, ns, stg, res_stg, out_s, 0, ch_ok);
-                            else if (p.res_mode == RES_UP2) frames_to_staging<OT, RES_UP2, false, ZP>(p, t_seg, f_lo, f_hi, T, cn_keep, lrelu, ns, stg, res_stg, out_s, 0, ch_ok);
-                            else frames_to_staging<OT, RES_AVG2, false, ZP>(p, t_seg, f_lo, f_hi, T, cn_keep, lrelu, ns, stg, res_stg, out_s, 0, ch_ok);
+                            if (ps) frames_to_staging<OT, RES_NONE, true, ZP>(p, t_seg, f_lo, f_hi, T, cn_keep, lrelu, ns, stg, res_stg, out_s, ps_r, ch_ok, sat);
+                            else if (p.res_mode == RES_NONE) frames_to_staging<OT, RES_NONE, false, ZP>(p, t_seg, f_lo, f_hi, T, cn_keep, lrelu, ns, stg, res_stg, out_s, 0, ch_ok, sat);
+                            else if (p.res_mode == RES_SAME) frames_to_staging<OT, RES_SAME, false, ZP>(p, t_seg, f_lo, f_hi, T, cn_keep, lrelu, ns, stg, res_stg, out_s, 0, ch_ok, sat);
+                            else if (p.res_mode == RES_UP2) frames_to_staging<OT, RES_UP2, false, ZP>(p, t_seg, f_lo, f_hi, T, cn_keep, lrelu, ns, stg, res_stg, out_s, 0, ch_ok, sat);
+                            else frames_to_staging<OT, RES_AVG2, false, ZP>(p, t_seg, f_lo, f_hi, T, cn_keep, lrelu, ns, stg, res_stg, out_s, 0, ch_ok, sat);
                         }
                         if (has_res && nt * p.nb + s0 < p.B) res_phase ^= 1;
                         const bool last = (s0 / p.rnd_ns == my_last) && (h + 1 == p.rnd_sub);
@@ -569,6 +584,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
                 }
             }
         }
+        if (sat && !p.no_sat && p.sat_count != nullptr) atomicAdd(p.sat_count, 1u);
     }
 
     tc_fence_before();

@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(GRU_THREADS, 1) gru_cluster_kernel(const GruPa
     constexpr int CPW = NSEQ / 2;      // TMEM columns (sequences) per gate warp
     constexpr int SPT = NSEQ / 4;      // sequences per gate thread
     const int H = p.H, KCH = H >> 6;
-    const int NC = (p.debug & 1) ? 1 : KCH;      // debug bit 0: pretend to be alone (no exchange, no peer waits)
+    const int NC = (ZS_DBG(p) & 1) ? 1 : KCH;      // debug bit 0: pretend to be alone (no exchange, no peer waits)
     uint8_t* sW = smem;                                   // [192 * H * 2]
     uint8_t* sH = smem + gru_w_image_bytes(H);            // [KCH chunks][32 rows][128 B]
     const int hbuf_bytes = NSEQ * H * 2;
@@ -204,10 +204,10 @@ __global__ void __launch_bounds__(GRU_THREADS, 1) gru_cluster_kernel(const GruPa
                 if (c != static_cast<int>(rank)) mbar_expect_tx(&h_chunk[c], slice_bytes);
         __syncwarp();
         for (int t = 0; t < p.T; ++t) {
-            const bool rec = (p.debug & 8) && p.dbg && blockIdx.x == 0 && lane == 0;
+            const bool rec = (ZS_DBG(p) & 8) && p.dbg && blockIdx.x == 0 && lane == 0;
             // r|z tile first, chunk by chunk in the order the slices land (mine, then the peers by ring distance):
             // the MMAs of the early chunks run while the late ones are still in flight
-            if ((p.debug & 32) && t > 0 && NC > 1)            // experiment: no MMA before every slice has landed
+            if ((ZS_DBG(p) & 32) && t > 0 && NC > 1)            // experiment: no MMA before every slice has landed
                 for (int c = 0; c < KCH; ++c) mbar_wait(&h_chunk[c], (t - 1) & 1);
             for (int j = 0; j < KCH; ++j) {
                 const int c = (static_cast<int>(rank) + KCH - j) % KCH;
@@ -275,7 +275,7 @@ __global__ void __launch_bounds__(GRU_THREADS, 1) gru_cluster_kernel(const GruPa
         const int gx_seq = p.T * 6 * H, out_seq = p.out_rows * p.out_pitch;
         int gx_off = ((seq0 * p.T + t_first) * 2 + dir) * 3 * H + unit;
         int out_off = (seq0 * p.out_rows + p.out_halo + t_first) * p.out_pitch + p.out_choff + dir * H + unit;
-        const bool no_gx = (p.debug & 2) != 0;
+        const bool no_gx = (ZS_DBG(p) & 2) != 0;
         auto load_gx = [&](int step, OT (&xr)[SPT], OT (&xz)[SPT], OT (&xn)[SPT]) {      // `step` must be the NEXT unread step
             const bool ok = step < p.T && !no_gx;
 #pragma unroll
@@ -295,7 +295,7 @@ __global__ void __launch_bounds__(GRU_THREADS, 1) gru_cluster_kernel(const GruPa
 #pragma unroll
             for (int i = 0; i < SPT; ++i) { gr[i] = pr[i]; gz[i] = pz[i]; gn[i] = pn[i]; }
             load_gx(t + 1, pr, pz, pn);
-            const bool rec = (p.debug & 8) && p.dbg && blockIdx.x == 0 && threadIdx.x == 0;
+            const bool rec = (ZS_DBG(p) & 8) && p.dbg && blockIdx.x == 0 && threadIdx.x == 0;
             if (rec) p.dbg[t * 8 + 2] = clock64();
             // ---- r and z while the n-tile MMAs still run ----
             mbar_wait(rz_done, t & 1);
@@ -347,7 +347,7 @@ __global__ void __launch_bounds__(GRU_THREADS, 1) gru_cluster_kernel(const GruPa
                 }
             }
             if (rec) p.dbg[t * 8 + 5] = clock64();
-            if ((p.debug & 64) && !(p.debug & 4)) {           // experiment: output stores before the exchange
+            if ((ZS_DBG(p) & 64) && !(ZS_DBG(p) & 4)) {           // experiment: output stores before the exchange
 #pragma unroll
                 for (int i = 0; i < SPT; ++i)
                     if (live >> i & 1) out[out_off + i * out_seq] = y[i];
@@ -387,7 +387,7 @@ __global__ void __launch_bounds__(GRU_THREADS, 1) gru_cluster_kernel(const GruPa
                 if (rec) p.dbg[t * 8 + 7] = clock64();
             }
             // h_t to the output buffer, off the exchange's critical path
-            if (!(p.debug & (4 | 64))) {
+            if (!(ZS_DBG(p) & (4 | 64))) {
 #pragma unroll
                 for (int i = 0; i < SPT; ++i)
                     if (live >> i & 1) out[out_off + i * out_seq] = y[i];

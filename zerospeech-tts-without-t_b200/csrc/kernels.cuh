@@ -48,21 +48,29 @@ __global__ void pack_nct_kernel(const float* __restrict__ x, OT* __restrict__ ou
 
 // The encoder's two views of its input in ONE pass over x (model/model.py:441-446): the conv bank reads x with a
 // 3-frame halo (`bank`, no activation), and conv2 reads cat([bank outputs, x]) after a leaky-relu (`cat`, channel offset
-// `cat_choff`, no halo).  Tiles of 64 channels x 32 frames: 128-byte reads along T, 128-byte half2 writes along C.
-template <typename OT>
-__global__ void __launch_bounds__(256) pack_x_dual_kernel(const float* __restrict__ x, int C, int T,
+// `cat_choff`, no halo).  IT = float | __half (an fp16 upload halves the PCIe bytes and rounds exactly like the fp32 path
+// does here).  NTC = false: x is (B, C, T) as Encoder.forward receives it - tiles of 64 channels x 32 frames, 128-byte reads
+// along T, 128-byte half2 writes along C.  NTC = true: x is (B, T, C), the layout Trainer.test_step is handed before its
+// permute (trainer.py:196) - already channels-last, so the tile is read along C and no transpose is needed.
+__device__ __forceinline__ float in_to_float(float v) { return v; }
+__device__ __forceinline__ float in_to_float(__half v) { return __half2float(v); }
+
+template <typename OT, typename IT, bool NTC>
+__global__ void __launch_bounds__(256) pack_x_dual_kernel(const IT* __restrict__ x, int C, int T,
                                                           OT* __restrict__ bank, int bank_rows, int bank_pitch, int bank_halo,
                                                           OT* __restrict__ cat, int cat_rows, int cat_pitch, int cat_choff, int cat_fill,
                                                           float ns, int zero_halo) {
     __shared__ float tile[64][33];
     const int t0 = blockIdx.x * 32, c0 = blockIdx.y * 64, b = blockIdx.z;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    if (!NTC) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const int c = c0 + ty + 8 * i, t = t0 + tx;
-        tile[ty + 8 * i][tx] = (c < C && t < T) ? x[(static_cast<size_t>(b) * C + c) * T + t] : 0.f;
+        for (int i = 0; i < 8; ++i) {
+            const int c = c0 + ty + 8 * i, t = t0 + tx;
+            tile[ty + 8 * i][tx] = (c < C && t < T) ? in_to_float(x[(static_cast<size_t>(b) * C + c) * T + t]) : 0.f;
+        }
+        __syncthreads();
     }
-    __syncthreads();
     OT* bb = bank + static_cast<size_t>(b) * bank_rows * bank_pitch;
     OT* cb = cat + static_cast<size_t>(b) * cat_rows * cat_pitch + cat_choff;
     const int c = c0 + 2 * tx;                       // this lane's channel pair
@@ -71,7 +79,15 @@ __global__ void __launch_bounds__(256) pack_x_dual_kernel(const float* __restric
     for (int i = 0; i < 4; ++i) {
         const int t = t0 + ty + 8 * i;
         if (t >= T) continue;
-        const float v0 = tile[2 * tx][ty + 8 * i], v1 = tile[2 * tx + 1][ty + 8 * i];
+        float v0, v1;
+        if (NTC) {
+            const IT* xr = x + (static_cast<size_t>(b) * T + t) * C;
+            v0 = c < C ? in_to_float(xr[c]) : 0.f;
+            v1 = c + 1 < C ? in_to_float(xr[c + 1]) : 0.f;
+        } else {
+            v0 = tile[2 * tx][ty + 8 * i];
+            v1 = tile[2 * tx + 1][ty + 8 * i];
+        }
         if (c < bank_pitch) {                        // channels >= C are the zero padding of the K dimension
             OT2 y; y.x = float_to_ot<OT>(v0); y.y = float_to_ot<OT>(v1);
             OT2 hv = y;
@@ -97,29 +113,62 @@ __global__ void __launch_bounds__(256) pack_x_dual_kernel(const float* __restric
 
 // ---------------------------------------------------------------------------------------------
 // Discrete bottleneck, one_hot mode: ids[b,t] = argmax_c(logits[b,c,t] + noise[b,t,c]) with first-index
-// tie-break (torch.max), act = one-hot.  One CTA per segment; the (C x T8) logits tile is staged in shared
-// memory so both the logits (time-fastest) and the noise (unit-fastest) are read coalesced.
+// tie-break (torch.max), act = one-hot (skipped when the caller passes no `act`: the batched front-end only
+// wants the ids).  One CTA per segment; the (C x T8) logits tile is staged in shared memory (16-byte global loads) so
+// both the logits (time-fastest) and the noise (unit-fastest, 16-byte loads) are read coalesced.
+// noise == nullptr: the Gumbel noise is generated in the kernel from a counter-based generator (splitmix64 of the
+// segment's seed + (t, c) -> 24-bit uniform like torch.rand -> -log(-log(u + eps) + eps), model/model.py:95-98): the
+// throughput mode of the streaming front-end - same distribution, not the reference's CPU generator stream.
 // ---------------------------------------------------------------------------------------------
-__global__ void bottleneck_onehot_kernel(const float* __restrict__ logits, const float* __restrict__ noise, int C,
-                                         int T8, float* __restrict__ act, int* __restrict__ ids) {
+__device__ __forceinline__ float gumbel_from_counter(unsigned long long seed, unsigned long long idx) {
+    unsigned long long z = seed + (idx + 1) * 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    const float u = static_cast<float>(static_cast<unsigned int>(z >> 40)) * (1.0f / 16777216.0f);
+    return -logf(-logf(u + 1e-20f) + 1e-20f);
+}
+
+__global__ void __launch_bounds__(512) bottleneck_onehot_kernel(const float* __restrict__ logits, const float* __restrict__ noise,
+                                                                const unsigned long long* __restrict__ seg_seeds, int C, int T8,
+                                                                float* __restrict__ act, int* __restrict__ ids) {
     extern __shared__ float s_log[];  // [C][T8 + 1]
     int* s_id = reinterpret_cast<int*>(s_log + static_cast<size_t>(C) * (T8 + 1));
     const int b = blockIdx.x;
     const int n = C * T8;
     const float* lb = logits + static_cast<size_t>(b) * n;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) s_log[(i / T8) * (T8 + 1) + (i % T8)] = lb[i];
+    if ((T8 & 3) == 0 && (reinterpret_cast<uintptr_t>(lb) & 15) == 0) {
+        const int q = T8 >> 2;                      // float4 per channel row
+        for (int i = threadIdx.x; i < (n >> 2); i += blockDim.x) {
+            const float4 v = reinterpret_cast<const float4*>(lb)[i];
+            float* d = s_log + (i / q) * (T8 + 1) + ((i % q) << 2);
+            d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+        }
+    } else {
+        for (int i = threadIdx.x; i < n; i += blockDim.x) s_log[(i / T8) * (T8 + 1) + (i % T8)] = lb[i];
+    }
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     for (int t = warp; t < T8; t += nwarps) {
-        const float* nz = noise + (static_cast<size_t>(b) * T8 + t) * C;
+        const size_t row = (static_cast<size_t>(b) * T8 + t) * C;
+        const float* nz = noise ? noise + row : nullptr;
+        const unsigned long long seed = nz ? 0ull : seg_seeds[b];      // per-segment stream: independent of the batch it rides in
         float best = -INFINITY;
         int bi = 0x7fffffff;
-        for (int c = lane; c < C; c += 32) {
-            const float v = s_log[c * (T8 + 1) + t] + nz[c];
-            if (v > best || bi == 0x7fffffff) {
+        auto take = [&](int c, float g) {
+            const float v = s_log[c * (T8 + 1) + t] + g;
+            if (v > best || bi == 0x7fffffff) {     // strictly greater: the first index wins ties (torch.max)
                 best = v;
                 bi = c;
             }
+        };
+        if (nz != nullptr && (C & 127) == 0 && (reinterpret_cast<uintptr_t>(nz) & 15) == 0) {
+            for (int c4 = lane * 4; c4 < C; c4 += 128) {         // lane visits its channels in increasing order
+                const float4 g = *reinterpret_cast<const float4*>(nz + c4);
+                take(c4, g.x); take(c4 + 1, g.y); take(c4 + 2, g.z); take(c4 + 3, g.w);
+            }
+        } else {
+            for (int c = lane; c < C; c += 32) take(c, nz ? nz[c] : gumbel_from_counter(seed, static_cast<unsigned long long>(t) * C + c));
         }
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) {
@@ -135,9 +184,17 @@ __global__ void bottleneck_onehot_kernel(const float* __restrict__ logits, const
             if (ids) ids[b * T8 + t] = bi;
         }
     }
+    if (act == nullptr) return;
     __syncthreads();
-    if (act) {
-        float* ab = act + static_cast<size_t>(b) * n;
+    float* ab = act + static_cast<size_t>(b) * n;
+    if ((T8 & 3) == 0 && (reinterpret_cast<uintptr_t>(ab) & 15) == 0) {
+        const int q = T8 >> 2;
+        for (int i = threadIdx.x; i < (n >> 2); i += blockDim.x) {
+            const int c = i / q, t = (i % q) << 2;
+            reinterpret_cast<float4*>(ab)[i] = make_float4(c == s_id[t] ? 1.f : 0.f, c == s_id[t + 1] ? 1.f : 0.f,
+                                                           c == s_id[t + 2] ? 1.f : 0.f, c == s_id[t + 3] ? 1.f : 0.f);
+        }
+    } else {
         for (int i = threadIdx.x; i < n; i += blockDim.x) ab[i] = (i / T8 == s_id[i % T8]) ? 1.f : 0.f;
     }
 }

@@ -523,7 +523,11 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
                             float* __restrict__ v, size_t n, const float* __restrict__ sq, float grad_mult, float max_norm,
                             float lr, float beta1, float beta2, float eps, float bc1, float bc2_sqrt, const float* __restrict__ bc_dev,
                             int* __restrict__ skip) {
-    if (bc_dev) { bc1 = bc_dev[0]; bc2_sqrt = bc_dev[1]; }     // CUDA-graph replays: the step count lives in device memory
+    if (bc_dev) {     // the step state lives in device memory (train_meta_*_kernel): {bc1, bc2_sqrt, apply}
+        if (reinterpret_cast<const int*>(bc_dev)[2] == 0) return;      // some network's gradient overflowed: nobody steps
+        bc1 = bc_dev[0];
+        bc2_sqrt = bc_dev[1];
+    }
     const float norm = sqrtf(*sq) * grad_mult;
     if (!isfinite(norm)) {
         if (skip && blockIdx.x == 0 && threadIdx.x == 0) *skip = 1;
@@ -537,6 +541,37 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
         m[i] = mi;
         v[i] = vi;
         p[i] -= (lr / bc1) * mi / (sqrtf(vi) / bc2_sqrt + eps);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Device-resident step state of the pretrain_AE iteration, so that a CUDA-graph replay (or an eager step) advances it on
+// the stream instead of through host writes that a still-running earlier replay could read too late.
+// 8 x 32-bit words: [0,1] dropout seed (u64) | [2] 1 - beta1^n | [3] sqrt(1 - beta2^n) | [4] apply (int) |
+//                   [5] n = optimiser steps actually applied | [6,7] iterations started (u64)
+// ---------------------------------------------------------------------------------------------
+__global__ void train_meta_begin_kernel(unsigned long long* __restrict__ meta, unsigned long long salt) {
+    const unsigned long long it = meta[3] + 1;
+    meta[3] = it;
+    unsigned long long z = it * 0x9E3779B97F4A7C15ull + salt;           // splitmix64 of (iteration, rank salt)
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    meta[0] = z ^ (z >> 31);
+}
+// after the gradient norms are known: either EVERY network steps (bias corrections of the next applied step) or none does
+__global__ void train_meta_commit_kernel(float* __restrict__ meta, const float* __restrict__ sq_a, const float* __restrict__ sq_b,
+                                         float beta1, float beta2, int* __restrict__ skipped) {
+    int* mi = reinterpret_cast<int*>(meta);
+    const bool ok = isfinite(*sq_a) && (sq_b == nullptr || isfinite(*sq_b));
+    if (ok) {
+        const int n = mi[5] + 1;
+        mi[5] = n;
+        meta[2] = 1.f - powf(beta1, static_cast<float>(n));
+        meta[3] = sqrtf(1.f - powf(beta2, static_cast<float>(n)));
+        mi[4] = 1;
+    } else {
+        mi[4] = 0;
+        if (skipped) *skipped = 1;
     }
 }
 

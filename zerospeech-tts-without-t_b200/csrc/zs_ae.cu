@@ -10,6 +10,9 @@
 #include <string.h>
 
 #include <algorithm>
+#include <map>
+#include <mutex>
+#include <utility>
 #include <vector>
 
 #include "conv_gemm.cuh"
@@ -45,7 +48,7 @@ static int fail(int code, const char* fmt, ...) {
     } while (0)
 
 extern "C" const char* zs_last_error(void) { return g_err; }
-extern "C" int zs_version(void) { return 100; }
+extern "C" int zs_version(void) { return 200; }
 
 // -------------------------------------------------------------------------------------------------
 // driver entry point for TMA descriptors (no -lcuda link dependency)
@@ -54,26 +57,84 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 static PFN_encodeTiled g_encode = nullptr;
-static int g_num_sms = 0;
+
+// Per-device state: SM count, the fp16 saturation counter the GEMM epilogues raise, and which kernels already carry
+// their dynamic-shared-memory opt-in (cudaFuncSetAttribute is per device, not per process).
+constexpr int MAX_DEV = 64;
+struct DevState {
+    int num_sms = 0;
+    unsigned int* sat = nullptr;          // device word: clamped-to-+-65504 events since the last reset
+};
+static DevState g_dev[MAX_DEV];
+static std::mutex g_dev_mu;
+static std::map<std::pair<int, const void*>, int> g_smem_attr;
+static thread_local int t_dev = 0;        // device of the call in flight on this host thread (set by ensure_device)
+#define g_num_sms (g_dev[t_dev].num_sms)
 
 static int ensure_device() {
-    if (g_encode && g_num_sms) return ZS_OK;
     int dev = 0;
     CUDA_TRY(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= MAX_DEV) return fail(ZS_ERR_CUDA, "device ordinal %d outside [0, %d)", dev, MAX_DEV);
+    t_dev = dev;
+    if (g_encode && g_dev[dev].num_sms) return ZS_OK;
+    std::lock_guard<std::mutex> lk(g_dev_mu);
     cudaDeviceProp prop;
     CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
     if (prop.major != 10)
         return fail(ZS_ERR_CUDA, "libzsae needs an sm_100-class GPU (tcgen05/TMEM); found sm_%d%d", prop.major,
                     prop.minor);
-    g_num_sms = prop.multiProcessorCount;
-    void* fn = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
-    if (!fn || qres != cudaDriverEntryPointSuccess) return fail(ZS_ERR_CUDA, "cuTensorMapEncodeTiled not available");
-    g_encode = reinterpret_cast<PFN_encodeTiled>(fn);
+    if (!g_encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        if (!fn || qres != cudaDriverEntryPointSuccess) return fail(ZS_ERR_CUDA, "cuTensorMapEncodeTiled not available");
+        g_encode = reinterpret_cast<PFN_encodeTiled>(fn);
+    }
+    if (!g_dev[dev].sat) {
+        CUDA_TRY(cudaMalloc(&g_dev[dev].sat, sizeof(unsigned int)));
+        CUDA_TRY(cudaMemset(g_dev[dev].sat, 0, sizeof(unsigned int)));
+    }
+    g_dev[dev].num_sms = prop.multiProcessorCount;
     return ZS_OK;
 }
 extern "C" int zs_device_check(void) { return ensure_device(); }
+
+// dynamic shared memory above 48 KB needs an opt-in per (device, kernel)
+static int set_smem_attr(const void* fn, int bytes) {
+    std::lock_guard<std::mutex> lk(g_dev_mu);
+    const auto key = std::make_pair(t_dev, fn);
+    auto it = g_smem_attr.find(key);
+    if (it != g_smem_attr.end() && it->second >= bytes) return ZS_OK;
+    CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    g_smem_attr[key] = bytes;
+    return ZS_OK;
+}
+
+// fp16 range: the GEMM epilogues clamp to +-65504 (cvt.rn.satfinite) and count every thread that had to; nothing on the
+// reference's value ranges gets near it, so a non-zero count means the checkpoint needs operand = bf16.
+extern "C" int zs_saturation_count(void* stream, unsigned long long* count, int reset) {
+    if (!count) return fail(ZS_ERR_ARG, "saturation_count: null argument");
+    ZS_TRY(ensure_device());
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    unsigned int v = 0;
+    CUDA_TRY(cudaMemcpyAsync(&v, g_dev[t_dev].sat, sizeof(v), cudaMemcpyDeviceToHost, st));
+    if (reset) CUDA_TRY(cudaMemsetAsync(g_dev[t_dev].sat, 0, sizeof(unsigned int), st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    *count = v;
+    return ZS_OK;
+}
+
+// Experiment knobs (ZS_GEMM_DEBUG, ZS_GRU_DEBUG, ZS_PDL, ZS_GRU_*, ZS_WGRAD_DIRECT ...) exist only in builds made with
+// -DZS_EXPERIMENTS (ZS_BUILD_EXPERIMENTS=1 for _lib.build); the shipped library never reads the environment.
+static inline int env_int(const char* name, int dflt) {
+#ifdef ZS_EXPERIMENTS
+    const char* e = getenv(name);
+    return e ? atoi(e) : dflt;
+#else
+    (void)name;
+    return dflt;
+#endif
+}
 
 // -------------------------------------------------------------------------------------------------
 // launch accounting + optional per-kernel-class CUDA-event timing (zs_profile_begin / zs_profile_end)
@@ -269,7 +330,8 @@ static int launch_conv(const zs_conv_desc* d, cudaStream_t stream, const ConvExt
     p.act = d->act; p.out_mode = d->out_mode; p.out = d->out; p.out_rows = d->out_rows; p.out_pitch = d->out_pitch;
     p.out_halo = d->out_halo; p.out_choff = d->out_choff; p.accumulate = d->accumulate;
     p.idesc = umma_idesc_f16(d->operand == ZS_OPERAND_BF16 ? 1 : 0, p.N);
-    { const char* dbg = getenv("ZS_GEMM_DEBUG"); p.debug = dbg ? atoi(dbg) : 0; }
+    p.debug = env_int("ZS_GEMM_DEBUG", 0);
+    p.sat_count = g_dev[t_dev].sat;
     if (ex) {
         p.stats = ex->stats; p.post_emb = ex->post_emb; p.post_spk = reinterpret_cast<const long long*>(ex->post_spk);
         p.post_pitch = ex->post_pitch; p.post_n = ex->post_n > 0 ? ex->post_n : 1; p.no_sat = ex->no_sat;
@@ -283,18 +345,14 @@ static int launch_conv(const zs_conv_desc* d, cudaStream_t stream, const ConvExt
     using KernelT = void (*)(const GemmParams);
     KernelT kern = zp ? (which ? conv_gemm_kernel<__nv_bfloat16, true> : conv_gemm_kernel<__half, true>)
                       : (which ? conv_gemm_kernel<__nv_bfloat16, false> : conv_gemm_kernel<__half, false>);
-    static bool attr_set[2][2] = {{false, false}, {false, false}};
-    if (!attr_set[which][zp]) {
-        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
-        attr_set[which][zp] = true;
-    }
+    ZS_TRY(set_smem_attr(reinterpret_cast<const void*>(kern), GEMM_SMEM_BYTES));
     {   // algorithmic FLOPs: 2 * valid out channels * true taps * true in channels * valid frames
         double taps_sum = d->bank ? 28.0 / 7.0 : static_cast<double>(d->taps);
         const double flops = 2.0 * d->m_valid * taps_sum * d->c_in_valid * static_cast<double>(d->B) * d->T_out;
         LaunchScope scope(stream, KC_GEMM, flops, d->stride == 2 ? "conv_gemm s2" : (d->taps > 1 ? "conv_gemm" : "conv_gemm k1"));
         // programmatic dependent launch (ZS_PDL=1): measured neutral on this path (9.505 vs 9.514 ms per step) - the
         // kernels run back to back without host gaps and every CTA needs a whole SM, so only prologues could overlap
-        static const int use_pdl = [] { const char* e = getenv("ZS_PDL"); return e ? atoi(e) : 0; }();
+        static const int use_pdl = env_int("ZS_PDL", 0);
         p.pdl = use_pdl;
         cudaLaunchConfig_t cfg;
         memset(&cfg, 0, sizeof(cfg));
@@ -327,18 +385,32 @@ static int launch_pack_nct(const float* x, int B, int C, int T, void* out, int r
     return ZS_OK;
 }
 // x -> (bank input with halo, leaky-relu'd copy inside the concat buffer) in one pass
-static int launch_pack_x_dual(const float* x, int B, int C, int T, void* bank_p, int bank_rows, int bank_pitch, int bank_halo, void* cat_p,
-                              int cat_rows, int cat_pitch, int cat_choff, float ns, int operand, cudaStream_t st) {
+// x_dtype: ZS_X_F32 | ZS_X_F16; x_layout: ZS_X_NCT (B, C, T) | ZS_X_NTC (B, T, C)
+template <typename OT>
+static void pack_x_dual_dispatch(const void* x, int x_dtype, int x_layout, dim3 grid, cudaStream_t st, int C, int T, OT* bank_p, int bank_rows,
+                                 int bank_pitch, int bank_halo, OT* cat_p, int cat_rows, int cat_pitch, int cat_choff, float ns) {
+#define ZS_PXD(IT, NTC) pack_x_dual_kernel<OT, IT, NTC><<<grid, 256, 0, st>>>(static_cast<const IT*>(x), C, T, bank_p, bank_rows, bank_pitch, \
+                                                                              bank_halo, cat_p, cat_rows, cat_pitch, cat_choff, C, ns, t_zero_pad)
+    if (x_dtype == ZS_X_F16) { if (x_layout == ZS_X_NTC) ZS_PXD(__half, true); else ZS_PXD(__half, false); }
+    else { if (x_layout == ZS_X_NTC) ZS_PXD(float, true); else ZS_PXD(float, false); }
+#undef ZS_PXD
+}
+static int launch_pack_x_dual(const void* x, int x_dtype, int x_layout, int B, int C, int T, void* bank_p, int bank_rows, int bank_pitch,
+                              int bank_halo, void* cat_p, int cat_rows, int cat_pitch, int cat_choff, float ns, int operand, cudaStream_t st) {
     if (bank_halo >= T) return fail(ZS_ERR_ARG, "pack: halo %d needs more than %d frames", bank_halo, T);
     if ((cat_choff & 1) || (bank_pitch & 1)) return fail(ZS_ERR_ARG, "pack: channel offsets / pitches must be even");
+    if (x_dtype != ZS_X_F32 && x_dtype != ZS_X_F16) return fail(ZS_ERR_ARG, "pack: x_dtype %d", x_dtype);
+    if (x_layout != ZS_X_NCT && x_layout != ZS_X_NTC) return fail(ZS_ERR_ARG, "pack: x_layout %d", x_layout);
+    if (x_dtype == ZS_X_F16 && operand != ZS_OPERAND_FP16)
+        return fail(ZS_ERR_ARG, "an fp16 input is rounded once more by bf16 operands: upload fp32 with operand = bf16");
     dim3 grid((T + 31) / 32, (C + 63) / 64, B);
     LaunchScope scope(st, KC_OTHER, 0.0, "pack_x_dual_kernel");
     if (operand == ZS_OPERAND_BF16)
-        pack_x_dual_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(x, C, T, static_cast<__nv_bfloat16*>(bank_p), bank_rows, bank_pitch, bank_halo,
-                                                                static_cast<__nv_bfloat16*>(cat_p), cat_rows, cat_pitch, cat_choff, C, ns, t_zero_pad);
+        pack_x_dual_dispatch<__nv_bfloat16>(x, x_dtype, x_layout, grid, st, C, T, static_cast<__nv_bfloat16*>(bank_p), bank_rows, bank_pitch, bank_halo,
+                                            static_cast<__nv_bfloat16*>(cat_p), cat_rows, cat_pitch, cat_choff, ns);
     else
-        pack_x_dual_kernel<__half><<<grid, 256, 0, st>>>(x, C, T, static_cast<__half*>(bank_p), bank_rows, bank_pitch, bank_halo,
-                                                         static_cast<__half*>(cat_p), cat_rows, cat_pitch, cat_choff, C, ns, t_zero_pad);
+        pack_x_dual_dispatch<__half>(x, x_dtype, x_layout, grid, st, C, T, static_cast<__half*>(bank_p), bank_rows, bank_pitch, bank_halo,
+                                     static_cast<__half*>(cat_p), cat_rows, cat_pitch, cat_choff, ns);
     CUDA_TRY(cudaGetLastError());
     return ZS_OK;
 }
@@ -348,23 +420,21 @@ extern "C" int zs_pack_nct(const float* x, int B, int C, int T, void* out, int r
     return launch_pack_nct(x, B, C, T, out, rows, pitch, halo, choff, lrelu, ns, operand, zero_pad_channels, static_cast<cudaStream_t>(stream));
 }
 
-static int launch_onehot(const float* logits, const float* noise, int B, int C, int T8, float* act, int32_t* ids, cudaStream_t st) {
+static int launch_onehot(const float* logits, const float* noise, const uint64_t* seg_seeds, int B, int C, int T8, float* act, int32_t* ids, cudaStream_t st) {
     const size_t smem = static_cast<size_t>(C) * (T8 + 1) * 4 + static_cast<size_t>(T8) * 4;
     if (smem > 200 * 1024) return fail(ZS_ERR_ARG, "bottleneck: C %d x T8 %d does not fit shared memory", C, T8);
-    static size_t attr = 0;
-    if (smem > 48 * 1024 && smem > attr) {
-        CUDA_TRY(cudaFuncSetAttribute(bottleneck_onehot_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr = 200 * 1024;
-    }
+    ZS_TRY(ensure_device());
+    if (smem > 48 * 1024) ZS_TRY(set_smem_attr(reinterpret_cast<const void*>(bottleneck_onehot_kernel), 200 * 1024));
     LaunchScope scope(st, KC_OTHER, 0.0, "bottleneck_onehot_kernel");
-    bottleneck_onehot_kernel<<<B, 512, smem, st>>>(logits, noise, C, T8, act, ids);
+    if (!noise && !seg_seeds) return fail(ZS_ERR_ARG, "bottleneck: neither a noise tensor nor per-segment seeds");
+    bottleneck_onehot_kernel<<<B, 512, smem, st>>>(logits, noise, reinterpret_cast<const unsigned long long*>(seg_seeds), C, T8, act, ids);
     CUDA_TRY(cudaGetLastError());
     return ZS_OK;
 }
 extern "C" int zs_bottleneck_one_hot(const float* logits, const float* noise, int B, int C, int T8, float* act,
                                      int32_t* unit_ids, void* stream) {
     if (!logits || !noise) return fail(ZS_ERR_ARG, "bottleneck: null logits/noise");
-    return launch_onehot(logits, noise, B, C, T8, act, unit_ids, static_cast<cudaStream_t>(stream));
+    return launch_onehot(logits, noise, nullptr, B, C, T8, act, unit_ids, static_cast<cudaStream_t>(stream));
 }
 
 static int launch_gru(const void* gx, const float* whhT, const float* bhh, int B, int T, int H, void* out, int rows,
@@ -400,19 +470,20 @@ static int launch_gru_cluster(const void* w_img, const float* bhh, const void* g
     p.gates = gates;
     // gates through tanh.approx.f32 (one MUFU each; 2^-11 relative error, below the fp16 rounding of the state that
     // feeds the next step's MMA) on the inference path; the training forward keeps the exp/rcp form
-    { const char* fa = getenv("ZS_GRU_FAST_ACT"); p.fast_act = fa ? atoi(fa) : (gates == nullptr ? 1 : 0); }
+    p.fast_act = env_int("ZS_GRU_FAST_ACT", gates == nullptr ? 1 : 0);
     p.w_img = w_img; p.bhh = bhh; p.gx = gx; p.out = out; p.B = B; p.T = T; p.H = H;
     p.out_rows = rows; p.out_pitch = pitch; p.out_halo = halo; p.out_choff = choff;
     p.fmt = operand == ZS_OPERAND_BF16 ? 1 : 0;
+    p.debug = 0;
+    p.dbg = nullptr;
+#ifdef ZS_EXPERIMENTS
     {   // timing experiments only (results are wrong with any bit set): 1 = no state exchange, 2 = no gx loads, 4 = no stores
-        const char* dbg = getenv("ZS_GRU_DEBUG");
-        p.debug = dbg ? atoi(dbg) : 0;
-        p.dbg = nullptr;
+        p.debug = env_int("ZS_GRU_DEBUG", 0);
         if (p.debug & 8) {
             static long long* dbuf = nullptr;
             if (!dbuf) cudaMalloc(&dbuf, 8 * 512 * sizeof(long long));
             p.dbg = dbuf;
-            if (T <= 512) {   // dump the previous call's stamps (host-synchronous; experiments only)
+            if (T <= 512) {   // dump the previous call's stamps (host-synchronous)
                 static bool first = true;
                 if (!first) {
                     std::vector<long long> hbuf(8 * T);
@@ -427,11 +498,12 @@ static int launch_gru_cluster(const void* w_img, const float* bhh, const void* g
             }
         }
     }
+#endif
     if (static_cast<long long>(B) * T * 6 * H >= (1ll << 31) || static_cast<long long>(B) * rows * pitch >= (1ll << 31))
         return fail(ZS_ERR_ARG, "gru: %d sequences x %d steps exceed the 32-bit element offsets of the recurrence kernel", B, T);
     {   // 64 sequences per cluster with the r|z rows of W_hh in TMEM (gru_wide.cuh): the shape for batches that need more than
         // one wave of 32-sequence clusters anyway.  ZS_GRU_WIDE=0 disables, =1 forces (where its preconditions hold).
-        static const int wide_mode = [] { const char* e = getenv("ZS_GRU_WIDE"); return e ? atoi(e) : 2; }();
+        static const int wide_mode = env_int("ZS_GRU_WIDE", 2);
         const int NCw = H / GRU_UNITS;
         // 64 sequences per cluster (2 gate passes), or 128 (4 passes) when the 64-sequence clusters would need a second wave and
         // the state of 128 sequences fits (H <= 512: 64 KB of n rows + 128 KB of state; H/2 + 256 TMEM columns)
@@ -442,7 +514,7 @@ static int launch_gru_cluster(const void* w_img, const float* bhh, const void* g
             auto cost = [&](int np) { const int cls = 2 * ((B + 32 * np - 1) / (32 * np)); return ((cls + per_wave - 1) / per_wave) * (5000 + 1900 * np); };
             if (cost(4) < cost(2)) npass = 4;
         }
-        { const char* e = getenv("ZS_GRU_NPASS"); if (e && (atoi(e) == 2 || atoi(e) == 4)) npass = atoi(e); }
+        { const int e = env_int("ZS_GRU_NPASS", 0); if (e == 2 || e == 4) npass = e; }
         const int nseq_w = 32 * npass, groups64 = (B + nseq_w - 1) / nseq_w;
         const size_t need = static_cast<size_t>(2) * groups64 * NCw * nseq_w * 128;
         const bool can = !gates && xchg && need <= xchg_bytes && NCw >= 2 && NCw <= 8 && H % 64 == 0;
@@ -457,11 +529,7 @@ static int launch_gru_cluster(const void* w_img, const float* bhh, const void* g
             using WideT = void (*)(const GruWideParams);
             WideT wk = npass == 4 ? (wp.fmt ? gru_wide_kernel<__nv_bfloat16, 4> : gru_wide_kernel<__half, 4>)
                                   : (wp.fmt ? gru_wide_kernel<__nv_bfloat16, 2> : gru_wide_kernel<__half, 2>);
-            static int wattr[2][2] = {{0, 0}, {0, 0}};
-            if (wattr[wp.fmt][npass == 4] < smem_w) {
-                CUDA_TRY(cudaFuncSetAttribute(wk, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_w));
-                wattr[wp.fmt][npass == 4] = smem_w;
-            }
+            ZS_TRY(set_smem_attr(reinterpret_cast<const void*>(wk), smem_w));
             cudaLaunchConfig_t wc;
             memset(&wc, 0, sizeof(wc));
             wc.gridDim = dim3(2 * groups64 * NCw); wc.blockDim = dim3(GRU_THREADS); wc.dynamicSmemBytes = smem_w; wc.stream = st;
@@ -478,18 +546,14 @@ static int launch_gru_cluster(const void* w_img, const float* bhh, const void* g
     // clusters are resident on a B200) the smaller shape halves the per-step exchange and gate math: lower latency
     const int NC = H / GRU_UNITS;
     int nseq = (2 * ((B + GRU_FWD_NSEQ_SMALL - 1) / GRU_FWD_NSEQ_SMALL) * NC <= 120) ? GRU_FWD_NSEQ_SMALL : GRU_FWD_NSEQ;
-    { const char* e = getenv("ZS_GRU_NSEQ"); if (e && (atoi(e) == 16 || atoi(e) == 32)) nseq = atoi(e); }
+    { const int e = env_int("ZS_GRU_NSEQ", 0); if (e == 16 || e == 32) nseq = e; }
     const int n_groups = (B + nseq - 1) / nseq;
     const int smem = gru_smem_bytes(H, nseq);
     using KernelT = void (*)(const GruParams);
     const int which = p.fmt;
     KernelT kern = nseq == 16 ? (which ? gru_cluster_kernel<__nv_bfloat16, 16> : gru_cluster_kernel<__half, 16>)
                               : (which ? gru_cluster_kernel<__nv_bfloat16, 32> : gru_cluster_kernel<__half, 32>);
-    static int attr_set[2][2] = {{0, 0}, {0, 0}};
-    if (attr_set[which][nseq == 16] < smem) {
-        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr_set[which][nseq == 16] = smem;
-    }
+    ZS_TRY(set_smem_attr(reinterpret_cast<const void*>(kern), smem));
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(2 * n_groups * NC);
@@ -500,13 +564,13 @@ static int launch_gru_cluster(const void* w_img, const float* bhh, const void* g
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = NC; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    if (p.debug & 16) {
+    if (ZS_DBG(p) & 16) {
         int ncl = 0;
         cudaError_t e = cudaOccupancyMaxActiveClusters(&ncl, kern, &cfg);
         fprintf(stderr, "gru: max active clusters of %d CTAs with %d B smem: %d (%s); launching %d clusters of %d sequences\n", NC, smem, ncl, cudaGetErrorString(e), 2 * n_groups, nseq);
     }
     {   // state exchange through L2 + multicast (ZS_GRU_XCHG=0: direct SM-to-SM bulk copies)
-        static const int xmode = [] { const char* e = getenv("ZS_GRU_XCHG"); return e ? atoi(e) : 1; }();
+        static const int xmode = env_int("ZS_GRU_XCHG", 1);
         p.xchg = nullptr;
         const size_t need = static_cast<size_t>(2) * n_groups * NC * nseq * 128;     // one slice per CTA of every cluster
         if (xmode && NC > 1 && xchg && need <= xchg_bytes) p.xchg = static_cast<uint8_t*>(xchg);
@@ -906,6 +970,7 @@ struct Carver {
 
 struct EncWs {
     Buf xp, cat, a[7], d[3], catr, gx, xch;
+    float* logits = nullptr;        // (B, n_out, T8) fp32 scratch for callers that do not want the logits back
     int T[4];
     size_t bytes;
 };
@@ -927,6 +992,7 @@ static EncWs carve_encoder(const zs_encoder* h, void* ws, int B, int T) {
     w.catr = c.act(B, w.T[3], 0, g.c_h2 + 2 * g.c_h3);
     w.gx = c.act(B, w.T[3], 0, 6 * g.c_h3, true);   // the recurrence indexes it as a dense [B][T][2][3H] array
     w.xch = c.act(round_up(B, 128), 2, 0, g.c_h3);   // GRU state exchange scratch: one H-wide fp16 row per (direction, sequence)
+    w.logits = static_cast<float*>(c.take(static_cast<size_t>(B) * h->n_out * w.T[3] * sizeof(float)));
     w.bytes = c.off;
     return w;
 }
@@ -1005,11 +1071,21 @@ static int run_layer(const Layer& L, int operand, float ns, const Buf& in, int B
 
 extern "C" int zs_encoder_forward(zs_encoder* h, const float* x, int B, int T, const float* gumbel_noise, float* logits,
                                   float* act, int32_t* unit_ids, void* workspace, size_t workspace_bytes, void* stream) {
-    if (!h || !x || !logits) return fail(ZS_ERR_ARG, "encoder_forward: null argument");
+    if (!logits) return fail(ZS_ERR_ARG, "encoder_forward: null argument");
+    if (h && h->cfg.enc_mode != ZS_ENC_CONTINUES && !gumbel_noise) return fail(ZS_ERR_ARG, "encoder_forward: enc_mode %d needs the Gumbel noise tensor", h->cfg.enc_mode);
+    return zs_encoder_forward_x(h, x, ZS_X_F32, ZS_X_NCT, B, T, gumbel_noise, nullptr, logits, act, unit_ids, workspace, workspace_bytes, stream);
+}
+
+extern "C" int zs_encoder_forward_x(zs_encoder* h, const void* x, int x_dtype, int x_layout, int B, int T, const float* gumbel_noise,
+                                    const uint64_t* noise_seeds, float* logits, float* act, int32_t* unit_ids, void* workspace,
+                                    size_t workspace_bytes, void* stream) {
+    if (!h || !x) return fail(ZS_ERR_ARG, "encoder_forward: null argument");
     if (B < 1) return fail(ZS_ERR_ARG, "encoder_forward: B %d", B);
     if (T < 9 || T > 256) return fail(ZS_ERR_ARG, "encoder_forward: T %d outside [9, 256] (convert.py MIN_LEN=9; segments are < 2*seg_len frames)", T);
     const zs_encoder_cfg& g = h->cfg;
-    if (g.enc_mode != ZS_ENC_CONTINUES && !gumbel_noise) return fail(ZS_ERR_ARG, "encoder_forward: enc_mode %d needs the Gumbel noise tensor", g.enc_mode);
+    if (g.enc_mode != ZS_ENC_CONTINUES && !gumbel_noise && !(g.enc_mode == ZS_ENC_ONE_HOT && noise_seeds))
+        return fail(ZS_ERR_ARG, "encoder_forward: enc_mode %d needs the Gumbel noise tensor (device-generated noise: one_hot with noise_seeds)", g.enc_mode);
+    if (g.enc_mode != ZS_ENC_ONE_HOT && !logits && !act) return fail(ZS_ERR_ARG, "encoder_forward: no output requested");
     t_zero_pad = g.seg_len < 64;           // model/model.py:36-38: 'constant' padding below seg_len 64
     EncWs w = carve_encoder(h, workspace, B, T);
     if (!workspace || workspace_bytes < w.bytes) return fail(ZS_ERR_WORKSPACE, "encoder_forward: workspace %zu < %zu bytes", workspace_bytes, w.bytes);
@@ -1018,7 +1094,8 @@ extern "C" int zs_encoder_forward(zs_encoder* h, const float* x, int B, int T, c
     const float ns = g.ns;
 
     // model/model.py:441-446: conv bank on x, concatenated with x, leaky-relu
-    ZS_TRY(launch_pack_x_dual(x, B, g.c_in, T, w.xp.p, w.xp.rows, w.xp.pitch, 3, w.cat.p, w.cat.rows, w.cat.pitch, 7 * g.c_h1, ns, op, st));
+    if (!logits) logits = w.logits;
+    ZS_TRY(launch_pack_x_dual(x, x_dtype, x_layout, B, g.c_in, T, w.xp.p, w.xp.rows, w.xp.pitch, 3, w.cat.p, w.cat.rows, w.cat.pitch, 7 * g.c_h1, ns, op, st));
     if (h->bank_merged) {
         ConvOpts o; o.bank = 1;
         ZS_TRY(run_layer(h->bank[0], op, ns, w.xp, B, T, &w.cat, nullptr, 0, 0, o, st));
@@ -1061,7 +1138,7 @@ extern "C" int zs_encoder_forward(zs_encoder* h, const float* x, int B, int T, c
         ZS_TRY(run_layer(h->linear, op, ns, w.catr, B, T8, nullptr, logits, 0, 0, o, st));
     }
     if (g.enc_mode == ZS_ENC_ONE_HOT) {
-        ZS_TRY(launch_onehot(logits, gumbel_noise, B, g.enc_size, T8, act, unit_ids, st));
+        ZS_TRY(launch_onehot(logits, gumbel_noise, noise_seeds, B, g.enc_size, T8, act, unit_ids, st));
     } else if (act) {
         const size_t n = g.enc_mode == ZS_ENC_GUMBEL_T ? static_cast<size_t>(B) * g.enc_size : static_cast<size_t>(B) * g.enc_size * T8;
         if (g.enc_mode == ZS_ENC_BINARY) CUDA_TRY(cudaMemsetAsync(act, 0, n * sizeof(float), st));

@@ -27,7 +27,7 @@ static int launch_wgrad(const zs_wgrad_desc* d, cudaStream_t st) {
     // At small batches the kernel is bound by its fp32 atomic adds (one per weight per K split), not by the MMAs:
     // when the gradient is known to be zero and the items fill at least half the SMs on their own, keep the reduction
     // whole and store (measured at B = 32 on one box: 2.35 ms of weight-gradient GEMMs per step -> 2.10 ms).
-    static const int direct_mode = [] { const char* e = getenv("ZS_WGRAD_DIRECT"); return e ? atoi(e) : 2; }();   // 0 off, 1 >= SMs, 2 >= SMs / 2 (measured best at B = 32)
+    static const int direct_mode = env_int("ZS_WGRAD_DIRECT", 2);   // 0 off, 1 >= SMs, 2 >= SMs / 2 (measured best at B = 32)
     p.direct = (d->grad_is_zero && direct_mode > 0 && direct_mode * items0 >= g_num_sms) ? 1 : 0;
     if (p.direct) ksplit = 1;
     p.ksplit = ksplit;
@@ -52,11 +52,7 @@ static int launch_wgrad(const zs_wgrad_desc* d, cudaStream_t st) {
         cuuint32_t box[4] = {64, 1, static_cast<cuuint32_t>(rows_ps), static_cast<cuuint32_t>(p.nb)};
         ZS_TRY(make_map(&p.tmB, ZS_OPERAND_FP16, const_cast<void*>(d->x), 4, dims, strides, box));
     }
-    static bool attr = false;
-    if (!attr) {
-        CUDA_TRY(cudaFuncSetAttribute(wgrad_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM_BYTES));
-        attr = true;
-    }
+    ZS_TRY(set_smem_attr(reinterpret_cast<const void*>(wgrad_gemm_kernel), WG_SMEM_BYTES));
     const int total = items0 * ksplit;
     {
         LaunchScope scope(st, KC_GEMM, 2.0 * d->c_out * d->c_in * d->taps * static_cast<double>(d->B) * d->T, "wgrad_gemm_kernel");
@@ -155,11 +151,7 @@ static int launch_gru_bptt_cluster(const void* whhT_img, const Buf& gates, const
     p.dout = static_cast<const __half*>(dout.p); p.do_rows = dout.rows; p.do_pitch = dout.pitch; p.do_choff = do_choff;
     p.dgx = static_cast<__half*>(dgx.p); p.dgh = static_cast<__half*>(dgh.p); p.B = B; p.T = T; p.H = H;
     const int NC = H / GRU_UNITS, n_groups = (B + GRU_NSEQ - 1) / GRU_NSEQ, smem = gb_smem_bytes(H);
-    static int attr_set = 0;
-    if (attr_set < smem) {
-        CUDA_TRY(cudaFuncSetAttribute(gru_bptt_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr_set = smem;
-    }
+    ZS_TRY(set_smem_attr(reinterpret_cast<const void*>(gru_bptt_cluster_kernel), smem));
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(2 * n_groups * NC);
@@ -177,7 +169,7 @@ static int launch_gru_bptt_cluster(const void* whhT_img, const Buf& gates, const
 
 static int launch_gru_bptt(const Buf& gates, const Buf& hbuf, int h_choff, const Buf& dout, int do_choff, const float* const* w_hh,
                            int B, int T, int H, const Buf& dgx, const Buf& dgh, cudaStream_t st, const void* whhT_img = nullptr) {
-    if (whhT_img && !getenv("ZS_GRU_BPTT_SIMPLE")) return launch_gru_bptt_cluster(whhT_img, gates, hbuf, h_choff, dout, do_choff, B, T, H, dgx, dgh, st);
+    if (whhT_img && !env_int("ZS_GRU_BPTT_SIMPLE", 0)) return launch_gru_bptt_cluster(whhT_img, gates, hbuf, h_choff, dout, do_choff, B, T, H, dgx, dgh, st);
     if (H > 1024) return fail(ZS_ERR_ARG, "gru bptt: H %d > 1024", H);
     constexpr int NBG = 4;
     dim3 grid((B + NBG - 1) / NBG, 2);
@@ -548,7 +540,7 @@ extern "C" int zs_encoder_forward_train(zs_encoder* h, const float* x, int B, in
         p.B = B; p.T = Tl; p.C = h2;
         return launch_combine(p, st);
     };
-    ZS_TRY(launch_pack_x_dual(x, B, g.c_in, T, w.xp.p, w.xp.rows, w.xp.pitch, 3, w.cat.p, w.cat.rows, w.cat.pitch, 7 * g.c_h1, ns, op, st));
+    ZS_TRY(launch_pack_x_dual(x, ZS_X_F32, ZS_X_NCT, B, g.c_in, T, w.xp.p, w.xp.rows, w.xp.pitch, 3, w.cat.p, w.cat.rows, w.cat.pitch, 7 * g.c_h1, ns, op, st));
     if (h->bank_merged) {
         ConvOpts o; o.bank = 1;
         ZS_TRY(run_layer(h->bank[0], op, ns, w.xp, B, T, &w.cat, nullptr, 0, 0, o, st));
@@ -596,7 +588,7 @@ extern "C" int zs_encoder_forward_train(zs_encoder* h, const float* x, int B, in
         ConvOpts o; o.lrelu = 0; o.out_mode = OUT_NCT32;
         ZS_TRY(run_layer(h->linear, op, ns, w.catr, B, T8, nullptr, logits, 0, 0, o, st));
     }
-    ZS_TRY(launch_onehot(logits, gumbel_noise, B, g.enc_size, T8, act, unit_ids, st));
+    ZS_TRY(launch_onehot(logits, gumbel_noise, nullptr, B, g.enc_size, T8, act, unit_ids, st));
     return ZS_OK;
 }
 
@@ -632,11 +624,7 @@ extern "C" int zs_encoder_backward(zs_encoder* h, const float* d_act, float d_ac
         const int C = g.enc_size;
         const size_t smem = static_cast<size_t>(2) * C * (T8 + 1) * 4;
         if (smem > 200 * 1024) return fail(ZS_ERR_ARG, "encoder_backward: enc_size %d x T8 %d does not fit shared memory", C, T8);
-        static size_t attr = 0;
-        if (smem > 48 * 1024 && smem > attr) {
-            CUDA_TRY(cudaFuncSetAttribute(gumbel_st_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-            attr = 200 * 1024;
-        }
+        if (smem > 48 * 1024) ZS_TRY(set_smem_attr(reinterpret_cast<const void*>(gumbel_st_bwd_kernel), 200 * 1024));
         LaunchScope scope(st, KC_OTHER, 0.0, "gumbel_st_bwd_kernel");
         gumbel_st_bwd_kernel<<<B, 512, smem, st>>>(logits, gumbel_noise, d_act, C, T8, 10.f /* 1 / temperature 0.1 */,
                                                    10.f * (loss_scale / d_act_scale), static_cast<__half*>(w.dlog.p), w.dlog.rows, w.dlog.pitch);
@@ -727,6 +715,24 @@ extern "C" int zs_adam_step(float* params, const float* grads, float* exp_avg, f
     LaunchScope scope(st, KC_OTHER, 0.0, "adam_kernel");
     adam_kernel<<<std::min<size_t>(8 * g_num_sms, (n + 255) / 256), 256, 0, st>>>(params, grads, exp_avg, exp_avg_sq, n, sqnorm, grad_mult, max_norm, lr,
                                                                                   beta1, beta2, eps, bc1, bc2, bias_corr_dev, skipped);
+    CUDA_TRY(cudaGetLastError());
+    return ZS_OK;
+}
+
+extern "C" int zs_train_meta_begin(void* meta, uint64_t seed_salt, void* stream) {
+    if (!meta) return fail(ZS_ERR_ARG, "train_meta_begin: null argument");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    LaunchScope scope(st, KC_OTHER, 0.0, "train_meta_begin_kernel");
+    train_meta_begin_kernel<<<1, 1, 0, st>>>(static_cast<unsigned long long*>(meta), seed_salt);
+    CUDA_TRY(cudaGetLastError());
+    return ZS_OK;
+}
+extern "C" int zs_train_meta_commit(void* meta, const float* sqnorm_a, const float* sqnorm_b, float beta1, float beta2, int* skipped,
+                                    void* stream) {
+    if (!meta || !sqnorm_a) return fail(ZS_ERR_ARG, "train_meta_commit: null argument");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    LaunchScope scope(st, KC_OTHER, 0.0, "train_meta_commit_kernel");
+    train_meta_commit_kernel<<<1, 1, 0, st>>>(static_cast<float*>(meta), sqnorm_a, sqnorm_b, beta1, beta2, skipped);
     CUDA_TRY(cudaGetLastError());
     return ZS_OK;
 }

@@ -54,6 +54,25 @@ def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+class OperandRangeError(RuntimeError):
+    """fp16 operands saturated (|value| > 65504 clamped in a GEMM epilogue): results are degraded."""
+
+
+def check_range(device=None, raise_on_saturation=True):
+    """Number of fp16 values the GEMM epilogues had to clamp on `device` since the last check (synchronises the current
+    stream; resets the counter).  The reference computes in fp32 (model/model.py:20-110) and cannot overflow; this path
+    stores activations as fp16 operands, which every InstanceNorm keeps O(1) - a trained checkpoint with a larger
+    pre-normalisation range must be run with `module.operand = 'bf16'`.  Never silent: the front-end calls this after every
+    batch it brings back to the host."""
+    dev = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
+    with torch.cuda.device(dev):
+        n = _lib.saturation_count(torch.cuda.current_stream().cuda_stream, reset=True)
+    if n and raise_on_saturation:
+        raise OperandRangeError(f'{n} GEMM epilogue threads clamped fp16 operands to +-65504 on {dev}: the activations of this '
+                                "checkpoint exceed the fp16 range - set `encoder.operand = decoder.operand = 'bf16'`")
+    return n
+
+
 class _Packed(nn.Module):
     """Shared plumbing: lazy packing of the fp32 parameters into the library handle."""
 
@@ -67,6 +86,8 @@ class _Packed(nn.Module):
         self._thandle = None
         self._tpacked_key = None
         self._tworkspace = None
+        self._train_ctx = None
+        self._train_ctx_version = 0     # bumped by every forward_train: a backward of an older forward is refused
 
     def _param_key(self):
         return tuple((p.data_ptr(), p._version, str(p.device)) for p in self.parameters()) + (self.operand,)
@@ -232,6 +253,7 @@ class Encoder(_Packed):
                                                     _ptr(seed_dev), km, _ptr(logits), _ptr(act), _ptr(ids), _ptr(ws), ws.numel(),
                                                     _stream()))
         self._train_ctx = (B, T, noise, logits, int(dropout_seed) & (2 ** 64 - 1), keep_masks, seed_dev)
+        self._train_ctx_version += 1
         return act, logits, ids
 
     @staticmethod
@@ -274,34 +296,65 @@ class Encoder(_Packed):
                 'continues': None}[self.enc_mode]
 
     @torch.no_grad()
-    def encode(self, x, noise=None):
-        """forward() plus the unit ids: returns (out_act, out, unit_ids or None)."""
+    def encode(self, x, noise=None, layout='nct', noise_seeds=None, want_act=True, want_logits=True):
+        """forward() plus the unit ids: returns (out_act, out, unit_ids or None).
+
+        Extras of the batched front-end (all optional, defaults = the reference's forward contract):
+          x            float32 or float16 (an fp16 upload is bit-identical: the path rounds to fp16 operands first thing);
+          layout       'nct' (B, c_in, T) as Encoder.forward gets it, or 'ntc' (B, T, c_in) as Trainer.test_step gets it
+                       before its permute (trainer.py:196) - no transpose copy;
+          noise_seeds  one_hot only, with noise=None: (B,) int64 device tensor - the Gumbel noise is drawn ON THE DEVICE, one
+                       counter-based stream per segment (same distribution, not the reference's CPU-generator stream;
+                       saves 4 KB of upload per unit frame; a segment's draw does not depend on its batch);
+          want_act / want_logits = False skip those outputs (one_hot: the ids say everything)."""
         self._check_input(x, 'x')
-        if x.dim() != 3 or x.shape[1] != self.c_in:
-            raise RuntimeError(f'Encoder: expected (B, {self.c_in}, T), got {tuple(x.shape)}')
-        B, _, T = x.shape
+        if layout not in ('nct', 'ntc'):
+            raise RuntimeError(f"Encoder: layout must be 'nct' or 'ntc', got {layout!r}")
+        c_axis = 1 if layout == 'nct' else 2
+        if x.dim() != 3 or x.shape[c_axis] != self.c_in:
+            want = f'(B, {self.c_in}, T)' if layout == 'nct' else f'(B, T, {self.c_in})'
+            raise RuntimeError(f'Encoder: expected {want}, got {tuple(x.shape)}')
+        B, T = x.shape[0], x.shape[3 - c_axis]
         dev = x.device
-        x = x.detach().contiguous().float()
+        x = x.detach()
+        if x.dtype not in (torch.float32, torch.float16):
+            x = x.float()
+        if x.dtype == torch.float16 and self.operand != 'fp16':
+            x = x.float()                                # bf16 operands: round once, from fp32
+        x = x.contiguous()
         shape = self.noise_shape(B, T)
+        device_noise = False
         if shape is not None:
-            if noise is None:
-                noise = sample_gumbel(shape)            # CPU generator, like the reference
-            if tuple(noise.shape) != shape:
-                raise RuntimeError(f'Encoder: noise must have shape {shape}, got {tuple(noise.shape)}')
-            noise = noise.to(dev, torch.float32, non_blocking=True).contiguous()
+            if noise is None and noise_seeds is not None:
+                if self.enc_mode != 'one_hot':
+                    raise RuntimeError('Encoder: device-generated Gumbel noise exists for enc_mode one_hot only')
+                if noise_seeds.dtype != torch.int64 or noise_seeds.numel() != B or not noise_seeds.is_cuda:
+                    raise RuntimeError('Encoder: noise_seeds must be a (B,) int64 CUDA tensor')
+                noise_seeds = noise_seeds.contiguous()
+                device_noise = True
+            else:
+                if noise is None:
+                    noise = sample_gumbel(shape)            # CPU generator, like the reference
+                if tuple(noise.shape) != shape:
+                    raise RuntimeError(f'Encoder: noise must have shape {shape}, got {tuple(noise.shape)}')
+                noise = noise.to(dev, torch.float32, non_blocking=True).contiguous()
         else:
             noise = None
+        ids_only = self.enc_mode == 'one_hot'
+        if not ids_only and not (want_act and want_logits):
+            raise RuntimeError('Encoder: want_act / want_logits = False need enc_mode one_hot (the ids carry the result)')
         lib = _lib.lib()
         with torch.cuda.device(dev):
             h = self._ensure_packed(dev)
             T8 = self.t8(T)
-            logits = torch.empty(B, self.n_out, T8, dtype=torch.float32, device=dev)
-            act = torch.empty(B, self.enc_size, T8, dtype=torch.float32, device=dev)
+            logits = torch.empty(B, self.n_out, T8, dtype=torch.float32, device=dev) if want_logits else None
+            act = torch.empty(B, self.enc_size, T8, dtype=torch.float32, device=dev) if want_act else None
             ids = torch.empty(B, T8, dtype=torch.int32, device=dev) if self.enc_mode == 'one_hot' else None
             nbytes = lib.zs_encoder_workspace_bytes(h, B, T)
             ws = self._get_workspace(nbytes, dev)
-            _lib.check(lib.zs_encoder_forward(h, _ptr(x), B, T, _ptr(noise), _ptr(logits), _ptr(act), _ptr(ids),
-                                              _ptr(ws), ws.numel(), _stream()))
+            _lib.check(lib.zs_encoder_forward_x(h, _ptr(x), 1 if x.dtype == torch.float16 else 0, 0 if layout == 'nct' else 1, B, T,
+                                                _ptr(None if device_noise else noise), _ptr(noise_seeds if device_noise else None),
+                                                _ptr(logits), _ptr(act), _ptr(ids), _ptr(ws), ws.numel(), _stream()))
         return act, logits, ids
 
     def forward(self, x, noise=None):
@@ -399,6 +452,7 @@ class Decoder(_Packed):
             ws = self._get_train_workspace(lib.zs_decoder_train_workspace_bytes(h, B, T8), dev)
             _lib.check(lib.zs_decoder_forward_train(h, _ptr(x), _ptr(c), B, T8, _ptr(spec), _ptr(ws), ws.numel(), _stream()))
         self._train_ctx = (B, T8, c, spec)
+        self._train_ctx_version += 1
         return spec
 
     def backward(self, grads, loss_scale, target=None, d_spec=None, loss_out=None, want_d_act=True):

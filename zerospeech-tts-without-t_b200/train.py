@@ -87,18 +87,25 @@ class PretrainAE:
         self.skipped = torch.zeros(1, dtype=torch.int32, device=dev)
         self._skipped_host = torch.zeros(1, dtype=torch.int32).pin_memory() if dev.type == 'cuda' else None
         self._skip_event = None
+        self._skip_ring = []
+        self._skip_hosts = [torch.zeros(1, dtype=torch.int32).pin_memory() for _ in range(4)] if dev.type == 'cuda' else []
         self.side = torch.cuda.Stream(device=dev) if self.world > 1 else None
         self.n_skipped = 0
         # CUDA-graph replay of the whole iteration (single rank; ~190 launches otherwise cost more host time than the
-        # GPU needs to run them).  What changes between replays lives in device memory, refreshed from `_meta_host`
-        # by a copy node at the head of the graph: the dropout seed and Adam's two bias corrections.
-        self.use_graph = bool(use_graph) and self.world == 1 and not cpu_noise and dev.type == 'cuda'
+        # GPU needs to run them).  What changes between replays (dropout seed, Adam's bias corrections) lives in
+        # `_meta` and is advanced by kernels inside the graph.
+        # With more than one rank the two NCCL all-reduces are captured too (NCCL collectives are capturable; the side
+        # stream forks from and joins the capturing stream), so data-parallel steps replay as one graph as well.
+        self.use_graph = bool(use_graph) and not cpu_noise and dev.type == 'cuda'
         self._graph = None
         self._graph_key = None
         self._warm = 0
-        if dev.type == 'cuda':
-            self._meta_host = torch.zeros(4, dtype=torch.float32).pin_memory()      # [seed lo, seed hi (as raw bits), bc1, bc2]
-            self._meta_dev = torch.zeros(4, dtype=torch.float32, device=dev)
+        # step state in DEVICE memory (include/zs_ae.h zs_train_meta_*): dropout seed, Adam bias corrections, the
+        # all-networks-or-none apply flag, the count of applied steps.  It advances on the stream - a graph replay
+        # needs no host write that an earlier, still running replay could observe too late.
+        self.rank = dist.get_rank(process_group) if self.world > 1 else 0
+        self.seed_salt = (0x1234567 + 0xD1B54A32D192ED03 * self.rank) & (2 ** 64 - 1)     # ranks draw different masks
+        self._meta = torch.zeros(8, dtype=torch.int32, device=dev)
 
     # ---- pieces -----------------------------------------------------------------------------------------
     def _noise(self, B, T8, dev):
@@ -108,39 +115,59 @@ class PretrainAE:
         return gumbel_from_uniform(torch.rand(shape, device=dev))
 
     def _poll_skip(self):
-        """Dynamic loss scaling, one step late (no host sync in the step): halve after an overflow, double after
-        1000 clean steps."""
-        if self._skip_event is not None and self._skip_event.query():
-            if int(self._skipped_host[0]):
-                self.loss_scale = max(self.loss_scale * 0.5, 1.0)
-                self.n_skipped += 1
-                self.good_steps = 0
-                self.skipped.zero_()
-            else:
-                self.good_steps += 1
-                if self.good_steps >= 1000 and self.loss_scale < 2.0 ** 24:
-                    self.loss_scale *= 2.0
-                    self.good_steps = 0
+        """Dynamic loss scaling without a host sync on the step just issued: halve after an overflow, double after 1000
+        clean steps.  One rank: the flag of the last finished step is read whenever it has arrived.  Several ranks: every
+        rank must change the scale (and re-capture its graph) at the SAME iteration, so the flag of iteration k-2 is
+        awaited at iteration k - deterministic, and two iterations stay in flight."""
+        if self.world > 1:
+            if len(self._skip_ring) < 2:
+                return
+            ev, host = self._skip_ring.pop(0)
+            ev.synchronize()
+            flag = int(host[0])
+        else:
+            if self._skip_event is None or not self._skip_event.query():
+                return
+            flag = int(self._skipped_host[0])
             self._skip_event = None
+        if flag:
+            self.loss_scale = max(self.loss_scale * 0.5, 1.0)
+            self.n_skipped += 1
+            self.good_steps = 0
+            self.skipped.zero_()
+        else:
+            self.good_steps += 1
+            if self.good_steps >= 1000 and self.loss_scale < 2.0 ** 24:
+                self.loss_scale *= 2.0
+                self.good_steps = 0
 
     def _allreduce(self, net, stream):
         """Summing all-reduce of one network's flat gradient on `stream` (zs_adam_step divides by the world size)."""
         with torch.cuda.stream(stream):
             reduce_gradients(net.grad, self.pg)
 
-    def _optim(self, net, bc_dev=None):
+    def _meta_ptr(self, word):
+        return C.c_void_p(self._meta.data_ptr() + 4 * word)
+
+    def _optim(self):
+        """utils.py:53-55 per-network clip + trainer.py:332 ae_opt.step(): ONE Adam over both networks, so an fp16
+        overflow in either skips both (and does not count as a step)."""
         lib = _lib.lib()
-        n = net.flat.numel()
-        net.sqnorm.zero_()
-        _lib.check(lib.zs_grad_sqnorm(_ptr(net.grad), n, _ptr(net.sqnorm), _stream()))
-        _lib.check(lib.zs_adam_step(_ptr(net.flat), _ptr(net.grad), _ptr(net.m), _ptr(net.v), n, _ptr(net.sqnorm),
-                                    1.0 / self.world, self.max_grad_norm, self.lr, self.betas[0], self.betas[1], self.eps,
-                                    max(self.step_count, 1), _ptr(bc_dev), _ptr(self.skipped), _stream()))
+        for net in (self.enc, self.dec):
+            net.sqnorm.zero_()
+            _lib.check(lib.zs_grad_sqnorm(_ptr(net.grad), net.flat.numel(), _ptr(net.sqnorm), _stream()))
+        _lib.check(lib.zs_train_meta_commit(self._meta_ptr(0), _ptr(self.enc.sqnorm), _ptr(self.dec.sqnorm), self.betas[0],
+                                            self.betas[1], _ptr(self.skipped), _stream()))
+        for net in (self.enc, self.dec):
+            _lib.check(lib.zs_adam_step(_ptr(net.flat), _ptr(net.grad), _ptr(net.m), _ptr(net.v), net.flat.numel(),
+                                        _ptr(net.sqnorm), 1.0 / self.world, self.max_grad_norm, self.lr, self.betas[0],
+                                        self.betas[1], self.eps, 1, self._meta_ptr(2), _ptr(self.skipped), _stream()))
 
     # ---- the iteration ----------------------------------------------------------------------------------
-    def forward_backward(self, x, c, noise=None, dropout_seed=None, keep_masks=None, seed_dev=None):
+    def forward_backward(self, x, c, noise=None, dropout_seed=None, keep_masks=None):
         """encode_step -> decode_step -> L1 -> backward.  Leaves the (local) gradients in the flat buffers and
-        returns (loss (device scalar), unit ids)."""
+        returns (loss (device scalar), unit ids).  The dropout masks come from the device-resident seed (a new one
+        every iteration, different on every rank) unless `dropout_seed` / `keep_masks` pin them."""
         enc, dec = self.enc.module, self.dec.module
         B, _, T = x.shape
         dev = x.device
@@ -148,8 +175,11 @@ class PretrainAE:
             self.loss_scale = float(2 ** 15 * B)
         if noise is None:
             noise = self._noise(B, enc.t8(T), dev)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().zs_train_meta_begin(self._meta_ptr(0), self.seed_salt, _stream()))
+        seed_dev = None
         if dropout_seed is None:
-            dropout_seed = self.step_count * 0x9E3779B1 + 12345
+            dropout_seed, seed_dev = 0, self._meta[0:2].view(torch.int64)
         self.enc.grad.zero_()
         self.dec.grad.zero_()
         self.loss.zero_()
@@ -162,25 +192,22 @@ class PretrainAE:
         enc.backward(d_act, self.enc.grad_views, self.loss_scale, d_act_scale=self.loss_scale)
         return self.loss, ids
 
-    def _set_meta(self):
-        import struct
-        seed = (self.step_count * 0x9E3779B97F4A7C15 + 0x1234567) & (2 ** 64 - 1)
-        # NaN bit patterns would not survive a float round trip through python: write the raw words instead
-        self._meta_host.view(torch.int32)[0:2] = torch.tensor(struct.unpack('ii', struct.pack('Q', seed)), dtype=torch.int32)
-        self._meta_host[2] = 1.0 - self.betas[0] ** self.step_count
-        self._meta_host[3] = (1.0 - self.betas[1] ** self.step_count) ** 0.5
+    def _finish(self, dev):
+        """Encoder gradient reduce (the decoder's is already in flight on the side stream), then trainer.py:330-332:
+        per-network clip, ONE Adam over both networks, and the in-place refresh of the tensor-core operands."""
+        if self.world > 1:
+            self.side.wait_stream(torch.cuda.current_stream())
+            self._allreduce(self.enc, self.side)
+            torch.cuda.current_stream().wait_stream(self.side)
+        with torch.cuda.device(dev):
+            self._optim()
+            self.enc.module._repack(dev)
+            self.dec.module._repack(dev)
 
     def _graph_body(self):
         """The iteration on static buffers; everything here is captured into the CUDA graph."""
-        self._meta_dev.copy_(self._meta_host, non_blocking=True)
-        seed_dev = self._meta_dev[0:2].view(torch.int64)
-        loss, _ = self.forward_backward(self._x_static, self._c_static, None, 0, None, seed_dev)
-        dev = self._x_static.device
-        with torch.cuda.device(dev):
-            self._optim(self.enc, self._meta_dev[2:4])
-            self._optim(self.dec, self._meta_dev[2:4])
-            self.enc.module._repack(dev)
-            self.dec.module._repack(dev)
+        self.forward_backward(self._x_static, self._c_static)
+        self._finish(self._x_static.device)
 
     def _step_graph(self, x, c):
         key = (tuple(x.shape), float(self.loss_scale) if self.loss_scale else None)
@@ -190,14 +217,14 @@ class PretrainAE:
             self._graph = torch.cuda.CUDAGraph()
             self._x_static.copy_(x)
             self._c_static.copy_(c)
-            self._set_meta()
             torch.cuda.synchronize()
-            with torch.cuda.graph(self._graph):
+            if self.world > 1:
+                dist.barrier(group=self.pg)         # every rank captures the same collectives at the same step
+            with torch.cuda.graph(self._graph):     # (a capture pass does not execute: `_meta` is untouched)
                 self._graph_body()
             self._graph_key = key
         self._x_static.copy_(x, non_blocking=True)
         self._c_static.copy_(c, non_blocking=True)
-        self._set_meta()
         self._graph.replay()
         self.enc.module._packed_key = self.dec.module._packed_key = None
         return self.loss
@@ -213,25 +240,28 @@ class PretrainAE:
             return loss
         self._warm += 1
         loss, _ = self.forward_backward(x, c, noise, dropout_seed, keep_masks)
-        if self.world > 1:
-            self.side.wait_stream(torch.cuda.current_stream())
-            self._allreduce(self.enc, self.side)
-            torch.cuda.current_stream().wait_stream(self.side)
-        with torch.cuda.device(x.device):
-            self._optim(self.enc)           # :330 grad_clip per network, :332 ae_opt.step()
-            self._optim(self.dec)
-            # refresh the tensor-core operands from the updated fp32 parameters (same allocations)
-            self.enc.module._repack(x.device)
-            self.dec.module._repack(x.device)
-            self.enc.module._packed_key = self.dec.module._packed_key = None     # the eval handles are stale now
+        self._finish(x.device)
+        self.enc.module._packed_key = self.dec.module._packed_key = None     # the eval handles are stale now
         self._after_step()
         return loss
 
     def _after_step(self):
-        if self._skipped_host is not None and self._skip_event is None:
+        if self._skipped_host is None:
+            return
+        if self.world > 1:
+            host = self._skip_hosts[self.step_count % len(self._skip_hosts)]
+            host.copy_(self.skipped, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+            self._skip_ring.append((ev, host))
+        elif self._skip_event is None:
             self._skipped_host.copy_(self.skipped, non_blocking=True)
             self._skip_event = torch.cuda.Event()
             self._skip_event.record()
+
+    def applied_steps(self):
+        """Optimiser steps actually applied (overflow-skipped iterations do not count); synchronises."""
+        return int(self._meta[5].item())
 
     def grad_norms(self):
         """(encoder, decoder) gradient L2 norms of the last step, before clipping (host floats; synchronises)."""
@@ -241,57 +271,96 @@ class PretrainAE:
 # ---------------------------------------------------------------------------------------------------------
 # autograd wrappers: the reference's loop shape (trainer.py:246-254, 325-329) with loss.backward()
 # ---------------------------------------------------------------------------------------------------------
-AUTOGRAD_LOSS_SCALE = 2.0 ** 20
+AUTOGRAD_LOSS_SCALE = 2.0 ** 20     # fallback when an encoder backward runs without a decoder backward before it
+_last_scale = [None]                 # loss scale the decoder backward of the running loss.backward() chose
+
+
+def _pick_scale(d):
+    """Power-of-two loss scale that puts max|d| near 0.5 in the fp16 gradient activations (a mean-L1 loss over
+    B x 513 x 128 elements gives 2^20 at B = 32).  Raises on non-finite incoming gradients."""
+    amax = float(d.abs().max())
+    if not (amax == amax) or amax == float('inf'):
+        raise RuntimeError('autograd wrapper: non-finite incoming gradient')
+    if amax == 0.0:
+        return AUTOGRAD_LOSS_SCALE
+    import math
+    return float(2.0 ** max(0, min(40, math.floor(math.log2(0.5 / amax)))))
+
+
+def _flat_grads(m, dev):
+    names = [n for n, _ in m.named_parameters()]
+    params = [p for _, p in m.named_parameters()]
+    flat = torch.zeros(sum(p.numel() for p in params), dtype=torch.float32, device=dev)
+    grads, off = {}, 0
+    for n, p in zip(names, params):
+        grads[n] = flat[off:off + p.numel()].view_as(p)
+        off += p.numel()
+    return names, flat, grads
+
+
+def _check_ctx(ctx, what):
+    if ctx.module._train_ctx_version != ctx.version:
+        raise RuntimeError(f'{what}: the module ran another training forward before this backward - it keeps ONE set of '
+                           'saved activations (call backward before the next forward of the same module)')
 
 
 class _EncodeFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, module, x, noise, dropout_seed, *params):
-        act, logits, _ = module.forward_train(x, noise, dropout_seed)
-        ctx.module = module
+    def forward(ctx, module, x, noise, dropout_seed, seed_dev, *params):
+        act, logits, _ = module.forward_train(x, noise, dropout_seed, seed_dev=seed_dev)
+        ctx.module, ctx.version = module, module._train_ctx_version
         ctx.mark_non_differentiable(logits)
         return act, logits
 
     @staticmethod
     def backward(ctx, d_act, _d_logits):
         m = ctx.module
-        names = [n for n, _ in m.named_parameters()]
-        params = [p for _, p in m.named_parameters()]
-        flat = torch.zeros(sum(p.numel() for p in params), dtype=torch.float32, device=d_act.device)
-        grads, off = {}, 0
-        for n, p in zip(names, params):
-            grads[n] = flat[off:off + p.numel()].view_as(p)
-            off += p.numel()
-        m.backward(d_act, grads, AUTOGRAD_LOSS_SCALE, d_act_scale=1.0)
-        return (None, None, None, None) + tuple(grads[n] for n in names)
+        _check_ctx(ctx, 'encode_step')
+        names, flat, grads = _flat_grads(m, d_act.device)
+        scale = _last_scale[0] or _pick_scale(d_act) / 64.0
+        m.backward(d_act, grads, scale, d_act_scale=1.0)
+        if not bool(torch.isfinite(flat).all()):
+            raise RuntimeError(f'encode_step backward: fp16 gradient overflow at loss scale {scale:g}')
+        return (None, None, None, None, None) + tuple(grads[n] for n in names)
 
 
 class _DecodeFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, module, x, c, *params):
-        ctx.module = module
-        return module.forward_train(x, c)
+        out = module.forward_train(x, c)
+        ctx.module, ctx.version = module, module._train_ctx_version
+        return out
 
     @staticmethod
     def backward(ctx, d_spec):
         m = ctx.module
-        names = [n for n, _ in m.named_parameters()]
-        params = [p for _, p in m.named_parameters()]
-        flat = torch.zeros(sum(p.numel() for p in params), dtype=torch.float32, device=d_spec.device)
-        grads, off = {}, 0
-        for n, p in zip(names, params):
-            grads[n] = flat[off:off + p.numel()].view_as(p)
-            off += p.numel()
-        d_act = m.backward(grads, AUTOGRAD_LOSS_SCALE, d_spec=d_spec)
-        return (None, d_act / AUTOGRAD_LOSS_SCALE, None) + tuple(grads[n] for n in names)
+        _check_ctx(ctx, 'decode_step')
+        names, flat, grads = _flat_grads(m, d_spec.device)
+        scale = _pick_scale(d_spec)
+        _last_scale[0] = scale
+        d_act = m.backward(grads, scale, d_spec=d_spec)
+        if not bool(torch.isfinite(flat).all()) or not bool(torch.isfinite(d_act).all()):
+            raise RuntimeError(f'decode_step backward: fp16 gradient overflow at loss scale {scale:g}')
+        return (None, d_act / scale, None) + tuple(grads[n] for n in names)
 
 
-def encode_step(encoder, x, noise=None, dropout_seed=0):
-    """`Trainer.encode_step` (trainer.py:246-249) with an autograd graph: returns (enc_act, enc)."""
+def encode_step(encoder, x, noise=None, dropout_seed=None):
+    """`Trainer.encode_step` (trainer.py:246-249) with an autograd graph: returns (enc_act, enc).
+
+    Every call draws NEW dropout masks (the reference's nn.Dropout does): the seed of the counter-based masks comes from
+    torch's CUDA generator - the generator the reference's dropout consumes with the model on a GPU - so
+    `torch.manual_seed` pins it and the CPU generator is consumed by the Gumbel draw alone, as in the reference.
+    Only `enc_act` carries a gradient: `enc` (the logits) is returned for inspection, a loss term on it contributes
+    nothing (the reference's pretrain_AE loss, trainer.py:327, uses x_dec only)."""
     if noise is None:
         B, _, T = x.shape
         noise = gumbel_from_uniform(torch.rand(B, encoder.t8(T), encoder.enc_size)).to(x.device)
-    return _EncodeFn.apply(encoder, x, noise, dropout_seed, *encoder.parameters())
+    seed_dev = None
+    if dropout_seed is None:
+        seed_dev = torch.randint(0, 2 ** 62, (1,), dtype=torch.int64, device=x.device)
+        dropout_seed = 0
+    _last_scale[0] = None
+    return _EncodeFn.apply(encoder, x, noise, dropout_seed, seed_dev, *encoder.parameters())
 
 
 def decode_step(decoder, enc_act, c):
