@@ -397,7 +397,7 @@ def sub_config5(dev, operand):
     for enc_size in (512, 1024):
         enc, dec, gen = build_models(dev, operand, enc_size, generator=True)
         path = AutoencoderPath(enc, dec, gen, g_mode='targeted', device=dev)
-        path.convert_utterances(specs[:8], spk[:8], enc_only=False, noise_seed=1, as_ids=True)      # warm-up: packing, workspaces
+        path.convert_utterances(specs, spk, enc_only=False, noise_seed=1, as_ids=True)      # warm-up: packing, workspaces, pinned staging
         torch.cuda.synchronize(dev)
         ms3, fl3, cnt = (C.c_double * 3)(), (C.c_double * 3)(), (C.c_longlong * 3)()
         lib.zs_profile_begin()
@@ -445,6 +445,70 @@ def sub_eager(dev):
             out[f'b{B}'] = {'ms_per_call': ms, 'frames_per_s': B * FRAMES / ms * 1e3}
             del xs, cs, nz
             torch.cuda.empty_cache()
+    return out
+
+
+def sub_dsp(dev, enc, dec, peaks):
+    """SURVEY 8f rows 1 and 3 next to the path: featurisation (preprocess.py:231-256) and the Griffin-Lim vocoder
+    (convert.py:39-62, 300 iterations), and the wav -> wav variant where only waveforms cross PCIe."""
+    import numpy as np
+    from zs_b200 import _lib, dsp
+    lib = _lib.lib()
+    n_utt, frames = 64, 512
+    L = 200 * (frames - 1) + 100
+    rng = np.random.Generator(np.random.PCG64(5))
+    wavs = [(0.1 * rng.standard_normal(L)).astype(np.float32) for _ in range(n_utt)]
+    wav_dev = [torch.from_numpy(w).to(dev) for w in wavs]
+    hbm = peaks.get('hbm_gbs', 6550.0)
+    out = {'workload': f'{n_utt} utterances x {frames} frames ({n_utt * frames} frames, {L} samples each)'}
+    dsp.get_spectrograms(wav_dev[:4], device=dev, to_host=False)
+
+    def prof(fn):
+        ms3, fl3, cnt = (C.c_double * 3)(), (C.c_double * 3)(), (C.c_longlong * 3)()
+        torch.cuda.synchronize(dev)
+        lib.zs_profile_begin()
+        r = fn()
+        _lib.check(lib.zs_profile_end(ms3, fl3, cnt))
+        return r, ms3[2], fl3[2], int(cnt[2])
+    specs, ms, fl, _ = prof(lambda: dsp.get_spectrograms(wav_dev, device=dev, dtype=torch.float16, to_host=False))
+    nf = n_utt * frames
+    by = n_utt * L * 4 + nf * 513 * 2
+    out['featurisation'] = {'kernel_ms': ms, 'frames_per_s': nf / ms * 1e3, 'algorithmic_gb_per_s': by / (ms * 1e-3) / 1e9,
+                            'frac_of_hbm_peak': by / (ms * 1e-3) / 1e9 / hbm, 'gflop_per_s': fl / (ms * 1e-3) / 1e9,
+                            'what': 'wav fp32 in -> fp16 (T, 513) encoder-input rows out, one kernel'}
+    rows = torch.cat(specs).float()
+    gl = dsp.GriffinLim(dev, n_iter=300)
+    gl.synthesize(rows[:4 * frames], [frames] * 4, trim=False, to_host=False)
+    _, ms, fl, launches = prof(lambda: gl.synthesize(rows, [frames] * n_utt, trim=False, to_host=False))
+    by = 300 * nf * 513 * (8 + 8 + 4) + nf * 513 * 8
+    out['griffin_lim_300'] = {'kernel_ms': ms, 'frames_per_s': nf / ms * 1e3, 'launches': launches,
+                              'algorithmic_gb_per_s': by / (ms * 1e-3) / 1e9, 'frac_of_hbm_peak': by / (ms * 1e-3) / 1e9 / hbm,
+                              'fft_gflop_per_s': fl / (ms * 1e-3) / 1e9,
+                              'what': 'per iteration and frame: 513 complex64 in + 513 fp32 magnitudes in + 513 complex64 out (20.5 KB); '
+                                      '2.23 real 1024-point FFTs (shared-memory radix-8, fp32)'}
+    # wav -> wav: pinned waveforms up, waveforms down; spectrograms never leave the device
+    wav_host = torch.from_numpy(np.stack(wavs)).pin_memory()
+    segs_per_utt = frames // FRAMES
+    seeds = torch.arange(n_utt * segs_per_utt, dtype=torch.int64, device=dev) * 7919 + 1
+    c = torch.zeros(n_utt * segs_per_utt, dtype=torch.int64, device=dev)
+
+    def wav2wav():
+        w = wav_host.to(dev, non_blocking=True)
+        sp = dsp.get_spectrograms([w[i] for i in range(n_utt)], device=dev, dtype=torch.float16, to_host=False)
+        x = torch.stack(sp).view(n_utt * segs_per_utt, FRAMES, 513)
+        _, _, ids = enc.encode(x, None, layout='ntc', noise_seeds=seeds, want_act=False, want_logits=False)
+        y = dec.decode(None, c, unit_ids=ids)                                   # (n, 513, 128)
+        rows_ = y.permute(0, 2, 1).reshape(n_utt * frames, 513)
+        return gl.synthesize(rows_, [frames] * n_utt, trim=False, to_host=True)
+    wav2wav()
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    res = wav2wav()
+    torch.cuda.synchronize(dev)
+    t = time.perf_counter() - t0
+    out['wav_to_wav'] = {'frames_per_s': nf / t, 'ms': t * 1e3, 'h2d_bytes': n_utt * L * 4, 'd2h_bytes': int(sum(len(r) for r in res)) * 4,
+                         'spectrogram_path_bytes_for_comparison': {'h2d': nf * 513 * 2, 'd2h': nf * 513 * 4},
+                         'what': 'featurise -> Encoder -> Decoder -> Griffin-Lim x 300 -> de-emphasis; wall clock, one batch'}
     return out
 
 
@@ -831,6 +895,10 @@ def run_ours(args):
         if extras and world == 1:
             line['configs'] = sub_small_batches(enc, dec, dev)
             line['configs']['config5_patcher_2000_frames'] = sub_config5(dev, args.operand)
+            try:
+                line['dsp'] = sub_dsp(dev, enc, dec, peaks)
+            except Exception as exc:
+                line['dsp'] = {'unavailable': f'{type(exc).__name__}: {exc}'[:300]}
             try:
                 line['cuda_eager_baseline'] = sub_eager(dev)
                 line['cuda_eager_baseline']['ours_vs_eager_b960'] = (value / world) / line['cuda_eager_baseline']['b960']['frames_per_s']

@@ -171,6 +171,70 @@ int zs_decoder_forward(zs_decoder* h, const float* enc_act, const int32_t* unit_
                        int B, int T8, float* spec, int accumulate,
                        void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- Spectrogram_Patcher (model/model.py:503-549): the TTS patcher of g_mode 'spectrogram' (trainer.py:78-79), applied as
+ * x_dec += Generator(x_dec, c - shift) (trainer.py:212-213, 280-281).  Per-frame Linear 513 -> c_h, two dense blocks
+ * conditioned on emb1, bi-GRU on out + emb2, dense5 on cat([out, rnn, emb2]), Linear -> sigmoid: the recurrent tail of the
+ * Decoder on a spectrogram input, run by the same kernels. */
+typedef struct zs_patcher zs_patcher;
+typedef struct {
+    int32_t c_in;         /* 513 */
+    int32_t c_out;        /* 513 */
+    int32_t c_h;          /* emb_size */
+    int32_t c_a;          /* n_target_speakers */
+    int32_t operand;
+    float ns;
+} zs_patcher_cfg;
+typedef struct {
+    const float* input_w;       /* input_layer (c_h, c_in) */
+    const float* input_b;
+    const float* dense_w[4];    /* (c_h, c_h) */
+    const float* dense_b[4];
+    const float* gru_w_ih[2];   /* (3*c_h/2, c_h) */
+    const float* gru_w_hh[2];
+    const float* gru_b_ih[2];
+    const float* gru_b_hh[2];
+    const float* dense5_w;      /* (c_h, 3*c_h) */
+    const float* dense5_b;
+    const float* linear_w;      /* (c_out, c_h) */
+    const float* linear_b;
+    const float* emb[2];        /* emb1, emb2 (c_a, c_h) */
+} zs_patcher_weights;
+int zs_patcher_pack(const zs_patcher_cfg* cfg, const zs_patcher_weights* w, void* stream, zs_patcher** out);
+void zs_patcher_free(zs_patcher* h);
+size_t zs_patcher_workspace_bytes(const zs_patcher* h, int B, int T);
+/* x (B, c_in, T) fp32, spk (B,) int64 in [0, c_a), spec (B, c_out, T) fp32; accumulate as in zs_decoder_forward (x and
+ * spec may alias: the input is consumed by the first kernel, the output written by the last). T <= 256. */
+int zs_patcher_forward(zs_patcher* h, const float* x, const int64_t* spk, int B, int T, float* spec, int accumulate,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- the DSP steps either side of the path: Griffin-Lim vocoder and featurisation --------------------
+ * Constants are the reference's (hps/hps.py:22-33): 16 kHz, n_fft 1024, hop 200, Hann window of 800, 513 bins,
+ * max_db 100, ref_db 20.  A batch holds U utterances back to back; `meta` is a DEVICE int32 array of 3 x (U + 1) prefix
+ * sums: frame_start[u], sample_start[u], tile_start[u] with tiles per utterance = ceil(frames / zs_stft_tile_frames()).
+ * librosa (stft / istft: centre = True, reflect padding, window sum-of-squares normalisation) is not part of the
+ * reference tree; its published algorithm is restated in oracle/dsp_oracle.py, which the tests hold these kernels to. */
+int zs_stft_tile_frames(void);
+size_t zs_griffin_lim_workspace_bytes(long long total_frames, long long total_samples);
+/* spectrogram2wav (convert.py:55-62) up to (not including) the final librosa.effects.trim:
+ *   spec  [total_frames][513] fp32 normalised log-magnitude rows (the Decoder's output, transposed to frames-major);
+ *         every utterance needs >= 4 frames
+ *   wav   [total_samples] fp32; utterance u has 200 * (frames_u - 1) samples at sample_start[u]
+ * = de-normalise, n_iter x { istft, stft, X = mag * est / max(1e-8, |est|) } (convert.py:39-52; one fused kernel per
+ * iteration, the waveform stays in shared memory), final istft, de-pre-emphasis y[t] = x[t] + preemphasis * y[t-1]. */
+int zs_griffin_lim(const float* spec, const int32_t* meta, int U, long long total_frames, long long total_samples,
+                   int total_tiles, int n_iter, float preemphasis, float* wav,
+                   void* workspace, size_t workspace_bytes, void* stream);
+/* mean-square power of the centred 2048-sample frames (hop 512, reflect padding) librosa.effects.trim thresholds
+ * (convert.py:61); pframe_start = device prefix sums of 1 + samples_u / 512; power[pframe_start[u] + f]. */
+int zs_frame_power(const float* wav, const int32_t* sample_start, const int32_t* pframe_start, int U, int max_frames,
+                   float* power, void* stream);
+/* get_spectrograms (preprocess.py:233-256) after file decoding / trimming: pre-emphasis, stft, magnitude,
+ * 20 log10(max(1e-5, .)), clip((db - 20 + 100) / 100, 1e-8, 1) -> [total_frames][513] rows, fp32 and / or fp16 (either may
+ * be NULL; the fp16 rows are the encoder's ZS_X_F16 / ZS_X_NTC input).  frames_u = 1 + samples_u / 200, samples_u >= 513;
+ * here sample_start are prefix sums of the INPUT lengths. */
+int zs_spectrogram(const float* wav, const int32_t* meta, int U, int total_tiles, float preemphasis,
+                   float* spec32, void* spec16, void* stream);
+
 /* ---- pretrain_AE step (trainer.py:321-332: encode_step, decode_step, L1 loss, backward, clip, Adam) -------------
  *
  * Training handles are packed with cfg.train = 1 and re-packed from the updated fp32 parameters after every

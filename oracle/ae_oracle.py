@@ -214,21 +214,56 @@ def decoder_forward(sd, enc_act, c, ns=0.01, seg_len=128, output_mask=False):
     return torch.tanh(out) if output_mask else torch.sigmoid(out)                             # :361-364
 
 
+def spectrogram_patcher_forward(sd, x, c, ns=0.01):
+    """Spectrogram_Patcher.forward: model/model.py:525-549 (emb1 conditions both dense blocks, emb2 the GRU input and the
+    appended channels; every layer is per-frame, so no padding mode is involved)."""
+    e1, e2 = sd['emb1.weight'][c], sd['emb2.weight'][c]
+    out = frame_linear(x, sd['input_layer.weight'], sd['input_layer.bias'])                    # :533-534
+    out = _dec_dense_block(out, sd, ['dense1', 'dense2'], e1, ns)                             # :536
+    out = _dec_dense_block(out, sd, ['dense3', 'dense4'], e1, ns)                             # :537
+    rnn = bi_gru(out + e2.unsqueeze(2), sd)                                                   # :538-541
+    out = torch.cat([out, rnn, e2.unsqueeze(2).expand(-1, -1, out.shape[2])], dim=1)          # :542-543
+    out = F.leaky_relu(frame_linear(out, sd['dense5.weight'], sd['dense5.bias']), ns)         # :544-545
+    return torch.sigmoid(frame_linear(out, sd['linear.weight'], sd['linear.bias']))           # :546-548
+
+
+def enhanced_generator_forward(sd, x, c, ns=0.01, seg_len=128):
+    """Enhanced_Generator.forward: model/model.py:499-502 - Encoder(enc_mode='continues') -> Decoder."""
+    enc_sd = {k[len('Encoder.'):]: v for k, v in sd.items() if k.startswith('Encoder.')}
+    dec_sd = {k[len('Decoder.'):]: v for k, v in sd.items() if k.startswith('Decoder.')}
+    act, _, _ = encoder_forward(enc_sd, x, None, ns, seg_len, 'continues')
+    return decoder_forward(dec_sd, act, c, ns, seg_len)
+
+
+def combine_generator(x_dec, act, c, gen_sd, g_mode, shift, ns=0.01, seg_len=128):
+    """The patcher combine rules shared by Trainer.test_step (trainer.py:206-213) and Trainer.gen_step (:274-281)."""
+    if g_mode == 'naive':                                     # :206-207 / :274-275
+        return x_dec + decoder_forward(gen_sd, act, c, ns, seg_len)
+    if g_mode == 'targeted':                                  # :208-209 / :276-277
+        return x_dec + decoder_forward(gen_sd, act, c - shift, ns, seg_len)
+    if g_mode == 'targeted_residual':                         # :210-211 / :278-279
+        return x_dec + x_dec * decoder_forward(gen_sd, act, c - shift, ns, seg_len, output_mask=True)
+    if g_mode == 'enhanced':                                  # :212-213 / :280-281
+        return x_dec + enhanced_generator_forward(gen_sd, x_dec, c - shift, ns, seg_len)
+    if g_mode == 'spectrogram':
+        return x_dec + spectrogram_patcher_forward(gen_sd, x_dec, c - shift, ns)
+    raise NotImplementedError(g_mode)
+
+
 def test_step(enc_sd, dec_sd, x, c, uniform, ns=0.01, seg_len=128, enc_mode='one_hot',
               gen_sd=None, g_mode='targeted', shift=100):
     """Trainer.test_step: trainer.py:194-221 (enc_only when gen_sd is None)."""
     act, logits, ids = encoder_forward(enc_sd, x, uniform, ns, seg_len, enc_mode)
     x_dec = decoder_forward(dec_sd, act, c, ns, seg_len)
     if gen_sd is not None:
-        if g_mode == 'naive':                                 # :206-207
-            x_dec = x_dec + decoder_forward(gen_sd, act, c, ns, seg_len)
-        elif g_mode == 'targeted':                            # :208-209
-            x_dec = x_dec + decoder_forward(gen_sd, act, c - shift, ns, seg_len)
-        elif g_mode == 'targeted_residual':                   # :210-211
-            x_dec = x_dec + x_dec * decoder_forward(gen_sd, act, c - shift, ns, seg_len, output_mask=True)
-        else:
-            raise NotImplementedError(g_mode)
+        x_dec = combine_generator(x_dec, act, c, gen_sd, g_mode, shift, ns, seg_len)
     return x_dec, act, logits, ids
+
+
+def gen_step(dec_sd, gen_sd, enc_act, c, g_mode='targeted', shift=100, ns=0.01, seg_len=128):
+    """Trainer.gen_step: trainer.py:272-284 - x_dec = Decoder(enc, c) combined with the Generator's output."""
+    x_dec = decoder_forward(dec_sd, enc_act, c, ns, seg_len)
+    return combine_generator(x_dec, enc_act, c, gen_sd, g_mode, shift, ns, seg_len)
 
 
 # ----------------------------------------------------------------------------

@@ -126,6 +126,19 @@ def test_write_encodings_format(tmp_path):
     assert p.read_text() == '0 1 0\n1 0 0\n'
 
 
+def test_write_unit_ids_equals_write_encodings(tmp_path):
+    """convert.py:120-126: the fast id writer produces byte-identical files to the reference format written from one-hot rows."""
+    rng = np.random.default_rng(0)
+    for enc_size, n in ((1024, 37), (6, 5), (512, 1), (32, 0)):
+        ids = rng.integers(0, enc_size, size=n)
+        a, b = tmp_path / 'a.txt', tmp_path / 'b.txt'
+        frontend.write_unit_ids(str(a), ids, enc_size)
+        frontend.write_encodings(str(b), frontend.one_hot_rows(ids, enc_size))
+        assert a.read_bytes() == b.read_bytes()
+    with pytest.raises(RuntimeError):
+        frontend.write_unit_ids(str(tmp_path / 'c.txt'), [7], 6)
+
+
 def test_synthetic_is_deterministic():
     a, b = syn.encoder_state_dict(0, enc_size=32, c_in=33, c_h1=16, c_h2=64, c_h3=16), \
         syn.encoder_state_dict(0, enc_size=32, c_in=33, c_h1=16, c_h2=64, c_h3=16)

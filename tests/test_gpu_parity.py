@@ -609,3 +609,85 @@ def test_trainer_test_step_surface(full_models, g_mode):
     if g_mode != 'naive':
         with pytest.raises(RuntimeError):
             path.test_step(x, torch.tensor([3, 101]), enc_only=False, noise=noise)   # not a target speaker
+
+
+# ------------------------------------------------------------------------------------------------
+# alternate TTS patchers (model/model.py:492-552) and their Trainer combine rule
+# ------------------------------------------------------------------------------------------------
+from test_oracle_golden import PATCHER_CASES, patcher_inputs       # noqa: E402
+from conftest import load_golden as _load_golden                   # noqa: E402
+
+
+def build_patcher(m, sd):
+    from zs_b200.patchers import Enhanced_Generator, Spectrogram_Patcher
+    if m['kind'] == 'spectrogram':
+        net = Spectrogram_Patcher(c_in=m['c_in'], c_out=m['c_in'], c_h=m['c_h'], c_a=m['c_a'], ns=0.01, seg_len=128)
+    else:
+        net = Enhanced_Generator(ns=0.01, dp=0.5, enc_size=m['enc_size'], emb_size=m['emb_size'], seg_len=128, n_speakers=m['n_spk'])
+        if m['c_in'] != 513:      # narrow fixture: the reference hard-codes the widths, the fixture script rebuilt the parts
+            net.Encoder = Encoder(c_in=m['c_in'], c_h1=m['c_h'][0], c_h2=m['c_h'][1], c_h3=m['c_h'][2], ns=0.01, dp=0.5,
+                                  enc_size=m['enc_size'], seg_len=128, enc_mode='continues')
+            net.Decoder = Decoder(c_in=m['enc_size'], c_out=m['c_in'], c_h=m['emb_size'], c_a=m['n_spk'], ns=0.01, seg_len=128)
+    net.load_state_dict(sd, strict=True)
+    return net.cuda().eval()
+
+
+@pytest.mark.parametrize('name', PATCHER_CASES)
+def test_patchers_match_reference_golden(name):
+    g = _load_golden(name)
+    m = g['meta']
+    sd, x, c = patcher_inputs(g)
+    net = build_patcher(m, sd)
+    assert list(net.state_dict().keys()) == list(sd.keys())          # checkpoint contract: same names, same order
+    y = net(x.cuda(), c.cuda())
+    ref = torch.from_numpy(g['out'])
+    assert relrms(y.cpu(), ref) < SPEC_RELRMS and (y.cpu() - ref).abs().max().item() < SPEC_MAXABS
+    # fused combine rule: x_dec += Generator(x_dec, c) with the output aliasing the input (trainer.py:212-213)
+    xd = x.cuda().clone()
+    net.patch(xd, c.cuda(), out=xd, accumulate=1)
+    assert torch.allclose(xd.cpu(), x + y.cpu(), atol=1e-6)
+
+
+@pytest.mark.parametrize('g_mode', ['enhanced', 'spectrogram'])
+def test_trainer_test_step_with_alternate_patchers(full_models, g_mode):
+    """Trainer.test_step(enc_only=False) for g_mode enhanced / spectrogram (trainer.py:212-213) against the oracle."""
+    from zs_b200.patchers import Enhanced_Generator, Spectrogram_Patcher
+    enc, dec, enc_sd, dec_sd = full_models
+    if g_mode == 'spectrogram':
+        gen_sd = syn.patcher_state_dict(4, c_in=513, c_out=513, c_h=1024, c_a=2)
+        gen = Spectrogram_Patcher(ns=0.01, c_in=513, c_h=1024, c_a=2, seg_len=128)          # trainer.py:79
+    else:
+        gen_sd = syn.enhanced_generator_state_dict(4)
+        gen = Enhanced_Generator(ns=0.01, dp=0.5, enc_size=1024, emb_size=1024, seg_len=128, n_speakers=102)   # trainer.py:77
+    gen.load_state_dict(gen_sd, strict=True)
+    path = AutoencoderPath(enc, dec, gen, g_mode=g_mode)
+    B, T = 2, 128
+    x = syn.spectrogram_batch(B, T, 81)
+    c = torch.tensor([100, 101])
+    u = syn.gumbel_uniform((B, 16, 1024), 81)
+    x_dec, enc_np = path.test_step(x.permute(0, 2, 1), c, enc_only=False, noise=gumbel_from_uniform(u))
+    torch.set_num_threads(os.cpu_count())
+    with torch.no_grad():
+        act = torch.from_numpy(enc_np)
+        o = orc.combine_generator(orc.decoder_forward(dec_sd, act, c), act, c, gen_sd, g_mode, 100)
+    # 'enhanced' chains a second Encoder + Decoder behind the first Decoder: its input already carries the first path's 1e-3
+    # error, which a random-init network amplifies - the stand-alone patchers are held to SPEC_RELRMS above
+    assert relrms(torch.from_numpy(x_dec), o) < (3e-2 if g_mode == 'enhanced' else SPEC_RELRMS)
+    with pytest.raises(RuntimeError, match='target speakers'):
+        path.test_step(x.permute(0, 2, 1), torch.tensor([3, 101]), enc_only=False, noise=gumbel_from_uniform(u))
+
+
+def test_encode_to_files_writes_the_reference_unit_format(full_models, tmp_path):
+    """test_encode (convert.py:342-360): one unit file per utterance, byte-identical to write_encodings of encode()'s rows."""
+    from zs_b200.frontend import encode_to_files, write_encodings
+    enc, dec, _, _ = full_models
+    path = AutoencoderPath(enc, dec, seg_len=128)
+    rng = np.random.Generator(np.random.PCG64(17))
+    named = [(f'utt{i}', np.clip(rng.random((L, 513), dtype=np.float32), 1e-8, 1)) for i, L in enumerate((5, 64, 300))]
+    done = encode_to_files(path, named, str(tmp_path), noise_seed=5)
+    assert done == ['utt0', 'utt1', 'utt2']
+    rows = path.encode_utterances([s for _, s in named], noise_seed=5)
+    for (name, _), r in zip(named, rows):
+        write_encodings(str(tmp_path / 'ref.txt'), r)
+        assert (tmp_path / (name + '.txt')).read_bytes() == (tmp_path / 'ref.txt').read_bytes()
+        assert r.shape[1] == 1024 and (r.sum(1) == 1).all()

@@ -463,3 +463,60 @@ def test_reference_training_loop_runs_unchanged_on_the_modules():
             rels[name] = ((logits2.cpu() - l_o).norm() / l_o.norm()).item()
     print('eval logits rel-RMS vs oracle on', rels)
     assert rels['updated'] < 3e-2, rels
+
+
+@pytest.mark.parametrize('g_mode', ['naive', 'targeted', 'targeted_residual'])
+def test_trainer_steps_gen_step_matches_oracle(g_mode):
+    """Trainer.permute_data / encode_step / decode_step / gen_step (trainer.py:238-254, 272-284) in train mode: forward
+    value and the Generator's / Decoder's gradients of a loss on x_gen against the oracle's autograd.  Leaky-relu slope 0.5 and
+    a squared-error loss keep the comparison away from the sign kinks that make per-element gradients ill-conditioned on the toy
+    fixture (see test_train_step_matches_reference); the wiring - which module gets which speaker ids, the combine rule,
+    the gradient paths through x_dec and x_dec * G - is what is under test."""
+    g = load_train_golden('train_small_dp0')
+    m = dict(g['meta'], ns=0.5)
+    enc_sd, dec_sd, x, c, u, keep = train_inputs(g)
+    enc, dec = build_train_models(m)
+    n_spk, n_tgt = m['n_spk'], 2
+    mask = g_mode == 'targeted_residual'
+    c_a = n_spk if g_mode == 'naive' else n_tgt
+    gen_sd = syn.decoder_state_dict(9, c_in=m['enc_size'], c_out=m['c_in'], c_h=m['emb_size'], c_a=c_a)
+    gen = Decoder(c_in=m['enc_size'], c_out=m['c_in'], c_h=m['emb_size'], c_a=c_a, ns=m['ns'], seg_len=m['seg_len'], output_mask=mask)
+    gen.load_state_dict(gen_sd)
+    gen.cuda().train()
+    steps = zt.TrainerSteps(enc, dec, gen, g_mode, n_speakers=n_spk, n_target_speakers=n_tgt)
+    c_t = (c % n_tgt) + (n_spk - n_tgt)                       # target-speaker ids, as the stage-2 loaders provide
+    C_, X = steps.permute_data((c_t, x.permute(0, 2, 1).contiguous()))
+    assert X.shape == x.shape and X.requires_grad and torch.equal(C_.cpu(), c_t)
+    enc.dp = 0.0
+    enc_act, _ = steps.encode_step(X, gumbel_from_uniform(u).cuda())
+    x_gen = steps.gen_step(enc_act.detach(), C_)
+    tgt = X.detach()
+    loss = torch.mean((x_gen - tgt) ** 2)
+    loss.backward()
+    torch.cuda.synchronize()
+    # oracle: same units (checked), autograd over the restatement
+    act_o = enc_act.detach().cpu()
+    dec_p = {k: v.clone().requires_grad_(True) for k, v in dec_sd.items()}
+    gen_p = {k: v.clone().requires_grad_(True) for k, v in gen_sd.items()}
+    x_dec_o = orc.decoder_forward(dec_p, act_o, c_t, m['ns'], m['seg_len'])
+    shift = n_spk - n_tgt
+    if g_mode == 'naive':
+        o = x_dec_o + orc.decoder_forward(gen_p, act_o, c_t, m['ns'], m['seg_len'])
+    elif g_mode == 'targeted':
+        o = x_dec_o + orc.decoder_forward(gen_p, act_o, c_t - shift, m['ns'], m['seg_len'])
+    else:
+        o = x_dec_o + x_dec_o * orc.decoder_forward(gen_p, act_o, c_t - shift, m['ns'], m['seg_len'], output_mask=True)
+    with torch.no_grad():
+        chk = orc.gen_step(dec_sd, gen_sd, act_o, c_t, g_mode, shift, m['ns'], m['seg_len'])
+    assert torch.allclose(chk, o.detach(), atol=1e-6)
+    assert ((x_gen.detach().cpu() - o.detach()).norm() / o.detach().norm()).item() < 1e-2
+    loss_o = torch.mean((o - x) ** 2)
+    loss_o.backward()
+    assert abs(loss.item() - loss_o.item()) <= 2e-3 * loss_o.item()
+    tot = lambda gs: torch.sqrt(sum(v.norm() ** 2 for v in gs)).item()
+    for mod, ps in ((gen, gen_p), (dec, dec_p)):
+        go = torch.cat([ps[k].grad.reshape(-1) for k, _ in mod.named_parameters()])
+        gg = torch.cat([p.grad.detach().cpu().reshape(-1) for _, p in mod.named_parameters()])
+        assert torch.isfinite(gg).all()
+        # whole-network gradient direction and size (per-tensor kink noise: see test_train_step_matches_reference)
+        assert cos(gg, go) >= 0.97 and 0.85 <= gg.norm().item() / go.norm().item() <= 1.18, (cos(gg, go), gg.norm().item(), go.norm().item())

@@ -164,3 +164,31 @@ def test_torch_module_baseline_matches_the_oracle():
             o_act, o_logits, _ = orc.encoder_forward(esd, x, u)
             o_spec = orc.decoder_forward(dsd, o_act, c)
         assert (logits - o_logits).abs().max() < 1e-4 and torch.equal(act, o_act) and (spec - o_spec).abs().max() < 1e-5
+
+
+PATCHER_CASES = ['patcher_small', 'patcher_small_t207', 'patcher_full', 'enhanced_small', 'enhanced_full']
+
+
+def patcher_inputs(g):
+    m = g['meta']
+    x = syn.spectrogram_batch(m['B'], m['T'], 900 + m['seed'], c_in=m['c_in'])
+    if m['kind'] == 'spectrogram':
+        sd = syn.patcher_state_dict(m['seed'], c_in=m['c_in'], c_out=m['c_in'], c_h=m['c_h'], c_a=m['c_a'])
+    else:
+        sd = syn.enhanced_generator_state_dict(m['seed'], c_in=m['c_in'], c_h1=m['c_h'][0], c_h2=m['c_h'][1], c_h3=m['c_h'][2],
+                                               enc_size=m['enc_size'], emb_size=m['emb_size'], n_speakers=m['n_spk'])
+    return sd, x, torch.from_numpy(g['c'])
+
+
+@pytest.mark.parametrize('name', PATCHER_CASES)
+def test_oracle_patchers_match_live_reference(name):
+    """Spectrogram_Patcher / Enhanced_Generator (model/model.py:492-552): the oracle's restatement against outputs of the
+    live reference modules (tests/golden/make_golden_patchers.py)."""
+    g = load_golden(name)
+    sd, x, c = patcher_inputs(g)
+    torch.set_num_threads(os.cpu_count())
+    with torch.no_grad():
+        y = (orc.spectrogram_patcher_forward(sd, x, c) if g['meta']['kind'] == 'spectrogram'
+             else orc.enhanced_generator_forward(sd, x, c))
+    assert y.shape == g['out'].shape
+    assert np.abs(y.numpy() - g['out']).max() <= 2e-5

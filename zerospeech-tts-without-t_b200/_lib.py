@@ -77,6 +77,18 @@ class DecoderWeights(C.Structure):
                 ('input_emb_w', C.c_void_p), ('input_emb_b', C.c_void_p), ('emb', C.c_void_p * 5)]
 
 
+class PatcherCfg(C.Structure):
+    _fields_ = [('c_in', C.c_int32), ('c_out', C.c_int32), ('c_h', C.c_int32), ('c_a', C.c_int32), ('operand', C.c_int32),
+                ('ns', C.c_float)]
+
+
+class PatcherWeights(C.Structure):
+    _fields_ = [('input_w', C.c_void_p), ('input_b', C.c_void_p), ('dense_w', C.c_void_p * 4), ('dense_b', C.c_void_p * 4),
+                ('gru_w_ih', C.c_void_p * 2), ('gru_w_hh', C.c_void_p * 2), ('gru_b_ih', C.c_void_p * 2),
+                ('gru_b_hh', C.c_void_p * 2), ('dense5_w', C.c_void_p), ('dense5_b', C.c_void_p), ('linear_w', C.c_void_p),
+                ('linear_b', C.c_void_p), ('emb', C.c_void_p * 2)]
+
+
 class ConvDesc(C.Structure):
     _fields_ = [('w', C.c_void_p), ('m_rows', C.c_int32), ('m_valid', C.c_int32), ('taps', C.c_int32),
                 ('c_in_pad', C.c_int32), ('w_taps', C.c_int32), ('bank', C.c_int32),
@@ -115,6 +127,15 @@ SYMBOLS = {
     'zs_encoder_forward': (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     'zs_encoder_forward_x': (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     'zs_decoder_forward': (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _i, _vp, _sz, _vp]),
+    'zs_patcher_pack': (_i, [C.POINTER(PatcherCfg), C.POINTER(PatcherWeights), _vp, C.POINTER(_vp)]),
+    'zs_patcher_free': (None, [_vp]),
+    'zs_patcher_workspace_bytes': (_sz, [_vp, _i, _i]),
+    'zs_patcher_forward': (_i, [_vp, _vp, _vp, _i, _i, _vp, _i, _vp, _sz, _vp]),
+    'zs_stft_tile_frames': (_i, []),
+    'zs_griffin_lim_workspace_bytes': (_sz, [C.c_longlong, C.c_longlong]),
+    'zs_griffin_lim': (_i, [_vp, _vp, _i, C.c_longlong, C.c_longlong, _i, _i, C.c_float, _vp, _vp, _sz, _vp]),
+    'zs_frame_power': (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp]),
+    'zs_spectrogram': (_i, [_vp, _vp, _i, _i, C.c_float, _vp, _vp, _vp]),
     'zs_profile_begin': (None, []),
     'zs_profile_end': (_i, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
     'zs_profile_detail': (_i, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int), _i]),

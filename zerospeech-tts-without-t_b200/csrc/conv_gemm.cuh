@@ -228,6 +228,8 @@ __device__ __forceinline__ void frames_to_staging(const GemmParams& p, uint32_t 
             }
         }
         OT y[16];
+        // fp16 range check covers what is STORED: valid channels, frames below T (padding columns hold garbage by design)
+        const int sat_lim = (ch_ok && !IS_BF16<OT>::value) ? min(16, T - c0) : 0;
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
             float x = __uint_as_float(v[i]) + cn.bias;
@@ -235,7 +237,7 @@ __device__ __forceinline__ void frames_to_staging(const GemmParams& p, uint32_t 
             x = fmaf(x, cn.scale, cn.shift);
             if (RES != RES_NONE) x += r[i];
             x += cn.post;
-            if (sizeof(OT) == 2 && !IS_BF16<OT>::value) sat |= fabsf(x) > 65504.f;
+            sat |= (i < sat_lim) && fabsf(x) > 65504.f;
             y[i] = p.no_sat ? float_to_ot_nosat<OT>(x) : float_to_ot<OT>(x);
         }
         OT* sp = stg + (c0 - f_lo) * (FSTEP * STG_PITCH);

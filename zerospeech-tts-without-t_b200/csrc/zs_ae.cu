@@ -1069,6 +1069,46 @@ static int run_layer(const Layer& L, int operand, float ns, const Buf& in, int B
     return launch_conv(&d, st, &ex);
 }
 
+// -------------------------------------------------------------------------------------------------
+// The recurrent tail shared by the Decoder (model/model.py:350-364) and the Spectrogram_Patcher (model/model.py:536-549):
+// two dense blocks conditioned on one embedding, bi-GRU on out + a second embedding, dense5 on cat([out, rnn, emb]) ->
+// lrelu -> linear -> sigmoid | tanh.  All speaker terms are folded into per-speaker bias tables at pack time.
+// -------------------------------------------------------------------------------------------------
+struct TailNet {
+    const Layer* dense;      // [4]
+    const Layer* gru_ih;
+    const float* whhT; const float* bhh; const void* whh_img;
+    const Layer* dense5; const Layer* linear;
+    int ch, output_mask, op; float ns;
+};
+struct TailBufs { const Buf* in; Buf* d; Buf* catr; Buf* d5; Buf* gx; Buf* xch; };
+static int run_tail(const TailNet& n, const TailBufs& w, const int64_t* spk, int B, int Tf, float* spec, int accumulate, cudaStream_t st) {
+    const int op = n.op, ch = n.ch;
+    const float ns = n.ns;
+    {   // two dense blocks, both conditioned on the same embedding (Decoder: emb4 twice, model/model.py:350-351)
+        ConvOpts o; o.spk = spk;
+        ZS_TRY(run_layer(n.dense[0], op, ns, *w.in, B, Tf, &w.d[0], nullptr, 0, 0, o, st));
+        ConvOpts r; r.inorm = 1; r.res_mode = RES_SAME; r.res = w.in; r.spk = spk;
+        ZS_TRY(run_layer(n.dense[1], op, ns, w.d[0], B, Tf, &w.d[1], nullptr, 0, 0, r, st));
+        ZS_TRY(run_layer(n.dense[2], op, ns, w.d[1], B, Tf, &w.d[2], nullptr, 0, 0, o, st));
+        ConvOpts r2; r2.inorm = 1; r2.res_mode = RES_SAME; r2.res = &w.d[1]; r2.spk = spk;
+        ZS_TRY(run_layer(n.dense[3], op, ns, w.d[2], B, Tf, w.catr, nullptr, 0, 0, r2, st));
+    }
+    {   // bi-GRU on out + emb (model/model.py:352-355)
+        ConvOpts o; o.lrelu = 0; o.c_in_valid = ch; o.spk = spk;
+        ZS_TRY(run_layer(*n.gru_ih, op, ns, *w.catr, B, Tf, w.gx, nullptr, 0, 0, o, st));
+        if (n.whh_img) ZS_TRY(launch_gru_cluster(n.whh_img, n.bhh, w.gx->p, B, Tf, ch / 2, w.catr->p, w.catr->rows, w.catr->pitch, 0, ch, op, st, nullptr, w.xch->p, static_cast<size_t>(w.xch->rows) * w.xch->pitch * 2 * round_up(B, 128)));
+        else ZS_TRY(launch_gru(w.gx->p, n.whhT, n.bhh, B, Tf, ch / 2, w.catr->p, w.catr->rows, w.catr->pitch, 0, ch, op, st));
+    }
+    {   // dense5 on cat([out, rnn, emb]) -> lrelu -> linear -> sigmoid | tanh (model/model.py:356-364)
+        ConvOpts o; o.spk = spk;
+        ZS_TRY(run_layer(*n.dense5, op, ns, *w.catr, B, Tf, w.d5, nullptr, 0, 0, o, st));
+        ConvOpts f; f.lrelu = 0; f.act = n.output_mask ? ACT_TANH : ACT_SIGMOID; f.out_mode = OUT_NCT32; f.accumulate = accumulate;
+        ZS_TRY(run_layer(*n.linear, op, ns, *w.d5, B, Tf, nullptr, spec, 0, 0, f, st));
+    }
+    return ZS_OK;
+}
+
 extern "C" int zs_encoder_forward(zs_encoder* h, const float* x, int B, int T, const float* gumbel_noise, float* logits,
                                   float* act, int32_t* unit_ids, void* workspace, size_t workspace_bytes, void* stream) {
     if (!logits) return fail(ZS_ERR_ARG, "encoder_forward: null argument");
@@ -1186,28 +1226,89 @@ extern "C" int zs_decoder_forward(zs_decoder* h, const float* enc_act, const int
         xin = &w.y[blk];
     }
     const int Tf = 8 * T8;
-    {   // :350-351 two dense blocks, both conditioned on emb4
-        ConvOpts o; o.spk = spk;
-        ZS_TRY(run_layer(h->dense[0], op, ns, w.y[2], B, Tf, &w.d[0], nullptr, 0, 0, o, st));
-        ConvOpts r; r.inorm = 1; r.res_mode = RES_SAME; r.res = &w.y[2]; r.spk = spk;
-        ZS_TRY(run_layer(h->dense[1], op, ns, w.d[0], B, Tf, &w.d[1], nullptr, 0, 0, r, st));
-        ZS_TRY(run_layer(h->dense[2], op, ns, w.d[1], B, Tf, &w.d[2], nullptr, 0, 0, o, st));
-        ConvOpts r2; r2.inorm = 1; r2.res_mode = RES_SAME; r2.res = &w.d[1]; r2.spk = spk;
-        ZS_TRY(run_layer(h->dense[3], op, ns, w.d[2], B, Tf, &w.catr, nullptr, 0, 0, r2, st));
+    TailNet net{h->dense, &h->gru_ih, h->whhT, h->bhh, h->whh_img, &h->dense5, &h->linear, ch, g.output_mask, op, ns};
+    TailBufs tb{&w.y[2], w.d, &w.catr, &w.d5, &w.gx, &w.xch};
+    return run_tail(net, tb, spk, B, Tf, spec, accumulate, st);
+}
+
+// -------------------------------------------------------------------------------------------------
+// Spectrogram_Patcher (model/model.py:503-549; Trainer g_mode 'spectrogram', trainer.py:78-79, 212-213)
+// -------------------------------------------------------------------------------------------------
+struct zs_patcher {
+    zs_patcher_cfg cfg;
+    DevPool pool;
+    Layer input, dense[4], gru_ih, dense5, linear;
+    float* whhT = nullptr;
+    float* bhh = nullptr;
+    void* whh_img = nullptr;
+};
+
+extern "C" int zs_patcher_pack(const zs_patcher_cfg* cfg, const zs_patcher_weights* w, void* stream, zs_patcher** out) {
+    if (!cfg || !w || !out) return fail(ZS_ERR_ARG, "patcher_pack: null argument");
+    ZS_TRY(ensure_device());
+    if (cfg->c_h % 64) return fail(ZS_ERR_ARG, "patcher: c_h %d must be a multiple of 64", cfg->c_h);
+    zs_patcher* h = new zs_patcher();
+    h->cfg = *cfg;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int op = cfg->operand, ch = cfg->c_h, ca = cfg->c_a;
+    int rc = pack_layer(h->pool, h->input, op, w->input_w, w->input_b, ch, cfg->c_in, 1, 0, cfg->c_in, 0, nullptr, 0, 0, 1, st);
+    for (int i = 0; i < 4 && rc == ZS_OK; ++i)     // emb1 conditions all four dense layers (model/model.py:538-539)
+        rc = pack_layer(h->pool, h->dense[i], op, w->dense_w[i], w->dense_b[i], ch, ch, 1, 0, ch, 0, w->emb[0], 0, ch, ca, st);
+    if (rc == ZS_OK) rc = pack_gru(h->pool, h->gru_ih, &h->whhT, &h->bhh, &h->whh_img, op, w->gru_w_ih, w->gru_w_hh, w->gru_b_ih, w->gru_b_hh, ch, ch / 2, w->emb[1], ca, st);
+    if (rc == ZS_OK) rc = pack_layer(h->pool, h->dense5, op, w->dense5_w, w->dense5_b, ch, 3 * ch, 1, 0, 2 * ch, 0, w->emb[1], 2 * ch, ch, ca, st);
+    if (rc == ZS_OK) rc = pack_layer(h->pool, h->linear, op, w->linear_w, w->linear_b, cfg->c_out, ch, 1, 0, ch, 0, nullptr, 0, 0, 1, st);
+    if (rc != ZS_OK) {
+        h->pool.release();
+        delete h;
+        return rc;
     }
-    {   // :352-355 bi-GRU on out + emb5
-        ConvOpts o; o.lrelu = 0; o.c_in_valid = ch; o.spk = spk;
-        ZS_TRY(run_layer(h->gru_ih, op, ns, w.catr, B, Tf, &w.gx, nullptr, 0, 0, o, st));
-        if (h->whh_img) ZS_TRY(launch_gru_cluster(h->whh_img, h->bhh, w.gx.p, B, Tf, ch / 2, w.catr.p, w.catr.rows, w.catr.pitch, 0, ch, op, st, nullptr, w.xch.p, static_cast<size_t>(w.xch.rows) * w.xch.pitch * 2 * round_up(B, 128)));
-        else ZS_TRY(launch_gru(w.gx.p, h->whhT, h->bhh, B, Tf, ch / 2, w.catr.p, w.catr.rows, w.catr.pitch, 0, ch, op, st));
-    }
-    {   // :356-364 dense5 on cat([out, rnn, emb5]) -> lrelu -> linear -> sigmoid | tanh
-        ConvOpts o; o.spk = spk;
-        ZS_TRY(run_layer(h->dense5, op, ns, w.catr, B, Tf, &w.d5, nullptr, 0, 0, o, st));
-        ConvOpts f; f.lrelu = 0; f.act = g.output_mask ? ACT_TANH : ACT_SIGMOID; f.out_mode = OUT_NCT32; f.accumulate = accumulate;
-        ZS_TRY(run_layer(h->linear, op, ns, w.d5, B, Tf, nullptr, spec, 0, 0, f, st));
-    }
+    *out = h;
     return ZS_OK;
+}
+extern "C" void zs_patcher_free(zs_patcher* h) {
+    if (!h) return;
+    h->pool.release();
+    delete h;
+}
+
+struct PatWs { Buf xp, x0, d[3], catr, d5, gx, xch; size_t bytes; };
+static PatWs carve_patcher(const zs_patcher* h, void* ws, int B, int T) {
+    PatWs w;
+    Carver c(ws);
+    const int ch = h->cfg.c_h;
+    w.xp = c.act(B, T, 0, h->cfg.c_in);
+    w.x0 = c.act(B, T, 0, ch);
+    for (int i = 0; i < 3; ++i) w.d[i] = c.act(B, T, 0, ch);
+    w.catr = c.act(B, T, 0, 2 * ch);
+    w.d5 = c.act(B, T, 0, ch);
+    w.gx = c.act(B, T, 0, 3 * ch, true);
+    w.xch = c.act(round_up(B, 128), 2, 0, ch / 2);
+    w.bytes = c.off;
+    return w;
+}
+extern "C" size_t zs_patcher_workspace_bytes(const zs_patcher* h, int B, int T) {
+    if (!h || B < 1 || T < 1) return 0;
+    return carve_patcher(h, nullptr, B, T).bytes;
+}
+
+extern "C" int zs_patcher_forward(zs_patcher* h, const float* x, const int64_t* spk, int B, int T, float* spec, int accumulate,
+                                  void* workspace, size_t workspace_bytes, void* stream) {
+    if (!h || !x || !spk || !spec) return fail(ZS_ERR_ARG, "patcher_forward: null argument");
+    if (B < 1 || T < 1 || T > 256) return fail(ZS_ERR_ARG, "patcher_forward: B %d, T %d (T must be in [1, 256])", B, T);
+    if (accumulate < 0 || accumulate > 2) return fail(ZS_ERR_ARG, "patcher_forward: accumulate %d", accumulate);
+    const zs_patcher_cfg& g = h->cfg;
+    t_zero_pad = 0;                        // every layer is per-frame (k = 1): pad_layer never pads here
+    PatWs w = carve_patcher(h, workspace, B, T);
+    if (!workspace || workspace_bytes < w.bytes) return fail(ZS_ERR_WORKSPACE, "patcher_forward: workspace %zu < %zu bytes", workspace_bytes, w.bytes);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    // model/model.py:533-534: out = linear(x, input_layer) - no activation
+    ZS_TRY(launch_pack_nct(x, B, g.c_in, T, w.xp.p, w.xp.rows, w.xp.pitch, 0, 0, 0, g.ns, g.operand, 1, st));
+    ConvOpts o; o.lrelu = 0;
+    ZS_TRY(run_layer(h->input, g.operand, g.ns, w.xp, B, T, &w.x0, nullptr, 0, 0, o, st));
+    TailNet net{h->dense, &h->gru_ih, h->whhT, h->bhh, h->whh_img, &h->dense5, &h->linear, g.c_h, 0, g.operand, g.ns};
+    TailBufs tb{&w.x0, w.d, &w.catr, &w.d5, &w.gx, &w.xch};
+    return run_tail(net, tb, spk, B, T, spec, accumulate, st);
 }
 
 #include "zs_train.cuh"
+#include "zs_dsp.cuh"

@@ -45,6 +45,43 @@ def write_encodings(path, encodings):
             f.write(' '.join(str(int(e)) for e in row) + '\n')
 
 
+def write_unit_ids(path, ids, enc_size):
+    """The file `write_encodings` (convert.py:120-126) produces for one-hot units, written from the unit IDS: every line
+    is enc_size ints, all '0' but a '1' at the unit's position.  One vectorised fill + one write instead of
+    enc_size str() calls per unit frame (the reference formats 1024 Python ints per 100 ms of speech)."""
+    ids = np.asarray(ids).reshape(-1).astype(np.int64)
+    if ids.size and (ids.min() < 0 or ids.max() >= enc_size):
+        raise RuntimeError(f'unit id outside [0, {enc_size})')
+    line = np.frombuffer(('0 ' * enc_size)[:-1].encode() + b'\n', dtype=np.uint8)
+    buf = np.tile(line, (ids.size, 1))
+    buf[np.arange(ids.size), 2 * ids] = ord('1')
+    with open(path, 'wb') as f:
+        f.write(buf.tobytes())
+
+
+def encode_to_files(path, named_specs, out_dir, ext='.txt', noise_seed=None, reference_noise_order=True):
+    """`test_encode` (convert.py:342-360) over in-memory features: every (name, (L, 513) spectrogram) pair becomes
+    `out_dir/name + ext` in the unit-file format the ZeroSpeech scorer reads.  All utterances go through the encoder in
+    large batches and only the ids (4 bytes per unit frame) come back from the device.  `path`: an AutoencoderPath (or a
+    shard.ShardedPath with gather=False semantics: each rank writes the files of its own utterances)."""
+    import os
+    names = [n for n, _ in named_specs]
+    specs = [s for _, s in named_specs]
+    enc = path.Encoder if hasattr(path, 'Encoder') else path.path.Encoder
+    if enc.enc_mode != 'one_hot':
+        units = path.encode_utterances(specs, reference_noise_order, noise_seed=noise_seed)
+        for n, u in zip(names, units):
+            write_encodings(os.path.join(out_dir, n + ext), u)
+        return names
+    if hasattr(path, 'shards'):          # sharded: per-rank file output, nothing is gathered
+        mine, units = path.encode_utterances(specs, reference_noise_order, as_ids=True, noise_seed=noise_seed, gather=False)
+    else:
+        mine, units = range(len(specs)), path.encode_utterances(specs, reference_noise_order, as_ids=True, noise_seed=noise_seed)
+    for i, u in zip(mine, units):
+        write_unit_ids(os.path.join(out_dir, names[i] + ext), u, enc.enc_size)
+    return [names[i] for i in mine]
+
+
 class StreamingResynthesizer:
     """Host-to-host encode -> decode over many 128-frame segments with copies overlapped with compute.
 
@@ -230,76 +267,153 @@ class AutoencoderPath:
         return x_dec
 
     # ---- convert.py:128-221 batched -----------------------------------------------------------
-    def _segments(self, specs):
-        segs = []          # (utt index, order in utt, T, padded spec slice)
-        keeps = []
+    def _plan(self, specs, want):
+        """Chunk plan of every wanted utterance (convert.py:139-165): list of (utt, chunk no, T, first frame, zero-padded frames),
+        plus per utterance the keep_units rule and the output frame offset of every chunk."""
+        segs, keeps, out_off, out_len = [], [], [], []
         for u, spec in enumerate(specs):
-            spec = np.asarray(spec, dtype=np.float32)
             padded, plan, keep = segment_plan(len(spec), self.seg_len)
-            if padded > len(spec):
-                spec = np.concatenate([spec, np.zeros((padded - len(spec), spec.shape[1]), np.float32)], axis=0)
             keeps.append(keep)
+            offs, o = [], 0
             for j, (s, e) in enumerate(plan):
-                segs.append((u, j, e - s, spec[s:e]))
-        return segs, keeps
+                offs.append(o)
+                o += 8 * Encoder.t8(e - s)
+                if u in want:
+                    segs.append((u, j, e - s, s, max(0, e - len(spec))))
+            out_off.append(offs)
+            out_len.append(o)
+        return segs, keeps, out_off, out_len
 
-    def _run(self, specs, speakers, enc_only, decode, reference_noise_order, only=None, as_ids=False, noise_seed=None):
+    def _staging(self, n, T, T_out, decode):
+        """Two sets of pinned host staging buffers (grow-only): segments are gathered into `x` by the host while the previous
+        batch computes, results land in `spec` / `units` by asynchronous D2H and are scattered to the per-utterance arrays."""
+        need_x, need_s = n * T * self.Encoder.c_in, n * T_out * self.Decoder.c_out
+        st = getattr(self, '_stage', None)
+        if st is None or st[0]['x'].numel() < need_x or (decode and st[0]['spec'].numel() < need_s):
+            torch.cuda.synchronize(self.device)
+            grow = lambda old, need: max(need, old.numel() if old is not None else 0)
+            st = [dict(x=torch.empty(grow(None if st is None else st[k]['x'], need_x)).pin_memory(),
+                       spec=torch.empty(grow(None if st is None else st[k]['spec'], need_s if decode else 1)).pin_memory(),
+                       done=None) for k in range(2)]
+            self._stage = st
+        return st
+
+    def _run(self, specs, speakers, enc_only, decode, reference_noise_order, only=None, as_ids=False, noise_seed=None,
+             vocoder=None, trim=True):
         """`only`: utterance indices this process is responsible for (multi-GPU sharding, shard.py).
+        `vocoder` (a dsp.GriffinLim): the decoded rows stay on the device and go straight into spectrogram2wav
+        (convert.py:170) - waveforms are returned in place of spectrograms.
         Noise: `reference_noise_order` draws every chunk's Gumbel noise in the reference's call order from torch's CPU
         generator (bit-identical units; an O(all chunks) serial section on every rank); with `noise_seed` the noise is
         drawn on the device, one stream per (utterance, chunk) - independent of batching and of the sharding."""
-        segs, keeps = self._segments(specs)
         enc = self.Encoder
         one_hot = enc.enc_mode == 'one_hot'
-        noises = None
-        if enc.enc_mode != 'continues' and noise_seed is None and reference_noise_order:
-            noises = [sample_gumbel(enc.noise_shape(1, T)) for (_, _, T, _) in segs]
         if noise_seed is not None and not one_hot:
             raise RuntimeError('device-generated noise exists for enc_mode one_hot only')
         wanted = range(len(specs)) if only is None else list(only)
         want = set(wanted)
+        specs = [np.asarray(s, dtype=np.float32) for s in specs]
+        segs, keeps, out_off, out_len = self._plan(specs, want)
+        noises = None
+        if enc.enc_mode != 'continues' and noise_seed is None and reference_noise_order:
+            # the reference draws per chunk, in call order, for EVERY utterance (also those other ranks own)
+            noises = {}
+            for u, spec in enumerate(specs):
+                for j, (s, e) in enumerate(segment_plan(len(spec), self.seg_len)[1]):
+                    g = sample_gumbel(enc.noise_shape(1, e - s))
+                    if u in want:
+                        noises[(u, j)] = g
+        c_in, c_out = enc.c_in, self.Decoder.c_out
+        # per-utterance results, allocated once and filled chunk by chunk
+        to_wav = decode and vocoder is not None
+        res_specs = {u: np.empty((out_len[u], c_out), np.float32) for u in wanted} if decode and not to_wav else {}
+        if to_wav:      # all decoded rows of the wanted utterances, utterance-major, on the device
+            row0, acc = {}, 0
+            for u in wanted:
+                row0[u] = acc
+                acc += out_len[u]
+            dev_rows = torch.empty(acc, c_out, dtype=torch.float32, device=self.device)
+        res_units = {u: (np.empty(out_len[u] // 8, np.int32) if one_hot else np.empty((out_len[u] // 8, enc.enc_size), np.float32))
+                     for u in wanted}
         by_len = {}
-        for i, (u, _, T, _) in enumerate(segs):
-            if u in want:
-                by_len.setdefault(T, []).append(i)
-        units = [None] * len(segs)
-        outs = [None] * len(segs)
-        for T, idxs in by_len.items():
-            for k in range(0, len(idxs), self.max_batch):
-                chunk = idxs[k:k + self.max_batch]
-                x = torch.from_numpy(np.stack([segs[i][3] for i in chunk])).pin_memory()     # (n, T, 513): consumed as is
-                x = x.to(self.device, non_blocking=True)
-                noise = seeds = None
-                if noises is not None:
-                    noise = torch.cat([noises[i] for i in chunk], dim=0)
-                elif noise_seed is not None:       # stream keyed by (utterance, chunk-in-utterance)
-                    key = torch.tensor([(segs[i][0] << 20) + segs[i][1] for i in chunk], dtype=torch.int64)
-                    seeds = (key.to(self.device) * 0x2545F4914F6CDD1D + int(noise_seed))
-                elif enc.enc_mode != 'continues':
-                    noise = sample_gumbel(enc.noise_shape(len(chunk), T))
-                act, _, ids = enc.encode(x, noise, layout='ntc', noise_seeds=seeds, want_act=not one_hot, want_logits=not one_hot)
-                if decode:
-                    c = torch.tensor([speakers[segs[i][0]] for i in chunk], dtype=torch.int64, device=self.device)
-                    x_dec = self._decode(act, ids, c, enc_only).permute(0, 2, 1).cpu().numpy()
-                # one_hot: 4 bytes per unit frame leave the device instead of 4 * enc_size
-                u_np = ids.cpu().numpy() if one_hot else act.permute(0, 2, 1).cpu().numpy()
-                for n, i in enumerate(chunk):
-                    units[i] = u_np[n]
-                    if decode:
-                        outs[i] = x_dec[n]
+        for i, sg in enumerate(segs):
+            by_len.setdefault(sg[2], []).append(i)
+        batches = [(T, idxs[k:k + self.max_batch]) for T, idxs in by_len.items() for k in range(0, len(idxs), self.max_batch)]
+        pending = None
+        if batches:
+            n_max, T_max = max(len(c) for _, c in batches), max(t for t, _ in batches)
+            self._staging(n_max, T_max, 8 * Encoder.t8(T_max), decode)
+
+        def finish(job):
+            chunk, T_out, T8, k, units_h = job
+            self._stage[k]['done'].synchronize()
+            spec_h = self._stage[k]['spec'][:len(chunk) * T_out * c_out].view(len(chunk), T_out, c_out).numpy() if decode and not to_wav else None
+            u_np = units_h.numpy()
+            for n, i in enumerate(chunk):
+                u, j = segs[i][0], segs[i][1]
+                o = out_off[u][j]
+                if spec_h is not None:
+                    res_specs[u][o:o + T_out] = spec_h[n]
+                res_units[u][o // 8:o // 8 + T8] = u_np[n] if one_hot else u_np[n].T
+
+        for b, (T, chunk) in enumerate(batches):
+            n, T8 = len(chunk), Encoder.t8(T)
+            T_out, k = 8 * T8, b % 2
+            st = self._stage[k]
+            if st['done'] is not None:
+                st['done'].synchronize()
+            xh = st['x'][:n * T * c_in].view(n, T, c_in)
+            xn = xh.numpy()
+            for m, i in enumerate(chunk):                      # gather the chunk rows (zero-padded tail of a MIN_LEN utterance)
+                u, _, _, s0, pad = segs[i]
+                if pad:
+                    xn[m, :T - pad] = specs[u][s0:s0 + T - pad]
+                    xn[m, T - pad:] = 0.0
+                else:
+                    xn[m] = specs[u][s0:s0 + T]
+            x = xh.to(self.device, non_blocking=True)          # (n, T, 513): consumed as is (layout 'ntc')
+            noise = seeds = None
+            if noises is not None:
+                noise = torch.cat([noises[(segs[i][0], segs[i][1])] for i in chunk], dim=0)
+            elif noise_seed is not None:                       # stream keyed by (utterance, chunk-in-utterance)
+                key = torch.tensor([(segs[i][0] << 20) + segs[i][1] for i in chunk], dtype=torch.int64)
+                seeds = (key.to(self.device) * 0x2545F4914F6CDD1D + int(noise_seed))
+            elif enc.enc_mode != 'continues':
+                noise = sample_gumbel(enc.noise_shape(n, T))
+            act, _, ids = enc.encode(x, noise, layout='ntc', noise_seeds=seeds, want_act=not one_hot, want_logits=not one_hot)
+            if decode:
+                c = torch.tensor([speakers[segs[i][0]] for i in chunk], dtype=torch.int64).to(self.device)
+                x_dec = self._decode(act, ids, c, enc_only)
+                if to_wav:
+                    dst = torch.tensor([row0[segs[i][0]] + out_off[segs[i][0]][segs[i][1]] for i in chunk], dtype=torch.int64)
+                    rows = (dst.to(self.device)[:, None] + torch.arange(T_out, device=self.device)[None, :]).reshape(-1)
+                    dev_rows.index_copy_(0, rows, x_dec.permute(0, 2, 1).reshape(-1, c_out))
+                else:
+                    st['spec'][:n * T_out * c_out].view(n, T_out, c_out).copy_(x_dec.permute(0, 2, 1), non_blocking=True)
+            # one_hot: 4 bytes per unit frame leave the device instead of 4 * enc_size
+            units_h = torch.empty((n, T8) if one_hot else (n, enc.enc_size, T8), dtype=torch.int32 if one_hot else torch.float32).pin_memory()
+            units_h.copy_(ids if one_hot else act, non_blocking=True)
+            st['done'] = torch.cuda.Event()
+            st['done'].record()
+            if pending is not None:
+                finish(pending)                                # scatter the previous batch while this one runs
+            pending = (chunk, T_out, T8, k, units_h)
+        if pending is not None:
+            finish(pending)
         check_range(self.device)
-        res_units, res_specs = [], []
+        out_units, out_specs = [], []
         for u in wanted:
-            mine = sorted((j, i) for i, (uu, j, _, _) in enumerate(segs) if uu == u)
-            e = np.concatenate([units[i] for _, i in mine], axis=0)
+            e = res_units[u]
             if keeps[u] is not None:
                 e = e[:keeps[u]]
             if one_hot and not as_ids:
                 e = one_hot_rows(e, enc.enc_size)
-            res_units.append(e)
-            if decode:
-                res_specs.append(np.concatenate([outs[i] for _, i in mine], axis=0))
-        return res_specs, res_units
+            out_units.append(e)
+            if decode and not to_wav:
+                out_specs.append(res_specs[u])
+        if to_wav:
+            out_specs = vocoder.synthesize(dev_rows, [out_len[u] for u in wanted], trim=trim)
+        return out_specs, out_units
 
     def encode_utterances(self, specs, reference_noise_order=True, only=None, as_ids=False, noise_seed=None):
         """encode() for a list of (L, 513) spectrograms -> list of (n_units, enc_size) arrays (convert.py:183-221), or of
@@ -307,6 +421,8 @@ class AutoencoderPath:
         return self._run(specs, None, True, False, reference_noise_order, only, as_ids, noise_seed)[1]
 
     def convert_utterances(self, specs, target_speakers, enc_only=True, reference_noise_order=True, only=None, as_ids=False,
-                           noise_seed=None):
-        """convert() up to (not including) Griffin-Lim: -> (list of (L', 513) spectrograms, list of unit arrays)."""
-        return self._run(specs, list(target_speakers), enc_only, True, reference_noise_order, only, as_ids, noise_seed)
+                           noise_seed=None, vocoder=None, trim=True):
+        """convert() (convert.py:128-180): -> (list of (L', 513) spectrograms, list of unit arrays); with `vocoder`
+        (a `dsp.GriffinLim`) the first list holds the waveforms of spectrogram2wav (convert.py:170) instead - the decoded
+        spectrograms then never leave the device."""
+        return self._run(specs, list(target_speakers), enc_only, True, reference_noise_order, only, as_ids, noise_seed, vocoder, trim)

@@ -88,6 +88,29 @@ def decoder_shapes(c_in=1024, c_out=513, c_h=1024, c_a=102):
     return s
 
 
+def patcher_shapes(c_in=513, c_out=513, c_h=1024, c_a=2):
+    """Ordered {name: (shape, fan_in)} of the reference Spectrogram_Patcher state_dict (model/model.py:503-523)."""
+    s = OrderedDict()
+    s['input_layer.weight'] = ((c_h, c_in), c_in)
+    s['input_layer.bias'] = ((c_h,), c_in)
+    for j in range(1, 5):
+        s[f'dense{j}.weight'] = ((c_h, c_h), c_h)
+        s[f'dense{j}.bias'] = ((c_h,), c_h)
+    hh = c_h // 2
+    for sfx in ('', '_reverse'):
+        s[f'RNN.weight_ih_l0{sfx}'] = ((3 * hh, c_h), hh)
+        s[f'RNN.weight_hh_l0{sfx}'] = ((3 * hh, hh), hh)
+        s[f'RNN.bias_ih_l0{sfx}'] = ((3 * hh,), hh)
+        s[f'RNN.bias_hh_l0{sfx}'] = ((3 * hh,), hh)
+    s['dense5.weight'] = ((c_h, 3 * c_h), 3 * c_h)
+    s['dense5.bias'] = ((c_h,), 3 * c_h)
+    s['linear.weight'] = ((c_out, c_h), c_h)
+    s['linear.bias'] = ((c_out,), c_h)
+    for j in (1, 2):
+        s[f'emb{j}.weight'] = ((c_a, c_h), 0)
+    return s
+
+
 def _fill(shapes, seed):
     rng = _rng(seed)
     sd = OrderedDict()
@@ -105,6 +128,20 @@ def encoder_state_dict(seed=0, **kw):
 
 def decoder_state_dict(seed=0, **kw):
     return _fill(decoder_shapes(**kw), 2000 + seed)
+
+
+def patcher_state_dict(seed=0, **kw):
+    return _fill(patcher_shapes(**kw), 6000 + seed)
+
+
+def enhanced_generator_state_dict(seed=0, c_in=513, c_h1=128, c_h2=512, c_h3=128, enc_size=1024, emb_size=1024, n_speakers=102):
+    """Enhanced_Generator (model/model.py:492-502): `Encoder.*` (continues mode) + `Decoder.*`."""
+    sd = OrderedDict()
+    for k, v in encoder_state_dict(seed + 50, c_in=c_in, c_h1=c_h1, c_h2=c_h2, c_h3=c_h3, enc_size=enc_size, enc_mode='continues').items():
+        sd['Encoder.' + k] = v
+    for k, v in decoder_state_dict(seed + 50, c_in=enc_size, c_out=c_in, c_h=emb_size, c_a=n_speakers).items():
+        sd['Decoder.' + k] = v
+    return sd
 
 
 def spectrogram_batch(n_seg, n_frames, seed=0, c_in=513):

@@ -366,3 +366,52 @@ def encode_step(encoder, x, noise=None, dropout_seed=None):
 def decode_step(decoder, enc_act, c):
     """`Trainer.decode_step` (trainer.py:251-254) with an autograd graph."""
     return _DecodeFn.apply(decoder, enc_act, c, *decoder.parameters())
+
+
+class TrainerSteps:
+    """The Trainer's train-mode step wrappers for this path (trainer.py:238-254, 272-284) on the B200 modules, with autograd
+    graphs, so the reference's training loops can call them unchanged:
+
+        C, X = steps.permute_data(next(loader))      # trainer.py:238-244
+        enc_act, enc = steps.encode_step(X)          # :246-249
+        x_dec = steps.decode_step(enc_act, C)        # :251-254
+        x_gen = steps.gen_step(enc_act, C)           # :272-284  (Decoder output combined with the Generator's)
+
+    `gen_step` differentiates through a `Decoder`-type Generator (g_mode naive / targeted / targeted_residual); the
+    alternate patchers (enhanced / spectrogram) are inference-only here - their training is the stage-2 GAN loop."""
+
+    def __init__(self, encoder, decoder, generator=None, g_mode='targeted', n_speakers=102, n_target_speakers=2):
+        self.Encoder, self.Decoder, self.Generator, self.g_mode = encoder, decoder, generator, g_mode
+        self.shift_c = n_speakers - n_target_speakers          # trainer.py:44-45
+        self.device = next(encoder.parameters()).device
+
+    def permute_data(self, data, load_mel=False):
+        """(speaker ids (B,), lin (B, T, 513)[, mel (B, T, 80)]) from the loader -> device tensors, spectrograms permuted
+        to (B, C, T) and - like utils.to_var (utils.py:43-45) - requiring grad."""
+        c = data[0].to(self.device)
+        x = data[1].to(self.device).float().requires_grad_(True).permute(0, 2, 1)
+        if load_mel:
+            return c, x, data[2].to(self.device).float().requires_grad_(True).permute(0, 2, 1)
+        return c, x
+
+    def encode_step(self, x, noise=None):
+        return encode_step(self.Encoder, x, noise)
+
+    def decode_step(self, enc, c):
+        return decode_step(self.Decoder, enc, c)
+
+    def gen_step(self, enc, c):
+        x_dec = decode_step(self.Decoder, enc, c)
+        if self.Generator is None:
+            raise RuntimeError('gen_step needs a Generator')
+        if self.g_mode == 'naive':
+            return x_dec + decode_step(self.Generator, enc, c)
+        if self.g_mode == 'targeted':
+            return x_dec + decode_step(self.Generator, enc, c - self.shift_c)
+        if self.g_mode == 'targeted_residual':
+            return x_dec + x_dec * decode_step(self.Generator, enc, c - self.shift_c)
+        if self.g_mode in ('enhanced', 'spectrogram'):
+            if torch.is_grad_enabled() and self.Generator.training:
+                raise NotImplementedError(f"gen_step: training a g_mode {self.g_mode!r} patcher is outside the autoencoder hot path")
+            return x_dec + self.Generator(x_dec.detach(), c - self.shift_c)
+        raise NotImplementedError('Invalid generator mode to call gen_step()!')
