@@ -197,7 +197,9 @@ __device__ __forceinline__ void chan_stats(const GemmParams& p, uint32_t t_seg, 
 //   stg      : staging slot of (frame f_lo, this thread's channel); frame stride = STG_PITCH elements
 //   res_stg  : residual tile in shared memory (TMA-loaded), slot of (first residual row of this sub-round, channel)
 //   out_s    : output buffer at (this segment, row 0, this thread's output channel) - for the halo rows only
-template <typename OT, int RES, bool PS, bool ZP>
+// TRAIN: the training extras (post-added embedding, unsaturated gradient outputs) exist - compile-time so that the
+// inference layers carry no instruction for what they do not use
+template <typename OT, int RES, bool PS, bool ZP, bool TRAIN>
 __device__ __forceinline__ void frames_to_staging(const GemmParams& p, uint32_t t_seg, int f_lo, int f_hi, int T,
                                                   const ChanNorm& cn, bool lrelu, float ns, OT* __restrict__ stg,
                                                   const OT* __restrict__ res_stg, OT* __restrict__ out_s, int ps_r,
@@ -236,9 +238,9 @@ __device__ __forceinline__ void frames_to_staging(const GemmParams& p, uint32_t 
             if (lrelu) x = fmaxf(x, x * ns);
             x = fmaf(x, cn.scale, cn.shift);
             if (RES != RES_NONE) x += r[i];
-            x += cn.post;
+            if (TRAIN) x += cn.post;
             sat |= (i < sat_lim) && fabsf(x) > 65504.f;
-            y[i] = p.no_sat ? float_to_ot_nosat<OT>(x) : float_to_ot<OT>(x);
+            y[i] = (TRAIN && p.no_sat) ? float_to_ot_nosat<OT>(x) : float_to_ot<OT>(x);
         }
         OT* sp = stg + (c0 - f_lo) * (FSTEP * STG_PITCH);
 #pragma unroll
@@ -305,8 +307,15 @@ __device__ __forceinline__ void frames_to_nct(const GemmParams& p, uint32_t t_se
     }
 }
 
-// ZP: zero-padding mode (seg_len < 64) - a separate instantiation so the reflect-mode kernel carries none of its code
-template <typename OT, bool ZP>
+}  // namespace zs
+#include "conv_epilogue_frag.cuh"
+namespace zs {
+
+// ZP: zero-padding mode (seg_len < 64) - a separate instantiation so the reflect-mode kernel carries none of its code.
+// FRAG: the fragment-layout epilogue (conv_epilogue_frag.cuh) - inference layers without training extras; the
+// lane-per-thread epilogue below stays for the training path, the zero-padding mode and as the A/B reference.
+// TRAIN: training extras compiled in (InstanceNorm statistics output, post-added embedding, unsaturated outputs).
+template <typename OT, bool ZP, bool FRAG, bool TRAIN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid_constant__ GemmParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_addr = smem_u32(smem_raw);
@@ -456,23 +465,41 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
             const int mt = tile % p.m_tiles, nt = tile / p.m_tiles;
             const int as = it & 1;
-            mbar_wait(&tfull[as], (it >> 1) & 1);
-            tc_fence_after();
             const int ch = mt * BM + row;  // weight row == bias index
             const bool ch_ok = ch < p.m_valid;
+            // the (speaker id -> bias table row -> bias) chain of the first segment this set touches is two dependent global
+            // loads: issue them now, in the shadow of the wait for the tile's MMAs
+            const int b_pf = nt * p.nb + eset * (p.out_mode == OUT_NCT32 ? 1 : p.rnd_ns);
+            float bias_pf = 0.f;
+            size_t off_pf = 0;
+            if (p.bias != nullptr && b_pf < p.B) {
+                if (p.spk) {
+                    long long sp = p.spk[b_pf];
+                    sp = sp < 0 ? 0 : (sp >= p.n_spk ? p.n_spk - 1 : sp);
+                    off_pf = static_cast<size_t>(sp) * p.bias_stride;
+                }
+                bias_pf = p.bias[off_pf + ch];
+            }
+            mbar_wait(&tfull[as], (it >> 1) & 1);
+            tc_fence_after();
             const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * MAX_BN;
             auto chan_norm = [&](int b, uint32_t t_seg) {
                 ChanNorm cn;
                 cn.bias = 0.f;
                 cn.edge_off = -1;
                 if (p.bias != nullptr) {  // tables are padded to m_tiles * 128 rows
-                    size_t off = 0;
-                    if (p.spk) {
-                        long long sp = p.spk[b];
-                        sp = sp < 0 ? 0 : (sp >= p.n_spk ? p.n_spk - 1 : sp);
-                        off = static_cast<size_t>(sp) * p.bias_stride;
+                    size_t off = off_pf;
+                    if (b == b_pf) {
+                        cn.bias = bias_pf;
+                    } else {
+                        off = 0;
+                        if (p.spk) {
+                            long long sp = p.spk[b];
+                            sp = sp < 0 ? 0 : (sp >= p.n_spk ? p.n_spk - 1 : sp);
+                            off = static_cast<size_t>(sp) * p.bias_stride;
+                        }
+                        cn.bias = p.bias[off + ch];
                     }
-                    cn.bias = p.bias[off + ch];
                     if (ZP && p.edge_lo != nullptr) cn.edge_off = static_cast<int>(off) + ch;
                 }
                 cn.scale = 1.f;
@@ -483,10 +510,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
                     chan_stats<ZP>(p, t_seg, T, cn.bias, lrelu, ns, cn, mean, rstd);
                     cn.scale = rstd;
                     cn.shift = -mean * rstd;
-                    if (p.stats != nullptr && ch_ok)
+                    if (TRAIN && p.stats != nullptr && ch_ok)
                         *reinterpret_cast<float2*>(p.stats + (static_cast<size_t>(b) * p.bias_stride + ch) * 2) = make_float2(mean, rstd);
                 }
-                if (p.post_emb != nullptr) {
+                if (TRAIN && p.post_emb != nullptr) {
                     long long sp = p.post_spk[b];
                     sp = sp < 0 ? 0 : (sp >= p.post_n ? p.post_n - 1 : sp);
                     const int oc = p.out_mode == OUT_PS ? (mt * 64 + (row & 63)) : ch;
@@ -498,6 +525,92 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tempty[as]);
+            } else if (FRAG) {
+                // ---------------- fragment-layout epilogue (conv_epilogue_frag.cuh) ----------------
+                const int ch0 = mt * BM + 32 * quad + (lane >> 2);              // slot sl adds 8 sl
+                const uint32_t t_q = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * MAX_BN;
+                if (p.out_mode == OUT_NCT32) {
+                    for (int s = eset; s < p.nb; s += EPI_SETS) {
+                        const int b = nt * p.nb + s;
+                        if (b >= p.B) break;
+                        FragCh fc;
+                        frag_chan_norm<OT>(p, fc, t_q + s * p.Tt, T, p.Tt, b, ch0, lane, lrelu, ns);
+                        frag_frames_to_nct<OT>(p, fc, t_q + s * p.Tt, T, p.Tt, lrelu, ns,
+                                               reinterpret_cast<float*>(p.out) + static_cast<size_t>(b) * p.m_valid * T, ch0, lane);
+                    }
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tempty[as]);
+                } else {
+                    const bool ps = p.out_mode == OUT_PS;
+                    const bool has_res = p.res_mode != RES_NONE;
+                    const int fstep = ps ? 2 : 1;
+                    const int res_rows_per_seg = p.res_mode == RES_UP2 ? p.rnd_rows / 2 : (p.res_mode == RES_AVG2 ? 2 * p.rnd_rows : p.rnd_rows);
+                    const int n_groups = (p.nb + p.rnd_ns - 1) / p.rnd_ns;
+                    const int my_last = ((n_groups - 1 - eset) & ~1) + eset;
+                    const bool half1_ok = !ps && mt * BM + 64 < p.m_valid;              // the tile's upper 64 channels exist
+                    if (my_last < 0 || eset >= n_groups) {
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&tempty[as]);
+                    }
+                    FragCh fc_keep;
+                    for (int s0 = eset * p.rnd_ns; s0 < p.nb; s0 += EPI_SETS * p.rnd_ns) {
+                        for (int h = 0; h < p.rnd_sub; ++h, ++rnd) {
+                            const int f_lo = h * p.rnd_frames, f_hi = min(T, f_lo + p.rnd_frames);
+                            uint8_t* tile_out = set_stage + (has_res ? 0 : (rnd & 1) * STG_TILE_BYTES);
+                            uint8_t* tile_res = set_stage + STG_TILE_BYTES;
+                            const bool live = nt * p.nb + s0 < p.B;
+                            if (has_res) {
+                                if (set_lead && live && elect_one()) {
+                                    const uint32_t half_bytes = static_cast<uint32_t>(p.rnd_ns) * res_rows_per_seg * 128;
+                                    mbar_expect_tx(my_rbar, half_bytes * (half1_ok ? 2 : 1));
+                                    const int r_row = p.res_halo + (p.res_mode == RES_UP2 ? f_lo / 2 : (p.res_mode == RES_AVG2 ? 2 * f_lo : f_lo));
+                                    tma_load_3d(&p.tmRes, tile_res, my_rbar, mt * BM, r_row, nt * p.nb + s0);
+                                    if (half1_ok) tma_load_3d(&p.tmRes, tile_res + 8192, my_rbar, mt * BM + 64, r_row, nt * p.nb + s0);
+                                }
+                                __syncwarp();
+                            }
+                            bool waited = false;
+                            for (int s = s0; s < min(s0 + p.rnd_ns, p.nb); ++s) {
+                                const int b = nt * p.nb + s;
+                                if (b >= p.B) break;
+                                const uint32_t t_seg = t_q + s * p.Tt;
+                                if (h == 0) frag_chan_norm<OT>(p, fc_keep, t_seg, T, p.Tt, b, ch0, lane, lrelu, ns);
+                                if (has_res && !waited) {
+                                    mbar_wait(my_rbar, res_phase);
+                                    waited = true;
+                                }
+                                OT* out_s = reinterpret_cast<OT*>(p.out) + static_cast<size_t>(b) * p.out_rows * p.out_pitch + p.out_choff +
+                                            (ps ? mt * 64 : mt * BM + 32 * quad);
+                                const int seg_row0 = (s - s0) * p.rnd_rows * fstep, res_row0 = (s - s0) * res_rows_per_seg;
+                                const uint32_t so = smem_u32(tile_out), sr = smem_u32(tile_res);
+                                if (ps) frag_frames_to_staging<OT, RES_NONE, true>(p, fc_keep, t_seg, f_lo, f_hi, T, p.Tt, lrelu, ns, so, sr, seg_row0, res_row0, out_s, quad, lane, sat);
+                                else if (p.res_mode == RES_NONE) frag_frames_to_staging<OT, RES_NONE, false>(p, fc_keep, t_seg, f_lo, f_hi, T, p.Tt, lrelu, ns, so, sr, seg_row0, res_row0, out_s, quad, lane, sat);
+                                else if (p.res_mode == RES_SAME) frag_frames_to_staging<OT, RES_SAME, false>(p, fc_keep, t_seg, f_lo, f_hi, T, p.Tt, lrelu, ns, so, sr, seg_row0, res_row0, out_s, quad, lane, sat);
+                                else if (p.res_mode == RES_UP2) frag_frames_to_staging<OT, RES_UP2, false>(p, fc_keep, t_seg, f_lo, f_hi, T, p.Tt, lrelu, ns, so, sr, seg_row0, res_row0, out_s, quad, lane, sat);
+                                else frag_frames_to_staging<OT, RES_AVG2, false>(p, fc_keep, t_seg, f_lo, f_hi, T, p.Tt, lrelu, ns, so, sr, seg_row0, res_row0, out_s, quad, lane, sat);
+                            }
+                            if (has_res && live) res_phase ^= 1;
+                            const bool last = (s0 / p.rnd_ns == my_last) && (h + 1 == p.rnd_sub);
+                            if (last) {   // every TMEM read of this tile is done: hand the accumulator back
+                                tc_fence_before();
+                                __syncwarp();
+                                if (lane == 0) mbar_arrive(&tempty[as]);
+                            }
+                            fence_proxy_async();                              // staging writes -> visible to the TMA engine
+                            asm volatile("bar.sync %0, 128;" ::"r"(set_bar) : "memory");
+                            if (set_lead && live && elect_one()) {
+                                tma_store_3d(&p.tmOut, tile_out, ps ? mt * 64 : mt * BM, p.out_halo + fstep * f_lo, nt * p.nb + s0);
+                                if (half1_ok) tma_store_3d(&p.tmOut, tile_out + 8192, mt * BM + 64, p.out_halo + fstep * f_lo, nt * p.nb + s0);
+                                tma_store_commit();
+                                if (has_res) tma_store_wait_read();            // single output tile: it must be free next round
+                                else tma_store_wait_read1();                   // the other tile's stores (2 rounds ago) are done
+                            }
+                            asm volatile("bar.sync %0, 128;" ::"r"(set_bar) : "memory");
+                        }
+                    }
+                }
             } else if (p.out_mode == OUT_NCT32) {
                 for (int s = eset; s < p.nb; s += EPI_SETS) {
                     const int b = nt * p.nb + s;
@@ -560,11 +673,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
                             const OT* res_stg = stage_res + static_cast<size_t>(s - s0) * res_rows_per_seg * 128 + row;
                             OT* out_s = reinterpret_cast<OT*>(p.out) + static_cast<size_t>(b) * p.out_rows * p.out_pitch +
                                         p.out_choff + out_ch;
-                            if (ps) frames_to_staging<OT, RES_NONE, true, ZP>(p, t_seg, f_lo, f_hi, T, cn_keep, lrelu, ns, stg, res_stg, out_s, ps_r, ch_ok, sat);
-                            else if (p.res_mode == RES_NONE) frames_to_staging<OT, RES_NONE, false, ZP>(p, t_seg, f_lo, f_hi, T, cn_keep, lrelu, ns, stg, res_stg, out_s, 0, ch_ok, sat);
-                            else if (p.res_mode == RES_SAME) frames_to_staging<OT, RES_SAME, false, ZP>(p, t_seg, f_lo, f_hi, T, cn_keep, lrelu, ns, stg, res_stg, out_s, 0, ch_ok, sat);
-                            else if (p.res_mode == RES_UP2) frames_to_staging<OT, RES_UP2, false, ZP>(p, t_seg, f_lo, f_hi, T, cn_keep, lrelu, ns, stg, res_stg, out_s, 0, ch_ok, sat);
-                            else frames_to_staging<OT, RES_AVG2, false, ZP>(p, t_seg, f_lo, f_hi, T, cn_keep, lrelu, ns, stg, res_stg, out_s, 0, ch_ok, sat);
+#define ZS_F2S(RES_, PS_) frames_to_staging<OT, RES_, PS_, ZP, TRAIN>(p, t_seg, f_lo, f_hi, T, cn_keep, lrelu, ns, stg, res_stg, out_s, PS_ ? ps_r : 0, ch_ok, sat)
+                            if (ps) ZS_F2S(RES_NONE, true);
+                            else if (p.res_mode == RES_NONE) ZS_F2S(RES_NONE, false);
+                            else if (p.res_mode == RES_SAME) ZS_F2S(RES_SAME, false);
+                            else if (p.res_mode == RES_UP2) ZS_F2S(RES_UP2, false);
+                            else ZS_F2S(RES_AVG2, false);
+#undef ZS_F2S
                         }
                         if (has_res && nt * p.nb + s0 < p.B) res_phase ^= 1;
                         const bool last = (s0 / p.rnd_ns == my_last) && (h + 1 == p.rnd_sub);
