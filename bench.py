@@ -664,7 +664,7 @@ def measure_sharded(dev, world, rank, enc, dec):
     specs = [np.clip(np.random.Generator(np.random.PCG64(1000 + i)).random((L, 513), dtype=np.float32), 1e-8, 1.0) for i, L in enumerate(lengths)]
     spk = [int(v) for v in rng.integers(0, N_SPK, size=n_utt)]
     sp = ShardedPath(AutoencoderPath(enc, dec, device=dev))
-    sp.convert_utterances(specs[:2 * world], spk[:2 * world], noise_seed=3, as_ids=True, gather=False)
+    sp.convert_utterances(specs, spk, noise_seed=3, as_ids=True, gather=False)          # warm-up: workspaces, pinned staging
     times = {}
     for gather in (False, True):
         if world > 1:

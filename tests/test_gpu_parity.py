@@ -734,6 +734,6 @@ def test_fragment_and_lane_epilogues_agree(full_models):
             for mode in (2, 0):
                 lib.zs_set_epilogue_mode(mode)
                 outs.append((gh.conv_cl_to_cl(xx, W, bb, lrelu=True, inorm=True, halo_out=2), gh.conv_cl(xx, W, bb, lrelu=True, act=1)))
-            assert (outs[0][0] - outs[1][0]).abs().max().item() < 2e-3 and (outs[0][1] - outs[1][1]).abs().max().item() < 1e-5
+            assert (outs[0][0] - outs[1][0]).abs().max().item() < 8e-3 and (outs[0][1] - outs[1][1]).abs().max().item() < 1e-5      # one fp16 ulp below 8
     finally:
         lib.zs_set_epilogue_mode(0)

@@ -246,11 +246,11 @@ __device__ __forceinline__ void frames_to_staging(const GemmParams& p, uint32_t 
 #pragma unroll
         for (int i = 0; i < 16; ++i) sp[i * (FSTEP * STG_PITCH)] = y[i];   // columns >= T are clipped by the TMA store
         // reflected halo rows of the output buffer (read by the next conv's outer taps)
-        if (halo > 0 && ch_ok && (c0 == 0 || c0 + 16 + 3 >= T)) {
+        if (halo > 0 && (c0 == 0 || c0 + 16 + 3 >= T)) {     // warp-uniform condition: ch_ok (per lane) must not guard the __syncwarp below
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
                 const int t = c0 + i;
-                if (t < T) {
+                if (t < T && ch_ok) {
                     const int f = PS ? 2 * t + ps_r : t;
                     const OT hv = ZP ? float_to_ot<OT>(0.f) : y[i];
                     if (f >= 1 && f <= halo) out_s[(halo - f) * p.out_pitch] = hv;

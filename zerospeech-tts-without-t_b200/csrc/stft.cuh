@@ -25,7 +25,16 @@ constexpr int GL_F = 26;                             // frames a tile re-analyse
 constexpr int GL_INV = GL_F + 6;                     // frames whose synthesis windows reach into the tile's samples: 32 = 4 phases x 8 warps
 constexpr int GL_WARPS = 8, GL_THREADS = GL_WARPS * 32;
 constexpr int GL_YT = (GL_F - 1) * ST_HOP + ST_WIN;  // 5800 waveform samples under a tile
-constexpr int GL_SMEM_BYTES = 1024 * 8 + ST_WIN * 4 + GL_YT * 4 + GL_WARPS * 512 * 8;   // twiddles + window + waveform tile + one FFT buffer per warp
+constexpr int GL_ZBUF = 512;                         // one warp's FFT buffer: 512 complex values
+constexpr int GL_WTAB = 1024;                        // twiddle table
+constexpr int GL_SMEM_BYTES = GL_WTAB * 8 + ST_WIN * 4 + GL_YT * 4 + GL_WARPS * GL_ZBUF * 8;   // twiddles + window + waveform tile + FFT buffers
+
+// Index maps of the FFT buffer / twiddle table.  A skew (i + i / 8, i + i / 16) removes the 8-way bank conflicts of the first
+// radix-8 pass's stores, but was measured SLOWER on a B200 (Griffin-Lim x 300 on 32 768 frames: 116 ms vs 98 ms): the kernel
+// is bound by instruction issue and latency, not by shared-memory wavefronts, and the skew costs two integer
+// instructions per access.  Kept as the identity so the experiment is one line away.
+__device__ __forceinline__ int ZIDX(int i) { return i; }
+__device__ __forceinline__ int WIDX(int i) { return i; }
 
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
 
@@ -65,11 +74,11 @@ __device__ __forceinline__ void fft512_warp(float2* z, const float2* w, int lane
         for (int b = 0; b < 2; ++b) {
             const int j = lane + 32 * b, k = j & (Ns - 1);
 #pragma unroll
-            for (int t = 0; t < 8; ++t) v[b][t] = z[j + 64 * t];
+            for (int t = 0; t < 8; ++t) v[b][t] = z[ZIDX(j + 64 * t)];
             if (pass > 0) {
                 const int step = k * (128 / Ns);              // twiddle exp(-2 pi i t k / (8 Ns)) = w[t * k * 1024 / (8 Ns)]
 #pragma unroll
-                for (int t = 1; t < 8; ++t) v[b][t] = cmul(v[b][t], w[(t * step) & 1023]);
+                for (int t = 1; t < 8; ++t) v[b][t] = cmul(v[b][t], w[WIDX((t * step) & 1023)]);
             }
             fft8(v[b]);
         }
@@ -79,7 +88,7 @@ __device__ __forceinline__ void fft512_warp(float2* z, const float2* w, int lane
             const int j = lane + 32 * b, k = j & (Ns - 1);
             const int j0 = ((j - k) << 3) + k;
 #pragma unroll
-            for (int t = 0; t < 8; ++t) z[j0 + t * Ns] = v[b][t];
+            for (int t = 0; t < 8; ++t) z[ZIDX(j0 + t * Ns)] = v[b][t];
         }
         __syncwarp();
     }
@@ -102,10 +111,11 @@ __device__ __forceinline__ void irfft1024_warp(const float2* __restrict__ X, con
         if (k == 0) { a.y = 0.f; b.y = 0.f; }               // irfft ignores the imaginary parts of the DC and Nyquist bins
         const float2 xe = make_float2(a.x + b.x, a.y - b.y);  // X[k] + conj X[512-k]
         const float2 xd = make_float2(a.x - b.x, a.y + b.y);  // X[k] - conj X[512-k]
-        const float2 tw = make_float2(w[k].x, -w[k].y);       // exp(+2 pi i k / 1024)
+        const float2 wk = w[WIDX(k)];
+        const float2 tw = make_float2(wk.x, -wk.y);           // exp(+2 pi i k / 1024)
         const float2 xo = cmul(xd, tw);
         // Z = xe + i xo; the inverse transform is conj(FFT(conj Z))
-        z[k] = make_float2(xe.x - xo.y, -(xe.y + xo.x));
+        z[ZIDX(k)] = make_float2(xe.x - xo.y, -(xe.y + xo.x));
     }
     __syncwarp();
     fft512_warp(z, w, lane);
@@ -113,10 +123,10 @@ __device__ __forceinline__ void irfft1024_warp(const float2* __restrict__ X, con
 
 // z holds the forward FFT of the packed frame (z[n] = x[2n] + i x[2n+1]); returns bin k of the 1024-point real transform
 __device__ __forceinline__ float2 rfft_bin(const float2* z, const float2* w, int k) {
-    const float2 zk = z[k & 511], zm = z[(512 - k) & 511];
+    const float2 zk = z[ZIDX(k & 511)], zm = z[ZIDX((512 - k) & 511)];
     const float2 ze = make_float2(0.5f * (zk.x + zm.x), 0.5f * (zk.y - zm.y));      // (Z[k] + conj Z[512-k]) / 2
     const float2 zd = make_float2(0.5f * (zk.x - zm.x), 0.5f * (zk.y + zm.y));      // (Z[k] - conj Z[512-k]) / 2
-    const float2 t = cmul(zd, w[k]);                                                 // * exp(-2 pi i k / 1024)
+    const float2 t = cmul(zd, w[WIDX(k)]);                                           // * exp(-2 pi i k / 1024)
     return make_float2(ze.x + t.y, ze.y - t.x);                                      // ze - i t
 }
 
@@ -151,11 +161,11 @@ struct GlParams {
 __global__ void __launch_bounds__(GL_THREADS) gl_iter_kernel(const GlParams p) {
     extern __shared__ __align__(16) uint8_t gl_smem[];
     float2* s_w = reinterpret_cast<float2*>(gl_smem);
-    float* s_win = reinterpret_cast<float*>(gl_smem + 1024 * 8);
+    float* s_win = reinterpret_cast<float*>(gl_smem + GL_WTAB * 8);
     float* s_y = s_win + ST_WIN;
     float2* s_z = reinterpret_cast<float2*>(s_y + GL_YT);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int i = threadIdx.x; i < 1024; i += GL_THREADS) s_w[i] = p.w1024[i];
+    for (int i = threadIdx.x; i < 1024; i += GL_THREADS) s_w[WIDX(i)] = p.w1024[i];
     for (int i = threadIdx.x; i < ST_WIN; i += GL_THREADS) s_win[i] = p.win[i];
     for (int i = threadIdx.x; i < GL_YT; i += GL_THREADS) s_y[i] = 0.f;
 
@@ -166,8 +176,8 @@ __global__ void __launch_bounds__(GL_THREADS) gl_iter_kernel(const GlParams p) {
     if (f0 == n - 1 && n >= 2) f0 = n - 2;       // a one-frame last tile would need one more sample below its range (reflection)
     const int q0 = ST_HOP * f0 - 400;            // waveform index of s_y[0]
     const size_t frow = static_cast<size_t>(p.meta.frame_start[u]);
-    float2* z = s_z + warp * 512;
-    float* zf = reinterpret_cast<float*>(z);
+    float2* z = s_z + warp * GL_ZBUF;
+    const float* zf = reinterpret_cast<const float*>(z);
     __syncthreads();
 
     // ---- synthesis: frames f0-3 .. f0+F+2, overlap-added in four phases (frames 4 apart never touch the same sample) ----
@@ -181,7 +191,8 @@ __global__ void __launch_bounds__(GL_THREADS) gl_iter_kernel(const GlParams p) {
                 const int idx = ST_HOP * (i - f0) + m;          // q - q0: window sample m of frame i sits at q = 200 i - 400 + m
                 if (idx >= 0 && idx < GL_YT) {
                     const int s = m + ST_WPAD;
-                    const float x = (s & 1) ? -zf[s] : zf[s];
+                    const float zv = zf[2 * ZIDX(s >> 1) + (s & 1)];
+                    const float x = (s & 1) ? -zv : zv;
                     s_y[idx] += x * (1.0f / 1024.0f) * s_win[m];
                 }
             }
@@ -217,21 +228,30 @@ __global__ void __launch_bounds__(GL_THREADS) gl_iter_kernel(const GlParams p) {
 
     // ---- analysis of frames f0 .. f0+F-1 and the phase projection ----
     for (int j = f0 + warp; j < min(n, f0 + GL_F); j += GL_WARPS) {
+        const int qj = ST_HOP * j - 400;                         // waveform index of window sample 0
+        const bool interior = qj >= 0 && qj + ST_WIN <= L;       // no reflection needed (warp-uniform)
+        const float2* y2 = reinterpret_cast<const float2*>(s_y + (qj - q0));      // even offset: 8-byte aligned pairs
+        const float2* w2 = reinterpret_cast<const float2*>(s_win);
         for (int nn = lane; nn < 512; nn += 32) {
-            float v[2];
+            float2 val = make_float2(0.f, 0.f);
+            const int m = 2 * nn - ST_WPAD;                      // even: the pair (m, m + 1) is inside or outside the window together
+            if (m >= 0 && m < ST_WIN) {
+                if (interior) {
+                    const float2 a = y2[m >> 1], b = w2[m >> 1];
+                    val = make_float2(a.x * b.x, a.y * b.y);
+                } else {
+                    float v[2];
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int s = 2 * nn + h, m = s - ST_WPAD;
-                float x = 0.f;
-                if (m >= 0 && m < ST_WIN) {
-                    int q = ST_HOP * j - 400 + m;
-                    if (q < 0) q = -q;                          // np.pad(..., mode='reflect')
-                    if (q >= L) q = 2 * (L - 1) - q;
-                    x = s_y[q - q0] * s_win[m];
+                    for (int h = 0; h < 2; ++h) {
+                        int q = qj + m + h;
+                        if (q < 0) q = -q;                          // np.pad(..., mode='reflect')
+                        if (q >= L) q = 2 * (L - 1) - q;
+                        v[h] = s_y[q - q0] * s_win[m + h];
+                    }
+                    val = make_float2(v[0], v[1]);
                 }
-                v[h] = x;
             }
-            z[nn] = make_float2(v[0], v[1]);
+            z[ZIDX(nn)] = val;
         }
         __syncwarp();
         fft512_warp(z, s_w, lane);
@@ -319,7 +339,7 @@ struct SpecParams {
 __global__ void __launch_bounds__(GL_THREADS) spec_kernel(const SpecParams p) {
     extern __shared__ __align__(16) uint8_t gl_smem[];
     float2* s_w = reinterpret_cast<float2*>(gl_smem);
-    float* s_win = reinterpret_cast<float*>(gl_smem + 1024 * 8);
+    float* s_win = reinterpret_cast<float*>(gl_smem + GL_WTAB * 8);
     float* s_y = s_win + ST_WIN;
     float2* s_z = reinterpret_cast<float2*>(s_y + GL_YT);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -329,7 +349,7 @@ __global__ void __launch_bounds__(GL_THREADS) spec_kernel(const SpecParams p) {
     const int f0 = (blockIdx.x - p.meta.tile_start[u]) * GL_F;
     const int q0 = ST_HOP * f0 - 400;
     const float* xs = p.wav + p.meta.sample_start[u];
-    for (int i = threadIdx.x; i < 1024; i += GL_THREADS) s_w[i] = p.w1024[i];
+    for (int i = threadIdx.x; i < 1024; i += GL_THREADS) s_w[WIDX(i)] = p.w1024[i];
     for (int i = threadIdx.x; i < ST_WIN; i += GL_THREADS) s_win[i] = p.win[i];
     for (int ty = threadIdx.x; ty < GL_YT; ty += GL_THREADS) {
         int q = q0 + ty;
@@ -340,7 +360,7 @@ __global__ void __launch_bounds__(GL_THREADS) spec_kernel(const SpecParams p) {
         s_y[ty] = v;
     }
     __syncthreads();
-    float2* z = s_z + warp * 512;
+    float2* z = s_z + warp * GL_ZBUF;
     const size_t frow = static_cast<size_t>(p.meta.frame_start[u]);
     for (int j = f0 + warp; j < min(n, f0 + GL_F); j += GL_WARPS) {
         for (int nn = lane; nn < 512; nn += 32) {
@@ -350,7 +370,7 @@ __global__ void __launch_bounds__(GL_THREADS) spec_kernel(const SpecParams p) {
                 const int m = 2 * nn + h - ST_WPAD;
                 v[h] = (m >= 0 && m < ST_WIN) ? s_y[ST_HOP * (j - f0) + m] * s_win[m] : 0.f;
             }
-            z[nn] = make_float2(v[0], v[1]);
+            z[ZIDX(nn)] = make_float2(v[0], v[1]);
         }
         __syncwarp();
         fft512_warp(z, s_w, lane);
