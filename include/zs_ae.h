@@ -171,6 +171,14 @@ int zs_decoder_forward(zs_decoder* h, const float* enc_act, const int32_t* unit_
                        int B, int T8, float* spec, int accumulate,
                        void* workspace, size_t workspace_bytes, void* stream);
 
+/* zs_decoder_forward with the output element type chosen: spec_dtype ZS_X_F32 (what Decoder.forward returns) or ZS_X_F16 -
+ * the sigmoid output in (0, 1) rounded once to fp16 (absolute error <= 2.5e-4, inside the path's 1e-2 tolerance), which halves
+ * the device-to-host bytes of the streaming front-end (the reference downloads fp32 after every chunk, trainer.py:221).
+ * The accumulate rules then read and write fp16. */
+int zs_decoder_forward_x(zs_decoder* h, const float* enc_act, const int32_t* unit_ids, const int64_t* spk,
+                         int B, int T8, void* spec, int spec_dtype, int accumulate,
+                         void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- Spectrogram_Patcher (model/model.py:503-549): the TTS patcher of g_mode 'spectrogram' (trainer.py:78-79), applied as
  * x_dec += Generator(x_dec, c - shift) (trainer.py:212-213, 280-281).  Per-frame Linear 513 -> c_h, two dense blocks
  * conditioned on emb1, bi-GRU on out + emb2, dense5 on cat([out, rnn, emb2]), Linear -> sigmoid: the recurrent tail of the
@@ -362,6 +370,7 @@ typedef struct {
     int32_t accumulate;      /* out_mode 2 only: 0 store, 1 out += y, 2 out += out*y */
     int32_t operand;         /* ZS_OPERAND_* */
     int32_t nb_hint;         /* segments per N tile, 0 = auto */
+    int32_t out_f16;         /* out_mode 2 only: the (B, m_valid, T_out) output is fp16 instead of fp32 */
 } zs_conv_desc;
 int zs_conv1d_cl(const zs_conv_desc* d, void* stream);
 /* The GEMM kernel has two epilogues: the lane-per-thread one (one thread = one channel, tcgen05.ld.32x32b; the default) and

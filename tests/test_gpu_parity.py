@@ -737,3 +737,32 @@ def test_fragment_and_lane_epilogues_agree(full_models):
             assert (outs[0][0] - outs[1][0]).abs().max().item() < 8e-3 and (outs[0][1] - outs[1][1]).abs().max().item() < 1e-5      # one fp16 ulp below 8
     finally:
         lib.zs_set_epilogue_mode(0)
+
+
+def test_fp16_spectrogram_output(full_models):
+    """Decoder.decode(out_dtype=float16): the fp32 result rounded once to fp16 (bit-exact to that rounding), also through the
+    accumulate rule and the streaming front-end's fp16 host buffers."""
+    from zs_b200.frontend import StreamingResynthesizer
+    enc, dec, _, _ = full_models
+    for B, T in ((3, 128), (2, 77)):
+        x = syn.spectrogram_batch(B, T, 95).cuda()
+        c = syn.speaker_ids(B, 102, 95).cuda()
+        noise = gumbel_from_uniform(syn.gumbel_uniform((B, Encoder.t8(T), 1024), 95)).cuda()
+        _, _, ids = enc.encode(x, noise)
+        s32 = dec.decode(None, c, unit_ids=ids)
+        s16 = dec.decode(None, c, unit_ids=ids, out_dtype=torch.float16)
+        assert s16.dtype == torch.float16 and torch.equal(s16, s32.half())
+        acc = s16.clone()
+        dec.decode(None, c, unit_ids=ids, out=acc, accumulate=1)
+        assert (acc.float() - 2 * s32).abs().max().item() < 2e-3
+    S, T = 20, 128
+    st = StreamingResynthesizer(enc, dec, micro_batch=8, n_buffers=2)
+    xh = syn.spectrogram_batch(S, T, 96).pin_memory()
+    ch = syn.speaker_ids(S, 102, 96).pin_memory()
+    nz = gumbel_from_uniform(syn.gumbel_uniform((S, 16, 1024), 96)).pin_memory()
+    out32, out16 = torch.zeros(S, 513, T).pin_memory(), torch.zeros(S, 513, T, dtype=torch.float16).pin_memory()
+    st.run(xh, ch, out32, None, nz)
+    torch.cuda.synchronize()
+    st.run(xh, ch, out16, None, nz)
+    torch.cuda.synchronize()
+    assert torch.equal(out16, out32.half())

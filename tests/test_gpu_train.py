@@ -520,3 +520,32 @@ def test_trainer_steps_gen_step_matches_oracle(g_mode):
         assert torch.isfinite(gg).all()
         # whole-network gradient direction and size (per-tensor kink noise: see test_train_step_matches_reference)
         assert cos(gg, go) >= 0.97 and 0.85 <= gg.norm().item() / go.norm().item() <= 1.18, (cos(gg, go), gg.norm().item(), go.norm().item())
+
+
+def test_twenty_step_loss_curve_follows_the_oracle():
+    """20 consecutive pretrain_AE iterations (trainer.py:321-332) at full width against the oracle's step, same
+    batches, same Gumbel noise, dropout off: the loss after every update stays within 1 % of the oracle's - i.e. forward, backward,
+    per-network clipping, Adam's bias corrections and the in-place operand re-pack all track the fp32 reference over a trajectory,
+    not only for one step."""
+    m = dict(seed=0, c_in=513, c_h=[128, 512, 128], enc_size=1024, emb_size=1024, n_spk=102, ns=0.01, seg_len=128, dp=0.0)
+    enc, dec = build_train_models(m)
+    lr = 1e-3
+    step = zt.PretrainAE(enc, dec, lr=lr)
+    o_enc = {k: v.detach().cpu().clone() for k, v in enc.state_dict().items()}
+    o_dec = {k: v.detach().cpu().clone() for k, v in dec.state_dict().items()}
+    state = {}
+    torch.set_num_threads(os.cpu_count())
+    B, T = 4, 128
+    ours, ref = [], []
+    for k in range(20):
+        x, c = syn.spectrogram_batch(B, T, 300 + k % 3), syn.speaker_ids(B, 102, 300 + k % 3)
+        u = syn.gumbel_uniform((B, 16, 1024), 400 + k)
+        loss = step.step(x.cuda(), c.cuda(), noise=gumbel_from_uniform(u).cuda(), dropout_seed=0)
+        ours.append(loss.item())
+        l_o, _, _ = orc.pretrain_ae_step(o_enc, o_dec, state, x, c, u, keep_masks=None, dp=0.0, ns=m['ns'], seg_len=m['seg_len'], lr=lr)
+        ref.append(float(l_o))
+    print('loss curve (ours / oracle):', ' '.join(f'{a:.4f}/{b:.4f}' for a, b in zip(ours, ref)))
+    assert step.n_skipped == 0 and step.applied_steps() == 20
+    assert ref[-1] < ref[0] - 0.01                              # the trajectory actually learns
+    for k, (a, b) in enumerate(zip(ours, ref)):
+        assert abs(a - b) <= 0.01 * b, (k, a, b)

@@ -98,7 +98,7 @@ class ConvDesc(C.Structure):
                 ('inorm', C.c_int32), ('res_mode', C.c_int32), ('res', C.c_void_p), ('res_rows', C.c_int32),
                 ('res_pitch', C.c_int32), ('res_halo', C.c_int32), ('act', C.c_int32), ('out_mode', C.c_int32),
                 ('out', C.c_void_p), ('out_rows', C.c_int32), ('out_pitch', C.c_int32), ('out_halo', C.c_int32),
-                ('out_choff', C.c_int32), ('accumulate', C.c_int32), ('operand', C.c_int32), ('nb_hint', C.c_int32)]
+                ('out_choff', C.c_int32), ('accumulate', C.c_int32), ('operand', C.c_int32), ('nb_hint', C.c_int32), ('out_f16', C.c_int32)]
 
 
 class WgradDesc(C.Structure):
@@ -127,6 +127,7 @@ SYMBOLS = {
     'zs_encoder_forward': (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     'zs_encoder_forward_x': (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     'zs_decoder_forward': (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _i, _vp, _sz, _vp]),
+    'zs_decoder_forward_x': (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _i, _i, _vp, _sz, _vp]),
     'zs_patcher_pack': (_i, [C.POINTER(PatcherCfg), C.POINTER(PatcherWeights), _vp, C.POINTER(_vp)]),
     'zs_patcher_free': (None, [_vp]),
     'zs_patcher_workspace_bytes': (_sz, [_vp, _i, _i]),

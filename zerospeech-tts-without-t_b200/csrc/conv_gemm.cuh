@@ -84,6 +84,7 @@ struct alignas(64) GemmParams {
     const long long* post_spk;
     int post_pitch, post_n;
     int no_sat;               // gradient outputs: let fp16 overflow to inf (the loss-scale logic detects it) instead of clamping
+    int out_f16;              // OUT_NCT32 only: write the (B, C, T) output as fp16 instead of fp32 (halves the D2H bytes of the spectrograms)
     unsigned int* sat_count;  // device word, += 1 per epilogue thread that clamped an fp16 output to +-65504 (never silent)
     // zero-padding mode (model/model.py:36-38, seg_len < 64): halo rows are zeros, and a layer whose speaker embedding is
     // folded into the bias loses the taps that fall into the padding: frame 0 gets -edge_lo, frame T-1 gets -edge_hi
@@ -266,11 +267,16 @@ __device__ __forceinline__ void frames_to_staging(const GemmParams& p, uint32_t 
     }
 }
 
-// Frames of one (segment, channel) -> the reference's (B, C, T) fp32 layout, 16 contiguous floats per chunk.
+// Frames of one (segment, channel) -> the reference's (B, C, T) layout, 16 contiguous values per chunk: fp32 (what
+// Decoder.forward returns), or fp16 when p.out_f16 (the streaming front-end's byte-saving download format).
 template <typename OT, bool ZP>
 __device__ __forceinline__ void frames_to_nct(const GemmParams& p, uint32_t t_seg, int T, const ChanNorm& cn,
-                                              bool lrelu, float ns, float* __restrict__ nct, bool ch_ok) {
-    const bool vec4 = (T & 3) == 0 && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0;
+                                              bool lrelu, float ns, void* __restrict__ nct_v, bool ch_ok) {
+    float* nct = reinterpret_cast<float*>(nct_v);
+    __half* nct16 = reinterpret_cast<__half*>(nct_v);
+    const bool f16 = p.out_f16 != 0;
+    const bool vec4 = !f16 && (T & 3) == 0 && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0;
+    const bool vec8 = f16 && (T & 7) == 0 && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0;
     for (int c0 = 0; c0 < T; c0 += 16) {
         __syncwarp();
         uint32_t v[16];
@@ -278,7 +284,7 @@ __device__ __forceinline__ void frames_to_nct(const GemmParams& p, uint32_t t_se
         float r[16];
         if (p.accumulate) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) r[i] = (ch_ok && c0 + i < T) ? nct[c0 + i] : 0.f;
+            for (int i = 0; i < 16; ++i) r[i] = (ch_ok && c0 + i < T) ? (f16 ? __half2float(nct16[c0 + i]) : nct[c0 + i]) : 0.f;
         }
         tmem_ld_wait();
         if (ZP && cn.edge_off >= 0) apply_edges(p, v, c0, T, cn);
@@ -295,7 +301,22 @@ __device__ __forceinline__ void frames_to_nct(const GemmParams& p, uint32_t t_se
             x[i] = y;
         }
         if (!ch_ok) continue;
-        if (vec4 && c0 + 16 <= T) {
+        if (f16) {
+            if (vec8 && c0 + 16 <= T) {
+                uint32_t h[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const __half2 hh = __floats2half2_rn(x[2 * i], x[2 * i + 1]);
+                    h[i] = *reinterpret_cast<const uint32_t*>(&hh);
+                }
+                *reinterpret_cast<uint4*>(nct16 + c0) = make_uint4(h[0], h[1], h[2], h[3]);
+                *reinterpret_cast<uint4*>(nct16 + c0 + 8) = make_uint4(h[4], h[5], h[6], h[7]);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i)
+                    if (c0 + i < T) nct16[c0 + i] = __float2half_rn(x[i]);
+            }
+        } else if (vec4 && c0 + 16 <= T) {
 #pragma unroll
             for (int i = 0; i < 16; i += 4)
                 *reinterpret_cast<float4*>(nct + c0 + i) = make_float4(x[i], x[i + 1], x[i + 2], x[i + 3]);
@@ -617,8 +638,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
                     if (b >= p.B) break;
                     const uint32_t t_seg = t_lane + s * p.Tt;
                     const ChanNorm cn = chan_norm(b, t_seg);
+                    const size_t el = (static_cast<size_t>(b) * p.m_valid + ch) * T;
                     frames_to_nct<OT, ZP>(p, t_seg, T, cn, lrelu, ns,
-                                      reinterpret_cast<float*>(p.out) + (static_cast<size_t>(b) * p.m_valid + ch) * T, ch_ok);
+                                          p.out_f16 ? static_cast<void*>(reinterpret_cast<__half*>(p.out) + el) : static_cast<void*>(reinterpret_cast<float*>(p.out) + el), ch_ok);
                 }
                 tc_fence_before();
                 __syncwarp();

@@ -99,6 +99,7 @@ __device__ __forceinline__ void fft512_warp(float2* z, const float2* w, int lane
 // the magnitudes with zero phase).
 __device__ __forceinline__ void irfft1024_warp(const float2* __restrict__ X, const float* __restrict__ Xreal, float2* z, const float2* w,
                                                int lane) {
+#pragma unroll 4
     for (int k = lane; k < 512; k += 32) {
         float2 a, b;
         if (Xreal != nullptr) {
@@ -214,7 +215,7 @@ __global__ void __launch_bounds__(GL_THREADS) gl_iter_kernel(const GlParams p) {
                 wss += wv * wv;
             }
         }
-        if (wss > 1.17549435e-38f) s_y[ty] /= wss;
+        if (wss > 1.17549435e-38f) s_y[ty] = __fdividef(s_y[ty], wss);
     }
     __syncthreads();
 
@@ -258,7 +259,9 @@ __global__ void __launch_bounds__(GL_THREADS) gl_iter_kernel(const GlParams p) {
         const size_t row = (frow + j) * ST_NBIN;
         for (int k = lane; k <= 512; k += 32) {
             const float2 est = rfft_bin(z, s_w, k);
-            const float sc = p.mag[row + k] / fmaxf(1e-8f, sqrtf(est.x * est.x + est.y * est.y));     // convert.py:48-49
+            // convert.py:48-49: mag * est / max(1e-8, |est|); one MUFU.RSQ instead of a square root and an IEEE division
+            // (the division's FCHK slow-path check alone took a quarter of the kernel's stall samples)
+            const float sc = p.mag[row + k] * rsqrtf(fmaxf(1e-16f, est.x * est.x + est.y * est.y));
             p.x_out[row + k] = make_float2(est.x * sc, est.y * sc);
         }
         __syncwarp();
@@ -379,7 +382,7 @@ __global__ void __launch_bounds__(GL_THREADS) spec_kernel(const SpecParams p) {
             const float2 X = rfft_bin(z, s_w, k);
             const float a = sqrtf(X.x * X.x + X.y * X.y);
             const float db = 20.f * log10f(fmaxf(1e-5f, a));
-            const float v = fminf(fmaxf((db - p.ref_db + p.max_db) / p.max_db, 1e-8f), 1.f);
+            const float v = fminf(fmaxf(__fdividef(db - p.ref_db + p.max_db, p.max_db), 1e-8f), 1.f);
             if (p.spec32) p.spec32[row + k] = v;
             if (p.spec16) p.spec16[row + k] = __float2half_rn(v);
         }

@@ -252,7 +252,8 @@ static int launch_conv(const zs_conv_desc* d, cudaStream_t stream, const ConvExt
     memset(&p, 0, sizeof(p));
     // fragment-layout epilogue: inference layers (no training extras, reflect padding)
     const bool train_ex = ex && (ex->stats || ex->post_emb || ex->no_sat);
-    const bool frag = g_epilogue_mode == 2 && !train_ex && !(ex && (ex->zero_halo || ex->edge_lo || ex->edge_hi));
+    const bool frag = g_epilogue_mode == 2 && !train_ex && !d->out_f16 && !(ex && (ex->zero_halo || ex->edge_lo || ex->edge_hi));
+    if (d->out_f16 && d->out_mode != OUT_NCT32) return fail(ZS_ERR_ARG, "conv: out_f16 applies to the (B, C, T) output mode");
     const int Tt = round_up(d->T_out, 16);
     const int m_tiles = d->m_rows / BM;
     int nb = d->nb_hint;
@@ -337,7 +338,7 @@ static int launch_conv(const zs_conv_desc* d, cudaStream_t stream, const ConvExt
     p.lrelu = d->lrelu; p.ns = d->ns; p.inorm = d->inorm;
     p.res_mode = d->res_mode; p.res = d->res; p.res_rows = d->res_rows; p.res_pitch = d->res_pitch; p.res_halo = d->res_halo;
     p.act = d->act; p.out_mode = d->out_mode; p.out = d->out; p.out_rows = d->out_rows; p.out_pitch = d->out_pitch;
-    p.out_halo = d->out_halo; p.out_choff = d->out_choff; p.accumulate = d->accumulate;
+    p.out_halo = d->out_halo; p.out_choff = d->out_choff; p.accumulate = d->accumulate; p.out_f16 = d->out_f16;
     p.idesc = umma_idesc_f16(d->operand == ZS_OPERAND_BF16 ? 1 : 0, p.N);
     p.debug = env_int("ZS_GEMM_DEBUG", 0);
     p.sat_count = g_dev[t_dev].sat;
@@ -1047,7 +1048,7 @@ extern "C" size_t zs_decoder_workspace_bytes(const zs_decoder* h, int B, int T8)
 // -------------------------------------------------------------------------------------------------
 struct ConvOpts {
     int stride = 1, lrelu = 1, inorm = 0, res_mode = RES_NONE, act = ACT_NONE, out_mode = OUT_CL, out_choff = 0,
-        accumulate = 0, bank = 0, c_in_valid = -1;
+        accumulate = 0, bank = 0, c_in_valid = -1, out_f16 = 0;
     const Buf* res = nullptr;
     const int64_t* spk = nullptr;
     int in_row0 = -1000;           // override (data-gradient GEMMs read zero-padded gradient buffers from row 0)
@@ -1074,7 +1075,7 @@ static int run_layer(const Layer& L, int operand, float ns, const Buf& in, int B
     d.act = o.act; d.out_mode = o.out_mode;
     if (out) { d.out = out->p; d.out_rows = out->rows; d.out_pitch = out->pitch; d.out_halo = out->halo; }
     else { d.out = out_raw; d.out_rows = out_raw_rows; d.out_pitch = out_raw_pitch; d.out_halo = 0; }
-    d.out_choff = o.out_choff; d.accumulate = o.accumulate; d.operand = operand; d.nb_hint = 0;
+    d.out_choff = o.out_choff; d.accumulate = o.accumulate; d.operand = operand; d.nb_hint = 0; d.out_f16 = o.out_f16;
     if (!t_zero_pad) return launch_conv(&d, st, o.ex);
     ConvExtras ex = o.ex ? *o.ex : ConvExtras();
     ex.zero_halo = 1; ex.edge_lo = L.edge_lo; ex.edge_hi = L.edge_hi;
@@ -1094,7 +1095,7 @@ struct TailNet {
     int ch, output_mask, op; float ns;
 };
 struct TailBufs { const Buf* in; Buf* d; Buf* catr; Buf* d5; Buf* gx; Buf* xch; };
-static int run_tail(const TailNet& n, const TailBufs& w, const int64_t* spk, int B, int Tf, float* spec, int accumulate, cudaStream_t st) {
+static int run_tail(const TailNet& n, const TailBufs& w, const int64_t* spk, int B, int Tf, void* spec, int accumulate, cudaStream_t st, int spec_f16 = 0) {
     const int op = n.op, ch = n.ch;
     const float ns = n.ns;
     {   // two dense blocks, both conditioned on the same embedding (Decoder: emb4 twice, model/model.py:350-351)
@@ -1115,7 +1116,7 @@ static int run_tail(const TailNet& n, const TailBufs& w, const int64_t* spk, int
     {   // dense5 on cat([out, rnn, emb]) -> lrelu -> linear -> sigmoid | tanh (model/model.py:356-364)
         ConvOpts o; o.spk = spk;
         ZS_TRY(run_layer(*n.dense5, op, ns, *w.catr, B, Tf, w.d5, nullptr, 0, 0, o, st));
-        ConvOpts f; f.lrelu = 0; f.act = n.output_mask ? ACT_TANH : ACT_SIGMOID; f.out_mode = OUT_NCT32; f.accumulate = accumulate;
+        ConvOpts f; f.lrelu = 0; f.act = n.output_mask ? ACT_TANH : ACT_SIGMOID; f.out_mode = OUT_NCT32; f.accumulate = accumulate; f.out_f16 = spec_f16;
         ZS_TRY(run_layer(*n.linear, op, ns, *w.d5, B, Tf, nullptr, spec, 0, 0, f, st));
     }
     return ZS_OK;
@@ -1204,7 +1205,14 @@ extern "C" int zs_encoder_forward_x(zs_encoder* h, const void* x, int x_dtype, i
 extern "C" int zs_decoder_forward(zs_decoder* h, const float* enc_act, const int32_t* unit_ids, const int64_t* spk, int B,
                                   int T8, float* spec, int accumulate, void* workspace, size_t workspace_bytes,
                                   void* stream) {
+    return zs_decoder_forward_x(h, enc_act, unit_ids, spk, B, T8, spec, ZS_X_F32, accumulate, workspace, workspace_bytes, stream);
+}
+
+extern "C" int zs_decoder_forward_x(zs_decoder* h, const float* enc_act, const int32_t* unit_ids, const int64_t* spk, int B,
+                                    int T8, void* spec, int spec_dtype, int accumulate, void* workspace, size_t workspace_bytes,
+                                    void* stream) {
     if (!h || !spk || !spec || (!enc_act && !unit_ids)) return fail(ZS_ERR_ARG, "decoder_forward: null argument");
+    if (spec_dtype != ZS_X_F32 && spec_dtype != ZS_X_F16) return fail(ZS_ERR_ARG, "decoder_forward: spec_dtype %d", spec_dtype);
     if (B < 1 || T8 < 2 || T8 > 32) return fail(ZS_ERR_ARG, "decoder_forward: B %d, T8 %d (T8 must be in [2, 32])", B, T8);
     if (accumulate < 0 || accumulate > 2) return fail(ZS_ERR_ARG, "decoder_forward: accumulate %d", accumulate);
     const zs_decoder_cfg& g = h->cfg;
@@ -1240,7 +1248,7 @@ extern "C" int zs_decoder_forward(zs_decoder* h, const float* enc_act, const int
     const int Tf = 8 * T8;
     TailNet net{h->dense, &h->gru_ih, h->whhT, h->bhh, h->whh_img, &h->dense5, &h->linear, ch, g.output_mask, op, ns};
     TailBufs tb{&w.y[2], w.d, &w.catr, &w.d5, &w.gx, &w.xch};
-    return run_tail(net, tb, spk, B, Tf, spec, accumulate, st);
+    return run_tail(net, tb, spk, B, Tf, spec, accumulate, st, spec_dtype == ZS_X_F16);
 }
 
 // -------------------------------------------------------------------------------------------------

@@ -478,11 +478,12 @@ class Decoder(_Packed):
         return d_act
 
     @torch.no_grad()
-    def decode(self, x=None, c=None, unit_ids=None, out=None, accumulate=0):
+    def decode(self, x=None, c=None, unit_ids=None, out=None, accumulate=0, out_dtype=torch.float32):
         """Decoder.forward with the extras the batched front-end uses:
         `unit_ids` (B, T8) int32 replaces a one-hot `x` (input_emb becomes a gather);
         `out`/`accumulate` fuse the patcher combine rules of trainer.py:206-211
-        (1: out += y, 2: out += out * y)."""
+        (1: out += y, 2: out += out * y);
+        `out_dtype` float16 rounds the (0, 1) output once to fp16 (<= 2.5e-4 absolute): half the download bytes."""
         src = x if x is not None else unit_ids
         self._check_input(src, 'x')
         dev = src.device
@@ -505,13 +506,16 @@ class Decoder(_Packed):
             if out is None:
                 if accumulate:
                     raise RuntimeError('Decoder: accumulate needs `out`')
-                out = torch.empty(B, self.c_out, 8 * T8, dtype=torch.float32, device=dev)
-            elif tuple(out.shape) != (B, self.c_out, 8 * T8) or out.dtype != torch.float32 or not out.is_contiguous():
-                raise RuntimeError('Decoder: `out` must be a contiguous float32 (B, c_out, 8*T8) tensor')
+                if out_dtype not in (torch.float32, torch.float16):
+                    raise RuntimeError('Decoder: out_dtype must be float32 or float16')
+                out = torch.empty(B, self.c_out, 8 * T8, dtype=out_dtype, device=dev)
+            elif tuple(out.shape) != (B, self.c_out, 8 * T8) or out.dtype not in (torch.float32, torch.float16) or not out.is_contiguous():
+                raise RuntimeError('Decoder: `out` must be a contiguous float32 / float16 (B, c_out, 8*T8) tensor')
             nbytes = lib.zs_decoder_workspace_bytes(h, B, T8)
             ws = self._get_workspace(nbytes, dev)
-            _lib.check(lib.zs_decoder_forward(h, _ptr(x), _ptr(unit_ids) if x is None else C.c_void_p(0), _ptr(c),
-                                              B, T8, _ptr(out), accumulate, _ptr(ws), ws.numel(), _stream()))
+            _lib.check(lib.zs_decoder_forward_x(h, _ptr(x), _ptr(unit_ids) if x is None else C.c_void_p(0), _ptr(c),
+                                                B, T8, _ptr(out), 1 if out.dtype == torch.float16 else 0, accumulate, _ptr(ws),
+                                                ws.numel(), _stream()))
         return out
 
     def forward(self, x, c):
