@@ -373,11 +373,6 @@ typedef struct {
     int32_t out_f16;         /* out_mode 2 only: the (B, m_valid, T_out) output is fp16 instead of fp32 */
 } zs_conv_desc;
 int zs_conv1d_cl(const zs_conv_desc* d, void* stream);
-/* The GEMM kernel has two epilogues: the lane-per-thread one (one thread = one channel, tcgen05.ld.32x32b; the default) and
- * a fragment-layout one (tcgen05.ld.16x256b + stmatrix.trans + ldmatrix.trans, 64-channel swizzled TMA boxes).  mode 2
- * selects the latter wherever it applies (inference layers, reflect padding) - measured slower on a B200 (profiles/README.md),
- * kept as a verified alternative that a test holds to the default; mode 0 restores the default.  Process-wide. */
-void zs_set_epilogue_mode(int mode);
 
 /* (B, C, T) fp32 -> channels-last operand buffer [B][rows][pitch] with `halo` reflected rows each side;
  * optional leaky-relu; channels C..pitch-1 are zero-filled. */

@@ -14,9 +14,6 @@ from zs_b200.model import Decoder, Encoder, gumbel_from_uniform  # noqa: E402
 def main():
     B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
     reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
-    if len(sys.argv) > 3:          # 2 = the fragment-layout epilogue (A/B against the default lane-per-thread epilogue)
-        from zs_b200 import _lib
-        _lib.lib().zs_set_epilogue_mode(int(sys.argv[3]))
     enc = Encoder(ns=0.01, dp=0.5, enc_size=1024, seg_len=128, enc_mode='one_hot')
     dec = Decoder(ns=0.01, c_in=1024, c_h=1024, c_a=102, seg_len=128)
     enc.load_state_dict(syn.encoder_state_dict(0, enc_size=1024, enc_mode='one_hot'))

@@ -144,7 +144,6 @@ SYMBOLS = {
     'zs_launch_counts': (None, [C.POINTER(C.c_longlong)]),
     'zs_bottleneck_one_hot': (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
     'zs_conv1d_cl': (_i, [C.POINTER(ConvDesc), _vp]),
-    'zs_set_epilogue_mode': (None, [_i]),
     'zs_pack_nct': (_i, [_vp, _i, _i, _i, _vp, _i, _i, _i, _i, _i, C.c_float, _i, _i, _vp]),
     'zs_gru_recurrence': (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     # pretrain_AE step

@@ -7,8 +7,9 @@
 // B box, a stride-2 conv reads the buffer through a (channel, row parity, row pair, segment) view so the
 // box stays dense.
 // One CTA per SM, persistent over output tiles of 128 channels x (nb segments x Tt frames <= 256 columns).
-// Warp 0 = TMA producer, warp 1 = MMA issuer (one elected thread), warps 2..9 = epilogue in two SETS of four
-// (one warp per TMEM lane quadrant in each set); the sets take alternate segment groups of a tile, each with its
+// Warp 0 = TMA producer, warp 1 = MMA issuer (one elected thread), warps 2-3 idle (they only exist so that the driver
+// warps form a warp group of their own that hands its registers to the epilogue: setmaxnreg 40 / 232), warps 4..11 =
+// epilogue in two SETS of four (one warp per TMEM lane quadrant in each set); the sets take alternate segment groups of a tile, each with its
 // own staging tiles, residual barrier and TMA stores, so two epilogue warps per scheduler hide each other's
 // TMEM-load / shared-memory latency.  Two fp32 accumulators of 256 TMEM columns each let the epilogue of tile i
 // overlap the main loop of tile i+1.
@@ -32,7 +33,8 @@ constexpr int STAGES = 3;
 constexpr int A_STAGE_BYTES = BM * BK * 2;
 constexpr int B_STAGE_BYTES = MAX_BN * BK * 2;
 constexpr int EPI_SETS = 2;
-constexpr int GEMM_THREADS = 64 + EPI_SETS * 128;
+constexpr int GEMM_THREADS = 128 + EPI_SETS * 128;   // warp group 0: TMA producer, MMA issuer, two idle warps; warp groups 1, 2: the epilogue sets
+constexpr int REGS_DRIVER = 56, REGS_EPILOGUE = 224;   // setmaxnreg split of the 168 x 384 register budget (40 + 2 x 232 = 504 <= 512 per scheduler)
 constexpr int TMEM_COLS = 512;
 constexpr int STAGING_BYTES = 65536;   // per epilogue set 2 staging tiles of 64 columns x 128 channels (or 128 x 64) x 2 B:
                                        // output double buffer, or output + residual tile
@@ -84,6 +86,7 @@ struct alignas(64) GemmParams {
     const long long* post_spk;
     int post_pitch, post_n;
     int no_sat;               // gradient outputs: let fp16 overflow to inf (the loss-scale logic detects it) instead of clamping
+    int nct_tma;              // OUT_NCT32 only: tmOut describes the (frames, channels, segments) output; the epilogue stages rows in shared memory and TMA-stores them
     int out_f16;              // OUT_NCT32 only: write the (B, C, T) output as fp16 instead of fp32 (halves the D2H bytes of the spectrograms)
     unsigned int* sat_count;  // device word, += 1 per epilogue thread that clamped an fp16 output to +-65504 (never silent)
     // zero-padding mode (model/model.py:36-38, seg_len < 64): halo rows are zeros, and a layer whose speaker embedding is
@@ -152,41 +155,113 @@ __device__ __forceinline__ __half float_to_ot_nosat<__half>(float v) { return __
 template <>
 __device__ __forceinline__ __nv_bfloat16 float_to_ot_nosat<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
 
+// 16-bit operand helpers of the packed epilogue
+template <typename OT> __device__ __forceinline__ float res_add(uint16_t r, float x);            // x + float(r), one FHADD
+template <> __device__ __forceinline__ float res_add<__half>(uint16_t r, float x) { return fhadd_f16(r, x); }
+template <> __device__ __forceinline__ float res_add<__nv_bfloat16>(uint16_t r, float x) { return fhadd_bf16(r, x); }
+// two frames -> one packed 16-bit pair (lo = first frame).  fp16 saturates at +-65504 unless NOSAT (gradient outputs)
+template <typename OT, bool NOSAT> __device__ __forceinline__ uint32_t cvt_pair(float lo, float hi);
+template <> __device__ __forceinline__ uint32_t cvt_pair<__half, false>(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+template <> __device__ __forceinline__ uint32_t cvt_pair<__half, true>(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+template <> __device__ __forceinline__ uint32_t cvt_pair<__nv_bfloat16, false>(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+template <> __device__ __forceinline__ uint32_t cvt_pair<__nv_bfloat16, true>(float lo, float hi) { return cvt_pair<__nv_bfloat16, false>(lo, hi); }
+// running max of |fp16 pair| (HMNMX2 with the abs modifier): the fp16 range check costs half an instruction per value
+__device__ __forceinline__ uint32_t absmax_h2(uint32_t pair, uint32_t m) {
+    const __half2 r = __hmax2(__habs2(*reinterpret_cast<const __half2*>(&pair)), *reinterpret_cast<const __half2*>(&m));
+    return *reinterpret_cast<const uint32_t*>(&r);
+}
+__device__ __forceinline__ bool h2_at_limit(uint32_t m) {       // either half reached the largest finite fp16 (what the clamp produces)
+    return (m & 0xffffu) >= 0x7bffu || (m >> 16) >= 0x7bffu;
+}
+
+// The epilogue's affine + leaky-relu chain in packed form.  With s = InstanceNorm scale (> 0) and ns the leaky slope,
+//   lrelu(a + bias) * s + shift (+ post)  =  max(a * s + t1, a * (ns s) + t2),   t1 = bias s + shift (+ post), t2 = ns bias s + shift (+ post)
+// so two FFMA2 and two FMNMX serve two frames (was add, mul, max, fma per frame).
+struct PackedAffine {
+    uint64_t S1, T1, S2, T2;
+};
+__device__ __forceinline__ PackedAffine packed_affine(const ChanNorm& cn, bool lrelu, float ns, bool with_post) {
+    const float post = with_post ? cn.post : 0.f;
+    const float t1 = fmaf(cn.bias, cn.scale, cn.shift) + post;
+    const float s2 = lrelu ? ns * cn.scale : cn.scale;
+    const float t2 = lrelu ? fmaf(ns * cn.bias, cn.scale, cn.shift) + post : t1;
+    PackedAffine pa;
+    pa.S1 = pk2(cn.scale, cn.scale);
+    pa.T1 = pk2(t1, t1);
+    pa.S2 = pk2(s2, s2);
+    pa.T2 = pk2(t2, t2);
+    return pa;
+}
+
 // InstanceNorm statistics of one (segment, channel) in ONE pass over TMEM: sums are taken relative to the
-// first frame's value so the variance does not cancel catastrophically.
+// first frame's value so the variance does not cancel catastrophically.  Packed math (two frames per instruction,
+// d = lrelu(a + bias) - x0 = max(a + c1, ns a + c2)), two independent accumulator pairs, next chunk's TMEM load in flight.
 template <bool ZP>
 __device__ __forceinline__ void chan_stats(const GemmParams& p, uint32_t t_seg, int T, float bias, bool lrelu, float ns,
                                            const ChanNorm& cn, float& mean, float& rstd) {
-    float s1 = 0.f, s2 = 0.f, x0 = 0.f;
+    uint32_t v[16], vn[16];
+    tmem_ld16(t_seg, v);
+    tmem_ld_wait();
+    if (ZP && cn.edge_off >= 0) apply_edges(p, v, 0, T, cn);
+    float x0 = __uint_as_float(v[0]) + bias;
+    if (lrelu) x0 = fmaxf(x0, x0 * ns);
+    const float nsv = lrelu ? ns : 1.f;
+    const float c1 = bias - x0, c2 = fmaf(nsv, bias, -x0);
+    const uint64_t C1 = pk2(c1, c1), C2 = pk2(c2, c2), NS = pk2(nsv, nsv);
+    uint64_t Sa = pk2(0.f, 0.f), Sb = Sa, Qa = Sa, Qb = Sa;
     for (int c0 = 0; c0 < T; c0 += 16) {
-        uint32_t v[16];
-        tmem_ld16(t_seg + c0, v);
-        tmem_ld_wait();
-        if (ZP && cn.edge_off >= 0) apply_edges(p, v, c0, T, cn);
-        if (c0 == 0) {
-            x0 = __uint_as_float(v[0]) + bias;
-            if (lrelu) x0 = fmaxf(x0, x0 * ns);
-        }
+        const bool more = c0 + 16 < T;
+        if (more) tmem_ld16(t_seg + c0 + 16, vn);
         if (c0 + 16 <= T) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                float x = __uint_as_float(v[i]) + bias;
-                if (lrelu) x = fmaxf(x, x * ns);
-                const float d = x - x0;
-                s1 += d;
-                s2 = fmaf(d, d, s2);
+            for (int i = 0; i < 16; i += 4) {
+                const uint64_t a0 = pk2u(v[i], v[i + 1]), a1 = pk2u(v[i + 2], v[i + 3]);
+                float p0, p1, q0, q1, p2, p3, q2, q3;
+                upk2(fadd2(a0, C1), p0, p1);
+                upk2(ffma2(a0, NS, C2), q0, q1);
+                upk2(fadd2(a1, C1), p2, p3);
+                upk2(ffma2(a1, NS, C2), q2, q3);
+                const uint64_t d0 = pk2(fmaxf(p0, q0), fmaxf(p1, q1)), d1 = pk2(fmaxf(p2, q2), fmaxf(p3, q3));
+                Sa = fadd2(Sa, d0);
+                Qa = ffma2(d0, d0, Qa);
+                Sb = fadd2(Sb, d1);
+                Qb = ffma2(d1, d1, Qb);
             }
         } else {
+            float s1 = 0.f, s2 = 0.f;
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
-                float x = __uint_as_float(v[i]) + bias;
-                if (lrelu) x = fmaxf(x, x * ns);
-                const float d = (c0 + i < T) ? x - x0 : 0.f;
+                const float a = __uint_as_float(v[i]);
+                const float d = (c0 + i < T) ? fmaxf(a + c1, fmaf(a, nsv, c2)) : 0.f;
                 s1 += d;
                 s2 = fmaf(d, d, s2);
             }
+            Sa = fadd2(Sa, pk2(s1, 0.f));
+            Qa = fadd2(Qa, pk2(s2, 0.f));
+        }
+        if (more) {
+            tmem_ld_wait();
+            if (ZP && cn.edge_off >= 0) apply_edges(p, vn, c0 + 16, T, cn);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = vn[i];
         }
     }
+    float sa, sb, qa, qb;
+    upk2(fadd2(Sa, Sb), sa, sb);
+    upk2(fadd2(Qa, Qb), qa, qb);
+    const float s1 = sa + sb, s2 = qa + qb;
     const float inv_T = 1.f / static_cast<float>(T);
     const float m1 = s1 * inv_T;
     mean = x0 + m1;
@@ -199,16 +274,23 @@ __device__ __forceinline__ void chan_stats(const GemmParams& p, uint32_t t_seg, 
 //   res_stg  : residual tile in shared memory (TMA-loaded), slot of (first residual row of this sub-round, channel)
 //   out_s    : output buffer at (this segment, row 0, this thread's output channel) - for the halo rows only
 // TRAIN: the training extras (post-added embedding, unsaturated gradient outputs) exist - compile-time so that the
-// inference layers carry no instruction for what they do not use
-template <typename OT, int RES, bool PS, bool ZP, bool TRAIN>
+// inference layers carry no instruction for what they do not use.  LR = false: the layer has no leaky-relu (GRU input
+// projections) - one FFMA2 per pair and no max.
+template <typename OT, int RES, bool PS, bool ZP, bool TRAIN, bool LR>
 __device__ __forceinline__ void frames_to_staging(const GemmParams& p, uint32_t t_seg, int f_lo, int f_hi, int T,
                                                   const ChanNorm& cn, bool lrelu, float ns, OT* __restrict__ stg,
                                                   const OT* __restrict__ res_stg, OT* __restrict__ out_s, int ps_r,
                                                   bool ch_ok, bool& sat) {
     constexpr int STG_PITCH = PS ? 64 : 128;          // channels per staging row
     constexpr int FSTEP = PS ? 2 : 1;                 // staging rows per input frame
+    constexpr bool F16 = !IS_BF16<OT>::value;
     const int T_out = PS ? 2 * T : T;
     const int halo = p.out_halo;
+    const PackedAffine pa = packed_affine(cn, LR && lrelu, ns, TRAIN);
+    const bool nosat = TRAIN && p.no_sat;
+    uint32_t satm = 0;                                // running |max| of the fp16 pairs this thread stored
+    uint16_t* stg16 = reinterpret_cast<uint16_t*>(stg);
+    const uint16_t* res16 = reinterpret_cast<const uint16_t*>(res_stg);
     uint32_t v[16], vn[16];
     tmem_ld16(t_seg + f_lo, v);
     for (int c0 = f_lo; c0 < f_hi; c0 += 16) {
@@ -216,46 +298,62 @@ __device__ __forceinline__ void frames_to_staging(const GemmParams& p, uint32_t 
         if (ZP && cn.edge_off >= 0) apply_edges(p, v, c0, T, cn);
         const bool more = c0 + 16 < f_hi;
         if (more) tmem_ld16(t_seg + c0 + 16, vn);       // next chunk's accumulators while this one is processed
-        float r[16];
-        if (RES == RES_SAME) {
+        uint32_t yp[8];                                 // 16 outputs as 8 packed 16-bit pairs
 #pragma unroll
-            for (int i = 0; i < 16; ++i) r[i] = ot_to_float<OT>(res_stg[(c0 - f_lo + i) * 128]);
-        } else if (RES == RES_UP2) {
+        for (int i = 0; i < 16; i += 2) {
+            const uint64_t a = pk2u(v[i], v[i + 1]);
+            float x0, x1;
+            upk2(ffma2(a, pa.S1, pa.T1), x0, x1);
+            if (LR) {
+                float q0, q1;
+                upk2(ffma2(a, pa.S2, pa.T2), q0, q1);
+                x0 = fmaxf(x0, q0);
+                x1 = fmaxf(x1, q1);
+            }
+            if (RES == RES_SAME) {
+                x0 = res_add<OT>(res16[(c0 - f_lo + i) * 128], x0);
+                x1 = res_add<OT>(res16[(c0 - f_lo + i + 1) * 128], x1);
+            } else if (RES == RES_UP2) {
+                const uint16_t r = res16[((c0 - f_lo + i) >> 1) * 128];
+                x0 = res_add<OT>(r, x0);
+                x1 = res_add<OT>(r, x1);
+            } else if (RES == RES_AVG2) {
+                const uint16_t* q = res16 + 2 * (c0 - f_lo + i) * 128;
+                x0 += 0.5f * res_add<OT>(q[0], ot_to_float<OT>(reinterpret_cast<const OT*>(q)[128]));
+                x1 += 0.5f * res_add<OT>(q[256], ot_to_float<OT>(reinterpret_cast<const OT*>(q)[384]));
+            }
+            yp[i >> 1] = nosat ? cvt_pair<OT, true>(x0, x1) : cvt_pair<OT, false>(x0, x1);
+        }
+        // fp16 range check covers what is STORED: frames below T (padding columns hold garbage by design)
+        if (F16 && !nosat) {
+            if (c0 + 16 <= T) {
 #pragma unroll
-            for (int i = 0; i < 16; i += 2) r[i] = r[i + 1] = ot_to_float<OT>(res_stg[((c0 - f_lo + i) >> 1) * 128]);
-        } else if (RES == RES_AVG2) {
+                for (int i = 0; i < 8; ++i) satm = absmax_h2(yp[i], satm);
+            } else {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                const OT* q = res_stg + 2 * (c0 - f_lo + i) * 128;
-                r[i] = 0.5f * (ot_to_float<OT>(q[0]) + ot_to_float<OT>(q[128]));
+                for (int i = 0; i < 8; ++i) {
+                    const uint32_t m = (c0 + 2 * i + 1 < T) ? 0xffffffffu : (c0 + 2 * i < T ? 0xffffu : 0u);
+                    satm = absmax_h2(yp[i] & m, satm);
+                }
             }
         }
-        OT y[16];
-        // fp16 range check covers what is STORED: valid channels, frames below T (padding columns hold garbage by design)
-        const int sat_lim = (ch_ok && !IS_BF16<OT>::value) ? min(16, T - c0) : 0;
+        uint16_t* sp = stg16 + (c0 - f_lo) * (FSTEP * STG_PITCH);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            float x = __uint_as_float(v[i]) + cn.bias;
-            if (lrelu) x = fmaxf(x, x * ns);
-            x = fmaf(x, cn.scale, cn.shift);
-            if (RES != RES_NONE) x += r[i];
-            if (TRAIN) x += cn.post;
-            sat |= (i < sat_lim) && fabsf(x) > 65504.f;
-            y[i] = (TRAIN && p.no_sat) ? float_to_ot_nosat<OT>(x) : float_to_ot<OT>(x);
+        for (int i = 0; i < 8; ++i) {                     // columns >= T are clipped by the TMA store
+            sp[(2 * i) * (FSTEP * STG_PITCH)] = static_cast<uint16_t>(yp[i]);
+            sp[(2 * i + 1) * (FSTEP * STG_PITCH)] = static_cast<uint16_t>(yp[i] >> 16);
         }
-        OT* sp = stg + (c0 - f_lo) * (FSTEP * STG_PITCH);
-#pragma unroll
-        for (int i = 0; i < 16; ++i) sp[i * (FSTEP * STG_PITCH)] = y[i];   // columns >= T are clipped by the TMA store
         // reflected halo rows of the output buffer (read by the next conv's outer taps)
         if (halo > 0 && (c0 == 0 || c0 + 16 + 3 >= T)) {     // warp-uniform condition: ch_ok (per lane) must not guard the __syncwarp below
+            uint16_t* out16 = reinterpret_cast<uint16_t*>(out_s);
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
                 const int t = c0 + i;
                 if (t < T && ch_ok) {
                     const int f = PS ? 2 * t + ps_r : t;
-                    const OT hv = ZP ? float_to_ot<OT>(0.f) : y[i];
-                    if (f >= 1 && f <= halo) out_s[(halo - f) * p.out_pitch] = hv;
-                    if (f >= T_out - 1 - halo && f <= T_out - 2) out_s[(halo + 2 * (T_out - 1) - f) * p.out_pitch] = hv;
+                    const uint16_t hv = ZP ? uint16_t(0) : static_cast<uint16_t>(yp[i >> 1] >> (16 * (i & 1)));
+                    if (f >= 1 && f <= halo) out16[(halo - f) * p.out_pitch] = hv;
+                    if (f >= T_out - 1 - halo && f <= T_out - 2) out16[(halo + 2 * (T_out - 1) - f) * p.out_pitch] = hv;
                 }
             }
             __syncwarp();
@@ -265,6 +363,7 @@ __device__ __forceinline__ void frames_to_staging(const GemmParams& p, uint32_t 
             for (int i = 0; i < 16; ++i) v[i] = vn[i];
         }
     }
+    if (F16 && ch_ok) sat |= h2_at_limit(satm);
 }
 
 // Frames of one (segment, channel) -> the reference's (B, C, T) layout, 16 contiguous values per chunk: fp32 (what
@@ -328,15 +427,80 @@ __device__ __forceinline__ void frames_to_nct(const GemmParams& p, uint32_t t_se
     }
 }
 
-}  // namespace zs
-#include "conv_epilogue_frag.cuh"
-namespace zs {
+// Same result through shared memory: the warp's 32 channels x one 128-byte row of frames (32 fp32 / 64 fp16) are staged with
+// the 128-byte swizzle (16-byte chunk j of row r sits at chunk j ^ (r & 7): the 32 lanes' 16-byte stores hit distinct banks) and
+// written by a per-warp TMA store, double buffered - no 64-byte strided global stores, no barrier wider than the warp.  Channels past
+// m_valid are clipped by the tensor map.  T is a multiple of the row's frames (launch_conv checks).
+template <typename OT>
+__device__ __forceinline__ void frames_to_nct_tma(const GemmParams& p, uint32_t t_seg, int T, const ChanNorm& cn, bool lrelu, float ns,
+                                                  uint8_t* __restrict__ wstage, int lane, int ch0, int b, int& grp) {
+    const PackedAffine pa = packed_affine(cn, lrelu, ns, false);
+    const bool f16 = p.out_f16 != 0;
+    const int fpr = f16 ? 64 : 32;                       // frames per staging row
+    const int sw = lane & 7;
+    uint32_t v[16], vn[16];
+    tmem_ld16(t_seg, v);
+    for (int c0 = 0; c0 < T; c0 += 16) {
+        tmem_ld_wait();
+        const bool more = c0 + 16 < T;
+        if (more) tmem_ld16(t_seg + c0 + 16, vn);
+        if (c0 % fpr == 0) {                              // starting a row group: the store that read this buffer two groups ago is done
+            if (elect_one()) tma_store_wait_read1();
+            __syncwarp();
+        }
+        uint8_t* rowp = wstage + (grp & 1) * 4096 + lane * 128;
+        float x[16];
+#pragma unroll
+        for (int i = 0; i < 16; i += 2) {
+            const uint64_t a = pk2u(v[i], v[i + 1]);
+            float x0, x1, q0, q1;
+            upk2(ffma2(a, pa.S1, pa.T1), x0, x1);
+            upk2(ffma2(a, pa.S2, pa.T2), q0, q1);
+            x[i] = fmaxf(x0, q0);
+            x[i + 1] = fmaxf(x1, q1);
+        }
+        if (p.act == ACT_SIGMOID) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) x[i] = sigmoid_f(x[i]);
+        } else if (p.act == ACT_TANH) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) x[i] = tanh_f(x[i]);
+        }
+        if (f16) {
+            const int j0 = (c0 & 63) >> 3;
+            uint32_t h[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const __half2 hh = __floats2half2_rn(x[2 * i], x[2 * i + 1]);
+                h[i] = *reinterpret_cast<const uint32_t*>(&hh);
+            }
+            *reinterpret_cast<uint4*>(rowp + (((j0) ^ sw) << 4)) = make_uint4(h[0], h[1], h[2], h[3]);
+            *reinterpret_cast<uint4*>(rowp + (((j0 + 1) ^ sw) << 4)) = make_uint4(h[4], h[5], h[6], h[7]);
+        } else {
+            const int j0 = (c0 & 31) >> 2;
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                *reinterpret_cast<float4*>(rowp + (((j0 + q) ^ sw) << 4)) = make_float4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
+        }
+        if ((c0 + 16) % fpr == 0) {
+            fence_proxy_async();                          // staged rows -> visible to the TMA engine
+            __syncwarp();
+            if (elect_one()) {
+                tma_store_3d(&p.tmOut, wstage + (grp & 1) * 4096, c0 + 16 - fpr, ch0, b);
+                tma_store_commit();
+            }
+            ++grp;
+        }
+        if (more) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = vn[i];
+        }
+    }
+}
 
 // ZP: zero-padding mode (seg_len < 64) - a separate instantiation so the reflect-mode kernel carries none of its code.
-// FRAG: the fragment-layout epilogue (conv_epilogue_frag.cuh) - inference layers without training extras; the
-// lane-per-thread epilogue below stays for the training path, the zero-padding mode and as the A/B reference.
 // TRAIN: training extras compiled in (InstanceNorm statistics output, post-added embedding, unsaturated outputs).
-template <typename OT, bool ZP, bool FRAG, bool TRAIN>
+template <typename OT, bool ZP, bool TRAIN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid_constant__ GemmParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_addr = smem_u32(smem_raw);
@@ -367,7 +531,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
         fence_barrier_init();
         tma_prefetch_desc(&p.tmA);
         tma_prefetch_desc(&p.tmB);
-        if (p.out_mode != OUT_NCT32) tma_prefetch_desc(&p.tmOut);
+        if (p.out_mode != OUT_NCT32 || p.nct_tma) tma_prefetch_desc(&p.tmOut);
         if (p.res_mode != RES_NONE) tma_prefetch_desc(&p.tmRes);
     }
     if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_slot);
@@ -385,6 +549,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
     const int total_tiles = p.m_tiles * p.n_tiles;
     const uint32_t stage_tx = A_STAGE_BYTES + static_cast<uint32_t>(p.N) * (BK * 2);
 
+    if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_DRIVER));
     if (warp == 0) {
         // ------------------------------ TMA producer (whole warp, one elected lane issues) ------
         {
@@ -467,11 +633,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
                 __syncwarp();
             }
         }
+    }
     } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_EPILOGUE));
         // ------------------------------ epilogue ----------------------------------
         const int quad = warp & 3;  // TMEM lane quadrant this warp may access
-        const int eset = (warp - 2) >> 2;                    // epilogue set: warps 2..5 / 6..9
-        const bool set_lead = ((warp - 2) & 3) == 0;         // the set's TMA-issuing warp
+        const int eset = (warp - 4) >> 2;                    // epilogue set: warps 4..7 / 8..11
+        const bool set_lead = (warp & 3) == 0;               // the set's TMA-issuing warp
         const int set_bar = 1 + eset;                        // named barrier of the set's 128 threads
         uint64_t* my_rbar = &rbar[eset];
         const int row = quad * 32 + lane;
@@ -546,98 +714,16 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tempty[as]);
-            } else if (FRAG) {
-                // ---------------- fragment-layout epilogue (conv_epilogue_frag.cuh) ----------------
-                const int ch0 = mt * BM + 32 * quad + (lane >> 2);              // slot sl adds 8 sl
-                const uint32_t t_q = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * MAX_BN;
-                if (p.out_mode == OUT_NCT32) {
-                    for (int s = eset; s < p.nb; s += EPI_SETS) {
-                        const int b = nt * p.nb + s;
-                        if (b >= p.B) break;
-                        FragCh fc;
-                        frag_chan_norm<OT>(p, fc, t_q + s * p.Tt, T, p.Tt, b, ch0, lane, lrelu, ns);
-                        frag_frames_to_nct<OT>(p, fc, t_q + s * p.Tt, T, p.Tt, lrelu, ns,
-                                               reinterpret_cast<float*>(p.out) + static_cast<size_t>(b) * p.m_valid * T, ch0, lane);
-                    }
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&tempty[as]);
-                } else {
-                    const bool ps = p.out_mode == OUT_PS;
-                    const bool has_res = p.res_mode != RES_NONE;
-                    const int fstep = ps ? 2 : 1;
-                    const int res_rows_per_seg = p.res_mode == RES_UP2 ? p.rnd_rows / 2 : (p.res_mode == RES_AVG2 ? 2 * p.rnd_rows : p.rnd_rows);
-                    const int n_groups = (p.nb + p.rnd_ns - 1) / p.rnd_ns;
-                    const int my_last = ((n_groups - 1 - eset) & ~1) + eset;
-                    const bool half1_ok = !ps && mt * BM + 64 < p.m_valid;              // the tile's upper 64 channels exist
-                    if (my_last < 0 || eset >= n_groups) {
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(&tempty[as]);
-                    }
-                    FragCh fc_keep;
-                    for (int s0 = eset * p.rnd_ns; s0 < p.nb; s0 += EPI_SETS * p.rnd_ns) {
-                        for (int h = 0; h < p.rnd_sub; ++h, ++rnd) {
-                            const int f_lo = h * p.rnd_frames, f_hi = min(T, f_lo + p.rnd_frames);
-                            uint8_t* tile_out = set_stage + (has_res ? 0 : (rnd & 1) * STG_TILE_BYTES);
-                            uint8_t* tile_res = set_stage + STG_TILE_BYTES;
-                            const bool live = nt * p.nb + s0 < p.B;
-                            if (has_res) {
-                                if (set_lead && live && elect_one()) {
-                                    const uint32_t half_bytes = static_cast<uint32_t>(p.rnd_ns) * res_rows_per_seg * 128;
-                                    mbar_expect_tx(my_rbar, half_bytes * (half1_ok ? 2 : 1));
-                                    const int r_row = p.res_halo + (p.res_mode == RES_UP2 ? f_lo / 2 : (p.res_mode == RES_AVG2 ? 2 * f_lo : f_lo));
-                                    tma_load_3d(&p.tmRes, tile_res, my_rbar, mt * BM, r_row, nt * p.nb + s0);
-                                    if (half1_ok) tma_load_3d(&p.tmRes, tile_res + 8192, my_rbar, mt * BM + 64, r_row, nt * p.nb + s0);
-                                }
-                                __syncwarp();
-                            }
-                            bool waited = false;
-                            for (int s = s0; s < min(s0 + p.rnd_ns, p.nb); ++s) {
-                                const int b = nt * p.nb + s;
-                                if (b >= p.B) break;
-                                const uint32_t t_seg = t_q + s * p.Tt;
-                                if (h == 0) frag_chan_norm<OT>(p, fc_keep, t_seg, T, p.Tt, b, ch0, lane, lrelu, ns);
-                                if (has_res && !waited) {
-                                    mbar_wait(my_rbar, res_phase);
-                                    waited = true;
-                                }
-                                OT* out_s = reinterpret_cast<OT*>(p.out) + static_cast<size_t>(b) * p.out_rows * p.out_pitch + p.out_choff +
-                                            (ps ? mt * 64 : mt * BM + 32 * quad);
-                                const int seg_row0 = (s - s0) * p.rnd_rows * fstep, res_row0 = (s - s0) * res_rows_per_seg;
-                                const uint32_t so = smem_u32(tile_out), sr = smem_u32(tile_res);
-                                if (ps) frag_frames_to_staging<OT, RES_NONE, true>(p, fc_keep, t_seg, f_lo, f_hi, T, p.Tt, lrelu, ns, so, sr, seg_row0, res_row0, out_s, quad, lane, sat);
-                                else if (p.res_mode == RES_NONE) frag_frames_to_staging<OT, RES_NONE, false>(p, fc_keep, t_seg, f_lo, f_hi, T, p.Tt, lrelu, ns, so, sr, seg_row0, res_row0, out_s, quad, lane, sat);
-                                else if (p.res_mode == RES_SAME) frag_frames_to_staging<OT, RES_SAME, false>(p, fc_keep, t_seg, f_lo, f_hi, T, p.Tt, lrelu, ns, so, sr, seg_row0, res_row0, out_s, quad, lane, sat);
-                                else if (p.res_mode == RES_UP2) frag_frames_to_staging<OT, RES_UP2, false>(p, fc_keep, t_seg, f_lo, f_hi, T, p.Tt, lrelu, ns, so, sr, seg_row0, res_row0, out_s, quad, lane, sat);
-                                else frag_frames_to_staging<OT, RES_AVG2, false>(p, fc_keep, t_seg, f_lo, f_hi, T, p.Tt, lrelu, ns, so, sr, seg_row0, res_row0, out_s, quad, lane, sat);
-                            }
-                            if (has_res && live) res_phase ^= 1;
-                            const bool last = (s0 / p.rnd_ns == my_last) && (h + 1 == p.rnd_sub);
-                            if (last) {   // every TMEM read of this tile is done: hand the accumulator back
-                                tc_fence_before();
-                                __syncwarp();
-                                if (lane == 0) mbar_arrive(&tempty[as]);
-                            }
-                            fence_proxy_async();                              // staging writes -> visible to the TMA engine
-                            asm volatile("bar.sync %0, 128;" ::"r"(set_bar) : "memory");
-                            if (set_lead && live && elect_one()) {
-                                tma_store_3d(&p.tmOut, tile_out, ps ? mt * 64 : mt * BM, p.out_halo + fstep * f_lo, nt * p.nb + s0);
-                                if (half1_ok) tma_store_3d(&p.tmOut, tile_out + 8192, mt * BM + 64, p.out_halo + fstep * f_lo, nt * p.nb + s0);
-                                tma_store_commit();
-                                if (has_res) tma_store_wait_read();            // single output tile: it must be free next round
-                                else tma_store_wait_read1();                   // the other tile's stores (2 rounds ago) are done
-                            }
-                            asm volatile("bar.sync %0, 128;" ::"r"(set_bar) : "memory");
-                        }
-                    }
-                }
             } else if (p.out_mode == OUT_NCT32) {
                 for (int s = eset; s < p.nb; s += EPI_SETS) {
                     const int b = nt * p.nb + s;
                     if (b >= p.B) break;
                     const uint32_t t_seg = t_lane + s * p.Tt;
                     const ChanNorm cn = chan_norm(b, t_seg);
+                    if (!ZP && p.nct_tma) {
+                        frames_to_nct_tma<OT>(p, t_seg, T, cn, lrelu, ns, set_stage + quad * 8192, lane, mt * BM + quad * 32, b, rnd);
+                        continue;
+                    }
                     const size_t el = (static_cast<size_t>(b) * p.m_valid + ch) * T;
                     frames_to_nct<OT, ZP>(p, t_seg, T, cn, lrelu, ns,
                                           p.out_f16 ? static_cast<void*>(reinterpret_cast<__half*>(p.out) + el) : static_cast<void*>(reinterpret_cast<float*>(p.out) + el), ch_ok);
@@ -695,12 +781,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
                             const OT* res_stg = stage_res + static_cast<size_t>(s - s0) * res_rows_per_seg * 128 + row;
                             OT* out_s = reinterpret_cast<OT*>(p.out) + static_cast<size_t>(b) * p.out_rows * p.out_pitch +
                                         p.out_choff + out_ch;
-#define ZS_F2S(RES_, PS_) frames_to_staging<OT, RES_, PS_, ZP, TRAIN>(p, t_seg, f_lo, f_hi, T, cn_keep, lrelu, ns, stg, res_stg, out_s, PS_ ? ps_r : 0, ch_ok, sat)
-                            if (ps) ZS_F2S(RES_NONE, true);
-                            else if (p.res_mode == RES_NONE) ZS_F2S(RES_NONE, false);
-                            else if (p.res_mode == RES_SAME) ZS_F2S(RES_SAME, false);
-                            else if (p.res_mode == RES_UP2) ZS_F2S(RES_UP2, false);
-                            else ZS_F2S(RES_AVG2, false);
+#define ZS_F2S(RES_, PS_, LR_) frames_to_staging<OT, RES_, PS_, ZP, TRAIN, LR_>(p, t_seg, f_lo, f_hi, T, cn_keep, lrelu, ns, stg, res_stg, out_s, PS_ ? ps_r : 0, ch_ok, sat)
+                            if (ps) ZS_F2S(RES_NONE, true, true);
+                            else if (p.res_mode == RES_NONE) {
+                                if (lrelu) ZS_F2S(RES_NONE, false, true);
+                                else ZS_F2S(RES_NONE, false, false);
+                            } else if (p.res_mode == RES_SAME) ZS_F2S(RES_SAME, false, true);
+                            else if (p.res_mode == RES_UP2) ZS_F2S(RES_UP2, false, true);
+                            else ZS_F2S(RES_AVG2, false, true);
 #undef ZS_F2S
                         }
                         if (has_res && nt * p.nb + s0 < p.B) res_phase ^= 1;
@@ -724,6 +812,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
             }
         }
         if (sat && !p.no_sat && p.sat_count != nullptr) atomicAdd(p.sat_count, 1u);
+        if (elect_one()) tma_store_wait_read();        // no bulk store may still be reading the staging tiles when the CTA retires
+        __syncwarp();
     }
 
     tc_fence_before();

@@ -176,4 +176,38 @@ __device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t (&v)[16]) 
 __device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t (&v)[8]) { tmem_ld8(taddr, v); }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// ---- packed fp32 pairs (FFMA2 / FADD2 on sm_100: one issue slot for two values) and mixed-precision adds -------------
+__device__ __forceinline__ uint64_t pk2(float lo, float hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ uint64_t pk2u(uint32_t lo, uint32_t hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+    return r;
+}
+__device__ __forceinline__ void upk2(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
+    uint64_t r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+// f32 + f16 / bf16 in ONE instruction (FHADD; the conversion is exact, so this equals cvt + add)
+__device__ __forceinline__ float fhadd_f16(uint16_t h, float f) {
+    float r;
+    asm("add.rn.f32.f16 %0, %1, %2;" : "=f"(r) : "h"(h), "f"(f));
+    return r;
+}
+__device__ __forceinline__ float fhadd_bf16(uint16_t h, float f) {
+    float r;
+    asm("add.rn.f32.bf16 %0, %1, %2;" : "=f"(r) : "h"(h), "f"(f));
+    return r;
+}
+
 }  // namespace zs

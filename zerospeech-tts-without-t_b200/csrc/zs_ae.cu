@@ -227,11 +227,6 @@ struct ConvExtras {        // training-path additions to a layer launch (not par
 // padding mode of the forward pass being issued on this host thread (set by zs_*_forward from cfg.seg_len)
 static thread_local int t_zero_pad = 0;
 
-// 0 = lane-per-thread epilogue (default: measured faster, profiles/README.md r02), 2 = fragment-layout epilogue wherever
-// it applies (kept as a verified alternative: tests hold the two to each other)
-static int g_epilogue_mode = 0;
-extern "C" void zs_set_epilogue_mode(int mode) { g_epilogue_mode = mode; }
-
 static int launch_conv(const zs_conv_desc* d, cudaStream_t stream, const ConvExtras* ex = nullptr) {
     ZS_TRY(ensure_device());
     if (!d->w || !d->in || !d->out) return fail(ZS_ERR_ARG, "conv: null operand pointer");
@@ -250,9 +245,7 @@ static int launch_conv(const zs_conv_desc* d, cudaStream_t stream, const ConvExt
 
     GemmParams p;
     memset(&p, 0, sizeof(p));
-    // fragment-layout epilogue: inference layers (no training extras, reflect padding)
     const bool train_ex = ex && (ex->stats || ex->post_emb || ex->no_sat);
-    const bool frag = g_epilogue_mode == 2 && !train_ex && !d->out_f16 && !(ex && (ex->zero_halo || ex->edge_lo || ex->edge_hi));
     if (d->out_f16 && d->out_mode != OUT_NCT32) return fail(ZS_ERR_ARG, "conv: out_f16 applies to the (B, C, T) output mode");
     const int Tt = round_up(d->T_out, 16);
     const int m_tiles = d->m_rows / BM;
@@ -313,18 +306,33 @@ static int launch_conv(const zs_conv_desc* d, cudaStream_t stream, const ConvExt
         if (T_rows > d->out_rows) return fail(ZS_ERR_ARG, "conv: output buffer has %d rows, needs %d", d->out_rows, T_rows);
         cuuint64_t dims[3] = {static_cast<cuuint64_t>(ps ? d->m_valid / 2 : d->m_valid), static_cast<cuuint64_t>(T_rows), static_cast<cuuint64_t>(d->B)};
         cuuint64_t strides[2] = {static_cast<cuuint64_t>(d->out_pitch) * 2, static_cast<cuuint64_t>(d->out_rows) * d->out_pitch * 2};
-        // fragment epilogue: 64-channel boxes with the 128-byte swizzle (two stores per round), else one unswizzled 128-channel box
-        cuuint32_t box[3] = {static_cast<cuuint32_t>((ps || frag) ? 64 : 128), static_cast<cuuint32_t>(ps ? 2 * p.rnd_rows : p.rnd_rows), static_cast<cuuint32_t>(p.rnd_ns)};
+        cuuint32_t box[3] = {static_cast<cuuint32_t>(ps ? 64 : 128), static_cast<cuuint32_t>(ps ? 2 * p.rnd_rows : p.rnd_rows), static_cast<cuuint32_t>(p.rnd_ns)};
         void* base = static_cast<uint8_t*>(d->out) + static_cast<size_t>(d->out_choff) * 2;
-        ZS_TRY(make_map(&p.tmOut, d->operand, base, 3, dims, strides, box, frag));
+        ZS_TRY(make_map(&p.tmOut, d->operand, base, 3, dims, strides, box, false));
         if (d->res_mode != RES_NONE) {   // residual tile: same channels, rows scaled by the mode
             if (d->res_pitch % 8 || reinterpret_cast<uintptr_t>(d->res) % 16) return fail(ZS_ERR_ARG, "conv: residual buffer must be 16-byte aligned with a pitch multiple of 8");
             const int rr = d->res_mode == RES_UP2 ? p.rnd_rows / 2 : (d->res_mode == RES_AVG2 ? 2 * p.rnd_rows : p.rnd_rows);
             if (rr < 1 || rr > 256) return fail(ZS_ERR_ARG, "conv: residual box rows %d", rr);
             cuuint64_t rdims[3] = {static_cast<cuuint64_t>(std::min(d->m_valid, d->res_pitch)), static_cast<cuuint64_t>(d->res_rows), static_cast<cuuint64_t>(d->B)};
             cuuint64_t rstrides[2] = {static_cast<cuuint64_t>(d->res_pitch) * 2, static_cast<cuuint64_t>(d->res_rows) * d->res_pitch * 2};
-            cuuint32_t rbox[3] = {static_cast<cuuint32_t>(frag ? 64 : 128), static_cast<cuuint32_t>(rr), static_cast<cuuint32_t>(p.rnd_ns)};
-            ZS_TRY(make_map(&p.tmRes, d->operand, const_cast<void*>(d->res), 3, rdims, rstrides, rbox, frag));
+            cuuint32_t rbox[3] = {128u, static_cast<cuuint32_t>(rr), static_cast<cuuint32_t>(p.rnd_ns)};
+            ZS_TRY(make_map(&p.tmRes, d->operand, const_cast<void*>(d->res), 3, rdims, rstrides, rbox, false));
+        }
+    }
+    else if (!d->accumulate && !(ex && ex->zero_halo)) {
+        // (B, C, T) output staged through shared memory: each epilogue warp stores {one 128-byte row of frames} x 32 channels boxes
+        // (128-byte swizzle -> conflict-free 16-byte shared stores).  Needs whole rows; anything else takes the direct-store path.
+        const int es = d->out_f16 ? 2 : 4, fpr = 128 / es;
+        if (d->T_out % fpr == 0 && reinterpret_cast<uintptr_t>(d->out) % 16 == 0) {
+            cuuint64_t dims[3] = {static_cast<cuuint64_t>(d->T_out), static_cast<cuuint64_t>(d->m_valid), static_cast<cuuint64_t>(d->B)};
+            cuuint64_t strides[2] = {static_cast<cuuint64_t>(d->T_out) * es, static_cast<cuuint64_t>(d->m_valid) * d->T_out * es};
+            cuuint32_t box[3] = {static_cast<cuuint32_t>(fpr), 32u, 1u};
+            cuuint32_t estr[3] = {1, 1, 1};
+            CUresult r = g_encode(&p.tmOut, d->out_f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, d->out, dims, strides,
+                                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) return fail(ZS_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for the (B, C, T) output", (int)r);
+            p.nct_tma = 1;
         }
     }
     p.m_tiles = m_tiles; p.n_tiles = n_tiles; p.nb = nb; p.Tt = Tt; p.T = d->T_out; p.B = d->B; p.N = nb * Tt;
@@ -354,10 +362,9 @@ static int launch_conv(const zs_conv_desc* d, cudaStream_t stream, const ConvExt
     const int zp = p.zero_halo ? 1 : 0;
     using KernelT = void (*)(const GemmParams);
     if (zp && train_ex) return fail(ZS_ERR_ARG, "conv: the zero-padding mode is inference only");
-    KernelT kern = zp ? (which ? conv_gemm_kernel<__nv_bfloat16, true, false, false> : conv_gemm_kernel<__half, true, false, false>)
-                 : frag ? (which ? conv_gemm_kernel<__nv_bfloat16, false, true, false> : conv_gemm_kernel<__half, false, true, false>)
-                 : train_ex ? (which ? conv_gemm_kernel<__nv_bfloat16, false, false, true> : conv_gemm_kernel<__half, false, false, true>)
-                            : (which ? conv_gemm_kernel<__nv_bfloat16, false, false, false> : conv_gemm_kernel<__half, false, false, false>);
+    KernelT kern = zp ? (which ? conv_gemm_kernel<__nv_bfloat16, true, false> : conv_gemm_kernel<__half, true, false>)
+                 : train_ex ? (which ? conv_gemm_kernel<__nv_bfloat16, false, true> : conv_gemm_kernel<__half, false, true>)
+                            : (which ? conv_gemm_kernel<__nv_bfloat16, false, false> : conv_gemm_kernel<__half, false, false>);
     ZS_TRY(set_smem_attr(reinterpret_cast<const void*>(kern), GEMM_SMEM_BYTES));
     {   // algorithmic FLOPs: 2 * valid out channels * true taps * true in channels * valid frames
         double taps_sum = d->bank ? 28.0 / 7.0 : static_cast<double>(d->taps);
