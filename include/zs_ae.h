@@ -373,6 +373,10 @@ typedef struct {
     int32_t out_f16;         /* out_mode 2 only: the (B, m_valid, T_out) output is fp16 instead of fp32 */
 } zs_conv_desc;
 int zs_conv1d_cl(const zs_conv_desc* d, void* stream);
+/* Layers with an even number of 128-channel tiles and of segments per tile run as CTA pairs (tcgen05 cta_group::2, M = 256; each CTA
+ * stages half of the tile's columns).  mode 0 turns that off process-wide (one CTA per tile everywhere: the tests' A/B reference),
+ * mode 1 (default) restores it.  Results are bit-identical either way. */
+void zs_set_gemm_pair_mode(int mode);
 
 /* (B, C, T) fp32 -> channels-last operand buffer [B][rows][pitch] with `halo` reflected rows each side;
  * optional leaky-relu; channels C..pitch-1 are zero-filled. */

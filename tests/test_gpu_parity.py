@@ -693,6 +693,41 @@ def test_encode_to_files_writes_the_reference_unit_format(full_models, tmp_path)
         assert r.shape[1] == 1024 and (r.sum(1) == 1).all()
 
 
+def test_cta_pair_gemm_is_bit_identical_to_single_cta(full_models):
+    """Layers with an even number of channel tiles and of segments per tile run as CTA pairs (tcgen05 cta_group::2, M = 256, each CTA
+    staging half of the tile's columns); `zs_set_gemm_pair_mode(0)` runs one CTA per tile everywhere.  Same MMAs on the same
+    operands in the same order per output element: the two must agree bit for bit - whole path (every epilogue variant), ragged and
+    short segments, batches that leave tiles partly empty, and single layers through the C ABI."""
+    lib = _lib.lib()
+    enc, dec, _, _ = full_models
+    try:
+        for B, T in ((6, 128), (37, 128), (4, 77), (2, 207), (5, 9), (40, 16), (300, 128)):
+            x = syn.spectrogram_batch(B, T, 93).cuda()
+            c = syn.speaker_ids(B, 102, 93).cuda()
+            noise = gumbel_from_uniform(syn.gumbel_uniform((B, Encoder.t8(T), 1024), 93)).cuda()
+            res = []
+            for mode in (0, 1):
+                lib.zs_set_gemm_pair_mode(mode)
+                act, logits, ids = enc.encode(x, noise)
+                spec = dec.decode(None, c, unit_ids=ids)
+                torch.cuda.synchronize()
+                res.append((logits.clone(), ids.clone(), spec.clone()))
+            (l0, i0, s0), (l1, i1, s1) = res
+            assert torch.equal(l0, l1) and torch.equal(i0, i1) and torch.equal(s0, s1), (B, T)
+        for cs in (dict(B=6, C_in=513, C_out=256, T=77, k=3), dict(B=40, C_in=64, C_out=512, T=256, k=3), dict(B=34, C_in=96, C_out=1024, T=16, k=1)):
+            torch.manual_seed(1)
+            xx = torch.randn(cs['B'], cs['C_in'], cs['T'], device='cuda')
+            W = torch.randn(cs['C_out'], cs['C_in'], cs['k'], device='cuda') / (cs['C_in'] * cs['k']) ** 0.5
+            bb = torch.randn(cs['C_out'], device='cuda') * 0.1
+            outs = []
+            for mode in (0, 1):
+                lib.zs_set_gemm_pair_mode(mode)
+                outs.append((gh.conv_cl_to_cl(xx, W, bb, lrelu=True, inorm=True, halo_out=2), gh.conv_cl(xx, W, bb, lrelu=True, act=1)))
+            assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1]), cs
+    finally:
+        lib.zs_set_gemm_pair_mode(1)
+
+
 def test_fp16_spectrogram_output(full_models):
     """Decoder.decode(out_dtype=float16): the fp32 result rounded once to fp16 (bit-exact to that rounding), also through the
     accumulate rule and the streaming front-end's fp16 host buffers."""

@@ -143,6 +143,7 @@ SYMBOLS = {
     'zs_profile_name': (C.c_char_p, [_i]),
     'zs_launch_counts': (None, [C.POINTER(C.c_longlong)]),
     'zs_bottleneck_one_hot': (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
+    'zs_set_gemm_pair_mode': (None, [_i]),
     'zs_conv1d_cl': (_i, [C.POINTER(ConvDesc), _vp]),
     'zs_pack_nct': (_i, [_vp, _i, _i, _i, _vp, _i, _i, _i, _i, _i, C.c_float, _i, _i, _vp]),
     'zs_gru_recurrence': (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _i, _i, _i, _i, _i, _i, _vp]),

@@ -41,6 +41,11 @@ constexpr int STAGING_BYTES = 65536;   // per epilogue set 2 staging tiles of 64
 constexpr int SET_STAGING_BYTES = STAGING_BYTES / EPI_SETS;
 constexpr int STG_TILE_BYTES = SET_STAGING_BYTES / 2;
 constexpr int GEMM_SMEM_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + STAGING_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+// CTA-pair variant (tcgen05 cta_group::2, M = 256): each CTA stages its own 128 weight rows and HALF of the tile's columns,
+// 32 KB per stage instead of 48 KB -> four stages in less shared memory, a third less L2 -> shared-memory traffic per FLOP
+constexpr int PAIR_STAGES = 4;
+constexpr int PAIR_B_STAGE_BYTES = B_STAGE_BYTES / 2;
+constexpr int MAX_STAGES = 4;
 constexpr float IN_EPS = 1e-5f;
 
 // timing-experiment bits (results are wrong with any bit set) exist only in -DZS_EXPERIMENTS builds
@@ -63,6 +68,7 @@ struct alignas(64) GemmParams {
     int rnd_ns, rnd_rows, rnd_sub, rnd_frames;
     int m_tiles, n_tiles, nb, Tt, T, B, N;
     int kc, taps, bank, stride, in_row0, c_in_pad;
+    int pair;            // CTA-pair launch (cluster of 2): tmB's box holds nb / 2 segments, idesc has M = 256
     int last_mmas;       // K = 16 MMAs of the LAST 64-channel chunk of a tap that hold valid input channels (1..4)
     int pdl;             // launched with programmatic stream serialization: wait for the producer grid before touching its data
     int m_valid;
@@ -86,7 +92,7 @@ struct alignas(64) GemmParams {
     const long long* post_spk;
     int post_pitch, post_n;
     int no_sat;               // gradient outputs: let fp16 overflow to inf (the loss-scale logic detects it) instead of clamping
-    int nct_tma;              // OUT_NCT32 only: tmOut describes the (frames, channels, segments) output; the epilogue stages rows in shared memory and TMA-stores them
+    int nct_tma;              // OUT_NCT32 only, != 0: tmOut describes the (frames, channels, segments) output; the epilogue stages rows of this many bytes (128 swizzled / 64 plain) in shared memory and TMA-stores them
     int out_f16;              // OUT_NCT32 only: write the (B, C, T) output as fp16 instead of fp32 (halves the D2H bytes of the spectrograms)
     unsigned int* sat_count;  // device word, += 1 per epilogue thread that clamped an fp16 output to +-65504 (never silent)
     // zero-padding mode (model/model.py:36-38, seg_len < 64): halo rows are zeros, and a layer whose speaker embedding is
@@ -205,25 +211,36 @@ __device__ __forceinline__ PackedAffine packed_affine(const ChanNorm& cn, bool l
     return pa;
 }
 
+// explicit shared-window accesses of the staging tiles (32-bit shared addresses: [base + immediate] forms, nothing for the
+// compiler to re-derive from a generic pointer inside the hot loops)
+__device__ __forceinline__ void sts16(uint32_t addr, uint32_t v) {
+    asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(static_cast<uint16_t>(v)));
+}
+__device__ __forceinline__ uint16_t lds16(uint32_t addr) {
+    uint16_t r;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(r) : "r"(addr));
+    return r;
+}
+
 // InstanceNorm statistics of one (segment, channel) in ONE pass over TMEM: sums are taken relative to the
 // first frame's value so the variance does not cancel catastrophically.  Packed math (two frames per instruction,
-// d = lrelu(a + bias) - x0 = max(a + c1, ns a + c2)), two independent accumulator pairs, next chunk's TMEM load in flight.
+// d = lrelu(a + bias) - x0 = max(a + c1, ns a + c2)), two independent accumulator pairs, two TMEM buffers in ping-pong
+// (the next chunk's load is in flight while this one is summed; no register copies).
 template <bool ZP>
 __device__ __forceinline__ void chan_stats(const GemmParams& p, uint32_t t_seg, int T, float bias, bool lrelu, float ns,
                                            const ChanNorm& cn, float& mean, float& rstd) {
-    uint32_t v[16], vn[16];
-    tmem_ld16(t_seg, v);
+    uint32_t va[16], vb[16];
+    tmem_ld16(t_seg, va);
     tmem_ld_wait();
-    if (ZP && cn.edge_off >= 0) apply_edges(p, v, 0, T, cn);
-    float x0 = __uint_as_float(v[0]) + bias;
+    if (T > 16) tmem_ld16(t_seg + 16, vb);
+    if (ZP && cn.edge_off >= 0) apply_edges(p, va, 0, T, cn);
+    float x0 = __uint_as_float(va[0]) + bias;
     if (lrelu) x0 = fmaxf(x0, x0 * ns);
     const float nsv = lrelu ? ns : 1.f;
     const float c1 = bias - x0, c2 = fmaf(nsv, bias, -x0);
     const uint64_t C1 = pk2(c1, c1), C2 = pk2(c2, c2), NS = pk2(nsv, nsv);
     uint64_t Sa = pk2(0.f, 0.f), Sb = Sa, Qa = Sa, Qb = Sa;
-    for (int c0 = 0; c0 < T; c0 += 16) {
-        const bool more = c0 + 16 < T;
-        if (more) tmem_ld16(t_seg + c0 + 16, vn);
+    auto chunk = [&](uint32_t (&v)[16], int c0) {
         if (c0 + 16 <= T) {
 #pragma unroll
             for (int i = 0; i < 16; i += 4) {
@@ -251,12 +268,18 @@ __device__ __forceinline__ void chan_stats(const GemmParams& p, uint32_t t_seg, 
             Sa = fadd2(Sa, pk2(s1, 0.f));
             Qa = fadd2(Qa, pk2(s2, 0.f));
         }
-        if (more) {
-            tmem_ld_wait();
-            if (ZP && cn.edge_off >= 0) apply_edges(p, vn, c0 + 16, T, cn);
-#pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = vn[i];
-        }
+    };
+    for (int c0 = 0; c0 < T; c0 += 32) {          // va holds chunk c0 (waited for, edges applied); vb's load (chunk c0 + 16) is in flight
+        chunk(va, c0);
+        if (c0 + 16 >= T) break;
+        tmem_ld_wait();
+        if (c0 + 32 < T) tmem_ld16(t_seg + c0 + 32, va);
+        if (ZP && cn.edge_off >= 0) apply_edges(p, vb, c0 + 16, T, cn);
+        chunk(vb, c0 + 16);
+        if (c0 + 32 >= T) break;
+        tmem_ld_wait();
+        if (c0 + 48 < T) tmem_ld16(t_seg + c0 + 48, vb);
+        if (ZP && cn.edge_off >= 0) apply_edges(p, va, c0 + 32, T, cn);
     }
     float sa, sb, qa, qb;
     upk2(fadd2(Sa, Sb), sa, sb);
@@ -270,34 +293,28 @@ __device__ __forceinline__ void chan_stats(const GemmParams& p, uint32_t t_seg, 
 
 // Frames [f_lo, f_hi) of one (segment, channel) -> shared-memory staging tile (channels-last rows that a TMA
 // store then writes out), plus the reflected halo rows written directly.  RES / PS are compile time.
-//   stg      : staging slot of (frame f_lo, this thread's channel); frame stride = STG_PITCH elements
-//   res_stg  : residual tile in shared memory (TMA-loaded), slot of (first residual row of this sub-round, channel)
+//   stg_a    : shared address of the staging slot of (frame f_lo, this thread's channel); a frame is ROWB bytes further
+//   res_a    : shared address of the residual tile's slot (TMA-loaded) of (first residual row of this sub-round, channel)
 //   out_s    : output buffer at (this segment, row 0, this thread's output channel) - for the halo rows only
 // TRAIN: the training extras (post-added embedding, unsaturated gradient outputs) exist - compile-time so that the
 // inference layers carry no instruction for what they do not use.  LR = false: the layer has no leaky-relu (GRU input
 // projections) - one FFMA2 per pair and no max.
 template <typename OT, int RES, bool PS, bool ZP, bool TRAIN, bool LR>
 __device__ __forceinline__ void frames_to_staging(const GemmParams& p, uint32_t t_seg, int f_lo, int f_hi, int T,
-                                                  const ChanNorm& cn, bool lrelu, float ns, OT* __restrict__ stg,
-                                                  const OT* __restrict__ res_stg, OT* __restrict__ out_s, int ps_r,
+                                                  const ChanNorm& cn, bool lrelu, float ns, uint32_t stg_a,
+                                                  uint32_t res_a, OT* __restrict__ out_s, int ps_r,
                                                   bool ch_ok, bool& sat) {
-    constexpr int STG_PITCH = PS ? 64 : 128;          // channels per staging row
-    constexpr int FSTEP = PS ? 2 : 1;                 // staging rows per input frame
+    constexpr int ROWB = 256;                         // bytes per input frame in the staging tile: 128 channels, or 2 rows of 64 (pixel shuffle)
     constexpr bool F16 = !IS_BF16<OT>::value;
     const int T_out = PS ? 2 * T : T;
     const int halo = p.out_halo;
     const PackedAffine pa = packed_affine(cn, LR && lrelu, ns, TRAIN);
     const bool nosat = TRAIN && p.no_sat;
     uint32_t satm = 0;                                // running |max| of the fp16 pairs this thread stored
-    uint16_t* stg16 = reinterpret_cast<uint16_t*>(stg);
-    const uint16_t* res16 = reinterpret_cast<const uint16_t*>(res_stg);
-    uint32_t v[16], vn[16];
-    tmem_ld16(t_seg + f_lo, v);
-    for (int c0 = f_lo; c0 < f_hi; c0 += 16) {
-        tmem_ld_wait();
+    auto chunk = [&](uint32_t (&v)[16], int c0) {
         if (ZP && cn.edge_off >= 0) apply_edges(p, v, c0, T, cn);
-        const bool more = c0 + 16 < f_hi;
-        if (more) tmem_ld16(t_seg + c0 + 16, vn);       // next chunk's accumulators while this one is processed
+        const int rel = c0 - f_lo;
+        const uint32_t ra = RES == RES_UP2 ? res_a + (rel >> 1) * 256 : (RES == RES_AVG2 ? res_a + rel * 512 : res_a + rel * 256);
         uint32_t yp[8];                                 // 16 outputs as 8 packed 16-bit pairs
 #pragma unroll
         for (int i = 0; i < 16; i += 2) {
@@ -311,16 +328,17 @@ __device__ __forceinline__ void frames_to_staging(const GemmParams& p, uint32_t 
                 x1 = fmaxf(x1, q1);
             }
             if (RES == RES_SAME) {
-                x0 = res_add<OT>(res16[(c0 - f_lo + i) * 128], x0);
-                x1 = res_add<OT>(res16[(c0 - f_lo + i + 1) * 128], x1);
+                x0 = res_add<OT>(lds16(ra + i * 256), x0);
+                x1 = res_add<OT>(lds16(ra + (i + 1) * 256), x1);
             } else if (RES == RES_UP2) {
-                const uint16_t r = res16[((c0 - f_lo + i) >> 1) * 128];
+                const uint16_t r = lds16(ra + (i >> 1) * 256);
                 x0 = res_add<OT>(r, x0);
                 x1 = res_add<OT>(r, x1);
             } else if (RES == RES_AVG2) {
-                const uint16_t* q = res16 + 2 * (c0 - f_lo + i) * 128;
-                x0 += 0.5f * res_add<OT>(q[0], ot_to_float<OT>(reinterpret_cast<const OT*>(q)[128]));
-                x1 += 0.5f * res_add<OT>(q[256], ot_to_float<OT>(reinterpret_cast<const OT*>(q)[384]));
+                const uint16_t r0 = lds16(ra + i * 512), r1 = lds16(ra + i * 512 + 256), r2 = lds16(ra + i * 512 + 512), r3 = lds16(ra + i * 512 + 768);
+                const OT o1 = *reinterpret_cast<const OT*>(&r1), o3 = *reinterpret_cast<const OT*>(&r3);
+                x0 += 0.5f * res_add<OT>(r0, ot_to_float<OT>(o1));
+                x1 += 0.5f * res_add<OT>(r2, ot_to_float<OT>(o3));
             }
             yp[i >> 1] = nosat ? cvt_pair<OT, true>(x0, x1) : cvt_pair<OT, false>(x0, x1);
         }
@@ -337,11 +355,11 @@ __device__ __forceinline__ void frames_to_staging(const GemmParams& p, uint32_t 
                 }
             }
         }
-        uint16_t* sp = stg16 + (c0 - f_lo) * (FSTEP * STG_PITCH);
+        const uint32_t sp = stg_a + rel * ROWB;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {                     // columns >= T are clipped by the TMA store
-            sp[(2 * i) * (FSTEP * STG_PITCH)] = static_cast<uint16_t>(yp[i]);
-            sp[(2 * i + 1) * (FSTEP * STG_PITCH)] = static_cast<uint16_t>(yp[i] >> 16);
+            sts16(sp + (2 * i) * ROWB, yp[i]);
+            sts16(sp + (2 * i + 1) * ROWB, yp[i] >> 16);
         }
         // reflected halo rows of the output buffer (read by the next conv's outer taps)
         if (halo > 0 && (c0 == 0 || c0 + 16 + 3 >= T)) {     // warp-uniform condition: ch_ok (per lane) must not guard the __syncwarp below
@@ -358,10 +376,18 @@ __device__ __forceinline__ void frames_to_staging(const GemmParams& p, uint32_t 
             }
             __syncwarp();
         }
-        if (more) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = vn[i];
-        }
+    };
+    uint32_t va[16], vb[16];                              // ping-pong: the next chunk's accumulators load while this one is processed
+    tmem_ld16(t_seg + f_lo, va);
+    for (int c0 = f_lo; c0 < f_hi; c0 += 32) {
+        tmem_ld_wait();
+        const bool more = c0 + 16 < f_hi;
+        if (more) tmem_ld16(t_seg + c0 + 16, vb);
+        chunk(va, c0);
+        if (!more) break;
+        tmem_ld_wait();
+        if (c0 + 32 < f_hi) tmem_ld16(t_seg + c0 + 32, va);
+        chunk(vb, c0 + 16);
     }
     if (F16 && ch_ok) sat |= h2_at_limit(satm);
 }
@@ -436,8 +462,9 @@ __device__ __forceinline__ void frames_to_nct_tma(const GemmParams& p, uint32_t 
                                                   uint8_t* __restrict__ wstage, int lane, int ch0, int b, int& grp) {
     const PackedAffine pa = packed_affine(cn, lrelu, ns, false);
     const bool f16 = p.out_f16 != 0;
-    const int fpr = f16 ? 64 : 32;                       // frames per staging row
-    const int sw = lane & 7;
+    const int rb = p.nct_tma;                            // bytes per staging row: 128 (swizzled) or 64
+    const int fpr = f16 ? rb >> 1 : rb >> 2;             // frames per staging row
+    const int sw = rb == 128 ? (lane & 7) : 0;
     uint32_t v[16], vn[16];
     tmem_ld16(t_seg, v);
     for (int c0 = 0; c0 < T; c0 += 16) {
@@ -448,7 +475,7 @@ __device__ __forceinline__ void frames_to_nct_tma(const GemmParams& p, uint32_t 
             if (elect_one()) tma_store_wait_read1();
             __syncwarp();
         }
-        uint8_t* rowp = wstage + (grp & 1) * 4096 + lane * 128;
+        uint8_t* rowp = wstage + (grp & 1) * 4096 + lane * rb;
         float x[16];
 #pragma unroll
         for (int i = 0; i < 16; i += 2) {
@@ -467,7 +494,7 @@ __device__ __forceinline__ void frames_to_nct_tma(const GemmParams& p, uint32_t 
             for (int i = 0; i < 16; ++i) x[i] = tanh_f(x[i]);
         }
         if (f16) {
-            const int j0 = (c0 & 63) >> 3;
+            const int j0 = (c0 & (fpr - 1)) >> 3;
             uint32_t h[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
@@ -477,7 +504,7 @@ __device__ __forceinline__ void frames_to_nct_tma(const GemmParams& p, uint32_t 
             *reinterpret_cast<uint4*>(rowp + (((j0) ^ sw) << 4)) = make_uint4(h[0], h[1], h[2], h[3]);
             *reinterpret_cast<uint4*>(rowp + (((j0 + 1) ^ sw) << 4)) = make_uint4(h[4], h[5], h[6], h[7]);
         } else {
-            const int j0 = (c0 & 31) >> 2;
+            const int j0 = (c0 & (fpr - 1)) >> 2;
 #pragma unroll
             for (int q = 0; q < 4; ++q)
                 *reinterpret_cast<float4*>(rowp + (((j0 + q) ^ sw) << 4)) = make_float4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
@@ -500,32 +527,40 @@ __device__ __forceinline__ void frames_to_nct_tma(const GemmParams& p, uint32_t 
 
 // ZP: zero-padding mode (seg_len < 64) - a separate instantiation so the reflect-mode kernel carries none of its code.
 // TRAIN: training extras compiled in (InstanceNorm statistics output, post-added embedding, unsaturated outputs).
-template <typename OT, bool ZP, bool TRAIN>
+// PAIR: launched as clusters of two CTAs that share one tcgen05.mma.cta_group::2 (M = 256 = two adjacent 128-channel tiles, the same
+// N columns).  Each CTA loads its own weight tile and half of the activation columns; the pair leader (cluster rank 0) collects both
+// CTAs' TMA bytes on its `full` barriers, issues the MMAs for both, and its commits are multicast to both CTAs' `empty` / `tfull`
+// barriers; each CTA runs the epilogue of its own 128 channels out of its own TMEM; both epilogues hand the accumulator back on the
+// leader's `tempty`.
+template <typename OT, bool ZP, bool TRAIN, bool PAIR>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid_constant__ GemmParams p) {
+    constexpr int NSTG = PAIR ? PAIR_STAGES : STAGES;
+    constexpr int B_BYTES = PAIR ? PAIR_B_STAGE_BYTES : B_STAGE_BYTES;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_addr = smem_u32(smem_raw);
     uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
     uint8_t* sA = smem;
-    uint8_t* sB = smem + STAGES * A_STAGE_BYTES;
-    uint8_t* sStage = smem + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES);
+    uint8_t* sB = smem + NSTG * A_STAGE_BYTES;
+    uint8_t* sStage = smem + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES);      // (the pair's four stages end 16 KB below)
     uint64_t* full = reinterpret_cast<uint64_t*>(sStage + STAGING_BYTES);
-    uint64_t* empty = full + STAGES;
-    uint64_t* tfull = empty + STAGES;
+    uint64_t* empty = full + MAX_STAGES;
+    uint64_t* tfull = empty + MAX_STAGES;
     uint64_t* tempty = tfull + 2;
     uint64_t* rbar = tempty + 2;   // [EPI_SETS] residual tile landed in the set's staging buffer
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rbar + EPI_SETS);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    const uint32_t rank = PAIR ? cluster_ctarank() : 0u;      // 0 = the pair's leader
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < STAGES; ++i) {
+        for (int i = 0; i < NSTG; ++i) {
             mbar_init(&full[i], 1);
             mbar_init(&empty[i], 1);
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tfull[i], 1);
-            mbar_init(&tempty[i], 4 * EPI_SETS);
+            mbar_init(&tempty[i], (PAIR ? 2 : 1) * 4 * EPI_SETS);
         }
         for (int i = 0; i < EPI_SETS; ++i) mbar_init(&rbar[i], 1);
         fence_barrier_init();
@@ -534,9 +569,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
         if (p.out_mode != OUT_NCT32 || p.nct_tma) tma_prefetch_desc(&p.tmOut);
         if (p.res_mode != RES_NONE) tma_prefetch_desc(&p.tmRes);
     }
-    if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_slot);
+    if (warp == 1) {
+        if (PAIR) tmem_alloc_pair<TMEM_COLS>(tmem_slot);
+        else tmem_alloc<TMEM_COLS>(tmem_slot);
+    }
     tc_fence_before();
     __syncthreads();
+    if (PAIR) cluster_sync_all();      // the peer's barriers are initialised and its TMEM allocated before anything is signalled across
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     if (p.pdl) {
@@ -546,8 +585,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
         asm volatile("griddepcontrol.wait;" ::: "memory");
     }
 
-    const int total_tiles = p.m_tiles * p.n_tiles;
-    const uint32_t stage_tx = A_STAGE_BYTES + static_cast<uint32_t>(p.N) * (BK * 2);
+    // a pair walks (m-tile pair, n-tile) units: CTA `rank` takes m-tile 2 mu + rank
+    const int m_units = PAIR ? p.m_tiles >> 1 : p.m_tiles;
+    const int total_tiles = m_units * p.n_tiles;
+    const int tile0 = PAIR ? blockIdx.x >> 1 : blockIdx.x, tile_step = PAIR ? gridDim.x >> 1 : gridDim.x;
+    const uint32_t stage_tx = PAIR ? 2u * (A_STAGE_BYTES + static_cast<uint32_t>(p.N >> 1) * (BK * 2))
+                                   : A_STAGE_BYTES + static_cast<uint32_t>(p.N) * (BK * 2);
 
     if (warp < 4) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_DRIVER));
@@ -556,10 +599,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
         {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int mt = tile % p.m_tiles, nt = tile / p.m_tiles;
+            const int seg_off = PAIR ? static_cast<int>(rank) * (p.nb >> 1) : 0;      // this CTA's half of the tile's segments
+            for (int tile = tile0; tile < total_tiles; tile += tile_step) {
+                const int mu = tile % m_units, nt = tile / m_units;
+                const int mt = PAIR ? 2 * mu + static_cast<int>(rank) : mu;
                 int tap_lo = 0, ntaps = p.taps;
-                if (p.bank) {
+                if (!PAIR && p.bank) {
                     ntaps = mt + 1;
                     tap_lo = 3 - ntaps / 2;
                 }
@@ -571,18 +616,26 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
                         if (ZS_DBG(p) & 1) {
                             if (elect_one()) mbar_arrive(&full[stage]);
                         } else if (elect_one()) {
-                            mbar_expect_tx(&full[stage], stage_tx);
-                            tma_load_2d(&p.tmA, sA + stage * A_STAGE_BYTES, &full[stage], tap * p.c_in_pad + c * BK,
-                                        mt * BM);
-                            if (p.stride == 2)  // buffer viewed as (channel, row parity, row pair, segment)
-                                tma_load_4d(&p.tmB, sB + stage * B_STAGE_BYTES, &full[stage], c * BK, row_b & 1,
-                                            row_b >> 1, nt * p.nb);
-                            else
-                                tma_load_3d(&p.tmB, sB + stage * B_STAGE_BYTES, &full[stage], c * BK, row_b,
-                                            nt * p.nb);
+                            uint8_t* dA = sA + stage * A_STAGE_BYTES;
+                            uint8_t* dB = sB + stage * B_BYTES;
+                            if (PAIR) {
+                                // both CTAs' bytes complete on the LEADER's barrier; only the leader arms it
+                                if (rank == 0) mbar_expect_tx(&full[stage], stage_tx);
+                                const uint32_t fb = mapa_shared(smem_u32(&full[stage]), 0);
+                                tma_load_2d_pair(&p.tmA, dA, fb, tap * p.c_in_pad + c * BK, mt * BM);
+                                if (p.stride == 2) tma_load_4d_pair(&p.tmB, dB, fb, c * BK, row_b & 1, row_b >> 1, nt * p.nb + seg_off);
+                                else tma_load_3d_pair(&p.tmB, dB, fb, c * BK, row_b, nt * p.nb + seg_off);
+                            } else {
+                                mbar_expect_tx(&full[stage], stage_tx);
+                                tma_load_2d(&p.tmA, dA, &full[stage], tap * p.c_in_pad + c * BK, mt * BM);
+                                if (p.stride == 2)  // buffer viewed as (channel, row parity, row pair, segment)
+                                    tma_load_4d(&p.tmB, dB, &full[stage], c * BK, row_b & 1, row_b >> 1, nt * p.nb);
+                                else
+                                    tma_load_3d(&p.tmB, dB, &full[stage], c * BK, row_b, nt * p.nb);
+                            }
                         }
                         __syncwarp();
-                        if (++stage == STAGES) {
+                        if (++stage == NSTG) {
                             stage = 0;
                             phase ^= 1;
                         }
@@ -590,16 +643,16 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
                 }
             }
         }
-    } else if (warp == 1) {
-        // ------------------------------ MMA issuer (whole warp, one elected lane issues) --------
+    } else if (warp == 1 && rank == 0) {
+        // ------------------------------ MMA issuer (whole warp, one elected lane issues; a pair's leader issues for both CTAs) --------
         {
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
             const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-                const int mt = tile % p.m_tiles;
-                const int ksteps = (p.bank ? mt + 1 : p.taps) * p.kc;
+            for (int tile = tile0; tile < total_tiles; tile += tile_step, ++it) {
+                const int mt = tile % m_units;          // (bank mode is never paired: mt is the m-tile there)
+                const int ksteps = ((!PAIR && p.bank) ? mt + 1 : p.taps) * p.kc;
                 const int as = it & 1;
                 mbar_wait(&tempty[as], ((it >> 1) & 1) ^ 1);
                 tc_fence_after();
@@ -609,7 +662,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
                     mbar_wait(&full[stage], phase);
                     tc_fence_after();
                     const uint64_t da = umma_desc_sw128(a0 + stage * A_STAGE_BYTES);
-                    const uint64_t db = umma_desc_sw128(b0 + stage * B_STAGE_BYTES);
+                    const uint64_t db = umma_desc_sw128(b0 + stage * B_BYTES);
                     // the zero-padded tail of the input channels (513 -> 576, 1409 -> 1472) needs no MMAs
                     const int n_mma = (++kc_pos == p.kc) ? p.last_mmas : BK / 16;
                     if (kc_pos == p.kc) kc_pos = 0;
@@ -618,18 +671,25 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
 #pragma unroll
                             for (int k = 0; k < BK / 16; ++k) {
                                 // advance 16 elements (32 B) along K inside the swizzle row: +2 in the >>4 address field
-                                if (k < n_mma) umma_f16(d_tmem, da + 2 * k, db + 2 * k, p.idesc, (ks | k) != 0);
+                                if (k < n_mma) {
+                                    if (PAIR) umma_f16_pair(d_tmem, da + 2 * k, db + 2 * k, p.idesc, (ks | k) != 0);
+                                    else umma_f16(d_tmem, da + 2 * k, db + 2 * k, p.idesc, (ks | k) != 0);
+                                }
                             }
                         }
-                        umma_commit(&empty[stage]);
+                        if (PAIR) umma_commit_pair(&empty[stage]);      // frees this stage in BOTH CTAs
+                        else umma_commit(&empty[stage]);
                     }
                     __syncwarp();
-                    if (++stage == STAGES) {
+                    if (++stage == NSTG) {
                         stage = 0;
                         phase ^= 1;
                     }
                 }
-                if (elect_one()) umma_commit(&tfull[as]);
+                if (elect_one()) {
+                    if (PAIR) umma_commit_pair(&tfull[as]);
+                    else umma_commit(&tfull[as]);
+                }
                 __syncwarp();
             }
         }
@@ -651,8 +711,17 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
         int it = 0, rnd = 0;
         uint32_t res_phase = 0;
         bool sat = false;           // this thread clamped an fp16 output (reported once per thread and launch)
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-            const int mt = tile % p.m_tiles, nt = tile / p.m_tiles;
+        // both epilogues of a pair hand the accumulator back on the LEADER's barrier
+        const uint32_t tempty_leader = PAIR ? mapa_shared(smem_u32(&tempty[0]), 0) : 0u;
+        auto release_acc = [&](int as_) {
+            if (lane == 0) {
+                if (PAIR && rank != 0) mbar_arrive_cluster(tempty_leader + 8u * as_);
+                else mbar_arrive(&tempty[as_]);
+            }
+        };
+        for (int tile = tile0; tile < total_tiles; tile += tile_step, ++it) {
+            const int mu = tile % m_units, nt = tile / m_units;
+            const int mt = PAIR ? 2 * mu + static_cast<int>(rank) : mu;
             const int as = it & 1;
             const int ch = mt * BM + row;  // weight row == bias index
             const bool ch_ok = ch < p.m_valid;
@@ -669,7 +738,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
                 }
                 bias_pf = p.bias[off_pf + ch];
             }
-            mbar_wait(&tfull[as], (it >> 1) & 1);
+            mbar_wait_relaxed(&tfull[as], (it >> 1) & 1);
             tc_fence_after();
             const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * MAX_BN;
             auto chan_norm = [&](int b, uint32_t t_seg) {
@@ -713,7 +782,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
             if (ZS_DBG(p) & 4) {            // timing experiment: main loop only
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&tempty[as]);
+                release_acc(as);
             } else if (p.out_mode == OUT_NCT32) {
                 for (int s = eset; s < p.nb; s += EPI_SETS) {
                     const int b = nt * p.nb + s;
@@ -730,7 +799,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&tempty[as]);
+                release_acc(as);
             } else {
                 // pixel shuffle: weight rows are packed so rows [0,64) of a tile hold r = 0, [64,128) r = 1
                 const bool ps = p.out_mode == OUT_PS;
@@ -749,7 +818,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
                 if (my_last < 0 || eset >= n_groups) {
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&tempty[as]);
+                    release_acc(as);
                 }
                 for (int s0 = eset * p.rnd_ns; s0 < p.nb; s0 += EPI_SETS * p.rnd_ns) {
                     for (int h = 0; h < p.rnd_sub; ++h, ++rnd) {
@@ -777,8 +846,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
                                 mbar_wait(my_rbar, res_phase);
                                 waited = true;
                             }
-                            OT* stg = stage_out + static_cast<size_t>(s - s0) * p.rnd_rows * fstep * stg_row + stg_ch;
-                            const OT* res_stg = stage_res + static_cast<size_t>(s - s0) * res_rows_per_seg * 128 + row;
+                            const uint32_t stg = smem_u32(stage_out + static_cast<size_t>(s - s0) * p.rnd_rows * fstep * stg_row + stg_ch);
+                            const uint32_t res_stg = smem_u32(stage_res + static_cast<size_t>(s - s0) * res_rows_per_seg * 128 + row);
                             OT* out_s = reinterpret_cast<OT*>(p.out) + static_cast<size_t>(b) * p.out_rows * p.out_pitch +
                                         p.out_choff + out_ch;
 #define ZS_F2S(RES_, PS_, LR_) frames_to_staging<OT, RES_, PS_, ZP, TRAIN, LR_>(p, t_seg, f_lo, f_hi, T, cn_keep, lrelu, ns, stg, res_stg, out_s, PS_ ? ps_r : 0, ch_ok, sat)
@@ -796,7 +865,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
                         if (last) {   // every TMEM read of this tile is done: hand the accumulator back
                             tc_fence_before();
                             __syncwarp();
-                            if (lane == 0) mbar_arrive(&tempty[as]);
+                            release_acc(as);
                         }
                         fence_proxy_async();                              // staging writes -> visible to the TMA engine
                         asm volatile("bar.sync %0, 128;" ::"r"(set_bar) : "memory");
@@ -818,7 +887,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc<TMEM_COLS>(tmem_base);
+    if (PAIR) cluster_sync_all();      // the leader's MMAs read the peer's shared memory, the peer arrives on the leader's barriers: leave together
+    if (warp == 1) {
+        if (PAIR) tmem_dealloc_pair<TMEM_COLS>(tmem_base);
+        else tmem_dealloc<TMEM_COLS>(tmem_base);
+    }
 }
 
 }  // namespace zs

@@ -67,24 +67,6 @@ __global__ void gru_pack_whh_kernel(const float* __restrict__ W, OT* __restrict_
     *dst = float_to_ot<OT>(W[i]);
 }
 
-__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t cta) {
-    uint32_t r;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(cta));
-    return r;
-}
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-    uint32_t r;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-    return r;
-}
-__device__ __forceinline__ uint32_t cluster_id_x() {
-    uint32_t r;
-    asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r));
-    return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
 // local shared -> peer CTA shared, completion (bytes) signalled on the PEER's mbarrier
 __device__ __forceinline__ void dsmem_bulk_copy(uint32_t dst_cluster_addr, uint32_t src_cta_addr, uint32_t bytes,
                                                 uint32_t mbar_cluster_addr) {
@@ -135,6 +117,8 @@ struct GruParams {
     void* gates;           // training: r, z, n, hn = W_hn h + b_hn per step, operand type [B][T][2][4][H]; null = not saved
 };
 
+__device__ __forceinline__ uint16_t ot_bits(__half v) { return __half_as_ushort(v); }
+__device__ __forceinline__ uint16_t ot_bits(__nv_bfloat16 v) { return __bfloat16_as_ushort(v); }
 __device__ __forceinline__ float tanh_mufu(float v) {
     float r;
     asm("tanh.approx.f32 %0, %1;" : "=f"(r) : "f"(v));
@@ -311,11 +295,13 @@ __global__ void __launch_bounds__(GRU_THREADS, 1) gru_cluster_kernel(const GruPa
                     const uint32_t got = __shfl_xor_sync(0xffffffffu, hi ? a[i] : a[SPT + i], 16);
                     const float hr = __uint_as_float(hi ? got : a[i]);
                     const float hz = __uint_as_float(hi ? a[SPT + i] : got);
-                    const float xr = ot_to_float<OT>(gr[i]) + hr + b_r, xz = ot_to_float<OT>(gz[i]) + hz + b_z;
                     if (fast) {
-                        r[i] = fmaf(0.5f, tanh_mufu(0.5f * xr), 0.5f);
-                        z[i] = fmaf(0.5f, tanh_mufu(0.5f * xz), 0.5f);
+                        // sigmoid(x) = 0.5 tanh(0.5 x) + 0.5 with x = gx + W h + b: one mixed-precision add, two FMAs, one MUFU
+                        // (the same expression as gru_wide.cuh: the kernels stay bit-identical to each other)
+                        r[i] = fmaf(0.5f, tanh_mufu(fmaf(0.5f, res_add<OT>(ot_bits(gr[i]), hr), 0.5f * b_r)), 0.5f);
+                        z[i] = fmaf(0.5f, tanh_mufu(fmaf(0.5f, res_add<OT>(ot_bits(gz[i]), hz), 0.5f * b_z)), 0.5f);
                     } else {
+                        const float xr = ot_to_float<OT>(gr[i]) + hr + b_r, xz = ot_to_float<OT>(gz[i]) + hz + b_z;
                         r[i] = sigmoid_f(xr);
                         z[i] = sigmoid_f(xz);
                     }

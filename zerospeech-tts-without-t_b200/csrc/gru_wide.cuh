@@ -9,6 +9,11 @@
 // trip of the exchange are paid once per 64 sequence-steps instead of once per 32.  The 8 gate warps walk the 64 columns in two
 // passes of 32 (warp w: TMEM quadrant w & 3, 16 columns per pass; thread: one unit x 8 sequences per pass, fp32 state in shared
 // memory).  Inference only (no gate save), tanh.approx gates.
+//
+// Measured and rejected (round 2): running the two 32-sequence halves as independent, software-pipelined recurrences (own
+// accumulators / barriers / 4 KB exchanges, a dedicated exchange warp, no block barrier).  The MMAs stream W_hh through the tensor
+// core at a cost that does not depend on N (33 cycles per M = 128 MMA for N = 32 as for N = 64), so two N = 32 groups double
+// the tensor time per step (~5 000 cycles) and the decoder GRU went from 1.17 to 1.68 ms per 960 segments.
 #pragma once
 #include "gru_cluster.cuh"
 
@@ -176,6 +181,7 @@ __global__ void __launch_bounds__(GRU_THREADS, 1) gru_wide_kernel(const GruWideP
         const int unit = rank * GRU_UNITS + u_loc;
         const float* bh = p.bhh + static_cast<size_t>(dir) * 3 * H;
         const float b_r = bh[unit], b_z = bh[H + unit], b_n = bh[2 * H + unit];
+        const float hb_r = 0.5f * b_r, hb_z = 0.5f * b_z;
         OT* out = reinterpret_cast<OT*>(p.out);
         const uint32_t lane_addr = static_cast<uint32_t>(32 * q) << 16;
         float* my_state = sState + threadIdx.x;                // [pass][i] at (pass * 8 + i) * 256
@@ -235,8 +241,10 @@ __global__ void __launch_bounds__(GRU_THREADS, 1) gru_wide_kernel(const GruWideP
                         const uint32_t got = __shfl_xor_sync(0xffffffffu, hi ? a[i] : a[8 + i], 16);
                         const float hr = __uint_as_float(hi ? got : a[i]);
                         const float hz = __uint_as_float(hi ? a[8 + i] : got);
-                        r[i] = fmaf(0.5f, tanh_mufu(0.5f * (ot_to_float<OT>(gr[i]) + hr + b_r)), 0.5f);
-                        z[i] = fmaf(0.5f, tanh_mufu(0.5f * (ot_to_float<OT>(gz[i]) + hz + b_z)), 0.5f);
+                        // sigmoid(x) = 0.5 tanh(0.5 x) + 0.5 with x = gx + W h + b: one mixed-precision add, two FMAs, one MUFU
+                        // (the same expression as gru_cluster.cuh: the kernels stay bit-identical to each other)
+                        r[i] = fmaf(0.5f, tanh_mufu(fmaf(0.5f, res_add<OT>(ot_bits(gr[i]), hr), hb_r)), 0.5f);
+                        z[i] = fmaf(0.5f, tanh_mufu(fmaf(0.5f, res_add<OT>(ot_bits(gz[i]), hz), hb_z)), 0.5f);
                     }
                 }
                 if (ps == 0) {

@@ -50,6 +50,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
 }
 
+// a wait that is long by design (an epilogue warp waiting for a whole tile of MMAs): back off between polls so the spinning
+// warps do not take issue slots and energy from the warps that work
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) __nanosleep(96);
+}
+
 // ---- TMA ------------------------------------------------------------------------------
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
@@ -122,13 +128,13 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
 
 // Instruction descriptor for kind::f16, fp32 accumulate, both operands K-major, M = 128.
 // fmt: 0 = fp16, 1 = bf16.
-__host__ __device__ inline uint32_t umma_idesc_f16(int fmt, int n) {
+__host__ __device__ inline uint32_t umma_idesc_f16(int fmt, int n, int m = 128) {
     uint32_t d = 0;
     d |= 1u << 4;                         // [4,6)   D format = F32
     d |= static_cast<uint32_t>(fmt) << 7;   // [7,10)  A format
     d |= static_cast<uint32_t>(fmt) << 10;  // [10,13) B format
     d |= static_cast<uint32_t>(n >> 3) << 17;   // [17,23) N >> 3
-    d |= static_cast<uint32_t>(128 >> 4) << 24; // [24,29) M >> 4
+    d |= static_cast<uint32_t>(m >> 4) << 24;   // [24,29) M >> 4 (256: the CTA-pair MMA)
     return d;
 }
 
@@ -175,6 +181,77 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
 __device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t (&v)[16]) { tmem_ld16(taddr, v); }
 __device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t (&v)[8]) { tmem_ld8(taddr, v); }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ---- thread-block clusters / CTA pairs (cta_group::2) ---------------------------------------------------------------
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t cta) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(cta));
+    return r;
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t cluster_id_x() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on an mbarrier of another CTA of the cluster (address from mapa_shared)
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA tile loads of a CTA pair: the completion is signalled on the mbarrier at `bar_cluster_addr`, which may live in the PEER CTA
+// (the pair leader collects both CTAs' bytes on one barrier)
+__device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap* m, void* dst, uint32_t bar_cluster_addr, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_pair(const CUtensorMap* m, void* dst, uint32_t bar_cluster_addr, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_pair(const CUtensorMap* m, void* dst, uint32_t bar_cluster_addr, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+// TMEM of a CTA pair: one warp of EACH CTA allocates / frees (tools/cta2_mma_test.cu)
+template <int COLS>
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* slot) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "n"(COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t addr) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "n"(COLS) : "memory");
+}
+// D[tmem of both CTAs] (+)= A * B with M = 256: CTA r of the pair supplies A rows [128 r, 128 r + 128) and B rows (columns of D)
+// [N/2 r, N/2 r + N/2) from the SAME shared-memory offsets, and receives D rows [128 r, +128) x all N columns in its own TMEM.
+// Issued by ONE thread of the pair's leader CTA (cluster rank 0).
+__device__ __forceinline__ void umma_f16_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrive (once all previously issued MMAs of this thread completed) on the mbarrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+                 "h"(static_cast<uint16_t>(3))
+                 : "memory");
+}
 
 // ---- packed fp32 pairs (FFMA2 / FADD2 on sm_100: one issue slot for two values) and mixed-precision adds -------------
 __device__ __forceinline__ uint64_t pk2(float lo, float hi) {

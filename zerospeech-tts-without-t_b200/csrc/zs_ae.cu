@@ -227,6 +227,10 @@ struct ConvExtras {        // training-path additions to a layer launch (not par
 // padding mode of the forward pass being issued on this host thread (set by zs_*_forward from cfg.seg_len)
 static thread_local int t_zero_pad = 0;
 
+// 1 (default) = layers that qualify run as CTA pairs (cta_group::2), 0 = one CTA per tile everywhere (the A/B reference of the tests)
+static int g_gemm_pair_mode = 1;
+extern "C" void zs_set_gemm_pair_mode(int mode) { g_gemm_pair_mode = mode; }
+
 static int launch_conv(const zs_conv_desc* d, cudaStream_t stream, const ConvExtras* ex = nullptr) {
     ZS_TRY(ensure_device());
     if (!d->w || !d->in || !d->out) return fail(ZS_ERR_ARG, "conv: null operand pointer");
@@ -267,6 +271,11 @@ static int launch_conv(const zs_conv_desc* d, cudaStream_t stream, const ConvExt
     if (nb * Tt > MAX_BN) return fail(ZS_ERR_ARG, "conv: nb %d x Tt %d exceeds 256 columns", nb, Tt);
     const int n_tiles = (d->B + nb - 1) / nb;
     const long long k_total = static_cast<long long>(d->w_taps) * d->c_in_pad;
+    // CTA pairs (tcgen05 cta_group::2, M = 256): two adjacent channel tiles share the columns - each CTA stages half of them.
+    // Inference layers with an even number of channel tiles and of segments per tile; everything else runs one CTA per tile.
+    const bool pair = g_gemm_pair_mode != 0 && !train_ex && !(ex && (ex->zero_halo || ex->edge_lo || ex->edge_hi)) && !d->bank &&
+                      m_tiles % 2 == 0 && nb % 2 == 0 && g_num_sms >= 2;
+    const int nb_box = pair ? nb / 2 : nb;
 
     {   // A: weights [m_rows][k_total]
         cuuint64_t dims[2] = {static_cast<cuuint64_t>(k_total), static_cast<cuuint64_t>(d->m_rows)};
@@ -277,13 +286,13 @@ static int launch_conv(const zs_conv_desc* d, cudaStream_t stream, const ConvExt
     if (d->stride == 1) {   // B: (channel, row, segment)
         cuuint64_t dims[3] = {static_cast<cuuint64_t>(d->c_in_valid), static_cast<cuuint64_t>(d->in_rows), static_cast<cuuint64_t>(d->B)};
         cuuint64_t strides[2] = {static_cast<cuuint64_t>(d->in_pitch) * 2, static_cast<cuuint64_t>(d->in_rows) * d->in_pitch * 2};
-        cuuint32_t box[3] = {BK, static_cast<cuuint32_t>(Tt), static_cast<cuuint32_t>(nb)};
+        cuuint32_t box[3] = {BK, static_cast<cuuint32_t>(Tt), static_cast<cuuint32_t>(nb_box)};
         ZS_TRY(make_map(&p.tmB, d->operand, const_cast<void*>(d->in), 3, dims, strides, box));
     } else {                // B: (channel, row parity, row pair, segment)
         cuuint64_t dims[4] = {static_cast<cuuint64_t>(d->c_in_valid), 2, static_cast<cuuint64_t>(d->in_rows / 2), static_cast<cuuint64_t>(d->B)};
         cuuint64_t strides[3] = {static_cast<cuuint64_t>(d->in_pitch) * 2, static_cast<cuuint64_t>(d->in_pitch) * 4,
                                  static_cast<cuuint64_t>(d->in_rows) * d->in_pitch * 2};
-        cuuint32_t box[4] = {BK, 1, static_cast<cuuint32_t>(Tt), static_cast<cuuint32_t>(nb)};
+        cuuint32_t box[4] = {BK, 1, static_cast<cuuint32_t>(Tt), static_cast<cuuint32_t>(nb_box)};
         ZS_TRY(make_map(&p.tmB, d->operand, const_cast<void*>(d->in), 4, dims, strides, box));
     }
     if (d->out_mode != OUT_NCT32) {   // epilogue rounds + the TMA store map of the channels-last output
@@ -322,17 +331,18 @@ static int launch_conv(const zs_conv_desc* d, cudaStream_t stream, const ConvExt
     else if (!d->accumulate && !(ex && ex->zero_halo)) {
         // (B, C, T) output staged through shared memory: each epilogue warp stores {one 128-byte row of frames} x 32 channels boxes
         // (128-byte swizzle -> conflict-free 16-byte shared stores).  Needs whole rows; anything else takes the direct-store path.
-        const int es = d->out_f16 ? 2 : 4, fpr = 128 / es;
-        if (d->T_out % fpr == 0 && reinterpret_cast<uintptr_t>(d->out) % 16 == 0) {
+        // rows of 128 bytes with the 128-byte swizzle, or (16-frame segments in fp32) plain 64-byte rows
+        const int es = d->out_f16 ? 2 : 4, fpr = std::min(128 / es, d->T_out), rb = fpr * es;
+        if ((rb == 128 || rb == 64) && d->T_out % fpr == 0 && reinterpret_cast<uintptr_t>(d->out) % 16 == 0) {
             cuuint64_t dims[3] = {static_cast<cuuint64_t>(d->T_out), static_cast<cuuint64_t>(d->m_valid), static_cast<cuuint64_t>(d->B)};
             cuuint64_t strides[2] = {static_cast<cuuint64_t>(d->T_out) * es, static_cast<cuuint64_t>(d->m_valid) * d->T_out * es};
             cuuint32_t box[3] = {static_cast<cuuint32_t>(fpr), 32u, 1u};
             cuuint32_t estr[3] = {1, 1, 1};
             CUresult r = g_encode(&p.tmOut, d->out_f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, d->out, dims, strides,
-                                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, rb == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             if (r != CUDA_SUCCESS) return fail(ZS_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for the (B, C, T) output", (int)r);
-            p.nct_tma = 1;
+            p.nct_tma = rb;
         }
     }
     p.m_tiles = m_tiles; p.n_tiles = n_tiles; p.nb = nb; p.Tt = Tt; p.T = d->T_out; p.B = d->B; p.N = nb * Tt;
@@ -347,7 +357,8 @@ static int launch_conv(const zs_conv_desc* d, cudaStream_t stream, const ConvExt
     p.res_mode = d->res_mode; p.res = d->res; p.res_rows = d->res_rows; p.res_pitch = d->res_pitch; p.res_halo = d->res_halo;
     p.act = d->act; p.out_mode = d->out_mode; p.out = d->out; p.out_rows = d->out_rows; p.out_pitch = d->out_pitch;
     p.out_halo = d->out_halo; p.out_choff = d->out_choff; p.accumulate = d->accumulate; p.out_f16 = d->out_f16;
-    p.idesc = umma_idesc_f16(d->operand == ZS_OPERAND_BF16 ? 1 : 0, p.N);
+    p.idesc = umma_idesc_f16(d->operand == ZS_OPERAND_BF16 ? 1 : 0, p.N, pair ? 256 : 128);
+    p.pair = pair ? 1 : 0;
     p.debug = env_int("ZS_GEMM_DEBUG", 0);
     p.sat_count = g_dev[t_dev].sat;
     if (ex) {
@@ -357,14 +368,15 @@ static int launch_conv(const zs_conv_desc* d, cudaStream_t stream, const ConvExt
         if (p.post_emb && !p.post_spk) return fail(ZS_ERR_ARG, "conv: post-add embedding needs speaker ids");
     }
 
-    const int grid = std::min(m_tiles * n_tiles, g_num_sms);
+    const int grid = pair ? 2 * std::min((m_tiles / 2) * n_tiles, g_num_sms / 2) : std::min(m_tiles * n_tiles, g_num_sms);
     const int which = d->operand == ZS_OPERAND_BF16 ? 1 : 0;
     const int zp = p.zero_halo ? 1 : 0;
     using KernelT = void (*)(const GemmParams);
     if (zp && train_ex) return fail(ZS_ERR_ARG, "conv: the zero-padding mode is inference only");
-    KernelT kern = zp ? (which ? conv_gemm_kernel<__nv_bfloat16, true, false> : conv_gemm_kernel<__half, true, false>)
-                 : train_ex ? (which ? conv_gemm_kernel<__nv_bfloat16, false, true> : conv_gemm_kernel<__half, false, true>)
-                            : (which ? conv_gemm_kernel<__nv_bfloat16, false, false> : conv_gemm_kernel<__half, false, false>);
+    KernelT kern = zp ? (which ? conv_gemm_kernel<__nv_bfloat16, true, false, false> : conv_gemm_kernel<__half, true, false, false>)
+                 : train_ex ? (which ? conv_gemm_kernel<__nv_bfloat16, false, true, false> : conv_gemm_kernel<__half, false, true, false>)
+                 : pair ? (which ? conv_gemm_kernel<__nv_bfloat16, false, false, true> : conv_gemm_kernel<__half, false, false, true>)
+                        : (which ? conv_gemm_kernel<__nv_bfloat16, false, false, false> : conv_gemm_kernel<__half, false, false, false>);
     ZS_TRY(set_smem_attr(reinterpret_cast<const void*>(kern), GEMM_SMEM_BYTES));
     {   // algorithmic FLOPs: 2 * valid out channels * true taps * true in channels * valid frames
         double taps_sum = d->bank ? 28.0 / 7.0 : static_cast<double>(d->taps);
@@ -377,10 +389,19 @@ static int launch_conv(const zs_conv_desc* d, cudaStream_t stream, const ConvExt
         cudaLaunchConfig_t cfg;
         memset(&cfg, 0, sizeof(cfg));
         cfg.gridDim = dim3(grid); cfg.blockDim = dim3(GEMM_THREADS); cfg.dynamicSmemBytes = GEMM_SMEM_BYTES; cfg.stream = stream;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        attr[0].val.programmaticStreamSerializationAllowed = 1;
-        cfg.attrs = attr; cfg.numAttrs = use_pdl ? 1 : 0;
+        cudaLaunchAttribute attr[2];
+        int na = 0;
+        if (use_pdl) {
+            attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            attr[na].val.programmaticStreamSerializationAllowed = 1;
+            ++na;
+        }
+        if (pair) {
+            attr[na].id = cudaLaunchAttributeClusterDimension;
+            attr[na].val.clusterDim.x = 2; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+            ++na;
+        }
+        cfg.attrs = attr; cfg.numAttrs = na;
         CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, p));
     }
     CUDA_TRY(cudaGetLastError());
