@@ -64,8 +64,13 @@ struct GruWideParams {
     int B, T, H, out_rows, out_pitch, out_halo, out_choff, fmt;
 };
 
-template <typename OT, int NPASS>
-__global__ void __launch_bounds__(GRU_THREADS, 1) gru_wide_kernel(const GruWideParams p) {
+// GW gate warps (8 or 16): with 16, a 32-sequence pass belongs to ONE set of eight warps (warp w: TMEM quadrant w & 3, 16-column half
+// (w >> 2) & 1, passes [PPW (w >> 3), +PPW)), so the passes of a step run side by side instead of back to back - the gate math is
+// latency-bound at two warps per scheduler.
+template <typename OT, int NPASS, int GW>
+__global__ void __launch_bounds__(32 * (GW + 1), 1) gru_wide_kernel(const GruWideParams p) {
+    constexpr int NTHR = 32 * (GW + 1);
+    constexpr int PPW = NPASS * 8 / GW;            // passes per gate warp
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_addr = smem_u32(smem_raw);
     uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
@@ -93,9 +98,9 @@ __global__ void __launch_bounds__(GRU_THREADS, 1) gru_wide_kernel(const GruWideP
                                                           (static_cast<size_t>(dir) * KCH + rank) * gru_w_image_bytes(H) + 128 * H * 2);
         uint4* dst = reinterpret_cast<uint4*>(sWn);
         const int n16 = gru_wide_wn_bytes(H) / 16;
-        for (int i = threadIdx.x; i < n16; i += GRU_THREADS) dst[i] = src[i];
+        for (int i = threadIdx.x; i < n16; i += NTHR) dst[i] = src[i];
         uint4* hz = reinterpret_cast<uint4*>(sH);
-        for (int i = threadIdx.x; i < (gru_wide_state_bytes(H, NPASS) + NPASS * 8 * 256 * 4) / 16; i += GRU_THREADS) hz[i] = make_uint4(0, 0, 0, 0);
+        for (int i = threadIdx.x; i < (gru_wide_state_bytes(H, NPASS) + NPASS * 8 * 256 * 4) / 16; i += NTHR) hz[i] = make_uint4(0, 0, 0, 0);
     }
     if (threadIdx.x == 0) {
         for (int c = 0; c < 8; ++c) mbar_init(&h_chunk[c], 1);
@@ -104,7 +109,7 @@ __global__ void __launch_bounds__(GRU_THREADS, 1) gru_wide_kernel(const GruWideP
         mbar_init(consumed, NC);
         fence_barrier_init();
     }
-    if (warp == GRU_GATE_WARPS) tmem_alloc<512>(tmem_slot);
+    if (warp == GW) tmem_alloc<512>(tmem_slot);
     fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
@@ -113,7 +118,7 @@ __global__ void __launch_bounds__(GRU_THREADS, 1) gru_wide_kernel(const GruWideP
     const uint32_t t_wrz = tmem_base;                          // columns [0, H/2): the r|z rows of W_hh
     const uint32_t t_drz = tmem_base + (H >> 1);               // NSEQ columns
     const uint32_t t_dn = t_drz + NSEQ;                        // NSEQ columns (H/2 + 2 NSEQ <= 512)
-    if (warp < GRU_GATE_WARPS) {
+    if (warp < 8) {
         // W_rz -> TMEM: this warp's quadrant (lane = row), its half of the K columns
         const int q = warp & 3, part = warp >> 2;
         const int row = 32 * q + lane;
@@ -133,7 +138,7 @@ __global__ void __launch_bounds__(GRU_THREADS, 1) gru_wide_kernel(const GruWideP
 
     const uint32_t slice_bytes = NSEQ * 128;                   // [NSEQ rows][128 B]
 
-    if (warp == GRU_GATE_WARPS) {
+    if (warp == GW) {
         // ------------------------------ control / MMA issue ------------------------------
         const uint32_t idesc_rz = umma_idesc_f16_m(p.fmt, 128, NSEQ);
         const uint32_t idesc_n = umma_idesc_f16_m(p.fmt, 64, NSEQ);
@@ -175,7 +180,7 @@ __global__ void __launch_bounds__(GRU_THREADS, 1) gru_wide_kernel(const GruWideP
         }
     } else {
         // ------------------------------ gate math (warps 0..7), two passes of 32 columns ------------------------------
-        const int q = warp & 3, half = warp >> 2;
+        const int q = warp & 3, half = (warp >> 2) & 1, pbase = (warp >> 3) * PPW;
         const int l = lane & 15, hi = lane >> 4;
         const int u_loc = 16 * q + l;
         const int unit = rank * GRU_UNITS + u_loc;
@@ -184,18 +189,18 @@ __global__ void __launch_bounds__(GRU_THREADS, 1) gru_wide_kernel(const GruWideP
         const float hb_r = 0.5f * b_r, hb_z = 0.5f * b_z;
         OT* out = reinterpret_cast<OT*>(p.out);
         const uint32_t lane_addr = static_cast<uint32_t>(32 * q) << 16;
-        float* my_state = sState + threadIdx.x;                // [pass][i] at (pass * 8 + i) * 256
+        float* my_state = sState + (threadIdx.x & 255);        // [pass][i] at (pass * 8 + i) * 256
         const OT* gx_base = reinterpret_cast<const OT*>(p.gx);
         const int gx_step = (dir ? -1 : 1) * 2 * 3 * H;
         const int out_step = (dir ? -1 : 1) * p.out_pitch;
         const int t_first = dir ? p.T - 1 : 0;
         const int gx_seq = p.T * 6 * H, out_seq = p.out_rows * p.out_pitch;
         // rows of the state tile / sequences of this thread: pass ps -> rows 32 ps + 16 half + 8 hi + i
-        int row0[NPASS], gx_off[NPASS], out_off[NPASS];
-        uint32_t live[NPASS];
+        int row0[PPW], gx_off[PPW], out_off[PPW];
+        uint32_t live[PPW];
 #pragma unroll
-        for (int ps = 0; ps < NPASS; ++ps) {
-            row0[ps] = 32 * ps + 16 * half + 8 * hi;
+        for (int ps = 0; ps < PPW; ++ps) {
+            row0[ps] = 32 * (pbase + ps) + 16 * half + 8 * hi;
             const int seq0 = b0 + row0[ps];
             live[ps] = 0;
 #pragma unroll
@@ -221,11 +226,12 @@ __global__ void __launch_bounds__(GRU_THREADS, 1) gru_wide_kernel(const GruWideP
         uint8_t* hnext = sH + rank * slice_bytes;
         for (int t = 0; t < p.T; ++t) {
 #pragma unroll
-            for (int ps = 0; ps < NPASS; ++ps) {
+            for (int ps = 0; ps < PPW; ++ps) {
+                const int gp = pbase + ps;                      // the pass (32-sequence column block) this iteration works on
 #pragma unroll
                 for (int i = 0; i < 8; ++i) { gr[i] = pr[i]; gz[i] = pz[i]; gn[i] = pn[i]; }
-                // prefetch the next pass: of this step, or pass 0 of the next one
-                if (ps + 1 < NPASS) load_gx(ps + 1, true, pr, pz, pn);
+                // prefetch the next pass: of this step, or this warp's first pass of the next one
+                if (ps + 1 < PPW) load_gx(ps + 1, true, pr, pz, pn);
                 else load_gx(0, t + 1 < p.T, pr, pz, pn);
                 if (ps == 0) {
                     mbar_wait(rz_done, t & 1);
@@ -234,7 +240,7 @@ __global__ void __launch_bounds__(GRU_THREADS, 1) gru_wide_kernel(const GruWideP
                 float r[8], z[8];
                 {
                     uint32_t a[16];
-                    tmem_ld16(t_drz + lane_addr + 32 * ps + 16 * half, a);
+                    tmem_ld16(t_drz + lane_addr + 32 * gp + 16 * half, a);
                     tmem_ld_wait();
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
@@ -254,17 +260,17 @@ __global__ void __launch_bounds__(GRU_THREADS, 1) gru_wide_kernel(const GruWideP
                 OT y[8];
                 {
                     uint32_t nn[16];
-                    tmem_ld16(t_dn + lane_addr + 32 * ps + 16 * half, nn);
+                    tmem_ld16(t_dn + lane_addr + 32 * gp + 16 * half, nn);
                     tmem_ld_wait();
-                    if (ps == NPASS - 1) tc_fence_before();
+                    if (ps == PPW - 1) tc_fence_before();
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
                         const uint32_t gotn = __shfl_xor_sync(0xffffffffu, nn[8 + i], 16);
                         const float hn = __uint_as_float(hi ? gotn : nn[i]) + b_n;
                         const float n = tanh_mufu(fmaf(r[i], hn, ot_to_float<OT>(gn[i])));
-                        const float hp = my_state[(ps * 8 + i) * 256];
+                        const float hp = my_state[(gp * 8 + i) * 256];
                         const float hv = fmaf(z[i], hp - n, n);
-                        my_state[(ps * 8 + i) * 256] = hv;
+                        my_state[(gp * 8 + i) * 256] = hv;
                         y[i] = float_to_ot<OT>(hv);
                     }
                 }
@@ -283,7 +289,7 @@ __global__ void __launch_bounds__(GRU_THREADS, 1) gru_wide_kernel(const GruWideP
             }
             if (t + 1 < p.T) {
                 fence_proxy_async_smem();
-                asm volatile("bar.sync 1, %0;" ::"n"(32 * GRU_GATE_WARPS) : "memory");
+                asm volatile("bar.sync 1, %0;" ::"n"(32 * GW) : "memory");
                 if (warp == 0 && elect_one()) {
                     mbar_arrive(&h_chunk[rank]);
                     if (NC > 1) {
@@ -302,7 +308,7 @@ __global__ void __launch_bounds__(GRU_THREADS, 1) gru_wide_kernel(const GruWideP
     tc_fence_before();
     __syncthreads();
     cluster_sync_all();
-    if (warp == GRU_GATE_WARPS) tmem_dealloc<512>(tmem_base);
+    if (warp == GW) tmem_dealloc<512>(tmem_base);
 }
 
 }  // namespace zs

@@ -568,12 +568,16 @@ static int launch_gru_cluster(const void* w_img, const float* bhh, const void* g
             wp.fmt = operand == ZS_OPERAND_BF16 ? 1 : 0;
             const int smem_w = gru_wide_smem_bytes(H, npass);
             using WideT = void (*)(const GruWideParams);
-            WideT wk = npass == 4 ? (wp.fmt ? gru_wide_kernel<__nv_bfloat16, 4> : gru_wide_kernel<__half, 4>)
-                                  : (wp.fmt ? gru_wide_kernel<__nv_bfloat16, 2> : gru_wide_kernel<__half, 2>);
+            // 16 gate warps: a step's passes run side by side (the gate math is latency-bound at two warps per scheduler)
+            const int gw = env_int("ZS_GRU_GW", 16) == 8 ? 8 : 16;
+            WideT wk = gw == 8 ? (npass == 4 ? (wp.fmt ? gru_wide_kernel<__nv_bfloat16, 4, 8> : gru_wide_kernel<__half, 4, 8>)
+                                             : (wp.fmt ? gru_wide_kernel<__nv_bfloat16, 2, 8> : gru_wide_kernel<__half, 2, 8>))
+                               : (npass == 4 ? (wp.fmt ? gru_wide_kernel<__nv_bfloat16, 4, 16> : gru_wide_kernel<__half, 4, 16>)
+                                             : (wp.fmt ? gru_wide_kernel<__nv_bfloat16, 2, 16> : gru_wide_kernel<__half, 2, 16>));
             ZS_TRY(set_smem_attr(reinterpret_cast<const void*>(wk), smem_w));
             cudaLaunchConfig_t wc;
             memset(&wc, 0, sizeof(wc));
-            wc.gridDim = dim3(2 * groups64 * NCw); wc.blockDim = dim3(GRU_THREADS); wc.dynamicSmemBytes = smem_w; wc.stream = st;
+            wc.gridDim = dim3(2 * groups64 * NCw); wc.blockDim = dim3(32 * (gw + 1)); wc.dynamicSmemBytes = smem_w; wc.stream = st;
             cudaLaunchAttribute wa[1];
             wa[0].id = cudaLaunchAttributeClusterDimension;
             wa[0].val.clusterDim.x = NCw; wa[0].val.clusterDim.y = 1; wa[0].val.clusterDim.z = 1;
