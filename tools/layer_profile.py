@@ -1,5 +1,7 @@
 """Warm per-launch table of one encode->decode micro-batch (CUDA events around every launch of the library, after
-warm-up, inputs rotating): layer, ms, algorithmic TFLOP/s, share.  python tools/layer_profile.py [MB] [reps]"""
+warm-up, inputs rotating): layer, ms, algorithmic TFLOP/s, share.  python tools/layer_profile.py [MB] [reps] [warm] [pair]
+warm = untimed steps before the table (default 5: burst clocks; ~400 puts a B200 into its power-capped sustained regime first),
+pair = 0 turns the CTA-pair GEMM off (zs_set_gemm_pair_mode) for an A/B table."""
 import ctypes as C
 import os
 import sys
@@ -21,6 +23,8 @@ NAMES = ['pack x (bank in + cat)', 'bank', 'conv2 IN', 'conv3', 'conv4 s2 IN+avg
 def main():
     B = int(sys.argv[1]) if len(sys.argv) > 1 else 224
     reps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
+    warm = int(sys.argv[3]) if len(sys.argv) > 3 else 5
+    pair = int(sys.argv[4]) if len(sys.argv) > 4 else 1
     enc = Encoder(ns=0.01, dp=0.5, enc_size=1024, seg_len=128, enc_mode='one_hot')
     dec = Decoder(ns=0.01, c_in=1024, c_h=1024, c_a=102, seg_len=128)
     enc.load_state_dict(syn.encoder_state_dict(0, enc_size=1024, enc_mode='one_hot'))
@@ -31,11 +35,12 @@ def main():
     c = syn.speaker_ids(B, 102, 0).cuda()
     noise = gumbel_from_uniform(syn.gumbel_uniform((B, 16, 1024), 0)).cuda()
     lib = _lib.lib()
+    lib.zs_set_gemm_pair_mode(pair)
 
     def step(i):
         act, logits, ids = enc.encode(xs[i % 3], noise)
         return dec.decode(None, c, unit_ids=ids)
-    for i in range(5):
+    for i in range(warm):
         step(i)
     torch.cuda.synchronize()
     MAX = 256
@@ -50,7 +55,7 @@ def main():
         rows = [(ms[i], fl[i], cl[i]) for i in range(n)]
         acc = rows if acc is None else [(a[0] + b[0], a[1], a[2]) for a, b in zip(acc, rows)]
     total = sum(a[0] for a in acc) / reps
-    print(f'MB={B}: {len(acc)} launches, {total:.3f} ms per micro-batch (sum of per-launch events), {B * 128 / total / 1e3:.2f} M frames/s')
+    print(f'MB={B} warm={warm} pair={pair}: {len(acc)} launches, {total:.3f} ms per micro-batch (sum of per-launch events), {B * 128 / total / 1e3:.2f} M frames/s')
     kinds = {0: 'gemm', 1: 'gru', 2: 'other'}
     for i, (t, f, k) in enumerate(acc):
         t /= reps

@@ -46,6 +46,10 @@ constexpr int GEMM_SMEM_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + STAGI
 constexpr int PAIR_STAGES = 4;
 constexpr int PAIR_B_STAGE_BYTES = B_STAGE_BYTES / 2;
 constexpr int MAX_STAGES = 4;
+// ... and the shared memory that frees holds a SECOND residual tile per epilogue set: the residual of round r + 1 is in flight
+// while round r is processed (with one tile its TMA load latency is exposed once per round: 17 % of the IN + residual epilogue)
+constexpr int PAIR_SET_STAGING_BYTES = SET_STAGING_BYTES + STG_TILE_BYTES;
+constexpr int PAIR_SMEM_BYTES = PAIR_STAGES * (A_STAGE_BYTES + PAIR_B_STAGE_BYTES) + EPI_SETS * PAIR_SET_STAGING_BYTES + 1024 + 256;
 constexpr float IN_EPS = 1e-5f;
 
 // timing-experiment bits (results are wrong with any bit set) exist only in -DZS_EXPERIMENTS builds
@@ -541,13 +545,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
     uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
     uint8_t* sA = smem;
     uint8_t* sB = smem + NSTG * A_STAGE_BYTES;
-    uint8_t* sStage = smem + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES);      // (the pair's four stages end 16 KB below)
-    uint64_t* full = reinterpret_cast<uint64_t*>(sStage + STAGING_BYTES);
+    constexpr int SET_BYTES = PAIR ? PAIR_SET_STAGING_BYTES : SET_STAGING_BYTES;
+    uint8_t* sStage = smem + NSTG * (A_STAGE_BYTES + B_BYTES);
+    uint64_t* full = reinterpret_cast<uint64_t*>(sStage + EPI_SETS * SET_BYTES);
     uint64_t* empty = full + MAX_STAGES;
     uint64_t* tfull = empty + MAX_STAGES;
     uint64_t* tempty = tfull + 2;
-    uint64_t* rbar = tempty + 2;   // [EPI_SETS] residual tile landed in the set's staging buffer
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rbar + EPI_SETS);
+    uint64_t* rbar = tempty + 2;   // [EPI_SETS][2] residual tile (slot 0 / 1) landed in the set's staging buffer
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rbar + 2 * EPI_SETS);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -562,7 +567,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
             mbar_init(&tfull[i], 1);
             mbar_init(&tempty[i], (PAIR ? 2 : 1) * 4 * EPI_SETS);
         }
-        for (int i = 0; i < EPI_SETS; ++i) mbar_init(&rbar[i], 1);
+        for (int i = 0; i < 2 * EPI_SETS; ++i) mbar_init(&rbar[i], 1);
         fence_barrier_init();
         tma_prefetch_desc(&p.tmA);
         tma_prefetch_desc(&p.tmB);
@@ -701,15 +706,16 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
         const int eset = (warp - 4) >> 2;                    // epilogue set: warps 4..7 / 8..11
         const bool set_lead = (warp & 3) == 0;               // the set's TMA-issuing warp
         const int set_bar = 1 + eset;                        // named barrier of the set's 128 threads
-        uint64_t* my_rbar = &rbar[eset];
+        uint64_t* my_rbar = &rbar[2 * eset];                  // [2]: one per residual slot (single-CTA kernels use slot 0 only)
         const int row = quad * 32 + lane;
         const bool lrelu = p.lrelu != 0;
         const float ns = p.ns;
         const int T = p.T;
-        uint8_t* set_stage = sStage + eset * SET_STAGING_BYTES;
+        uint8_t* set_stage = sStage + eset * SET_BYTES;
         OT* stage = reinterpret_cast<OT*>(set_stage);
         int it = 0, rnd = 0;
-        uint32_t res_phase = 0;
+        uint32_t res_phase = 0;     // bit k = phase of residual slot k's barrier
+        int rres = 0;               // residual rounds this set has consumed (PAIR: slot = rres & 1)
         bool sat = false;           // this thread clamped an fp16 output (reported once per thread and launch)
         // both epilogues of a pair hand the accumulator back on the LEADER's barrier
         const uint32_t tempty_leader = PAIR ? mapa_shared(smem_u32(&tempty[0]), 0) : 0u;
@@ -826,14 +832,21 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
                         // staging: with a residual, tile 0 = output and tile 1 = residual; otherwise the two tiles
                         // alternate as output buffers so a store's shared-memory read overlaps the next round
                         OT* stage_out = stage + (has_res ? 0 : (rnd & 1) * (STG_TILE_BYTES / 2));
-                        const OT* stage_res = stage + STG_TILE_BYTES / 2;
+                        const int rslot = PAIR ? (rres & 1) : 0;
+                        const OT* stage_res = stage + (1 + rslot) * (STG_TILE_BYTES / 2);
+                        const bool live = nt * p.nb + s0 < p.B;
+                        // the residual tile of round (s0_, h_) -> slot; the slot's previous readers passed an end-of-round barrier
+                        auto issue_res = [&](int s0_, int h_, int slot) {
+                            mbar_expect_tx(&my_rbar[slot], static_cast<uint32_t>(p.rnd_ns) * res_rows_per_seg * 256);
+                            const int fl = h_ * p.rnd_frames;
+                            const int r_row = p.res_halo + (p.res_mode == RES_UP2 ? fl / 2 : (p.res_mode == RES_AVG2 ? 2 * fl : fl));
+                            tma_load_3d(&p.tmRes, set_stage + (1 + slot) * STG_TILE_BYTES, &my_rbar[slot], mt * BM, r_row, nt * p.nb + s0_);
+                        };
                         if (has_res) {
-                            if (set_lead && nt * p.nb + s0 < p.B && elect_one()) {
-                                // the previous round's readers passed the end-of-round barrier: tile 1 is free
-                                mbar_expect_tx(my_rbar, static_cast<uint32_t>(p.rnd_ns) * res_rows_per_seg * 256);
-                                const int r_row = p.res_halo + (p.res_mode == RES_UP2 ? f_lo / 2 : (p.res_mode == RES_AVG2 ? 2 * f_lo : f_lo));
-                                tma_load_3d(&p.tmRes, set_stage + STG_TILE_BYTES, my_rbar, mt * BM, r_row, nt * p.nb + s0);
-                            }
+                            // single-CTA kernels: one slot, loaded at the start of its round.  PAIR: the first round of a tile loads its own
+                            // tile here; every later round's tile was requested one round ahead (below)
+                            const bool first = s0 == eset * p.rnd_ns && h == 0;
+                            if ((!PAIR || first) && set_lead && live && elect_one()) issue_res(s0, h, rslot);
                             __syncwarp();
                         }
                         bool waited = false;
@@ -843,8 +856,17 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
                             const uint32_t t_seg = t_lane + s * p.Tt;
                             if (h == 0) cn_keep = chan_norm(b, t_seg);
                             if (has_res && !waited) {
-                                mbar_wait(my_rbar, res_phase);
+                                mbar_wait(&my_rbar[rslot], (res_phase >> rslot) & 1);
                                 waited = true;
+                                if (PAIR) {     // request the NEXT round's residual into the other slot while this round is processed
+                                    int s0n = s0, hn = h + 1;
+                                    if (hn == p.rnd_sub) {
+                                        hn = 0;
+                                        s0n = s0 + EPI_SETS * p.rnd_ns;
+                                    }
+                                    if (s0n < p.nb && nt * p.nb + s0n < p.B && set_lead && elect_one()) issue_res(s0n, hn, rslot ^ 1);
+                                    __syncwarp();
+                                }
                             }
                             const uint32_t stg = smem_u32(stage_out + static_cast<size_t>(s - s0) * p.rnd_rows * fstep * stg_row + stg_ch);
                             const uint32_t res_stg = smem_u32(stage_res + static_cast<size_t>(s - s0) * res_rows_per_seg * 128 + row);
@@ -860,7 +882,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
                             else ZS_F2S(RES_AVG2, false, true);
 #undef ZS_F2S
                         }
-                        if (has_res && nt * p.nb + s0 < p.B) res_phase ^= 1;
+                        if (has_res && live) {
+                            res_phase ^= 1u << rslot;
+                            ++rres;
+                        }
                         const bool last = (s0 / p.rnd_ns == my_last) && (h + 1 == p.rnd_sub);
                         if (last) {   // every TMEM read of this tile is done: hand the accumulator back
                             tc_fence_before();
@@ -869,7 +894,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
                         }
                         fence_proxy_async();                              // staging writes -> visible to the TMA engine
                         asm volatile("bar.sync %0, 128;" ::"r"(set_bar) : "memory");
-                        if (set_lead && nt * p.nb + s0 < p.B && elect_one()) {
+                        if (set_lead && live && elect_one()) {
                             tma_store_3d(&p.tmOut, stage_out, ps ? mt * 64 : mt * BM, p.out_halo + fstep * f_lo, nt * p.nb + s0);
                             tma_store_commit();
                             if (has_res) tma_store_wait_read();            // single output tile: it must be free next round

@@ -272,9 +272,10 @@ static int launch_conv(const zs_conv_desc* d, cudaStream_t stream, const ConvExt
     const int n_tiles = (d->B + nb - 1) / nb;
     const long long k_total = static_cast<long long>(d->w_taps) * d->c_in_pad;
     // CTA pairs (tcgen05 cta_group::2, M = 256): two adjacent channel tiles share the columns - each CTA stages half of them.
-    // Inference layers with an even number of channel tiles and of segments per tile; everything else runs one CTA per tile.
+    // Inference layers with an even number of channel tiles and of segments per tile and >= 64 frames per segment (measured: the
+    // 16- / 32-frame layers gain nothing or lose - d.conv3 355 -> 391 us; mode 2 pairs them too, for the tests); the rest runs one CTA per tile.
     const bool pair = g_gemm_pair_mode != 0 && !train_ex && !(ex && (ex->zero_halo || ex->edge_lo || ex->edge_hi)) && !d->bank &&
-                      m_tiles % 2 == 0 && nb % 2 == 0 && g_num_sms >= 2;
+                      m_tiles % 2 == 0 && nb % 2 == 0 && g_num_sms >= 2 && (Tt >= 64 || g_gemm_pair_mode == 2);
     const int nb_box = pair ? nb / 2 : nb;
 
     {   // A: weights [m_rows][k_total]
@@ -377,7 +378,8 @@ static int launch_conv(const zs_conv_desc* d, cudaStream_t stream, const ConvExt
                  : train_ex ? (which ? conv_gemm_kernel<__nv_bfloat16, false, true, false> : conv_gemm_kernel<__half, false, true, false>)
                  : pair ? (which ? conv_gemm_kernel<__nv_bfloat16, false, false, true> : conv_gemm_kernel<__half, false, false, true>)
                         : (which ? conv_gemm_kernel<__nv_bfloat16, false, false, false> : conv_gemm_kernel<__half, false, false, false>);
-    ZS_TRY(set_smem_attr(reinterpret_cast<const void*>(kern), GEMM_SMEM_BYTES));
+    const int smem_bytes = pair ? PAIR_SMEM_BYTES : GEMM_SMEM_BYTES;
+    ZS_TRY(set_smem_attr(reinterpret_cast<const void*>(kern), smem_bytes));
     {   // algorithmic FLOPs: 2 * valid out channels * true taps * true in channels * valid frames
         double taps_sum = d->bank ? 28.0 / 7.0 : static_cast<double>(d->taps);
         const double flops = 2.0 * d->m_valid * taps_sum * d->c_in_valid * static_cast<double>(d->B) * d->T_out;
@@ -388,7 +390,7 @@ static int launch_conv(const zs_conv_desc* d, cudaStream_t stream, const ConvExt
         p.pdl = use_pdl;
         cudaLaunchConfig_t cfg;
         memset(&cfg, 0, sizeof(cfg));
-        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(GEMM_THREADS); cfg.dynamicSmemBytes = GEMM_SMEM_BYTES; cfg.stream = stream;
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(GEMM_THREADS); cfg.dynamicSmemBytes = smem_bytes; cfg.stream = stream;
         cudaLaunchAttribute attr[2];
         int na = 0;
         if (use_pdl) {
