@@ -365,17 +365,22 @@ __device__ __forceinline__ void frames_to_staging(const GemmParams& p, uint32_t 
             sts16(sp + (2 * i) * ROWB, yp[i]);
             sts16(sp + (2 * i + 1) * ROWB, yp[i] >> 16);
         }
-        // reflected halo rows of the output buffer (read by the next conv's outer taps)
+        // reflected halo rows of the output buffer (read by the next conv's outer taps): only output rows 1..halo and
+        // T_out-1-halo..T_out-2 are mirrored, i.e. (halo <= 3, checked at launch) at most the first and the last four frames - read
+        // back from the staging row this thread just wrote instead of selecting among the packed registers
         if (halo > 0 && (c0 == 0 || c0 + 16 + 3 >= T)) {     // warp-uniform condition: ch_ok (per lane) must not guard the __syncwarp below
             uint16_t* out16 = reinterpret_cast<uint16_t*>(out_s);
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                const int t = c0 + i;
-                if (t < T && ch_ok) {
+            for (int j = 0; j < 8; ++j) {
+                const int t = j < 4 ? j : T - 1 - (j - 4);        // candidates: frames 0..3, then T-1..T-4 (those >= 4: no frame twice)
+                if (t >= c0 && t < c0 + 16 && t < T && (j < 4 || t >= 4) && ch_ok) {
                     const int f = PS ? 2 * t + ps_r : t;
-                    const uint16_t hv = ZP ? uint16_t(0) : static_cast<uint16_t>(yp[i >> 1] >> (16 * (i & 1)));
-                    if (f >= 1 && f <= halo) out16[(halo - f) * p.out_pitch] = hv;
-                    if (f >= T_out - 1 - halo && f <= T_out - 2) out16[(halo + 2 * (T_out - 1) - f) * p.out_pitch] = hv;
+                    const bool top = f >= 1 && f <= halo, bot = f >= T_out - 1 - halo && f <= T_out - 2;
+                    if (top || bot) {
+                        const uint16_t hv = ZP ? uint16_t(0) : lds16(sp + (t - c0) * ROWB);
+                        if (top) out16[(halo - f) * p.out_pitch] = hv;
+                        if (bot) out16[(halo + 2 * (T_out - 1) - f) * p.out_pitch] = hv;
+                    }
                 }
             }
             __syncwarp();

@@ -310,6 +310,7 @@ static int launch_conv(const zs_conv_desc* d, cudaStream_t stream, const ConvExt
         if (Tt <= rf)
             for (int c = std::min(rf / Tt, nb); c >= 1; --c)
                 if (nb % c == 0) { p.rnd_ns = c; break; }
+        if (d->out_halo < 0 || d->out_halo > 3) return fail(ZS_ERR_ARG, "conv: out_halo %d outside [0, 3] (kernel sizes up to 7)", d->out_halo);
         if (d->out_choff % 8 || d->out_pitch % 8) return fail(ZS_ERR_ARG, "conv: out_choff %d / out_pitch %d must be multiples of 8", d->out_choff, d->out_pitch);
         if (reinterpret_cast<uintptr_t>(d->out) % 16) return fail(ZS_ERR_ARG, "conv: output pointer must be 16-byte aligned");
         const int T_rows = d->out_halo + (ps ? 2 * d->T_out : d->T_out);
