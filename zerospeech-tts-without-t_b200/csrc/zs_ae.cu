@@ -100,6 +100,7 @@ static int ensure_device() {
 extern "C" int zs_device_check(void) { return ensure_device(); }
 
 // dynamic shared memory above 48 KB needs an opt-in per (device, kernel)
+static std::map<std::pair<int, int>, int> g_pair_clusters;      // (device, operand) -> resident CTA pairs of the PAIR GEMM kernel
 static int set_smem_attr(const void* fn, int bytes) {
     std::lock_guard<std::mutex> lk(g_dev_mu);
     const auto key = std::make_pair(t_dev, fn);
@@ -370,7 +371,29 @@ static int launch_conv(const zs_conv_desc* d, cudaStream_t stream, const ConvExt
         if (p.post_emb && !p.post_spk) return fail(ZS_ERR_ARG, "conv: post-add embedding needs speaker ids");
     }
 
-    const int grid = pair ? 2 * std::min((m_tiles / 2) * n_tiles, g_num_sms / 2) : std::min(m_tiles * n_tiles, g_num_sms);
+    int max_pairs = g_num_sms / 2;
+    if (pair) {   // CTA pairs the device can keep resident at once (a TPC with one SM fused off holds none): asked once per device and kernel
+        std::lock_guard<std::mutex> lk(g_dev_mu);
+        const auto key = std::make_pair(t_dev, static_cast<int>(d->operand == ZS_OPERAND_BF16));
+        auto it = g_pair_clusters.find(key);
+        if (it == g_pair_clusters.end()) {
+            using KT = void (*)(const GemmParams);
+            KT k2 = d->operand == ZS_OPERAND_BF16 ? conv_gemm_kernel<__nv_bfloat16, false, false, true> : conv_gemm_kernel<__half, false, false, true>;
+            CUDA_TRY(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM_BYTES));
+            cudaLaunchConfig_t qc;
+            memset(&qc, 0, sizeof(qc));
+            qc.gridDim = dim3(2 * max_pairs); qc.blockDim = dim3(GEMM_THREADS); qc.dynamicSmemBytes = PAIR_SMEM_BYTES;
+            cudaLaunchAttribute qa[1];
+            qa[0].id = cudaLaunchAttributeClusterDimension;
+            qa[0].val.clusterDim.x = 2; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
+            qc.attrs = qa; qc.numAttrs = 1;
+            int n = 0;
+            if (cudaOccupancyMaxActiveClusters(&n, k2, &qc) != cudaSuccess || n < 1) { cudaGetLastError(); n = max_pairs; }
+            it = g_pair_clusters.emplace(key, std::min(n, max_pairs)).first;
+        }
+        max_pairs = it->second;
+    }
+    const int grid = pair ? 2 * std::min((m_tiles / 2) * n_tiles, max_pairs) : std::min(m_tiles * n_tiles, g_num_sms);
     const int which = d->operand == ZS_OPERAND_BF16 ? 1 : 0;
     const int zp = p.zero_halo ? 1 : 0;
     using KernelT = void (*)(const GemmParams);
