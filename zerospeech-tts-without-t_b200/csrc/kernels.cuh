@@ -394,22 +394,41 @@ __global__ void transpose_emb_kernel(const float* __restrict__ W, OT* __restrict
 }
 
 // Decoder input from unit ids: x0[b][halo + t][c] = input_emb.weight[c][id] + bias[c], reflected halo rows.
+// One thread = 8 consecutive channels of one unit frame (16-byte loads of the transposed table row and 16-byte stores of the
+// operand row; c_h and the pitch are multiples of 8), blockDim.y unit frames per CTA; the scalar tail covers c_h % 8.
 template <typename OT>
 __global__ void unit_gather_kernel(const int* __restrict__ ids, const OT* __restrict__ WT,
                                    const float* __restrict__ bias, OT* __restrict__ out, int T8, int c_h, int rows,
                                    int pitch, int halo, int n_units, int zero_halo) {
-    const int t = blockIdx.x, b = blockIdx.y;
+    const int t = blockIdx.x * blockDim.y + threadIdx.y, b = blockIdx.y;
+    if (t >= T8) return;
     int id = ids[b * T8 + t];
     id = min(max(id, 0), n_units - 1);
     OT* ob = out + static_cast<size_t>(b) * rows * pitch;
-    for (int c = threadIdx.x; c < c_h; c += blockDim.x) {
-        const OT y = float_to_ot<OT>(ot_to_float<OT>(WT[static_cast<size_t>(id) * c_h + c]) + bias[c]);
+    const OT* wr = WT + static_cast<size_t>(id) * c_h;
+    const bool top = halo > 0 && t >= 1 && t <= halo, bot = halo > 0 && t >= T8 - 1 - halo && t <= T8 - 2;
+    const bool vec = (c_h & 7) == 0 && (pitch & 7) == 0 && ((reinterpret_cast<uintptr_t>(WT) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(bias)) & 15) == 0;
+    const int c_vec = vec ? c_h : 0;
+    for (int c = threadIdx.x * 8; c < c_vec; c += blockDim.x * 8) {
+        const uint4 w = *reinterpret_cast<const uint4*>(wr + c);
+        const float4 b0 = *reinterpret_cast<const float4*>(bias + c), b1 = *reinterpret_cast<const float4*>(bias + c + 4);
+        const OT* wv = reinterpret_cast<const OT*>(&w);
+        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+        uint4 y;
+        OT* yv = reinterpret_cast<OT*>(&y);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) yv[i] = float_to_ot<OT>(ot_to_float<OT>(wv[i]) + bb[i]);
+        *reinterpret_cast<uint4*>(ob + static_cast<size_t>(halo + t) * pitch + c) = y;
+        const uint4 hv = zero_halo ? make_uint4(0, 0, 0, 0) : y;
+        if (top) *reinterpret_cast<uint4*>(ob + static_cast<size_t>(halo - t) * pitch + c) = hv;
+        if (bot) *reinterpret_cast<uint4*>(ob + static_cast<size_t>(halo + 2 * (T8 - 1) - t) * pitch + c) = hv;
+    }
+    for (int c = c_vec + threadIdx.x; c < c_h; c += blockDim.x) {
+        const OT y = float_to_ot<OT>(ot_to_float<OT>(wr[c]) + bias[c]);
         ob[static_cast<size_t>(halo + t) * pitch + c] = y;
-        if (halo > 0) {
-            const OT hv = zero_halo ? float_to_ot<OT>(0.f) : y;
-            if (t >= 1 && t <= halo) ob[static_cast<size_t>(halo - t) * pitch + c] = hv;
-            if (t >= T8 - 1 - halo && t <= T8 - 2) ob[static_cast<size_t>(halo + 2 * (T8 - 1) - t) * pitch + c] = hv;
-        }
+        const OT hv = zero_halo ? float_to_ot<OT>(0.f) : y;
+        if (top) ob[static_cast<size_t>(halo - t) * pitch + c] = hv;
+        if (bot) ob[static_cast<size_t>(halo + 2 * (T8 - 1) - t) * pitch + c] = hv;
     }
 }
 

@@ -1282,12 +1282,13 @@ extern "C" int zs_decoder_forward_x(zs_decoder* h, const float* enc_act, const i
     const float ns = g.ns;
 
     if (unit_ids) {   // one-hot input: input_emb is a column gather (model/model.py:346)
-        dim3 grid(T8, B);
+        // 128 threads x 8 channels cover a 1024-channel row; 4 unit frames per CTA
+        const dim3 blk(128, 4), grid((T8 + 3) / 4, B);
         LaunchScope scope(st, KC_OTHER, 0.0, "unit_gather_kernel");
         if (op == ZS_OPERAND_BF16)
-            unit_gather_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(unit_ids, static_cast<const __nv_bfloat16*>(h->emb_table), h->input_emb.bias, static_cast<__nv_bfloat16*>(w.x0.p), T8, ch, w.x0.rows, w.x0.pitch, 1, g.c_in, t_zero_pad);
+            unit_gather_kernel<__nv_bfloat16><<<grid, blk, 0, st>>>(unit_ids, static_cast<const __nv_bfloat16*>(h->emb_table), h->input_emb.bias, static_cast<__nv_bfloat16*>(w.x0.p), T8, ch, w.x0.rows, w.x0.pitch, 1, g.c_in, t_zero_pad);
         else
-            unit_gather_kernel<__half><<<grid, 256, 0, st>>>(unit_ids, static_cast<const __half*>(h->emb_table), h->input_emb.bias, static_cast<__half*>(w.x0.p), T8, ch, w.x0.rows, w.x0.pitch, 1, g.c_in, t_zero_pad);
+            unit_gather_kernel<__half><<<grid, blk, 0, st>>>(unit_ids, static_cast<const __half*>(h->emb_table), h->input_emb.bias, static_cast<__half*>(w.x0.p), T8, ch, w.x0.rows, w.x0.pitch, 1, g.c_in, t_zero_pad);
         CUDA_TRY(cudaGetLastError());
     } else {
         ZS_TRY(launch_pack_nct(enc_act, B, g.c_in, T8, w.actp.p, w.actp.rows, w.actp.pitch, 0, 0, 0, ns, op, 0, st));
