@@ -1,7 +1,7 @@
 """Warm per-launch table of one encode->decode micro-batch (CUDA events around every launch of the library, after
 warm-up, inputs rotating): layer, ms, algorithmic TFLOP/s, share.  python tools/layer_profile.py [MB] [reps] [warm] [pair]
 warm = untimed steps before the table (default 5: burst clocks; ~400 puts a B200 into its power-capped sustained regime first),
-pair = 0 turns the CTA-pair GEMM off (zs_set_gemm_pair_mode) for an A/B table."""
+pair = 0 turns the CTA-pair GEMM off, 0x101 keeps pairs but turns the four-stage single-CTA ring off (zs_set_gemm_pair_mode) for A/B tables."""
 import ctypes as C
 import os
 import sys
@@ -24,7 +24,7 @@ def main():
     B = int(sys.argv[1]) if len(sys.argv) > 1 else 224
     reps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
     warm = int(sys.argv[3]) if len(sys.argv) > 3 else 5
-    pair = int(sys.argv[4]) if len(sys.argv) > 4 else 1
+    pair = int(sys.argv[4], 0) if len(sys.argv) > 4 else 1
     enc = Encoder(ns=0.01, dp=0.5, enc_size=1024, seg_len=128, enc_mode='one_hot')
     dec = Decoder(ns=0.01, c_in=1024, c_h=1024, c_a=102, seg_len=128)
     enc.load_state_dict(syn.encoder_state_dict(0, enc_size=1024, enc_mode='one_hot'))

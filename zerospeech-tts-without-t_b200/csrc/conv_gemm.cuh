@@ -49,6 +49,12 @@ constexpr int MAX_STAGES = 4;
 // ... and the shared memory that frees holds a SECOND residual tile per epilogue set: the residual of round r + 1 is in flight
 // while round r is processed (with one tile its TMA load latency is exposed once per round: 17 % of the IN + residual epilogue)
 constexpr int PAIR_SET_STAGING_BYTES = SET_STAGING_BYTES + STG_TILE_BYTES;
+// Single-CTA layers WITHOUT a residual and with a channels-last output (conv bank, conv2/3/7, the 16- / 32-frame up-convs ...) run
+// a deeper ring instead: four 48 KB stages and ONE 16 KB output tile per epilogue set (template DEEP) - their main loop waits on TMA
+// latency with three stages in flight (ncu: producer and MMA warp both > 55 % in their barrier waits on `bank`)
+constexpr int DEEP_STAGES = 4;
+constexpr int DEEP_SET_STAGING_BYTES = STG_TILE_BYTES;
+constexpr int DEEP_SMEM_BYTES = DEEP_STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + EPI_SETS * DEEP_SET_STAGING_BYTES + 1024 + 256;
 constexpr int PAIR_SMEM_BYTES = PAIR_STAGES * (A_STAGE_BYTES + PAIR_B_STAGE_BYTES) + EPI_SETS * PAIR_SET_STAGING_BYTES + 1024 + 256;
 constexpr float IN_EPS = 1e-5f;
 
@@ -541,16 +547,17 @@ __device__ __forceinline__ void frames_to_nct_tma(const GemmParams& p, uint32_t 
 // CTAs' TMA bytes on its `full` barriers, issues the MMAs for both, and its commits are multicast to both CTAs' `empty` / `tfull`
 // barriers; each CTA runs the epilogue of its own 128 channels out of its own TMEM; both epilogues hand the accumulator back on the
 // leader's `tempty`.
-template <typename OT, bool ZP, bool TRAIN, bool PAIR>
+template <typename OT, bool ZP, bool TRAIN, bool PAIR, bool DEEP = false>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid_constant__ GemmParams p) {
-    constexpr int NSTG = PAIR ? PAIR_STAGES : STAGES;
+    static_assert(!(PAIR && DEEP), "the pair kernel already runs four stages");
+    constexpr int NSTG = PAIR ? PAIR_STAGES : (DEEP ? DEEP_STAGES : STAGES);
     constexpr int B_BYTES = PAIR ? PAIR_B_STAGE_BYTES : B_STAGE_BYTES;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_addr = smem_u32(smem_raw);
     uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
     uint8_t* sA = smem;
     uint8_t* sB = smem + NSTG * A_STAGE_BYTES;
-    constexpr int SET_BYTES = PAIR ? PAIR_SET_STAGING_BYTES : SET_STAGING_BYTES;
+    constexpr int SET_BYTES = PAIR ? PAIR_SET_STAGING_BYTES : (DEEP ? DEEP_SET_STAGING_BYTES : SET_STAGING_BYTES);
     uint8_t* sStage = smem + NSTG * (A_STAGE_BYTES + B_BYTES);
     uint64_t* full = reinterpret_cast<uint64_t*>(sStage + EPI_SETS * SET_BYTES);
     uint64_t* empty = full + MAX_STAGES;
@@ -836,7 +843,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
                         const int f_lo = h * p.rnd_frames, f_hi = min(T, f_lo + p.rnd_frames);
                         // staging: with a residual, tile 0 = output and tile 1 = residual; otherwise the two tiles
                         // alternate as output buffers so a store's shared-memory read overlaps the next round
-                        OT* stage_out = stage + (has_res ? 0 : (rnd & 1) * (STG_TILE_BYTES / 2));
+                        OT* stage_out = stage + ((has_res || DEEP) ? 0 : (rnd & 1) * (STG_TILE_BYTES / 2));
                         const int rslot = PAIR ? (rres & 1) : 0;
                         const OT* stage_res = stage + (1 + rslot) * (STG_TILE_BYTES / 2);
                         const bool live = nt * p.nb + s0 < p.B;
@@ -902,7 +909,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
                         if (set_lead && live && elect_one()) {
                             tma_store_3d(&p.tmOut, stage_out, ps ? mt * 64 : mt * BM, p.out_halo + fstep * f_lo, nt * p.nb + s0);
                             tma_store_commit();
-                            if (has_res) tma_store_wait_read();            // single output tile: it must be free next round
+                            if (has_res || DEEP) tma_store_wait_read();    // single output tile: it must be free next round
                             else tma_store_wait_read1();                   // the other tile's store (2 rounds ago) is done
                         }
                         asm volatile("bar.sync %0, 128;" ::"r"(set_bar) : "memory");

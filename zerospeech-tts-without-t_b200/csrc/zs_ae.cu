@@ -230,7 +230,8 @@ static thread_local int t_zero_pad = 0;
 
 // 1 (default) = layers that qualify run as CTA pairs (cta_group::2), 0 = one CTA per tile everywhere (the A/B reference of the tests)
 static int g_gemm_pair_mode = 1;
-extern "C" void zs_set_gemm_pair_mode(int mode) { g_gemm_pair_mode = mode; }
+static int g_gemm_deep_mode = 1;         // bit 8 of zs_set_gemm_pair_mode's argument turns the deeper single-CTA ring off (A/B)
+extern "C" void zs_set_gemm_pair_mode(int mode) { g_gemm_pair_mode = mode & 0xff; g_gemm_deep_mode = (mode & 0x100) ? 0 : ((mode & 0x200) ? 2 : 1); }
 
 static int launch_conv(const zs_conv_desc* d, cudaStream_t stream, const ConvExtras* ex = nullptr) {
     ZS_TRY(ensure_device());
@@ -278,6 +279,12 @@ static int launch_conv(const zs_conv_desc* d, cudaStream_t stream, const ConvExt
     const bool pair = g_gemm_pair_mode != 0 && !train_ex && !(ex && (ex->zero_halo || ex->edge_lo || ex->edge_hi)) && !d->bank &&
                       m_tiles % 2 == 0 && nb % 2 == 0 && g_num_sms >= 2 && (Tt >= 64 || g_gemm_pair_mode == 2);
     const int nb_box = pair ? nb / 2 : nb;
+    // the deeper single-CTA ring (four stages, one output tile per epilogue set) is possible for inference layers without a residual
+    // whose output is channels-last; measured per layer (tools/layer_profile.py 960 10 5 1 | 0x101) it pays on the pixel-shuffle
+    // up-convs on 16 / 32 frames (d.conv3 310 -> 280 us, d.conv1 172 -> 166) and costs 1-3 % on bank / conv2 / conv3 / the encoder's
+    // dense layers (their main loop is bound by L2 -> shared-memory bandwidth, not latency): used for the pixel-shuffle layers only
+    const bool deep = g_gemm_deep_mode != 0 && !pair && !train_ex && !(ex && (ex->zero_halo || ex->edge_lo || ex->edge_hi)) &&
+                      d->res_mode == RES_NONE && (d->out_mode == OUT_PS || (g_gemm_deep_mode == 2 && d->out_mode != OUT_NCT32));
 
     {   // A: weights [m_rows][k_total]
         cuuint64_t dims[2] = {static_cast<cuuint64_t>(k_total), static_cast<cuuint64_t>(d->m_rows)};
@@ -401,8 +408,9 @@ static int launch_conv(const zs_conv_desc* d, cudaStream_t stream, const ConvExt
     KernelT kern = zp ? (which ? conv_gemm_kernel<__nv_bfloat16, true, false, false> : conv_gemm_kernel<__half, true, false, false>)
                  : train_ex ? (which ? conv_gemm_kernel<__nv_bfloat16, false, true, false> : conv_gemm_kernel<__half, false, true, false>)
                  : pair ? (which ? conv_gemm_kernel<__nv_bfloat16, false, false, true> : conv_gemm_kernel<__half, false, false, true>)
+                 : deep ? (which ? conv_gemm_kernel<__nv_bfloat16, false, false, false, true> : conv_gemm_kernel<__half, false, false, false, true>)
                         : (which ? conv_gemm_kernel<__nv_bfloat16, false, false, false> : conv_gemm_kernel<__half, false, false, false>);
-    const int smem_bytes = pair ? PAIR_SMEM_BYTES : GEMM_SMEM_BYTES;
+    const int smem_bytes = pair ? PAIR_SMEM_BYTES : (deep ? DEEP_SMEM_BYTES : GEMM_SMEM_BYTES);
     ZS_TRY(set_smem_attr(reinterpret_cast<const void*>(kern), smem_bytes));
     {   // algorithmic FLOPs: 2 * valid out channels * true taps * true in channels * valid frames
         double taps_sum = d->bank ? 28.0 / 7.0 : static_cast<double>(d->taps);
