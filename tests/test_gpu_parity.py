@@ -706,7 +706,7 @@ def test_cta_pair_gemm_is_bit_identical_to_single_cta(full_models):
             c = syn.speaker_ids(B, 102, 93).cuda()
             noise = gumbel_from_uniform(syn.gumbel_uniform((B, Encoder.t8(T), 1024), 93)).cuda()
             res = []
-            for mode in (0x100, 0x202):  # 0x100: one CTA per tile, three-stage ring everywhere; 0x202: every layer that CAN pair does, four-stage ring wherever it applies
+            for mode in (0x500, 0xa02):  # 0x500: one CTA per tile, three-stage ring, every tap re-stages its tile; 0xa02: pairs, tap reuse (in pairs too) and the four-stage ring wherever they apply
                 lib.zs_set_gemm_pair_mode(mode)
                 act, logits, ids = enc.encode(x, noise)
                 spec = dec.decode(None, c, unit_ids=ids)
@@ -720,7 +720,7 @@ def test_cta_pair_gemm_is_bit_identical_to_single_cta(full_models):
             W = torch.randn(cs['C_out'], cs['C_in'], cs['k'], device='cuda') / (cs['C_in'] * cs['k']) ** 0.5
             bb = torch.randn(cs['C_out'], device='cuda') * 0.1
             outs = []
-            for mode in (0x100, 0x202):
+            for mode in (0x500, 0xa02):
                 lib.zs_set_gemm_pair_mode(mode)
                 outs.append((gh.conv_cl_to_cl(xx, W, bb, lrelu=True, inorm=True, halo_out=2), gh.conv_cl(xx, W, bb, lrelu=True, act=1)))
             assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1]), cs

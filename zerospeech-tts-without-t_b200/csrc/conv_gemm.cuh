@@ -55,6 +55,21 @@ constexpr int PAIR_SET_STAGING_BYTES = SET_STAGING_BYTES + STG_TILE_BYTES;
 constexpr int DEEP_STAGES = 4;
 constexpr int DEEP_SET_STAGING_BYTES = STG_TILE_BYTES;
 constexpr int DEEP_SMEM_BYTES = DEEP_STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + EPI_SETS * DEEP_SET_STAGING_BYTES + 1024 + 256;
+// Tap-reusing main loop (template REUSE; stride-1 convs with more than one tap whose MMAs stay >= 128 columns wide): the B stage
+// holds the frames of a tile WITH the taps' extra rows ({64 channels, Tt + taps - 1 rows} per segment) and every tap's MMA reads
+// it through a descriptor that starts `tap` rows further - a K-major 128-byte-swizzled operand may start at any 128-byte row of a
+// 1024-byte-aligned tile with base offset 0 (tools/desc_offset_test.cu: the swizzle is a function of the absolute address).  B is
+// then staged once per 64-channel chunk instead of once per (tap, chunk): 43 % fewer staged bytes for k = 3, 49 % for the bank.
+// The rows of consecutive segments are (taps - 1) apart from contiguous, so the tile takes one MMA per segment (N = Tt; CTA pairs:
+// N = 2 Tt over segment 2g of the leader and 2g + 1 of the peer).  A and B travel through separate rings.
+constexpr int REUSE_A_STAGES = 5, REUSE_B_STAGES = 2;
+constexpr int REUSE_B_BYTES = 35 * 1024;             // 2 segments x (128 + 6) rows x 128 B = 34 304
+constexpr int REUSE_PAIR_A_STAGES = 4, REUSE_PAIR_B_STAGES = 3;
+constexpr int REUSE_PAIR_B_BYTES = 17 * 1024;        // per CTA: (128 + 2) rows, or 2 segments x (64 + 2) rows
+constexpr int REUSE_SMEM_BYTES = REUSE_A_STAGES * A_STAGE_BYTES + REUSE_B_STAGES * REUSE_B_BYTES + STAGING_BYTES + 1024 + 256;
+constexpr int REUSE_PAIR_SMEM_BYTES = REUSE_PAIR_A_STAGES * A_STAGE_BYTES + REUSE_PAIR_B_STAGES * REUSE_PAIR_B_BYTES +
+                                      EPI_SETS * PAIR_SET_STAGING_BYTES + 1024 + 256;
+constexpr int MAX_A_STAGES = 5, MAX_B_STAGES = 3;
 constexpr int PAIR_SMEM_BYTES = PAIR_STAGES * (A_STAGE_BYTES + PAIR_B_STAGE_BYTES) + EPI_SETS * PAIR_SET_STAGING_BYTES + 1024 + 256;
 constexpr float IN_EPS = 1e-5f;
 
@@ -79,6 +94,9 @@ struct alignas(64) GemmParams {
     int m_tiles, n_tiles, nb, Tt, T, B, N;
     int kc, taps, bank, stride, in_row0, c_in_pad;
     int pair;            // CTA-pair launch (cluster of 2): tmB's box holds nb / 2 segments, idesc has M = 256
+    // tap-reusing main loop: tmB's box = {64 channels, reuse_rb rows, all nb segments (single CTA) | 1 segment (pair)}; reuse_g MMAs of
+    // reuse_nm columns per K = 16 step (idesc is built for reuse_nm), the B operand of group g and tap j starts (g reuse_rb + j) rows in
+    int reuse_rb, reuse_g, reuse_nm;
     int last_mmas;       // K = 16 MMAs of the LAST 64-channel chunk of a tap that hold valid input channels (1..4)
     int pdl;             // launched with programmatic stream serialization: wait for the producer grid before touching its data
     int m_valid;
@@ -547,21 +565,26 @@ __device__ __forceinline__ void frames_to_nct_tma(const GemmParams& p, uint32_t 
 // CTAs' TMA bytes on its `full` barriers, issues the MMAs for both, and its commits are multicast to both CTAs' `empty` / `tfull`
 // barriers; each CTA runs the epilogue of its own 128 channels out of its own TMEM; both epilogues hand the accumulator back on the
 // leader's `tempty`.
-template <typename OT, bool ZP, bool TRAIN, bool PAIR, bool DEEP = false>
+template <typename OT, bool ZP, bool TRAIN, bool PAIR, bool DEEP = false, bool REUSE = false>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid_constant__ GemmParams p) {
     static_assert(!(PAIR && DEEP), "the pair kernel already runs four stages");
-    constexpr int NSTG = PAIR ? PAIR_STAGES : (DEEP ? DEEP_STAGES : STAGES);
-    constexpr int B_BYTES = PAIR ? PAIR_B_STAGE_BYTES : B_STAGE_BYTES;
+    static_assert(!REUSE || (!ZP && !TRAIN && !DEEP), "the tap-reusing loop exists for the inference kernels");
+    // NSTG = stages of the A ring (= of the joint A + B stages without REUSE), NSTG_B = stages of REUSE's separate B ring
+    constexpr int NSTG = REUSE ? (PAIR ? REUSE_PAIR_A_STAGES : REUSE_A_STAGES) : (PAIR ? PAIR_STAGES : (DEEP ? DEEP_STAGES : STAGES));
+    constexpr int NSTG_B = REUSE ? (PAIR ? REUSE_PAIR_B_STAGES : REUSE_B_STAGES) : NSTG;
+    constexpr int B_BYTES = REUSE ? (PAIR ? REUSE_PAIR_B_BYTES : REUSE_B_BYTES) : (PAIR ? PAIR_B_STAGE_BYTES : B_STAGE_BYTES);
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_addr = smem_u32(smem_raw);
     uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
     uint8_t* sA = smem;
     uint8_t* sB = smem + NSTG * A_STAGE_BYTES;
     constexpr int SET_BYTES = PAIR ? PAIR_SET_STAGING_BYTES : (DEEP ? DEEP_SET_STAGING_BYTES : SET_STAGING_BYTES);
-    uint8_t* sStage = smem + NSTG * (A_STAGE_BYTES + B_BYTES);
-    uint64_t* full = reinterpret_cast<uint64_t*>(sStage + EPI_SETS * SET_BYTES);
-    uint64_t* empty = full + MAX_STAGES;
-    uint64_t* tfull = empty + MAX_STAGES;
+    uint8_t* sStage = smem + NSTG * A_STAGE_BYTES + NSTG_B * B_BYTES;
+    uint64_t* full = reinterpret_cast<uint64_t*>(sStage + EPI_SETS * SET_BYTES);      // A ring (A + B stages without REUSE)
+    uint64_t* empty = full + MAX_A_STAGES;
+    uint64_t* fullB = empty + MAX_A_STAGES;                                           // REUSE: the B ring
+    uint64_t* emptyB = fullB + MAX_B_STAGES;
+    uint64_t* tfull = emptyB + MAX_B_STAGES;
     uint64_t* tempty = tfull + 2;
     uint64_t* rbar = tempty + 2;   // [EPI_SETS][2] residual tile (slot 0 / 1) landed in the set's staging buffer
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rbar + 2 * EPI_SETS);
@@ -575,6 +598,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
             mbar_init(&full[i], 1);
             mbar_init(&empty[i], 1);
         }
+        if (REUSE)
+            for (int i = 0; i < NSTG_B; ++i) {
+                mbar_init(&fullB[i], 1);
+                mbar_init(&emptyB[i], 1);
+            }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tfull[i], 1);
             mbar_init(&tempty[i], (PAIR ? 2 : 1) * 4 * EPI_SETS);
@@ -614,8 +642,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
     if (warp == 0) {
         // ------------------------------ TMA producer (whole warp, one elected lane issues) ------
         {
-            int stage = 0;
-            uint32_t phase = 0;
+            int stage = 0, stage_b = 0;
+            uint32_t phase = 0, phase_b = 0;
             const int seg_off = PAIR ? static_cast<int>(rank) * (p.nb >> 1) : 0;      // this CTA's half of the tile's segments
             for (int tile = tile0; tile < total_tiles; tile += tile_step) {
                 const int mu = tile % m_units, nt = tile / m_units;
@@ -625,17 +653,48 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
                     ntaps = mt + 1;
                     tap_lo = 3 - ntaps / 2;
                 }
-                for (int j = 0; j < ntaps; ++j) {
-                    const int tap = tap_lo + j;
-                    const int row_b = p.in_row0 + tap;
-                    for (int c = 0; c < p.kc; ++c) {
+                // chunk-major, taps inside (every variant of the kernel accumulates in this order: results do not depend on
+                // which variant ran a layer)
+                for (int c = 0; c < p.kc; ++c) {
+                    if (REUSE) {
+                        // ---- B(c): the tile's frames with the taps' extra rows, once per chunk ----
+                        mbar_wait(&emptyB[stage_b], phase_b ^ 1);
+                        if (elect_one()) {
+                            uint8_t* dB = sB + stage_b * B_BYTES;
+                            if (PAIR) {
+                                if (rank == 0) mbar_expect_tx(&fullB[stage_b], 2u * p.reuse_g * p.reuse_rb * 128u);
+                                const uint32_t fb = mapa_shared(smem_u32(&fullB[stage_b]), 0);
+                                for (int g = 0; g < p.reuse_g; ++g)      // segment 2g (leader) / 2g + 1 (peer): MMA g spans both
+                                    tma_load_3d_pair(&p.tmB, dB + g * p.reuse_rb * 128, fb, c * BK, p.in_row0, nt * p.nb + 2 * g + static_cast<int>(rank));
+                            } else {
+                                mbar_expect_tx(&fullB[stage_b], static_cast<uint32_t>(p.nb) * p.reuse_rb * 128u);
+                                tma_load_3d(&p.tmB, dB, &fullB[stage_b], c * BK, p.in_row0, nt * p.nb);
+                            }
+                        }
+                        __syncwarp();
+                        if (++stage_b == NSTG_B) {
+                            stage_b = 0;
+                            phase_b ^= 1;
+                        }
+                    }
+                    for (int j = 0; j < ntaps; ++j) {
+                        const int tap = tap_lo + j;
+                        const int row_b = p.in_row0 + tap;
                         mbar_wait(&empty[stage], phase ^ 1);
                         if (ZS_DBG(p) & 1) {
                             if (elect_one()) mbar_arrive(&full[stage]);
                         } else if (elect_one()) {
                             uint8_t* dA = sA + stage * A_STAGE_BYTES;
                             uint8_t* dB = sB + stage * B_BYTES;
-                            if (PAIR) {
+                            if (REUSE) {
+                                if (PAIR) {
+                                    if (rank == 0) mbar_expect_tx(&full[stage], 2u * A_STAGE_BYTES);
+                                    tma_load_2d_pair(&p.tmA, dA, mapa_shared(smem_u32(&full[stage]), 0), tap * p.c_in_pad + c * BK, mt * BM);
+                                } else {
+                                    mbar_expect_tx(&full[stage], A_STAGE_BYTES);
+                                    tma_load_2d(&p.tmA, dA, &full[stage], tap * p.c_in_pad + c * BK, mt * BM);
+                                }
+                            } else if (PAIR) {
                                 // both CTAs' bytes complete on the LEADER's barrier; only the leader arms it
                                 if (rank == 0) mbar_expect_tx(&full[stage], stage_tx);
                                 const uint32_t fb = mapa_shared(smem_u32(&full[stage]), 0);
@@ -663,44 +722,80 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
     } else if (warp == 1 && rank == 0) {
         // ------------------------------ MMA issuer (whole warp, one elected lane issues; a pair's leader issues for both CTAs) --------
         {
-            int stage = 0;
-            uint32_t phase = 0;
+            int stage = 0, stage_b = 0;
+            uint32_t phase = 0, phase_b = 0;
             int it = 0;
             const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
             for (int tile = tile0; tile < total_tiles; tile += tile_step, ++it) {
                 const int mt = tile % m_units;          // (bank mode is never paired: mt is the m-tile there)
-                const int ksteps = ((!PAIR && p.bank) ? mt + 1 : p.taps) * p.kc;
+                int tap_lo = 0, ntaps = p.taps;
+                if (!PAIR && p.bank) {
+                    ntaps = mt + 1;
+                    tap_lo = 3 - ntaps / 2;
+                }
                 const int as = it & 1;
                 mbar_wait(&tempty[as], ((it >> 1) & 1) ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + as * MAX_BN;
-                int kc_pos = 0;                      // chunk index within the current tap
-                for (int ks = 0; ks < ksteps; ++ks) {
-                    mbar_wait(&full[stage], phase);
-                    tc_fence_after();
-                    const uint64_t da = umma_desc_sw128(a0 + stage * A_STAGE_BYTES);
-                    const uint64_t db = umma_desc_sw128(b0 + stage * B_BYTES);
+                for (int c = 0; c < p.kc; ++c) {
                     // the zero-padded tail of the input channels (513 -> 576, 1409 -> 1472) needs no MMAs
-                    const int n_mma = (++kc_pos == p.kc) ? p.last_mmas : BK / 16;
-                    if (kc_pos == p.kc) kc_pos = 0;
-                    if (elect_one()) {
-                        if (!(ZS_DBG(p) & 2)) {
+                    const int n_mma = (c + 1 == p.kc) ? p.last_mmas : BK / 16;
+                    uint64_t db_c = 0;
+                    if (REUSE) {
+                        mbar_wait(&fullB[stage_b], phase_b);
+                        db_c = umma_desc_sw128(b0 + stage_b * B_BYTES);
+                    }
+                    for (int j = 0; j < ntaps; ++j) {
+                        mbar_wait(&full[stage], phase);
+                        tc_fence_after();
+                        const uint64_t da = umma_desc_sw128(a0 + stage * A_STAGE_BYTES);
+                        const uint32_t first = (c | j) == 0 ? 0u : 1u;      // 0: the tile's first MMAs overwrite the accumulator
+                        if (elect_one()) {
+                            if (!(ZS_DBG(p) & 2)) {
+                                if (REUSE) {
+                                    // one MMA per segment (pair: per segment pair); tap = a row offset of the operand: +8 per row in the >>4 field
+                                    for (int g = 0; g < p.reuse_g; ++g) {
+                                        const uint64_t db = db_c + static_cast<uint64_t>((g * p.reuse_rb + tap_lo + j) * 8);
+                                        const uint32_t dg = d_tmem + g * p.reuse_nm;
 #pragma unroll
-                            for (int k = 0; k < BK / 16; ++k) {
-                                // advance 16 elements (32 B) along K inside the swizzle row: +2 in the >>4 address field
-                                if (k < n_mma) {
-                                    if (PAIR) umma_f16_pair(d_tmem, da + 2 * k, db + 2 * k, p.idesc, (ks | k) != 0);
-                                    else umma_f16(d_tmem, da + 2 * k, db + 2 * k, p.idesc, (ks | k) != 0);
+                                        for (int k = 0; k < BK / 16; ++k) {
+                                            if (k < n_mma) {
+                                                if (PAIR) umma_f16_pair(dg, da + 2 * k, db + 2 * k, p.idesc, first | static_cast<uint32_t>(k != 0));
+                                                else umma_f16(dg, da + 2 * k, db + 2 * k, p.idesc, first | static_cast<uint32_t>(k != 0));
+                                            }
+                                        }
+                                    }
+                                } else {
+                                    const uint64_t db = umma_desc_sw128(b0 + stage * B_BYTES);
+#pragma unroll
+                                    for (int k = 0; k < BK / 16; ++k) {
+                                        // advance 16 elements (32 B) along K inside the swizzle row: +2 in the >>4 address field
+                                        if (k < n_mma) {
+                                            if (PAIR) umma_f16_pair(d_tmem, da + 2 * k, db + 2 * k, p.idesc, first | static_cast<uint32_t>(k != 0));
+                                            else umma_f16(d_tmem, da + 2 * k, db + 2 * k, p.idesc, first | static_cast<uint32_t>(k != 0));
+                                        }
+                                    }
                                 }
                             }
+                            if (PAIR) umma_commit_pair(&empty[stage]);      // frees this stage in BOTH CTAs
+                            else umma_commit(&empty[stage]);
                         }
-                        if (PAIR) umma_commit_pair(&empty[stage]);      // frees this stage in BOTH CTAs
-                        else umma_commit(&empty[stage]);
+                        __syncwarp();
+                        if (++stage == NSTG) {
+                            stage = 0;
+                            phase ^= 1;
+                        }
                     }
-                    __syncwarp();
-                    if (++stage == NSTG) {
-                        stage = 0;
-                        phase ^= 1;
+                    if (REUSE) {
+                        if (elect_one()) {
+                            if (PAIR) umma_commit_pair(&emptyB[stage_b]);
+                            else umma_commit(&emptyB[stage_b]);
+                        }
+                        __syncwarp();
+                        if (++stage_b == NSTG_B) {
+                            stage_b = 0;
+                            phase_b ^= 1;
+                        }
                     }
                 }
                 if (elect_one()) {

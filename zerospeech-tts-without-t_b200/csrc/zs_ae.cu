@@ -230,8 +230,13 @@ static thread_local int t_zero_pad = 0;
 
 // 1 (default) = layers that qualify run as CTA pairs (cta_group::2), 0 = one CTA per tile everywhere (the A/B reference of the tests)
 static int g_gemm_pair_mode = 1;
+static int g_gemm_reuse_mode = 1;        // bit 10 turns the tap-reusing main loop off (A/B)
 static int g_gemm_deep_mode = 1;         // bit 8 of zs_set_gemm_pair_mode's argument turns the deeper single-CTA ring off (A/B)
-extern "C" void zs_set_gemm_pair_mode(int mode) { g_gemm_pair_mode = mode & 0xff; g_gemm_deep_mode = (mode & 0x100) ? 0 : ((mode & 0x200) ? 2 : 1); }
+extern "C" void zs_set_gemm_pair_mode(int mode) {
+    g_gemm_pair_mode = mode & 0xff;
+    g_gemm_deep_mode = (mode & 0x100) ? 0 : ((mode & 0x200) ? 2 : 1);
+    g_gemm_reuse_mode = (mode & 0x400) ? 0 : ((mode & 0x800) ? 2 : 1);
+}
 
 static int launch_conv(const zs_conv_desc* d, cudaStream_t stream, const ConvExtras* ex = nullptr) {
     ZS_TRY(ensure_device());
@@ -278,12 +283,24 @@ static int launch_conv(const zs_conv_desc* d, cudaStream_t stream, const ConvExt
     // 16- / 32-frame layers gain nothing or lose - d.conv3 355 -> 391 us; mode 2 pairs them too, for the tests); the rest runs one CTA per tile.
     const bool pair = g_gemm_pair_mode != 0 && !train_ex && !(ex && (ex->zero_halo || ex->edge_lo || ex->edge_hi)) && !d->bank &&
                       m_tiles % 2 == 0 && nb % 2 == 0 && g_num_sms >= 2 && (Tt >= 64 || g_gemm_pair_mode == 2);
-    const int nb_box = pair ? nb / 2 : nb;
+    // tap-reusing main loop (conv_gemm.cuh, REUSE): stride-1 layers with several taps whose per-segment MMAs stay >= 128 columns wide
+    // (single CTA: 128-frame segments; pairs: from 64 frames) and whose B stage with the taps' extra rows fits its slot
+    const int reuse_rb = Tt + (d->bank ? d->w_taps : d->taps) - 1;
+    const int reuse_g = pair ? nb / 2 : nb, reuse_nm = pair ? 2 * Tt : Tt;
+    // Measured per layer (tools/layer_profile.py, mode 0x202 vs 0x602): the conv bank gains 14 % (561 -> 481 us; its main loop is bound
+    // by the bytes staged per FLOP), conv2 / conv3 (one channel tile) are neutral, and the CTA-PAIR layers lose - they already stage
+    // half the columns per CTA and run near the tensor pipe's rate (d.conv6, one MMA per step: 527 -> 543 us; d.conv5 / d.conv4 /
+    // conv5 with two M = 256, N = 128 MMAs per step: 514 -> 584 us).  Default: single-CTA layers only; mode bit 0x800 also reuses in pairs.
+    const bool reuse = g_gemm_reuse_mode != 0 && (!pair || g_gemm_reuse_mode == 2) && !train_ex && !(ex && (ex->zero_halo || ex->edge_lo || ex->edge_hi)) && d->stride == 1 &&
+                       (d->taps > 1 || d->bank) && reuse_nm >= 128 && reuse_rb <= 256 &&
+                       reuse_g * reuse_rb * 128 <= (pair ? REUSE_PAIR_B_BYTES : REUSE_B_BYTES);
+    const int nb_box = reuse ? (pair ? 1 : nb) : (pair ? nb / 2 : nb);
+    const int rows_box = reuse ? reuse_rb : Tt;
     // the deeper single-CTA ring (four stages, one output tile per epilogue set) is possible for inference layers without a residual
     // whose output is channels-last; measured per layer (tools/layer_profile.py 960 10 5 1 | 0x101) it pays on the pixel-shuffle
     // up-convs on 16 / 32 frames (d.conv3 310 -> 280 us, d.conv1 172 -> 166) and costs 1-3 % on bank / conv2 / conv3 / the encoder's
     // dense layers (their main loop is bound by L2 -> shared-memory bandwidth, not latency): used for the pixel-shuffle layers only
-    const bool deep = g_gemm_deep_mode != 0 && !pair && !train_ex && !(ex && (ex->zero_halo || ex->edge_lo || ex->edge_hi)) &&
+    const bool deep = g_gemm_deep_mode != 0 && !pair && !reuse && !train_ex && !(ex && (ex->zero_halo || ex->edge_lo || ex->edge_hi)) &&
                       d->res_mode == RES_NONE && (d->out_mode == OUT_PS || (g_gemm_deep_mode == 2 && d->out_mode != OUT_NCT32));
 
     {   // A: weights [m_rows][k_total]
@@ -295,7 +312,7 @@ static int launch_conv(const zs_conv_desc* d, cudaStream_t stream, const ConvExt
     if (d->stride == 1) {   // B: (channel, row, segment)
         cuuint64_t dims[3] = {static_cast<cuuint64_t>(d->c_in_valid), static_cast<cuuint64_t>(d->in_rows), static_cast<cuuint64_t>(d->B)};
         cuuint64_t strides[2] = {static_cast<cuuint64_t>(d->in_pitch) * 2, static_cast<cuuint64_t>(d->in_rows) * d->in_pitch * 2};
-        cuuint32_t box[3] = {BK, static_cast<cuuint32_t>(Tt), static_cast<cuuint32_t>(nb_box)};
+        cuuint32_t box[3] = {BK, static_cast<cuuint32_t>(rows_box), static_cast<cuuint32_t>(nb_box)};
         ZS_TRY(make_map(&p.tmB, d->operand, const_cast<void*>(d->in), 3, dims, strides, box));
     } else {                // B: (channel, row parity, row pair, segment)
         cuuint64_t dims[4] = {static_cast<cuuint64_t>(d->c_in_valid), 2, static_cast<cuuint64_t>(d->in_rows / 2), static_cast<cuuint64_t>(d->B)};
@@ -367,8 +384,9 @@ static int launch_conv(const zs_conv_desc* d, cudaStream_t stream, const ConvExt
     p.res_mode = d->res_mode; p.res = d->res; p.res_rows = d->res_rows; p.res_pitch = d->res_pitch; p.res_halo = d->res_halo;
     p.act = d->act; p.out_mode = d->out_mode; p.out = d->out; p.out_rows = d->out_rows; p.out_pitch = d->out_pitch;
     p.out_halo = d->out_halo; p.out_choff = d->out_choff; p.accumulate = d->accumulate; p.out_f16 = d->out_f16;
-    p.idesc = umma_idesc_f16(d->operand == ZS_OPERAND_BF16 ? 1 : 0, p.N, pair ? 256 : 128);
+    p.idesc = umma_idesc_f16(d->operand == ZS_OPERAND_BF16 ? 1 : 0, reuse ? reuse_nm : p.N, pair ? 256 : 128);
     p.pair = pair ? 1 : 0;
+    p.reuse_rb = reuse_rb; p.reuse_g = reuse_g; p.reuse_nm = reuse_nm;
     p.debug = env_int("ZS_GEMM_DEBUG", 0);
     p.sat_count = g_dev[t_dev].sat;
     if (ex) {
@@ -407,10 +425,12 @@ static int launch_conv(const zs_conv_desc* d, cudaStream_t stream, const ConvExt
     if (zp && train_ex) return fail(ZS_ERR_ARG, "conv: the zero-padding mode is inference only");
     KernelT kern = zp ? (which ? conv_gemm_kernel<__nv_bfloat16, true, false, false> : conv_gemm_kernel<__half, true, false, false>)
                  : train_ex ? (which ? conv_gemm_kernel<__nv_bfloat16, false, true, false> : conv_gemm_kernel<__half, false, true, false>)
+                 : (pair && reuse) ? (which ? conv_gemm_kernel<__nv_bfloat16, false, false, true, false, true> : conv_gemm_kernel<__half, false, false, true, false, true>)
+                 : reuse ? (which ? conv_gemm_kernel<__nv_bfloat16, false, false, false, false, true> : conv_gemm_kernel<__half, false, false, false, false, true>)
                  : pair ? (which ? conv_gemm_kernel<__nv_bfloat16, false, false, true> : conv_gemm_kernel<__half, false, false, true>)
                  : deep ? (which ? conv_gemm_kernel<__nv_bfloat16, false, false, false, true> : conv_gemm_kernel<__half, false, false, false, true>)
                         : (which ? conv_gemm_kernel<__nv_bfloat16, false, false, false> : conv_gemm_kernel<__half, false, false, false>);
-    const int smem_bytes = pair ? PAIR_SMEM_BYTES : (deep ? DEEP_SMEM_BYTES : GEMM_SMEM_BYTES);
+    const int smem_bytes = reuse ? (pair ? REUSE_PAIR_SMEM_BYTES : REUSE_SMEM_BYTES) : (pair ? PAIR_SMEM_BYTES : (deep ? DEEP_SMEM_BYTES : GEMM_SMEM_BYTES));
     ZS_TRY(set_smem_attr(reinterpret_cast<const void*>(kern), smem_bytes));
     {   // algorithmic FLOPs: 2 * valid out channels * true taps * true in channels * valid frames
         double taps_sum = d->bank ? 28.0 / 7.0 : static_cast<double>(d->taps);
