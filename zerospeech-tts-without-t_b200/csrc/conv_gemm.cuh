@@ -8,7 +8,7 @@
 // box stays dense.
 // One CTA per SM, persistent over output tiles of 128 channels x (nb segments x Tt frames <= 256 columns).
 // Warp 0 = TMA producer, warp 1 = MMA issuer (one elected thread), warps 2-3 idle (they only exist so that the driver
-// warps form a warp group of their own that hands its registers to the epilogue: setmaxnreg 40 / 232), warps 4..11 =
+// warps form a warp group of their own that hands its registers to the epilogue: setmaxnreg 56 / 224), warps 4..11 =
 // epilogue in two SETS of four (one warp per TMEM lane quadrant in each set); the sets take alternate segment groups of a tile, each with its
 // own staging tiles, residual barrier and TMA stores, so two epilogue warps per scheduler hide each other's
 // TMEM-load / shared-memory latency.  Two fp32 accumulators of 256 TMEM columns each let the epilogue of tile i
@@ -18,6 +18,12 @@
 // InstanceNorm statistics never leave the thread): + bias[speaker] -> leaky-relu -> InstanceNorm ->
 // + residual (same frame / avg-pool-2 / nearest-up-2) -> sigmoid|tanh -> store (channels-last with
 // reflected halo rows for the next conv, pixel-shuffled channels-last, or the reference's (B, C, T) fp32).
+//
+// Variants of the main loop (template arguments of conv_gemm_kernel; launch_conv in zs_ae.cu picks per layer from measurements, every
+// variant accumulates chunk-major with the taps inside so that all of them give bit-identical results):
+//   PAIR   clusters of two CTAs share one tcgen05.mma.cta_group::2 (M = 256), each CTA stages half of the tile's columns, 4 stages
+//   REUSE  the B stage carries the taps' extra rows and is staged once per 64-channel chunk; tap = a row offset of the MMA's descriptor
+//   DEEP   four 48 KB stages and one output tile per epilogue set (pixel-shuffle up-convs on 16 / 32 frames)
 #pragma once
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
