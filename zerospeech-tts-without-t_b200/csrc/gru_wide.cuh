@@ -11,9 +11,12 @@
 // memory).  Inference only (no gate save), tanh.approx gates.
 //
 // Measured and rejected (round 2): running the two 32-sequence halves as independent, software-pipelined recurrences (own
-// accumulators / barriers / 4 KB exchanges, a dedicated exchange warp, no block barrier).  The MMAs stream W_hh through the tensor
-// core at a cost that does not depend on N (33 cycles per M = 128 MMA for N = 32 as for N = 64), so two N = 32 groups double
-// the tensor time per step (~5 000 cycles) and the decoder GRU went from 1.17 to 1.68 ms per 960 segments.
+// accumulators / barriers / 4 KB exchanges, no block barrier).  With ONE control warp walking the groups in order the decoder GRU
+// went from 1.17 to 1.68 ms per 960 segments (waiting for group 0's late slices blocks the issue of group 1's ready MMAs); with an
+// MMA-issue warp and an exchange warp PER GROUP (20 warps, 96 registers, bit-identical results), staggered or not, it measures
+// 1.15 - 1.20 ms: exactly the one-group kernel.  The step is a latency chain (MMAs -> gate math -> exchange through L2), two groups
+// have the same chain as one, and throughput only grows with more independent groups per cluster than a B200 can hold at 960
+// segments (128 sequences per cluster are 16 clusters against the 15 resident ones).
 #pragma once
 #include "gru_cluster.cuh"
 
