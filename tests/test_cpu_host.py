@@ -179,3 +179,29 @@ def test_bench_has_single_definitions():
     assert len(names) == len(set(names)), sorted(n for n in names if names.count(n) > 1)
     src = open(os.path.join(root, 'bench.py')).read()
     assert 'environ.pop' not in src and "environ['NCCL_DEBUG']" not in src       # the driver reads NCCL's own log: leave it on
+
+
+def test_front_end_copy_pool_covers_every_index_once():
+    """The batched front-end splits its segment gather / result scatter over a small thread pool (frontend._parallel_ranges):
+    contiguous slices, every index exactly once, inline below two tasks' worth of work, exceptions of a worker surface."""
+    import numpy as np
+    from zs_b200 import frontend as fe
+    pool = fe._copy_pool()
+    assert pool is fe._copy_pool() and pool._max_workers >= 1
+    for n in (0, 1, 31, 32, 100, 960, 1001):
+        hits = np.zeros(n, np.int64)
+        slices = []
+
+        def fn(lo, hi):
+            slices.append((lo, hi))
+            hits[lo:hi] += 1
+        fe._parallel_ranges(pool, n, fn)
+        assert (hits == 1).all(), n
+        assert sorted(slices) == sorted(set(slices)) and all(lo < hi for lo, hi in slices if n)
+        if n < 32:
+            assert slices in ([(0, n)], [(0, 0)]) or n == 0
+
+    def boom(lo, hi):
+        raise ValueError('worker failed')
+    with pytest.raises(ValueError, match='worker failed'):
+        fe._parallel_ranges(pool, 960, boom)
