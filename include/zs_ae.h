@@ -375,7 +375,7 @@ typedef struct {
 int zs_conv1d_cl(const zs_conv_desc* d, void* stream);
 /* Layers with an even number of 128-channel tiles and of segments per tile run as CTA pairs (tcgen05 cta_group::2, M = 256; each CTA
  * stages half of the tile's columns).  mode 0 turns that off process-wide (one CTA per tile everywhere: the tests' A/B reference),
- * mode 1 (default) pairs the layers with >= 64 frames per segment (where it measures faster), mode 2 every layer that qualifies.
+ * mode 1 (default; 2 is accepted as a synonym) pairs every layer that qualifies.
  * Adding 0x100 also turns the four-stage ring of the single-CTA pixel-shuffle layers off (three stages, two output tiles); adding
  * 0x200 uses it for every single-CTA layer without a residual (tests); adding 0x400 turns the tap-reusing main loop off (every
  * tap then re-stages its shifted activation tile), adding 0x800 uses it in CTA pairs too (tests; measured slower there).

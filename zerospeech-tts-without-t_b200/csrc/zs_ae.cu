@@ -279,10 +279,11 @@ static int launch_conv(const zs_conv_desc* d, cudaStream_t stream, const ConvExt
     const int n_tiles = (d->B + nb - 1) / nb;
     const long long k_total = static_cast<long long>(d->w_taps) * d->c_in_pad;
     // CTA pairs (tcgen05 cta_group::2, M = 256): two adjacent channel tiles share the columns - each CTA stages half of them.
-    // Inference layers with an even number of channel tiles and of segments per tile and >= 64 frames per segment (measured: the
-    // 16- / 32-frame layers gain nothing or lose - d.conv3 355 -> 391 us; mode 2 pairs them too, for the tests); the rest runs one CTA per tile.
+    // Every inference layer with an even number of channel tiles and of segments per tile.  (Before the halo-row path of the epilogue
+    // was slimmed, the 16- / 32-frame layers lost as pairs - d.conv3 355 -> 391 us - and were excluded; measured again afterwards,
+    // tools/layer_profile.py 960 10 5 1 | 2: d.conv2 189 -> 166 us, d.conv3 283 -> 271, the 16-frame layers unchanged.)
     const bool pair = g_gemm_pair_mode != 0 && !train_ex && !(ex && (ex->zero_halo || ex->edge_lo || ex->edge_hi)) && !d->bank &&
-                      m_tiles % 2 == 0 && nb % 2 == 0 && g_num_sms >= 2 && (Tt >= 64 || g_gemm_pair_mode == 2);
+                      m_tiles % 2 == 0 && nb % 2 == 0 && g_num_sms >= 2;
     // tap-reusing main loop (conv_gemm.cuh, REUSE): stride-1 layers with several taps whose per-segment MMAs stay >= 128 columns wide
     // (single CTA: 128-frame segments; pairs: from 64 frames) and whose B stage with the taps' extra rows fits its slot
     const int reuse_rb = Tt + (d->bank ? d->w_taps : d->taps) - 1;
