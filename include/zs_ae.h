@@ -366,7 +366,7 @@ typedef struct {
     const void* res; int32_t res_rows, res_pitch, res_halo;
     int32_t act;             /* 0 none, 1 sigmoid, 2 tanh */
     int32_t out_mode;        /* 0 channels-last operand-type, 1 pixel-shuffle channels-last, 2 fp32 (B, m_valid, T_out) */
-    void* out; int32_t out_rows, out_pitch, out_halo, out_choff;
+    void* out; int32_t out_rows, out_pitch, out_halo, out_choff;   /* out_halo: reflected rows written each side, 0..3 (kernel sizes up to 7) */
     int32_t accumulate;      /* out_mode 2 only: 0 store, 1 out += y, 2 out += out*y */
     int32_t operand;         /* ZS_OPERAND_* */
     int32_t nb_hint;         /* segments per N tile, 0 = auto */
