@@ -3,7 +3,7 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload resynthesis|train]
 
 One "step" = one pass of Encoder -> one-hot bottleneck -> speaker-conditioned Decoder over `--calls-per-step` x
-`--segments` segments of 128 frames per GPU (default 20 x 960 = 19 200 segments = 2.46 M frames; enc_size 1024,
+`--segments` segments of 128 frames per GPU (default 24 x 960 = 23 040 segments = 2.95 M frames; enc_size 1024,
 emb_size 1024, 102 speakers, random-init weights, synthetic spectrograms), issued as library calls of 960 segments.  A step
 is that large so that the default 20 timed steps keep the GPU under load for > 3 s: the clocks settle in the sustained
 regime MEASURED_PEAKS.json's `bf16_tflops_sustained` was taken in.  Segments are independent, so ranks shard them with
@@ -84,7 +84,7 @@ def parse():
                     help='128-frame segments per library call: 960 x 128 frames = 480 column tiles, x 8 row tiles = 3840 tiles = 25.95 '
                          'waves of 148 CTAs on the 1024-channel layers (same on the 2048-channel up-convs), and 30 decoder-GRU clusters '
                          'of 64 sequences = exactly 2 waves of the 15 eight-CTA clusters that fit a B200')
-    ap.add_argument('--calls-per-step', type=int, default=20, help='library calls per step (per GPU)')
+    ap.add_argument('--calls-per-step', type=int, default=24, help='library calls per step (per GPU); 24 keeps 20 timed steps above 3 s at 16-17 M frames/s')
     ap.add_argument('--e2e-buffers', type=int, default=4, help='device buffer sets (= calls in flight) of the host-to-host pipeline')
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--operand', default='fp16', choices=['fp16', 'bf16'])

@@ -111,6 +111,80 @@ __global__ void __launch_bounds__(256) pack_x_dual_kernel(const IT* __restrict__
     }
 }
 
+// The same two views for the (B, C, T) layout with 16-byte traffic on both sides: a CTA takes 64 channels x 128 frames, a warp
+// reads a WHOLE 512-byte channel row per request (one float4 per lane; the 32-frame tiles of the kernel above read 128-byte pieces
+// of 64 different rows), the tile sits in shared memory as float4 with the float4 index XOR-ed by f(ch) = (ch >> 3) ^ (ch & 7)
+// (conflict-free both for the row-wise writes and for the channel-wise reads below), and a thread writes 8 consecutive channels of
+// one frame (16 bytes; 8 lanes cover a 128-byte piece of an operand row).  Needs T % 4 == 0 (16-byte aligned rows) and 16-byte
+// aligned operand rows (pitches and the concat offset multiples of 8); everything else takes the kernel above.
+template <typename OT, typename IT>
+__global__ void __launch_bounds__(256) pack_x_dual_wide_kernel(const IT* __restrict__ x, int C, int T,
+                                                               OT* __restrict__ bank, int bank_rows, int bank_pitch, int bank_halo,
+                                                               OT* __restrict__ cat, int cat_rows, int cat_pitch, int cat_choff, int cat_fill,
+                                                               float ns, int zero_halo) {
+    __shared__ float4 tile[64][32];
+    const int t0 = blockIdx.x * 128, c0 = blockIdx.y * 64, b = blockIdx.z;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int ch = warp + 8 * i, c = c0 + ch, t = t0 + 4 * lane;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c < C && t < T) {                         // T % 4 == 0: a float4 is inside or outside as a whole
+            const IT* src = x + (static_cast<size_t>(b) * C + c) * T + t;
+            if (sizeof(IT) == 4) {
+                v = *reinterpret_cast<const float4*>(src);
+            } else {
+                const uint2 h = *reinterpret_cast<const uint2*>(src);
+                const __half2 h0 = *reinterpret_cast<const __half2*>(&h.x), h1 = *reinterpret_cast<const __half2*>(&h.y);
+                v = make_float4(__low2float(h0), __high2float(h0), __low2float(h1), __high2float(h1));
+            }
+        }
+        tile[ch][lane ^ (((ch >> 3) ^ ch) & 7)] = v;
+    }
+    __syncthreads();
+    OT* bb = bank + static_cast<size_t>(b) * bank_rows * bank_pitch;
+    OT* cb = cat + static_cast<size_t>(b) * cat_rows * cat_pitch + cat_choff;
+    const int g = lane & 7, ts = lane >> 3;           // 8 channels x one of 4 consecutive frames
+    const int c = c0 + 8 * g;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int tl = 4 * (warp + 8 * i) + ts, t = t0 + tl;
+        if (t >= T) continue;
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int ch = 8 * g + j;
+            const float4 q = tile[ch][(tl >> 2) ^ (((ch >> 3) ^ ch) & 7)];
+            v[j] = (tl & 3) == 0 ? q.x : ((tl & 3) == 1 ? q.y : ((tl & 3) == 2 ? q.z : q.w));
+        }
+        if (c < bank_pitch) {                         // channels >= C are the zero padding of the K dimension (v = 0 there)
+            uint4 y;
+            OT* yv = reinterpret_cast<OT*>(&y);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) yv[j] = float_to_ot<OT>(v[j]);
+            const uint4 hv = zero_halo ? make_uint4(0, 0, 0, 0) : y;
+            *reinterpret_cast<uint4*>(bb + static_cast<size_t>(bank_halo + t) * bank_pitch + c) = y;
+            if (t >= 1 && t <= bank_halo) *reinterpret_cast<uint4*>(bb + static_cast<size_t>(bank_halo - t) * bank_pitch + c) = hv;
+            if (t >= T - 1 - bank_halo && t <= T - 2)
+                *reinterpret_cast<uint4*>(bb + static_cast<size_t>(bank_halo + 2 * (T - 1) - t) * bank_pitch + c) = hv;
+        }
+        if (c < cat_fill) {
+            OT* dst = cb + static_cast<size_t>(t) * cat_pitch + c;
+            if (c + 8 <= cat_fill) {
+                uint4 y;
+                OT* yv = reinterpret_cast<OT*>(&y);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) yv[j] = float_to_ot<OT>(fmaxf(v[j], v[j] * ns));
+                *reinterpret_cast<uint4*>(dst) = y;
+            } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    if (c + j < cat_fill) dst[j] = float_to_ot<OT>(fmaxf(v[j], v[j] * ns));
+            }
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Discrete bottleneck, one_hot mode: ids[b,t] = argmax_c(logits[b,c,t] + noise[b,t,c]) with first-index
 // tie-break (torch.max), act = one-hot (skipped when the caller passes no `act`: the batched front-end only

@@ -501,6 +501,20 @@ static int launch_pack_x_dual(const void* x, int x_dtype, int x_layout, int B, i
         return fail(ZS_ERR_ARG, "an fp16 input is rounded once more by bf16 operands: upload fp32 with operand = bf16");
     dim3 grid((T + 31) / 32, (C + 63) / 64, B);
     LaunchScope scope(st, KC_OTHER, 0.0, "pack_x_dual_kernel");
+    // (B, C, T) input with 16-byte aligned rows on both sides: whole 512-byte channel rows in, 16-byte operand stores out
+    const bool wide = x_layout == ZS_X_NCT && T % 4 == 0 && bank_pitch % 8 == 0 && cat_pitch % 8 == 0 && cat_choff % 8 == 0 &&
+                      reinterpret_cast<uintptr_t>(x) % 16 == 0 && reinterpret_cast<uintptr_t>(bank_p) % 16 == 0 && reinterpret_cast<uintptr_t>(cat_p) % 16 == 0;
+    if (wide) {
+        const dim3 wgrid((T + 127) / 128, (C + 63) / 64, B);
+#define ZS_PXW(OT_, IT_) pack_x_dual_wide_kernel<OT_, IT_><<<wgrid, 256, 0, st>>>(static_cast<const IT_*>(x), C, T, static_cast<OT_*>(bank_p), bank_rows, \
+                                                                                 bank_pitch, bank_halo, static_cast<OT_*>(cat_p), cat_rows, cat_pitch, cat_choff, C, ns, t_zero_pad)
+        if (operand == ZS_OPERAND_BF16) ZS_PXW(__nv_bfloat16, float);
+        else if (x_dtype == ZS_X_F16) ZS_PXW(__half, __half);
+        else ZS_PXW(__half, float);
+#undef ZS_PXW
+        CUDA_TRY(cudaGetLastError());
+        return ZS_OK;
+    }
     if (operand == ZS_OPERAND_BF16)
         pack_x_dual_dispatch<__nv_bfloat16>(x, x_dtype, x_layout, grid, st, C, T, static_cast<__nv_bfloat16*>(bank_p), bank_rows, bank_pitch, bank_halo,
                                             static_cast<__nv_bfloat16*>(cat_p), cat_rows, cat_pitch, cat_choff, ns);
