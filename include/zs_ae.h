@@ -289,6 +289,16 @@ int zs_decoder_backward(zs_decoder* h, const float* spec, const float* target, c
                         const zs_decoder_weights* grads, float* d_act,
                         void* workspace, size_t workspace_bytes, void* stream);
 
+/* Weight / bias gradients off the critical path.  The reference's loss.backward() (trainer.py:329) leaves the order of
+ * independent gradient kernels to autograd; here zs_wgrad_async(1) makes every following zs_*_backward call of THIS host
+ * thread launch its weight- and bias-gradient kernels on a library-owned side stream of the current device, forked from
+ * `stream` right after the kernel that produced their input (event record / wait: capturable into a CUDA graph), so they
+ * overlap the data-gradient chain.  The gradient buffers are then complete on `stream` only after zs_wgrad_join(stream);
+ * data gradients (d_act) and the loss are unaffected.  zs_wgrad_async(0) restores in-order launches (the default); it
+ * fails while gradients are in flight.  Call zs_wgrad_async(1) once outside a stream capture (it creates the stream). */
+int zs_wgrad_async(int on);
+int zs_wgrad_join(void* stream);
+
 /* sum of squares of a flat fp32 gradient buffer: *out += sum g^2 (zero it first) */
 int zs_grad_sqnorm(const float* g, size_t n, float* out, void* stream);
 /* nn.utils.clip_grad_norm_(max_norm) over ONE network (utils.py:53-55) fused with torch.optim.Adam's update

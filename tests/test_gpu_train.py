@@ -295,6 +295,48 @@ def test_train_step_full_batch32_vs_oracle():
             assert 0.8 <= (flat_g.norm() / flat_o.norm()).item() <= 1.25
 
 
+def test_side_stream_weight_gradients_equal_in_order_ones():
+    """zs_wgrad_async (include/zs_ae.h): weight / bias gradients launched on the library's side streams are the ones the
+    in-order launches produce (same kernels, same inputs; only split-K atomic order may differ), eagerly and in the CUDA
+    graph, and zs_wgrad_async(0) refuses while gradients are in flight."""
+    m = dict(seed=0, c_in=513, c_h=[128, 512, 128], enc_size=1024, emb_size=1024, n_spk=102, ns=0.01, seg_len=128, dp=0.5)
+    B, T = 8, 128
+    x, c = syn.spectrogram_batch(B, T, 5).cuda(), syn.speaker_ids(B, 102, 5).cuda()
+    noise = gumbel_from_uniform(syn.gumbel_uniform((B, 16, 1024), 5)).cuda()
+    flats = {}
+    for mode in (False, True):
+        enc, dec = build_train_models(m)
+        step = zt.PretrainAE(enc, dec, async_wgrad=mode, use_graph=False)
+        loss, _ = step.forward_backward(x, c, noise=noise, dropout_seed=7)
+        torch.cuda.synchronize()
+        flats[mode] = (loss.item(), step.enc.grad.clone(), step.dec.grad.clone())
+    assert abs(flats[True][0] - flats[False][0]) <= 1e-5 * flats[False][0], (flats[True][0], flats[False][0])   # (atomic partial sums)
+    for a, b in zip(flats[True][1:], flats[False][1:]):
+        assert torch.isfinite(a).all()
+        assert (a - b).norm().item() <= 1e-5 * b.norm().item(), ((a - b).norm().item(), b.norm().item())
+        assert (a - b).abs().max().item() <= 1e-4 * b.abs().max().item()
+    # graph replays with the fork / join captured.  lr = 0 keeps the parameters fixed, so the gradients of the last replay
+    # are comparable (with real updates Adam's early +-lr steps amplify the atomic-order noise of near-zero gradients)
+    grads = {}
+    for mode in (False, True):
+        torch.manual_seed(3)                   # same device-drawn Gumbel noise in both runs
+        enc, dec = build_train_models(m)
+        step = zt.PretrainAE(enc, dec, lr=0.0, async_wgrad=mode, use_graph=True)
+        losses = [step.step(x, c).item() for _ in range(4)]            # two eager steps, capture, two replays
+        torch.cuda.synchronize()
+        assert step._graph is not None and step.applied_steps() == 4
+        grads[mode] = (losses, step.enc.grad.clone(), step.dec.grad.clone())
+    for a, b in zip(grads[True][0], grads[False][0]):
+        assert abs(a - b) <= 1e-5 * b
+    for a, b in zip(grads[True][1:], grads[False][1:]):
+        assert b.norm().item() > 0
+        assert (a - b).norm().item() <= 1e-5 * b.norm().item(), ((a - b).norm().item(), b.norm().item())
+    lib = _lib.lib()
+    _lib.check(lib.zs_wgrad_async(1))
+    _lib.check(lib.zs_wgrad_join(None))        # nothing pending: no-op
+    _lib.check(lib.zs_wgrad_async(0))
+
+
 def test_training_reduces_loss_and_eval_sees_updates():
     """A few real steps: loss goes down, no overflow skips, and the eval path picks up the updated weights."""
     m = dict(seed=0, c_in=513, c_h=[128, 512, 128], enc_size=1024, emb_size=1024, n_spk=102, ns=0.01, seg_len=128, dp=0.5)

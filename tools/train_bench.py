@@ -14,7 +14,8 @@ dec = Decoder(ns=0.01, c_in=1024, c_h=1024, c_a=102, seg_len=128)
 enc.load_state_dict(syn.encoder_state_dict(0, enc_size=1024, enc_mode='one_hot'))
 dec.load_state_dict(syn.decoder_state_dict(0, c_in=1024, c_h=1024, c_a=102))
 enc.cuda().train(); dec.cuda().train()
-step = zt.PretrainAE(enc, dec, use_graph=(len(sys.argv) <= 3 or sys.argv[3] != 'eager'))
+step = zt.PretrainAE(enc, dec, use_graph=(len(sys.argv) <= 3 or sys.argv[3] != 'eager'),
+                     async_wgrad=(len(sys.argv) <= 4 or sys.argv[4] != 'sync'))     # argv: B steps eager|graph sync|async
 xs = [syn.spectrogram_batch(B, 128, s).cuda() for s in range(4)]
 cs = [syn.speaker_ids(B, 102, s).cuda() for s in range(4)]
 for i in range(5):

@@ -159,6 +159,8 @@ SYMBOLS = {
     'zs_decoder_forward_train': (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _sz, _vp]),
     'zs_decoder_backward': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, C.c_float, _vp, C.POINTER(DecoderWeights), _vp,
                                  _vp, _sz, _vp]),
+    'zs_wgrad_async': (_i, [C.c_int]),
+    'zs_wgrad_join': (_i, [_vp]),
     'zs_grad_sqnorm': (_i, [_vp, _sz, _vp, _vp]),
     'zs_adam_step': (_i, [_vp, _vp, _vp, _vp, _sz, _vp, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
                           C.c_float, _i, _vp, _vp, _vp]),

@@ -7,7 +7,12 @@
 // -------------------------------------------------------------------------------------------------
 // weight-gradient GEMM launcher
 // -------------------------------------------------------------------------------------------------
+// K splits fill this many QUARTER waves of SMs.  Measured at B = 32 (pretrain_AE step, graph replay, in-order launches): 8 quarter
+// waves 6.42 ms, 4: 6.14, 2: 5.82 - the fp32 atomic adds of the split partial sums cost more than the idle SMs; with the
+// launches on the side streams of zs_wgrad_async 1 quarter wave is best (5.26 ms) because concurrent launches fill the rest.
+static int g_wgrad_waves = 1;
 static int launch_wgrad(const zs_wgrad_desc* d, cudaStream_t st) {
+    { static const int w = env_int("ZS_WGRAD_QWAVES", 1); g_wgrad_waves = w < 1 ? 1 : w; }
     ZS_TRY(ensure_device());
     if (!d->dy || !d->x || !d->grad) return fail(ZS_ERR_ARG, "wgrad: null pointer");
     if (d->dy_pitch % 8 || d->x_pitch % 8) return fail(ZS_ERR_ARG, "wgrad: buffer pitches must be multiples of 8");
@@ -22,13 +27,16 @@ static int launch_wgrad(const zs_wgrad_desc* d, cudaStream_t st) {
     p.m_tiles = (d->c_in + 127) / 128; p.n_tiles = (d->c_out + 255) / 256; p.taps = d->taps;     // M = input channels
     p.n_blk_last = (d->c_out - (p.n_tiles - 1) * 256 + 63) / 64;
     const int k_stages = p.n_groups * p.seg_steps, items0 = p.m_tiles * p.n_tiles * p.taps;
-    int ksplit = (2 * g_num_sms + items0 - 1) / items0;
+    int ksplit = (g_wgrad_waves * g_num_sms / 4 + items0 - 1) / items0;
+    // large batches (not measured above): no CTA reduces more than 256 stages while SMs are left to split over
+    const int ksplit_deep = std::min((k_stages + 255) / 256, std::max(1, 2 * g_num_sms / items0));
+    ksplit = std::max(ksplit, ksplit_deep);
     ksplit = std::max(1, std::min(ksplit, std::max(1, k_stages / 4)));
     // At small batches the kernel is bound by its fp32 atomic adds (one per weight per K split), not by the MMAs:
     // when the gradient is known to be zero and the items fill at least half the SMs on their own, keep the reduction
     // whole and store (measured at B = 32 on one box: 2.35 ms of weight-gradient GEMMs per step -> 2.10 ms).
-    static const int direct_mode = env_int("ZS_WGRAD_DIRECT", 2);   // 0 off, 1 >= SMs, 2 >= SMs / 2 (measured best at B = 32)
-    p.direct = (d->grad_is_zero && direct_mode > 0 && direct_mode * items0 >= g_num_sms) ? 1 : 0;
+    static const int direct_mode = env_int("ZS_WGRAD_DIRECT", 8);   // 0 off, n: items >= SMs / n (8 measured best at B = 32: 5.25 ms vs 5.29 at 2)
+    p.direct = (d->grad_is_zero && direct_mode > 0 && direct_mode * items0 >= g_num_sms && ksplit_deep == 1) ? 1 : 0;
     if (p.direct) ksplit = 1;
     p.ksplit = ksplit;
     p.grad = d->grad; p.c_in = d->c_in; p.c_in_total = d->c_in_total; p.ci_off = d->ci_off; p.c_out = d->c_out; p.k = d->k; p.tap0 = d->tap0;
@@ -126,8 +134,63 @@ struct WgradOpts {
     int pad_left = -1;    // frames of left padding the forward conv saw (default k / 2)
     int x_shift = 0;      // extra row offset (GRU: h_{t-1} / h_{t+1})
 };
+// Weight (and bias) gradients are leaves of the backward pass: nothing downstream of the data-gradient chain reads them
+// before the optimiser.  zs_wgrad_async(1) moves them onto a per-device side stream that forks from the caller's stream
+// after the kernel that produced `dpre` (an event record / wait pair, capturable into a CUDA graph), so the small-batch
+// step overlaps the latency-bound weight-gradient GEMMs with the data-gradient / element-wise / GRU chain.  Every gradient
+// buffer of a backward pass is written once and forward activations are read-only there, so the fork needs no
+// write-after-read edges.  The caller joins with zs_wgrad_join(stream) before it reads the gradients.
+constexpr int WGRAD_STREAMS_MAX = 4;
+struct WgradSide { cudaStream_t s[WGRAD_STREAMS_MAX] = {}; cudaEvent_t fork[WGRAD_STREAMS_MAX] = {}, join[WGRAD_STREAMS_MAX] = {}; };
+static WgradSide g_wside[MAX_DEV];
+static thread_local int t_wgrad_async = 0, t_wgrad_next = 0;
+static thread_local unsigned t_wgrad_pending = 0;          // bit i: side stream i holds unjoined work
+static int wgrad_streams() {     // concurrent weight-gradient launches: each fills at most half the SMs (see launch_wgrad)
+    static const int n = std::max(1, std::min(WGRAD_STREAMS_MAX, env_int("ZS_WGRAD_STREAMS", 3)));
+    return n;
+}
+extern "C" int zs_wgrad_async(int on) {
+    ZS_TRY(ensure_device());
+    if (t_wgrad_pending) return fail(ZS_ERR_ARG, "wgrad_async: weight gradients still in flight - call zs_wgrad_join first");
+    if (on) {
+        std::lock_guard<std::mutex> lk(g_dev_mu);
+        WgradSide& w = g_wside[t_dev];
+        for (int i = 0; i < WGRAD_STREAMS_MAX && !w.s[WGRAD_STREAMS_MAX - 1]; ++i) {
+            CUDA_TRY(cudaStreamCreateWithFlags(&w.s[i], cudaStreamNonBlocking));
+            CUDA_TRY(cudaEventCreateWithFlags(&w.fork[i], cudaEventDisableTiming));
+            CUDA_TRY(cudaEventCreateWithFlags(&w.join[i], cudaEventDisableTiming));
+        }
+    }
+    t_wgrad_async = on ? 1 : 0;
+    t_wgrad_next = 0;
+    return ZS_OK;
+}
+extern "C" int zs_wgrad_join(void* stream) {
+    if (!t_wgrad_pending) return ZS_OK;
+    ZS_TRY(ensure_device());
+    WgradSide& w = g_wside[t_dev];
+    for (int i = 0; i < WGRAD_STREAMS_MAX; ++i)
+        if (t_wgrad_pending & (1u << i)) {
+            CUDA_TRY(cudaEventRecord(w.join[i], w.s[i]));
+            CUDA_TRY(cudaStreamWaitEvent(static_cast<cudaStream_t>(stream), w.join[i], 0));
+        }
+    t_wgrad_pending = 0;
+    return ZS_OK;
+}
+
 static int run_wgrad(const Buf& dpre, const Buf& x, int B, int T, float* grad_w, float* grad_b, float inv_scale, const WgradOpts& o,
                      cudaStream_t st) {
+    if (t_wgrad_async && !g_prof_on) {       // (per-launch profiling keeps one stream so that its times add up)
+        ZS_TRY(ensure_device());
+        WgradSide& w = g_wside[t_dev];
+        const int i = t_wgrad_next;
+        t_wgrad_next = (i + 1) % wgrad_streams();
+        if (!w.s[i]) return fail(ZS_ERR_ARG, "wgrad: zs_wgrad_async(1) was called on another device");
+        CUDA_TRY(cudaEventRecord(w.fork[i], st));
+        CUDA_TRY(cudaStreamWaitEvent(w.s[i], w.fork[i], 0));
+        st = w.s[i];
+        t_wgrad_pending |= 1u << i;
+    }
     zs_wgrad_desc d;
     memset(&d, 0, sizeof(d));
     d.dy = dpre.p; d.dy_rows = dpre.rows; d.dy_pitch = dpre.pitch; d.dy_channels = dpre.pitch; d.dy_ch0 = o.dy_ch0; d.dy_row0 = dpre.halo; d.c_out = o.c_out;

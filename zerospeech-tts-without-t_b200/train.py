@@ -71,7 +71,7 @@ class PretrainAE:
     """One object = the (Encoder, Decoder, ae_opt) triple of trainer.py:58-66 with `step()` = trainer.py:321-332."""
 
     def __init__(self, encoder: Encoder, decoder: Decoder, lr=1e-4, betas=(0.5, 0.9), eps=1e-8, max_grad_norm=5.0,
-                 loss_scale=None, process_group=None, cpu_noise=False, use_graph=True):
+                 loss_scale=None, process_group=None, cpu_noise=False, use_graph=True, async_wgrad=True):
         if encoder.enc_mode != 'one_hot':
             raise RuntimeError("PretrainAE: the training path implements enc_mode 'one_hot'")
         self.enc, self.dec = _Net(encoder), _Net(decoder)
@@ -80,8 +80,13 @@ class PretrainAE:
         self.step_count = 0
         self.good_steps = 0
         self.cpu_noise = cpu_noise
+        # weight-gradient GEMMs on the library's side streams (include/zs_ae.h zs_wgrad_async): single-rank steps only.
+        # A 2-GPU run with it enabled next to the captured NCCL all-reduces did not finish within its time limit
+        # (gpurun_out/r4d, cause not isolated), so data-parallel steps keep the in-order launches measured in round 2.
+        self.async_wgrad = bool(async_wgrad)
         self.pg = process_group
         self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
+        self.async_wgrad = self.async_wgrad and self.world == 1
         dev = self.enc.flat.device
         self.loss = torch.zeros(1, dtype=torch.float32, device=dev)
         self.skipped = torch.zeros(1, dtype=torch.int32, device=dev)
@@ -185,11 +190,19 @@ class PretrainAE:
         self.loss.zero_()
         act, _, ids = enc.forward_train(x, noise, dropout_seed, keep_masks, seed_dev)   # trainer.py:325
         dec.forward_train(act, c)                                                        # :326
-        d_act = dec.backward(self.dec.grad_views, self.loss_scale, target=x, loss_out=self.loss)   # :327-329
-        if self.world > 1:                  # decoder gradients travel while the encoder backward runs
-            self.side.wait_stream(torch.cuda.current_stream())
-            self._allreduce(self.dec, self.side)
-        enc.backward(d_act, self.enc.grad_views, self.loss_scale, d_act_scale=self.loss_scale)
+        lib = _lib.lib()
+        with torch.cuda.device(dev):
+            if self.async_wgrad:            # weight-gradient GEMMs leave the data-gradient chain (include/zs_ae.h)
+                _lib.check(lib.zs_wgrad_async(1))
+            try:
+                d_act = dec.backward(self.dec.grad_views, self.loss_scale, target=x, loss_out=self.loss)   # :327-329
+                if self.world > 1:          # decoder gradients travel while the encoder backward runs
+                    self.side.wait_stream(torch.cuda.current_stream())
+                    self._allreduce(self.dec, self.side)
+                enc.backward(d_act, self.enc.grad_views, self.loss_scale, d_act_scale=self.loss_scale)
+            finally:
+                _lib.check(lib.zs_wgrad_join(_stream()))
+                _lib.check(lib.zs_wgrad_async(0))
         return self.loss, ids
 
     def _finish(self, dev):
