@@ -607,6 +607,9 @@ def measure_train(args, dev, world, rank, steps, warmup, clocks=False):
            'e2e_ms_per_step': t_e2e / steps * 1e3, 'e2e_frames_per_s': frames * steps / t_e2e,
            'h2d_bytes_per_step': B * (513 * FRAMES * 4 + 8), 'd2h_bytes_per_step': 4,
            'cuda_graph': bool(step.use_graph and step._graph is not None), 'n_ranks': world,
+           'wgrad_side_streams': bool(step.async_wgrad),     # zs_wgrad_async: weight-gradient GEMMs overlap the data-gradient chain
+           'kernel_ms_note': 'per-class times of one eager iteration with in-order launches (they add up); the timed graph replays overlap '
+                             'the weight-gradient GEMMs with the rest, so ms_per_step is below their sum' if world == 1 else None,
            'allreduce': None if world == 1 else {'backend': 'nccl', 'bytes_per_step': n_params * 4, 'tensors': 2,
                                                  'ms_alone': ar_ms, 'algbw_gb_per_s': n_params * 4 / (ar_ms * 1e-3) / 1e9,
                                                  'overlap': 'decoder gradients (170 MB) reduce on a side stream under the encoder backward; '
