@@ -392,6 +392,23 @@ int zs_conv1d_cl(const zs_conv_desc* d, void* stream);
  * Results are bit-identical in all modes. */
 void zs_set_gemm_pair_mode(int mode);
 
+/* ---- 2-D critic / classifier forward (model/model.py:113-226: PatchDiscriminator, TargetClassifier) --------
+ * A k x k stride-s Conv2d over (H, W) with reflect padding (pad_layer(is_2d=True), model/model.py:29-38) runs as ONE zs_conv1d_cl
+ * call (taps = k along W, stride s, c_in = KH * C): zs_conv2d_gather writes, for segment (b, ho) and padded frame wp, the KH
+ * source rows reflect(stride_h * ho + kh - pad_h) side by side, channel kh * C + ci, frame reflect(wp - pad_w); fp16.
+ *   src: fp32 (B, H, W) single-channel network input (src_is_f32 = 1, C = 1, out_pitch = 8) or the fp16 channels-last
+ *        output of the previous layer, [(b*H + h)*W + w][src_pitch].
+ *   stats / inv_count: [B][C] x 2 int64 = (sum, sum of squares) x 2^20 per (b, c) of the source from zs_instnorm2d_stats (fixed
+ *        point, so that the split reduction is order-independent) and 1 / (H*W): the source is
+ *        normalised on the way (nn.InstanceNorm2d, biased variance, eps 1e-5: model/model.py:139-144); NULL = as is.
+ * zs_instnorm2d_stats: stats[b][c] = 2^20 x (sum, sum of squares) over the P rows of sample b of y = fp16 [B][P][pitch].
+ * zs_critic_head: conv7 / conv_classify, whose kernel covers the whole remaining map (model/model.py:123-131):
+ *   out[b][j] = bias[j] + sum_(p, c) y[b][p][c] * w[j][p][c]   (w fp32 [J][P][C]). */
+int zs_conv2d_gather(const void* src, int src_is_f32, int B, int H, int W, int C, int src_pitch, int KH, int stride_h, int pad_h,
+                     int pad_w, int Ho, int Wp, const void* stats, float inv_count, void* out, int out_pitch, void* stream);
+int zs_instnorm2d_stats(const void* y, int B, long long P, int C, int pitch, void* stats, void* stream);
+int zs_critic_head(const void* y, int B, int P, int C, int pitch, const float* w, const float* bias, int J, float* out, void* stream);
+
 /* (B, C, T) fp32 -> channels-last operand buffer [B][rows][pitch] with `halo` reflected rows each side;
  * optional leaky-relu; channels C..pitch-1 are zero-filled. */
 int zs_pack_nct(const float* x, int B, int C, int T, void* out, int rows, int pitch, int halo, int choff,

@@ -159,6 +159,10 @@ SYMBOLS = {
     'zs_decoder_forward_train': (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _sz, _vp]),
     'zs_decoder_backward': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, C.c_float, _vp, C.POINTER(DecoderWeights), _vp,
                                  _vp, _sz, _vp]),
+    'zs_conv2d_gather': (_i, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                              _vp, C.c_float, _vp, C.c_int, _vp]),
+    'zs_instnorm2d_stats': (_i, [_vp, C.c_int, C.c_longlong, C.c_int, C.c_int, _vp, _vp]),
+    'zs_critic_head': (_i, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, C.c_int, _vp, _vp]),
     'zs_wgrad_async': (_i, [C.c_int]),
     'zs_wgrad_join': (_i, [_vp]),
     'zs_grad_sqnorm': (_i, [_vp, _sz, _vp, _vp]),

@@ -1434,3 +1434,4 @@ extern "C" int zs_patcher_forward(zs_patcher* h, const float* x, const int64_t* 
 
 #include "zs_train.cuh"
 #include "zs_dsp.cuh"
+#include "critic.cuh"

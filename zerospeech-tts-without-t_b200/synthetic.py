@@ -134,6 +134,31 @@ def patcher_state_dict(seed=0, **kw):
     return _fill(patcher_shapes(**kw), 6000 + seed)
 
 
+def critic_shapes(n_class=33, seg_len=128, with_value=True):
+    """PatchDiscriminator (with_value) / TargetClassifier (model/model.py:113-131, 169-187): name -> (shape, fan_in)."""
+    kw = {128: 4, 64: 2, 32: 1}[seg_len]
+    chans = [(1, 64), (64, 128), (128, 256), (256, 512), (512, 512)]
+    sh = OrderedDict()
+    for i, (ci, co) in enumerate(chans, 1):
+        sh[f'conv{i}.weight'] = ((co, ci, 5, 5), ci * 25)
+        sh[f'conv{i}.bias'] = ((co,), ci * 25)
+    sh['conv6.weight'] = ((32, 512, 1, 1), 512)
+    sh['conv6.bias'] = ((32,), 512)
+    if with_value:
+        sh['conv7.weight'] = ((1, 32, 17, kw), 32 * 17 * kw)
+        sh['conv7.bias'] = ((1,), 32 * 17 * kw)
+    sh['conv_classify.weight'] = ((n_class, 32, 17, kw), 32 * 17 * kw)
+    sh['conv_classify.bias'] = ((n_class,), 32 * 17 * kw)
+    if not with_value:      # TargetClassifier declares conv7 too (model/model.py:180-187) although its forward never uses it
+        sh['conv7.weight'] = ((1, 32, 17, kw), 32 * 17 * kw)
+        sh['conv7.bias'] = ((1,), 32 * 17 * kw)
+    return sh
+
+
+def critic_state_dict(seed=0, **kw):
+    return _fill(critic_shapes(**kw), 7000 + seed)
+
+
 def enhanced_generator_state_dict(seed=0, c_in=513, c_h1=128, c_h2=512, c_h3=128, enc_size=1024, emb_size=1024, n_speakers=102):
     """Enhanced_Generator (model/model.py:492-502): `Encoder.*` (continues mode) + `Decoder.*`."""
     sd = OrderedDict()
