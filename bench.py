@@ -656,6 +656,35 @@ def run_train(args):
 # ------------------------------------------------------------------------------------------------
 # sharded product API (every N): ShardedPath.convert_utterances over the ranks
 # ------------------------------------------------------------------------------------------------
+def sub_critic(dev, check=True):
+    """SURVEY 8 f4, forward part: PatchDiscriminator (model/model.py:113-166) value + auxiliary logits on 32 and 256 segments of
+    128 frames (trainer.py:257-259 calls it on a 32-segment batch twice per step), checked against the oracle on two samples."""
+    from zs_b200 import critic as zc, synthetic as syn
+    sd = syn.critic_state_dict(3, n_class=33, seg_len=FRAMES)
+    net = zc.PatchDiscriminator(n_class=33, seg_len=FRAMES)
+    net.load_state_dict(sd, strict=True)
+    net.to(dev).eval()
+    flop_per_segment = 0.0
+    H, W = 513, FRAMES
+    for ci, co in ((1, 64), (64, 128), (128, 256), (256, 512), (512, 512)):
+        H, W = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+        flop_per_segment += 2.0 * H * W * co * ci * 25
+    flop_per_segment += 2.0 * H * W * 32 * 512 + 2.0 * 34 * 32 * H * W
+    rec = {'workload': f'PatchDiscriminator.forward(x, classify=True), (B, 513, {FRAMES}) fp32 in HBM -> value + 33 logits, eval mode',
+           'gflop_per_segment': flop_per_segment / 1e9}
+    for B in (32, 256):
+        x = syn.spectrogram_batch(B, FRAMES, 970).to(dev)
+        ms = event_time(lambda i: net(x, classify=True), 10, 3, dev)
+        rec[f'b{B}'] = {'ms': ms, 'frames_per_s': B * FRAMES / ms * 1e3, 'tflops': B * flop_per_segment / (ms * 1e-3) / 1e12}
+    if check:       # the oracle as the checker (CPU leg)
+        from oracle import critic_oracle as corc
+        x2 = syn.spectrogram_batch(2, FRAMES, 971)
+        v, lg = net(x2.to(dev), classify=True)
+        v_o, lg_o = corc.patch_discriminator(sd, x2)
+        rec['max_abs_vs_oracle'] = max((v.cpu() - v_o).abs().max().item(), (lg.cpu() - lg_o).abs().max().item())
+    return rec
+
+
 def measure_sharded(dev, world, rank, enc, dec):
     import numpy as np
     import torch.distributed as dist
@@ -907,6 +936,10 @@ def run_ours(args):
                 line['dsp'] = sub_dsp(dev, enc, dec, peaks)
             except Exception as exc:
                 line['dsp'] = {'unavailable': f'{type(exc).__name__}: {exc}'[:300]}
+            try:
+                line['critic'] = sub_critic(dev, check=not args.no_cpu_baseline)
+            except Exception as exc:
+                line['critic'] = {'unavailable': f'{type(exc).__name__}: {exc}'[:300]}
             try:
                 line['cuda_eager_baseline'] = sub_eager(dev)
                 line['cuda_eager_baseline']['ours_vs_eager_b960'] = (value / world) / line['cuda_eager_baseline']['b960']['frames_per_s']
