@@ -86,7 +86,7 @@ class PretrainAE:
         self.async_wgrad = bool(async_wgrad)
         self.pg = process_group
         self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
-        self.async_wgrad = self.async_wgrad and self.world == 1
+        self.async_wgrad = async_wgrad == 'force' or (self.async_wgrad and self.world == 1)     # 'force': tools/wgrad_async_dp_probe.py
         dev = self.enc.flat.device
         self.loss = torch.zeros(1, dtype=torch.float32, device=dev)
         self.skipped = torch.zeros(1, dtype=torch.int32, device=dev)
