@@ -197,6 +197,7 @@ class PretrainAE:
             try:
                 d_act = dec.backward(self.dec.grad_views, self.loss_scale, target=x, loss_out=self.loss)   # :327-329
                 if self.world > 1:          # decoder gradients travel while the encoder backward runs
+                    _lib.check(lib.zs_wgrad_join(_stream()))          # (no-op unless async_wgrad was forced on)
                     self.side.wait_stream(torch.cuda.current_stream())
                     self._allreduce(self.dec, self.side)
                 enc.backward(d_act, self.enc.grad_views, self.loss_scale, d_act_scale=self.loss_scale)
